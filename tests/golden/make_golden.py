@@ -1,0 +1,223 @@
+"""Generate golden vectors by running the UNMODIFIED reference on seeded inputs.
+
+Run in the build container only (needs /root/reference):
+
+    python tests/golden/make_golden.py
+
+It imports the reference's own modules with the two shims of SURVEY.md App. B
+(an `easydict` stub; `get_pose_net -> nn.Identity()` so that
+`KPDetector3DMulti.forward` runs its lines 67-88 on supplied logits), calls
+them on the synthetic inputs of `x-as-supervision_b200/synth.py`, and stores
+the outputs as `tests/golden/*.npz`.  Inputs are regenerated from seeds at
+test time; an input checksum is stored to catch RNG drift.
+
+Nothing here is read on the GPU box; only the .npz files travel.
+"""
+import importlib
+import os
+import sys
+import types
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+REF = os.environ.get("XSUP_REFERENCE", "/root/reference")
+sys.path.insert(0, ROOT)
+synth = importlib.import_module("x-as-supervision_b200.synth")
+
+
+def load_reference():
+    ed = types.ModuleType("easydict")
+
+    class EasyDict(dict):
+        def __getattr__(self, k):
+            try:
+                return self[k]
+            except KeyError:
+                raise AttributeError(k)
+
+        def __setattr__(self, k, v):
+            self[k] = v
+
+    ed.EasyDict = EasyDict
+    sys.modules["easydict"] = ed
+    sys.path.insert(0, REF)
+    multi = importlib.import_module("modules.keypoint_detector_integral_multi")
+    single = importlib.import_module("modules.keypoint_detector_integral")
+    multi.get_pose_net = lambda cfg, num_joints: nn.Identity()
+    single.get_pose_net = lambda cfg, num_joints: nn.Identity()
+    util = importlib.import_module("modules.util")
+    lf = importlib.import_module("modules.base_losses.loss_func")
+    return multi, single, util, lf
+
+
+def checksum(t):
+    t = t.double().flatten()
+    return np.array([t.sum().item(), (t * torch.arange(1, t.numel() + 1, dtype=torch.float64) % 7.0).sum().item(),
+                     t[0].item(), t[-1].item()])
+
+
+def run_in(dtype, fn):
+    old = torch.get_default_dtype()
+    torch.set_default_dtype(dtype)   # the reference builds its aranges with the default dtype (:50-51,57)
+    try:
+        return fn()
+    finally:
+        torch.set_default_dtype(old)
+
+
+def head_case(multi, name, gen, B, K, R, NH, NS, seed, grad_stride):
+    logits32 = gen(B, K, R, R, R, seed=seed)
+    out = {"meta": np.array([B, K, R, R, R, NH, NS, seed, grad_stride]), "in_checksum": checksum(logits32)}
+    gw = torch.randn(B, NH, K, 3, generator=torch.Generator().manual_seed(100 + seed), dtype=torch.float64)
+    out["g_kps"] = gw.numpy()
+    for tag, dt in (("f32", torch.float32), ("f64", torch.float64)):
+        def go():
+            det = multi.KPDetector3DMulti("resnet_multi", K, R, NH, NS)
+            x = logits32.to(dt).clone().requires_grad_(True)
+            kps, dmap = det(x)
+            # peak bins exactly as the module computes them
+            with torch.no_grad():
+                p = torch.softmax(x.detach().view(B, K, -1), 2).view(B, K, R, R, R)
+                idx = det.find_peak(p.sum(dim=3).sum(dim=3))
+            (kps * gw.to(dt)).sum().backward()
+            return kps.detach(), dmap.detach(), idx, x.grad.detach()
+        kps, dmap, idx, g = run_in(dt, go)
+        out["kps_" + tag] = kps.numpy()
+        out["dmap_" + tag] = dmap.numpy()
+        out["idx_" + tag] = idx.numpy()
+        gf = g.flatten()
+        out["grad_sub_" + tag] = gf[::grad_stride].numpy().astype(np.float64 if dt == torch.float64 else np.float32)
+        out["grad_norms_" + tag] = np.array([gf.double().abs().max().item(), gf.double().norm().item(),
+                                             gf.double().sum().item()])
+    # number of genuine local maxima per row (fp64), so tests know which slots are defined
+    p = torch.softmax(logits32.double().view(B, K, -1), 2).view(B, K, R, R, R)
+    pz = p.sum(dim=(3, 4))
+    mid = pz[..., 1:-1]
+    out["num_peaks"] = ((mid >= pz[..., :-2]) & (mid >= pz[..., 2:])).sum(-1).numpy()
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
+    print("wrote", name, {k: v.shape for k, v in out.items()})
+
+
+def single_case(single, name, B, K, R, seed):
+    logits32 = synth.iid_logits(B, K, R, R, R, seed=seed)
+    out = {"meta": np.array([B, K, R, seed]), "in_checksum": checksum(logits32)}
+    for tag, dt in (("f32", torch.float32), ("f64", torch.float64)):
+        def go():
+            det = single.KPDetector3D("resnet", K, R)
+            kps, dmap = det(logits32.to(dt))
+            return kps, dmap
+        kps, dmap = run_in(dt, go)
+        out["kps_" + tag] = kps.numpy()
+        out["dmap_" + tag] = dmap.numpy()
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
+    print("wrote", name)
+
+
+def geometry_case(util, name, B, K, seed, mpi):
+    cams = synth.cameras(B, seed=seed, mpi=mpi)
+    kps = synth.pseudo_joints(B, K, seed=seed + 1)
+    out = {"meta": np.array([B, K, seed, int(mpi)]), "in_checksum": checksum(kps)}
+    for tag, dt in (("f32", torch.float32), ("f64", torch.float64)):
+        c = {k: v.to(dt) for k, v in cams.items()}
+        params = synth.camera_dict(c, "cam_0")
+        k = kps.to(dt)
+        world = util.convert_patch_to_world(k, params, "cam_0", is_norm=True)
+        back = util.convert_world_to_patch(world, params, "cam_0", is_norm=True)
+        mono = util.convert_patch_to_world(k, params, "cam_0", is_norm=True, RECT_WIDTH=256, mono=True, patch=False)
+        img = util.convert_patch_to_image(k, c["trans_image"].clone(), 256, 256, 256, 2000.0 / 256, c["pelvis"])
+        out["world_" + tag] = world.numpy()
+        out["back_" + tag] = back.numpy()
+        out["mono_" + tag] = mono.numpy()
+        out["image_" + tag] = img.numpy()
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
+    print("wrote", name)
+
+
+def loss_case(multi, util, lf, name, gen, B, K, R, NH, NS, seed, weights, grad_stride, mpi=False):
+    """model.py:71-79 (per-hypothesis world lift), :105-114 (symmetry min), :158-162 (pseudo min),
+    driven with the reference's own functions, fwd + bwd to the logits."""
+    w_mse, w_bone, w_kp, w_kp2d = weights
+    logits32 = gen(B, K, R, R, R, seed=seed)
+    target = synth.pseudo_joints(B, K, seed=seed + 2)
+    cams = synth.cameras(B, seed=seed + 3, mpi=mpi)
+    # every (b,k) row must have >= NH genuine depth peaks, else the reference's loss rides on
+    # torch.topk's arbitrary order among tied zeros
+    p = torch.softmax(logits32.double().view(B, K, -1), 2).view(B, K, R, R, R)
+    pz = p.sum(dim=(3, 4))
+    mid = pz[..., 1:-1]
+    assert int(((mid >= pz[..., :-2]) & (mid >= pz[..., 2:])).sum(-1).min()) >= NH, name
+    out = {"meta": np.array([B, K, R, NH, NS, seed, grad_stride, int(mpi)]),
+           "weights": np.array([w if w is not None else np.nan for w in weights], dtype=np.float64),
+           "in_checksum": checksum(logits32)}
+    for tag, dt in (("f32", torch.float32), ("f64", torch.float64)):
+        def go():
+            det = multi.KPDetector3DMulti("resnet_multi", K, R, NH, NS)
+            x = logits32.to(dt).clone().requires_grad_(True)
+            c = {k: v.to(dt) for k, v in cams.items()}
+            params = synth.camera_dict(c, "cam_0")
+            kps, _ = det(x)
+            world = torch.stack([util.convert_patch_to_world(kps[:, i], params, "cam_0", is_norm=True)
+                                 for i in range(NH)], dim=1)
+            pseudo = [lf.compute_supervision(kps[:, i], target.to(dt)) for i in range(NH)]
+            loss_p = torch.min(torch.stack(pseudo)) * w_mse
+            sym = []
+            use_sym = any(w is not None for w in (w_bone, w_kp, w_kp2d))
+            loss_s = torch.zeros((), dtype=dt)
+            if use_sym:
+                for i in range(NH):
+                    t = 0
+                    t = t + lf.compute_bone_sym_loss(world[:, i]) * (w_bone or 0.0)
+                    t = t + lf.compute_kp_sym_loss(world[:, i]) * (w_kp or 0.0)
+                    if w_kp2d is not None:
+                        t = t + lf.compute_kp_sym_loss(kps[:, i, :, :2], is_3D=False) * 1e2 * w_kp2d
+                    sym.append(t)
+                loss_s = torch.min(torch.stack(sym))
+            (loss_p + loss_s).backward()
+            return (kps.detach(), world.detach(), torch.stack(pseudo).detach(),
+                    torch.stack(sym).detach() if use_sym else torch.zeros(NH, dtype=dt),
+                    loss_p.detach(), loss_s.detach(), x.grad.detach())
+        kps, world, pseudo, sym, lp, ls, g = run_in(dt, go)
+        out["kps_" + tag] = kps.numpy()
+        out["world_" + tag] = world.numpy()
+        out["pseudo_h_" + tag] = pseudo.numpy()
+        out["sym_h_" + tag] = sym.numpy()
+        out["loss_" + tag] = np.array([lp.item(), ls.item()])
+        gf = g.flatten()
+        out["grad_sub_" + tag] = gf[::grad_stride].numpy()
+        out["grad_norms_" + tag] = np.array([gf.double().abs().max().item(), gf.double().norm().item(),
+                                             gf.double().sum().item()])
+    # eval-style per-joint best hypothesis (eval.py:138-145), fp64
+    k64 = torch.from_numpy(out["kps_f64"])
+    best_idx = (k64 - target.double()[:, None]).pow(2).sum(dim=-1).argmin(dim=1)
+    out["best_idx_f64"] = best_idx.numpy()
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
+    print("wrote", name, "loss", out["loss_f64"], "pseudo_h", out["pseudo_h_f64"], "sym_h", out["sym_h_f64"])
+
+
+def main():
+    torch.manual_seed(0)
+    torch.set_num_threads(8)
+    multi, single, util, lf = load_reference()
+    head_case(multi, "head_iid_k18_r16", synth.iid_logits, B=2, K=18, R=16, NH=3, NS=5, seed=0, grad_stride=7)
+    head_case(multi, "head_blob_k17_r32", synth.blob_logits, B=2, K=17, R=32, NH=3, NS=15, seed=1, grad_stride=61)
+    head_case(multi, "head_blob_k18_r64", synth.blob_logits, B=1, K=18, R=64, NH=3, NS=15, seed=4, grad_stride=997)
+    head_case(multi, "head_iid_k3_r8_nh2", synth.iid_logits, B=3, K=3, R=8, NH=2, NS=3, seed=5, grad_stride=1)
+    single_case(single, "single_iid_k18_r16", B=2, K=18, R=16, seed=6)
+    geometry_case(util, "geom_h36m", B=8, K=18, seed=7, mpi=False)
+    geometry_case(util, "geom_mpi", B=8, K=18, seed=8, mpi=True)
+    # SurS1: pseudo-MSE x3.0 only (HM36_Multi_SurS1.yaml:72-73)
+    loss_case(multi, util, lf, "loss_surs1_k17_r16", synth.iid_logits, B=4, K=17, R=16, NH=3, NS=5, seed=10,
+              weights=(3.0, None, None, None), grad_stride=13)
+    # SynthS2: pseudo 1.0, bone 0.1, kp 0.1, kp_2d 0.0 (HM36_Multi_SynthS2.yaml:66-86)
+    loss_case(multi, util, lf, "loss_synths2_k18_r32", synth.blob_logits, B=2, K=18, R=32, NH=3, NS=15, seed=12,
+              weights=(1.0, 0.1, 0.1, 0.0), grad_stride=53)
+    loss_case(multi, util, lf, "loss_synths2_k17_r32_mpi", synth.iid_logits, B=2, K=17, R=32, NH=4, NS=15, seed=12,
+              weights=(1.0, 0.1, 0.1, 0.5), grad_stride=127, mpi=True)
+
+
+if __name__ == "__main__":
+    main()

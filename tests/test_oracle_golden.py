@@ -1,0 +1,139 @@
+"""Pin the CPU oracle against outputs of the reference itself (tests/golden/*.npz,
+made by tests/golden/make_golden.py from /root/reference).  CPU only."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import input_checksum, load_golden, rel_inf, rel_l2
+
+HEAD_CASES = [
+    ("head_iid_k18_r16", "iid_logits"),
+    ("head_blob_k17_r32", "blob_logits"),
+    ("head_blob_k18_r64", "blob_logits"),
+    ("head_iid_k3_r8_nh2", "iid_logits"),
+]
+
+
+def _defined_slots(num_peaks, NH):
+    """mask[B,K,NH]: slot h is defined by the reference iff the row has > h local maxima."""
+    return np.arange(NH)[None, None, :] < num_peaks[..., None]
+
+
+@pytest.mark.parametrize("name,gen", HEAD_CASES)
+# fp64 is the strict pin.  fp32: the reference's CPU F.softmax uses a ~1e-5-accurate vector exp on long
+# rows, so its own fp32-vs-fp64 self-error reaches 1.7e-4 on peaked logits -> 5e-4.
+@pytest.mark.parametrize("tag,dtype,tol", [("f64", torch.float64, 1e-12), ("f32", torch.float32, 5e-4)])
+def test_head_forward_matches_reference(oracle, synth, name, gen, tag, dtype, tol):
+    g = load_golden(name)
+    B, K, D, H, W, NH, NS, seed, _ = [int(v) for v in g["meta"]]
+    logits = getattr(synth, gen)(B, K, D, H, W, seed=seed)
+    np.testing.assert_allclose(input_checksum(logits), g["in_checksum"], rtol=1e-12)
+    kps, dmap, idx = oracle.integral_multi(logits.to(dtype), K, NH, NS)
+    defined = _defined_slots(g["num_peaks"], NH)
+    ref_idx = g["idx_" + tag]
+    # bit-exact peak bins wherever the reference defines them
+    assert np.array_equal(idx.numpy()[defined], ref_idx[defined])
+    assert rel_inf(dmap.numpy(), g["dmap_" + tag]) < tol
+    ref_kps = g["kps_" + tag]
+    mask = np.broadcast_to(defined.transpose(0, 2, 1)[..., None], ref_kps.shape)
+    assert np.abs(kps.numpy() - ref_kps)[mask].max() < tol
+    # x,y do not depend on the slot at all
+    assert np.abs(kps.numpy()[..., :2] - ref_kps[..., :2]).max() < tol
+
+
+@pytest.mark.parametrize("name,gen", HEAD_CASES)
+def test_head_backward_matches_reference(oracle, synth, name, gen):
+    """autograd through the oracle AND the closed form (App. A.2) against the reference's autograd, fp64."""
+    g = load_golden(name)
+    B, K, D, H, W, NH, NS, seed, stride = [int(v) for v in g["meta"]]
+    if not _defined_slots(g["num_peaks"], NH).all():
+        pytest.skip("filler slots present: reference gradient routes through undefined indices")
+    logits = getattr(synth, gen)(B, K, D, H, W, seed=seed).double().requires_grad_(True)
+    gw = torch.from_numpy(g["g_kps"])
+    kps, _, _ = oracle.integral_multi(logits, K, NH, NS)
+    (kps * gw).sum().backward()
+    auto = logits.grad.flatten().numpy()
+    closed = oracle.integral_multi_backward(logits.detach(), gw, K, NH, NS).flatten().numpy()
+    ref = g["grad_sub_f64"]
+    assert rel_inf(auto[::stride], ref) < 1e-11
+    assert rel_inf(closed[::stride], ref) < 1e-11
+    np.testing.assert_allclose([np.abs(closed).max(), np.linalg.norm(closed)], g["grad_norms_f64"][:2], rtol=1e-10)
+
+
+def test_single_hypothesis_head(oracle, synth):
+    g = load_golden("single_iid_k18_r16")
+    B, K, R, seed = [int(v) for v in g["meta"]]
+    logits = synth.iid_logits(B, K, R, R, R, seed=seed)
+    for tag, dt, tol in (("f64", torch.float64, 1e-12), ("f32", torch.float32, 2e-5)):
+        kps, dmap = oracle.integral_single(logits.to(dt), K)
+        assert kps.shape == (B, 1, K, 3)
+        assert np.abs(kps.numpy() - g["kps_" + tag]).max() < tol
+        assert rel_inf(dmap.numpy(), g["dmap_" + tag]) < tol
+
+
+@pytest.mark.parametrize("name", ["geom_h36m", "geom_mpi"])
+def test_geometry_matches_reference(oracle, synth, name):
+    g = load_golden(name)
+    B, K, seed, mpi = [int(v) for v in g["meta"]]
+    cams = synth.cameras(B, seed=seed, mpi=bool(mpi))
+    kps = synth.pseudo_joints(B, K, seed=seed + 1)
+    for tag, dt, tol in (("f64", torch.float64, 1e-11), ("f32", torch.float32, 2e-5)):
+        c = {k: v.to(dt) for k, v in cams.items()}
+        k = kps.to(dt)
+        world = oracle.patch_to_world(k, c)
+        assert rel_inf(world.numpy(), g["world_" + tag]) < tol
+        img = oracle.patch_to_image(k, c["trans_image"], 256, 256, 256, 2000.0 / 256, c["pelvis"])
+        assert rel_inf(img.numpy(), g["image_" + tag]) < tol
+        mono = oracle.patch_to_world(k, c, rect_width=256, mono=True, patch=False)
+        assert rel_inf(mono.numpy(), g["mono_" + tag]) < tol
+        back = oracle.world_to_patch(torch.from_numpy(g["world_" + tag]), c)
+        # fp32: the round trip amplifies rounding by Z/f ~ 1e3 px -> looser
+        assert np.abs(back.numpy() - g["back_" + tag]).max() < (1e-9 if dt == torch.float64 else 5e-3)
+    # projection really is the inverse (fp64)
+    c = {k: v.double() for k, v in cams.items()}
+    rt = oracle.world_to_patch(oracle.patch_to_world(kps.double(), c), c)
+    assert np.abs(rt.numpy() - kps.double().numpy()).max() < 1e-9
+
+
+LOSS_CASES = [("loss_surs1_k17_r16", "iid_logits"), ("loss_synths2_k18_r32", "blob_logits"),
+              ("loss_synths2_k17_r32_mpi", "iid_logits")]
+
+
+@pytest.mark.parametrize("name,gen", LOSS_CASES)
+def test_fused_loss_matches_reference(oracle, synth, name, gen):
+    g = load_golden(name)
+    B, K, R, NH, NS, seed, stride, mpi = [int(v) for v in g["meta"]]
+    w = [None if np.isnan(v) else float(v) for v in g["weights"]]
+    logits = getattr(synth, gen)(B, K, R, R, R, seed=seed)
+    target = synth.pseudo_joints(B, K, seed=seed + 2)
+    cams = synth.cameras(B, seed=seed + 3, mpi=bool(mpi))
+    for tag, dt, tol, gtol in (("f64", torch.float64, 1e-11, 1e-10), ("f32", torch.float32, 5e-4, 5e-3)):
+        x = logits.to(dt).clone().requires_grad_(True)
+        c = {k: v.to(dt) for k, v in cams.items()}
+        lp, ls, sel, kps, world, _, _ = oracle.fused_forward(
+            x, K, NH, NS, target.to(dt), c, w_mse=w[0], w_bone=w[1], w_kp=w[2], w_kp2d=w[3], reduction="batch")
+        (lp + ls).backward()
+        assert rel_inf(kps.detach().numpy(), g["kps_" + tag]) < tol
+        assert rel_inf(world.detach().numpy(), g["world_" + tag]) < max(tol, 1e-9) * (1 if dt == torch.float64 else 30)
+        np.testing.assert_allclose([lp.item(), ls.item()], g["loss_" + tag], rtol=tol * 10, atol=1e-12)
+        # selected slots are bit-exact
+        assert int(sel[0]) == int(np.argmin(g["pseudo_h_" + tag]))
+        if w[1] is not None or w[2] is not None or w[3] is not None:
+            assert int(sel[1]) == int(np.argmin(g["sym_h_" + tag]))
+        assert rel_inf(x.grad.flatten().numpy()[::stride], g["grad_sub_" + tag]) < gtol
+    # eval-style per-joint argmin (eval.py:138-145)
+    idx, best = oracle.best_hypothesis(torch.from_numpy(g["kps_f64"]), target.double())
+    assert np.array_equal(idx.numpy(), g["best_idx_f64"])
+    lj, _, selj, _ = oracle.reproj_min_loss(torch.from_numpy(g["kps_f64"]), target.double(),
+                                            {k: v.double() for k, v in cams.items()}, reduction="joint")
+    assert np.array_equal(selj.numpy(), g["best_idx_f64"])
+
+
+def test_filler_slots_are_deterministic(oracle):
+    """Rows with fewer than NH local maxima: ours fills with the lowest non-peak interior bins."""
+    pz = torch.tensor([[[0.05, 0.1, 0.5, 0.1, 0.05, 0.05, 0.1, 0.05]]], dtype=torch.float64)
+    pz = pz / pz.sum()
+    idx = oracle.depth_peaks(pz, 4)
+    assert idx.tolist() == [[[2, 6, 1, 3]]]
+    flat = torch.full((1, 1, 8), 0.125, dtype=torch.float64)          # plateau: every interior bin is a peak
+    assert oracle.depth_peaks(flat, 3).tolist() == [[[1, 2, 3]]]

@@ -1,0 +1,124 @@
+"""Deterministic synthetic inputs for the integral + reprojection-loss path.
+
+The shapes and value ranges follow the input contract the reference's data
+loader defines: logits as `[B, K*D, H, W]`
+(`modules/keypoint_detector_integral_multi.py:67-70`), pseudo joints with
+x,y in [-1,1] and z in metres/2 (`human_utils/dataloader/dataloader.py:226-227`),
+H36M-like cameras (`human_utils/dataset/hm36.py:163-186,284-304`).
+
+Everything is generated on the CPU from a seeded `torch.Generator` in fp32 so
+that the CPU oracle and the GPU kernels receive identical bits.
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict
+
+import torch
+
+__all__ = ["iid_logits", "blob_logits", "pseudo_joints", "cameras", "camera_dict", "CAM_FIELDS"]
+
+# order of the per-sample camera tensors everywhere in this package
+CAM_FIELDS = ("trans_image", "pelvis", "k_mat", "trans_world", "rot_world")
+
+
+def _gen(seed: int) -> torch.Generator:
+    g = torch.Generator(device="cpu")
+    g.manual_seed(int(seed))
+    return g
+
+
+def iid_logits(B: int, K: int, D: int, H: int, W: int, seed: int = 0, scale: float = 1.0) -> torch.Tensor:
+    """iid N(0, scale^2) logits, `[B, K*D, H, W]` fp32 (stress case: many depth peaks)."""
+    return torch.randn(B, K * D, H, W, generator=_gen(seed), dtype=torch.float32) * scale
+
+
+def blob_logits(B: int, K: int, D: int, H: int, W: int, seed: int = 1, modes: int = 3) -> torch.Tensor:
+    """Multi-modal depth "blob" logits: `modes` Gaussian depth
+    modes at one shared (h, w) centre per (b, k) on top of N(0,1) noise."""
+    g = _gen(seed)
+    L = torch.randn(B, K, D, H, W, generator=g, dtype=torch.float32)
+    cx = (0.2 + 0.6 * torch.rand(B, K, generator=g)) * W
+    cy = (0.2 + 0.6 * torch.rand(B, K, generator=g)) * H
+    hh = torch.arange(H, dtype=torch.float32).view(1, 1, H, 1)
+    ww = torch.arange(W, dtype=torch.float32).view(1, 1, 1, W)
+    gxy = -((hh - cy.view(B, K, 1, 1)) ** 2 + (ww - cx.view(B, K, 1, 1)) ** 2) / (2 * 2.5 ** 2)
+    dd = torch.arange(D, dtype=torch.float32).view(1, 1, D)
+    for _ in range(modes):
+        cz = (0.1 + 0.8 * torch.rand(B, K, generator=g)) * D
+        amp = 12.0 * (0.5 + 0.5 * torch.rand(B, K, generator=g))
+        gz = -((dd - cz.view(B, K, 1)) ** 2) / (2 * 2.0 ** 2)
+        L += amp.view(B, K, 1, 1, 1) * torch.exp(gz.view(B, K, D, 1, 1) + gxy.view(B, K, 1, H, W))
+    return L.view(B, K * D, H, W).contiguous()
+
+
+def pseudo_joints(B: int, K: int, seed: int = 2) -> torch.Tensor:
+    """Pseudo-GT joints `[B, K, 3]`: x,y ~ U(-1,1), z ~ U(-0.5,0.5)."""
+    g = _gen(seed)
+    xy = torch.rand(B, K, 2, generator=g) * 2 - 1
+    z = torch.rand(B, K, 1, generator=g) - 0.5
+    return torch.cat((xy, z), dim=-1).contiguous()
+
+
+def cameras(B: int, seed: int = 3, mpi: bool = False, img: int = 256, rect_width: float = 2000.0) -> Dict[str, torch.Tensor]:
+    """Per-sample camera tensors keyed by `CAM_FIELDS` (H36M-like; `mpi=True`
+    uses MPI-INF-3DHP intrinsics, `human_utils/dataset/mpi_inf_3dhp.py:53,176-187`)."""
+    g = _gen(seed)
+    if mpi:
+        f = 1497.7 + torch.randn(B, 1, generator=g) * 0.5
+        fx, fy = f, f.clone()
+        cx = 1024.0 + torch.randn(B, 1, generator=g)
+        cy = 1024.0 + torch.randn(B, 1, generator=g)
+    else:
+        fx = 1140.0 + 10.0 * torch.rand(B, 1, generator=g)
+        fy = 1140.0 + 10.0 * torch.rand(B, 1, generator=g)
+        cx = 500.0 + 20.0 * torch.rand(B, 1, generator=g)
+        cy = 500.0 + 20.0 * torch.rand(B, 1, generator=g)
+    k_mat = torch.zeros(B, 3, 3)
+    k_mat[:, 0, 0] = fx[:, 0]
+    k_mat[:, 1, 1] = fy[:, 0]
+    k_mat[:, 0, 2] = cx[:, 0]
+    k_mat[:, 1, 2] = cy[:, 0]
+    k_mat[:, 2, 2] = 1.0
+
+    pelvis = torch.empty(B, 3)
+    pelvis[:, :2] = torch.randn(B, 2, generator=g) * 300.0
+    pelvis[:, 2] = 3000.0 + 3000.0 * torch.rand(B, generator=g)
+
+    # crop affine: scale so that rect_width mm at the pelvis depth spans the patch,
+    # translation puts the pelvis projection at the patch centre
+    # patch-px per image-px: rect_width mm at depth Z span rect_width*fx/Z image px -> img patch px
+    s = img * pelvis[:, 2] / (rect_width * fx[:, 0])  # ~0.3-0.7 for H36M
+    u0 = pelvis[:, 0] / pelvis[:, 2] * fx[:, 0] + cx[:, 0]
+    v0 = pelvis[:, 1] / pelvis[:, 2] * fy[:, 0] + cy[:, 0]
+    trans_image = torch.zeros(B, 2, 3)
+    trans_image[:, 0, 0] = s
+    trans_image[:, 1, 1] = s
+    trans_image[:, :, :2] += torch.randn(B, 2, 2, generator=g) * 1e-3
+    trans_image[:, 0, 2] = img / 2.0 - s * u0
+    trans_image[:, 1, 2] = img / 2.0 - s * v0
+
+    q, r = torch.linalg.qr(torch.randn(B, 3, 3, generator=g))
+    q = q * torch.sign(torch.diagonal(r, dim1=-2, dim2=-1)).unsqueeze(-2)
+    det = torch.linalg.det(q)
+    q[:, :, 2] *= det.sign().unsqueeze(-1)
+    rot_world = q.contiguous()
+    trans_world = torch.randn(B, 3, generator=g) * 2000.0
+
+    return {
+        "trans_image": trans_image.contiguous(),
+        "pelvis": pelvis.contiguous(),
+        "k_mat": k_mat.contiguous(),
+        "trans_world": trans_world.contiguous(),
+        "rot_world": rot_world,
+    }
+
+
+def camera_dict(cams: Dict[str, torch.Tensor], mode: str = "cam_0", img: int = 256) -> Dict[str, torch.Tensor]:
+    """The reference's dict-keyed parameter bundle (`modules/util.py:129-134`):
+    `'{mode}_trans_image'`, `'{mode}_img'` (only `.shape` is read), ..."""
+    B = cams["pelvis"].shape[0]
+    out = {"{}_{}".format(mode, k): v for k, v in cams.items()}
+    # a zero-stride view: only the shape is ever read (util.py:130,137-138)
+    out["{}_img".format(mode)] = torch.zeros(1, dtype=cams["pelvis"].dtype, device=cams["pelvis"].device).expand(B, 3, img, img)
+    return out
