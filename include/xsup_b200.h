@@ -1,0 +1,144 @@
+/*
+ * xsup_b200 — C ABI of the B200-native integral + multi-hypothesis reprojection-loss path.
+ *
+ * The reference (Charrrrrlie/X-as-Supervision) is pure Python and has no operator/plugin
+ * interface of its own; the seam is the parameter-free code after `self.net(x)`.  Each entry
+ * point below names the reference lines it replaces.  Plain pointers and sizes only: no torch
+ * types, no allocation, no hidden synchronisation.  See INTEGRATION.md for the reference-side
+ * binding (ctypes stub inside `KPDetector3DMulti.forward` / `Counter3DModel.forward`).
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer owned by the caller, 16-byte aligned, contiguous;
+ *   - `stream` is a `cudaStream_t` passed as `void*`; all work is enqueued on it, nothing
+ *     synchronises, every call is CUDA-graph capturable;
+ *   - return value 0 = success; negative = rejected before launch (XSUP_E_*), positive = a
+ *     `cudaError_t` from the launch.  `xsup_last_error()` returns a thread-local message;
+ *   - there is NO CPU fallback: without a CUDA device the compute calls fail with a
+ *     cudaError, they never compute on the host.
+ */
+#ifndef XSUP_B200_H_
+#define XSUP_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define XSUP_ABI_VERSION 1
+
+enum { XSUP_F32 = 0, XSUP_BF16 = 1 };
+enum { XSUP_HEAD_MULTI = 0, XSUP_HEAD_SINGLE = 1 };
+enum { XSUP_REDUCE_BATCH = 0, XSUP_REDUCE_SAMPLE = 1, XSUP_REDUCE_JOINT = 2 };
+enum {
+    XSUP_OK = 0,
+    XSUP_E_SHAPE = -1,     /* unsupported / inconsistent shape (D != W, NS even, NH > D-2, ...) */
+    XSUP_E_ALIGN = -2,     /* pointer not 16-byte aligned */
+    XSUP_E_NULL = -3,      /* required pointer is NULL */
+    XSUP_E_DTYPE = -4,
+    XSUP_E_DEVICE = -5     /* not an sm_100 device / no device */
+};
+
+/* One heat-map volume batch: logits are `[B, K*D, H, W]` contiguous (w fastest), i.e. each
+ * (b,k) "unit" is one contiguous D*H*W block — keypoint_detector_integral_multi.py:69-74. */
+typedef struct {
+    int32_t B, K, D, H, W;
+    int32_t NH;        /* num_hypo      (keypoint_detector_integral_multi.py:17); 1 in single mode */
+    int32_t NS;        /* neighbor_size (…:18), odd; ignored in single mode */
+    int32_t dtype;     /* XSUP_F32 | XSUP_BF16 : element type of logits and of g_logits */
+    int32_t head;      /* XSUP_HEAD_MULTI (…_multi.py:66-88) | XSUP_HEAD_SINGLE (keypoint_detector_integral.py:45-65) */
+} xsup_shape_t;
+
+/* Per-sample camera tensors exactly as the reference's data loader hands them over
+ * (human_utils/dataloader/dataloader.py:170-182; unpacked at modules/util.py:129-134). */
+typedef struct {
+    const float* trans_image;  /* [B,2,3] crop affine          */
+    const float* pelvis;       /* [B,3]   root joint, camera mm */
+    const float* k_mat;        /* [B,3,3] intrinsics            */
+    const float* trans_world;  /* [B,3]   extrinsic translation */
+    const float* rot_world;    /* [B,3,3] extrinsic rotation    */
+} xsup_cam_t;
+
+/* Loss graph of one camera: modules/model.py:71-79 (world lift per hypothesis),
+ * :105-114 (symmetry, min over hypotheses), :158-162 (pseudo-GT MSE, min over hypotheses). */
+typedef struct {
+    int32_t B, K, NH;
+    int32_t img_h, img_w;     /* params['{mode}_img'].shape[-2:]  (util.py:130,137-138) */
+    float rect_width;         /* RECT_WIDTH (util.py:128), 2000 mm */
+    float w_mse;              /* smpl_pseudo_img_loss.weight (model.py:164) */
+    float w_bone, w_kp, w_kp2d; /* symmetry_loss.weight.{bone,kp,kp_2d} (model.py:108-112) */
+    int32_t use_sym;          /* 0: symmetry term absent from the loss config */
+    int32_t reduction;        /* XSUP_REDUCE_* */
+    int32_t batch_total;      /* denominator batch size: B, or the global batch when sharded */
+} xsup_loss_cfg_t;
+
+#define XSUP_LOSS_TERMS 4     /* mse, bone, kp, kp2d */
+
+int xsup_abi_version(void);
+const char* xsup_last_error(void);
+/* kernels launched by this library since load (all threads); evidence for bench.py's gpu_launches */
+uint64_t xsup_launch_count(void);
+
+/* floats per (b,k) unit of the saved-for-backward block / of the backward coefficient block */
+size_t xsup_stats_stride(const xsup_shape_t* s);
+size_t xsup_coef_stride(const xsup_shape_t* s);
+
+/* Replaces keypoint_detector_integral_multi.py:69-88 (softmax over D*H*W, the three marginals,
+ * x/y expectations, find_peak + topk, windowed depth expectation, normalisation, assembly).
+ *   logits          [B,K*D,H,W]   (s->dtype)
+ *   kps             [B,NH,K,3]    fp32
+ *   depth_prob_map  [K,D]         fp32, sample 0 (…:48)
+ *   peak_idx        [B,K,NH]      int64 (…:24-34); NULL allowed
+ *   stats           [B*K*xsup_stats_stride]  fp32, consumed by xsup_integral_bwd            */
+int xsup_integral_fwd(const void* logits, float* kps, float* depth_prob_map, int64_t* peak_idx,
+                      float* stats, const xsup_shape_t* s, void* stream);
+
+/* Replaces KPDetector3DMulti.find_peak (keypoint_detector_integral_multi.py:24-34) on a depth
+ * marginal `pz [rows, D]` fp32 -> `idx [rows, NH]` int64 (ties and filler slots: lowest bin first). */
+int xsup_find_peak(const float* pz, int64_t* idx, int32_t rows, int32_t D, int32_t NH, void* stream);
+
+/* The autograd of the above in one pass over the volume.
+ *   g_kps    [B,NH,K,3] fp32  (d loss / d kps)
+ *   g_logits [B,K*D,H,W]      (s->dtype); may alias `logits` for an in-place gradient
+ *   coef_ws  [B*K*xsup_coef_stride] fp32 scratch                                           */
+int xsup_integral_bwd(const void* logits, const float* stats, const float* g_kps, void* g_logits,
+                      float* coef_ws, const xsup_shape_t* s, void* stream);
+
+/* Replaces modules/util.py:128-152 (convert_patch_to_world = :61-82 then :85-95) on `[B,J,3]`.
+ * flags: bit0 is_norm, bit1 mono (:145-150), bit2 patch.  `_bwd` is its vector-Jacobian product
+ * (it takes the forward input `kps` again: the Jacobian depends on the projected point). */
+int xsup_patch_to_world_fwd(const float* kps, const xsup_cam_t* cam, float* world, int32_t B, int32_t J,
+                            int32_t img_h, int32_t img_w, float rect_width, int32_t flags, void* stream);
+int xsup_patch_to_world_bwd(const float* kps, const float* g_world, const xsup_cam_t* cam, float* g_kps, int32_t B, int32_t J,
+                            int32_t img_h, int32_t img_w, float rect_width, int32_t flags, void* stream);
+/* Replaces modules/util.py:155-168 (convert_world_to_patch = :116-125 then :98-113): the forward
+ * perspective projection, inverse of the above. */
+int xsup_world_to_patch_fwd(const float* world, const xsup_cam_t* cam, float* kps, int32_t B, int32_t J,
+                            int32_t img_h, int32_t img_w, float rect_width, int32_t flags, void* stream);
+
+/* Replaces the per-hypothesis Python loops of modules/model.py:71-79,105-114,158-162 and the loss
+ * primitives modules/base_losses/loss_func.py:18-52 for one camera.
+ *   kps      [B,NH,K,3]  from xsup_integral_fwd        target [B,K,3] pseudo joints
+ *   world    [B,NH,K,3]  out: world mm
+ *   sample_terms [B,XSUP_LOSS_TERMS,NH] out: per-sample un-normalised sums
+ *   partial  [XSUP_LOSS_TERMS,NH] out: their fixed-order sum over this rank's batch
+ *            (the only thing that crosses ranks: one all-reduce(SUM) in global scope)          */
+int xsup_reproj_loss_fwd(const float* kps, const float* target, const xsup_cam_t* cam, float* world,
+                         float* sample_terms, float* partial, const xsup_loss_cfg_t* cfg, void* stream);
+
+/* min / argmin over hypotheses (model.py:114,162; loss_func.py:59; eval.py:138-145).
+ *   loss [2] out: (pseudo term * w_mse, symmetry term)
+ *   sel  out int64: batch -> [2] (slot or -1); sample -> [2,B]; joint -> [B,K]                 */
+int xsup_reproj_select(const float* kps, const float* target, const float* sample_terms, const float* partial,
+                       float* loss, int64_t* sel, const xsup_loss_cfg_t* cfg, void* stream);
+
+/* d (g_loss[0]*pseudo + g_loss[1]*symmetry) / d kps -> g_kps [B,NH,K,3]; only the selected slots
+ * receive gradient (torch.min semantics; exact ties resolve to the lowest slot).              */
+int xsup_reproj_loss_bwd(const float* kps, const float* target, const xsup_cam_t* cam, const int64_t* sel,
+                         const float* g_loss, float* g_kps, const xsup_loss_cfg_t* cfg, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* XSUP_B200_H_ */

@@ -44,15 +44,15 @@ def softmax_volume(logits: torch.Tensor, num_kp: int) -> torch.Tensor:
     joint's whole D*H*W volume (keypoint_detector_integral_multi.py:69-74)."""
     B, C, H, W = logits.shape
     D = C // num_kp
-    flat = logits.reshape(B, num_kp, D * H * W)
-    flat = flat - flat.amax(dim=2, keepdim=True)
-    e = flat.exp()
-    return (e / e.sum(dim=2, keepdim=True)).reshape(B, num_kp, D, H, W)
+    # the same ATen kernel the reference calls (F.softmax, :71), so the fp32 mode of this oracle has the
+    # reference's own numerics and CPU cost; fp64 mode is the ground truth
+    return torch.softmax(logits.reshape(B, num_kp, D * H * W), dim=2).reshape(B, num_kp, D, H, W)
 
 
 def marginals(p: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
     """(ax[B,K,W], ay[B,K,H], pz[B,K,D]) as in :39-44."""
-    return p.sum(dim=(2, 3)), p.sum(dim=(2, 4)), p.sum(dim=(3, 4))
+    over_d = p.sum(dim=2)                                             # [B,K,H,W]
+    return over_d.sum(dim=2), over_d.sum(dim=3), p.sum(dim=3).sum(dim=3)
 
 
 def depth_peaks(pz: torch.Tensor, num_hypo: int) -> torch.Tensor:

@@ -1,0 +1,384 @@
+"""GPU parity tests (run with `-m gpu` on a B200): the CUDA path, called through the C ABI, against
+  (1) the golden vectors produced by the reference itself (tests/golden/*.npz),
+  (2) the fp64 CPU oracle on the same seeded inputs,
+  (3) size-independent properties at the BASELINE sizes.
+
+Tolerances (north_star): selected-hypothesis / peak indices bit-exact; coordinates, loss and heat-map
+gradients within 1e-5 relative in fp32 (gradients norm-wise: grad = p*(g-gbar) cancels where g ~ gbar,
+SURVEY.md §7 hard part 4); bf16: coordinates 1e-5 against the oracle on the bf16-rounded logits (the math
+is fp32), gradients 2^-8 relative-to-max (one bf16 rounding of the output)."""
+import importlib
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_golden, rel_inf, rel_l2
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-5
+TOL_BF16_GRAD = 2.0 ** -8
+
+
+@pytest.fixture(scope="module")
+def ops():
+    import __graft_entry__ as ge
+    ge.build()
+    pkg = importlib.import_module("x-as-supervision_b200")
+    return pkg.load_native()
+
+
+@pytest.fixture(scope="module")
+def dev():
+    return torch.device("cuda:0")
+
+
+def _defined(num_peaks, NH):
+    return np.arange(NH)[None, None, :] < num_peaks[..., None]
+
+
+def _num_peaks(pz):
+    mid = pz[..., 1:-1]
+    return ((mid >= pz[..., :-2]) & (mid >= pz[..., 2:])).sum(-1).numpy()
+
+
+def _near_tie_rows(pz64, NH, margin=1e-5):
+    """rows whose top-(NH+1) peak values or peak/neighbour comparisons are closer than `margin` relative:
+    genuine near-ties where fp32 summation order decides (SURVEY.md §7 hard part 1)."""
+    mid = pz64[..., 1:-1]
+    left, right = pz64[..., :-2], pz64[..., 2:]
+    scale = pz64.amax(-1, keepdim=True)
+    close_cmp = (((mid - left).abs() < margin * scale) | ((mid - right).abs() < margin * scale)).any(-1)
+    cand = torch.where((mid >= left) & (mid >= right), mid, torch.zeros_like(mid))
+    top = torch.sort(cand, dim=-1, descending=True).values[..., :NH + 1]
+    close_rank = ((top[..., :-1] - top[..., 1:]).abs() < margin * scale).any(-1)
+    return (close_cmp | close_rank).numpy()
+
+
+# ------------------------------------------------------------------------------------------ golden vectors
+HEAD_CASES = [("head_iid_k18_r16", "iid_logits"), ("head_blob_k17_r32", "blob_logits"),
+              ("head_blob_k18_r64", "blob_logits"), ("head_iid_k3_r8_nh2", "iid_logits")]
+
+
+@pytest.mark.parametrize("name,gen", HEAD_CASES)
+def test_head_against_reference_golden(ops, synth, dev, name, gen):
+    g = load_golden(name)
+    B, K, D, H, W, NH, NS, seed, stride = [int(v) for v in g["meta"]]
+    x = getattr(synth, gen)(B, K, D, H, W, seed=seed).to(dev).requires_grad_(True)
+    kps, dmap, idx = ops.integral_multi_head(x, K, NH, NS)
+    defined = _defined(g["num_peaks"], NH)
+    assert np.array_equal(idx.cpu().numpy()[defined], g["idx_f64"][defined])
+    assert rel_inf(dmap.cpu().numpy(), g["dmap_f64"]) < TOL
+    ref = g["kps_f64"]
+    mask = np.broadcast_to(defined.transpose(0, 2, 1)[..., None], ref.shape)
+    assert np.abs(kps.detach().cpu().numpy() - ref)[mask].max() < TOL
+    if defined.all():
+        (kps * torch.from_numpy(g["g_kps"]).float().to(dev)).sum().backward()
+        got = x.grad.flatten().cpu().numpy()
+        assert rel_inf(got[::stride], g["grad_sub_f64"]) < TOL
+        np.testing.assert_allclose(np.linalg.norm(got.astype(np.float64)), g["grad_norms_f64"][1], rtol=TOL)
+
+
+def test_single_head_against_reference_golden(ops, synth, dev):
+    g = load_golden("single_iid_k18_r16")
+    B, K, R, seed = [int(v) for v in g["meta"]]
+    kps, dmap = ops.integral_single_head(synth.iid_logits(B, K, R, R, R, seed=seed).to(dev), K)
+    assert kps.shape == (B, 1, K, 3)
+    assert np.abs(kps.cpu().numpy() - g["kps_f64"]).max() < TOL
+    assert rel_inf(dmap.cpu().numpy(), g["dmap_f64"]) < TOL
+
+
+@pytest.mark.parametrize("name", ["geom_h36m", "geom_mpi"])
+def test_geometry_against_reference_golden(ops, synth, dev, name):
+    g = load_golden(name)
+    B, K, seed, mpi = [int(v) for v in g["meta"]]
+    cams = {k: v.to(dev) for k, v in synth.cameras(B, seed=seed, mpi=bool(mpi)).items()}
+    params = synth.camera_dict(cams, "cam_0")
+    kps = synth.pseudo_joints(B, K, seed=seed + 1).to(dev)
+    world = ops.convert_patch_to_world(kps, params, "cam_0", is_norm=True)
+    assert rel_inf(world.cpu().numpy(), g["world_f64"]) < TOL
+    mono = ops.convert_patch_to_world(kps, params, "cam_0", is_norm=True, RECT_WIDTH=256, mono=True, patch=False)
+    assert rel_inf(mono.cpu().numpy(), g["mono_f64"]) < TOL
+    back = ops.convert_world_to_patch(torch.from_numpy(g["world_f64"]).float().to(dev), params, "cam_0")
+    # fp32 projection of mm-scale world points: rounding of ~5e3 mm coordinates, amplified by f/Z
+    assert np.abs(back.cpu().numpy() - g["back_f64"]).max() < 2e-3
+    # encode -> decode round trip in fp32
+    rt = ops.convert_world_to_patch(world, params, "cam_0")
+    assert (rt - kps).abs().max().item() < 2e-3
+
+
+LOSS_CASES = [("loss_surs1_k17_r16", "iid_logits"), ("loss_synths2_k18_r32", "blob_logits"),
+              ("loss_synths2_k17_r32_mpi", "iid_logits")]
+
+
+@pytest.mark.parametrize("name,gen", LOSS_CASES)
+def test_fused_loss_against_reference_golden(ops, synth, dev, name, gen):
+    g = load_golden(name)
+    B, K, R, NH, NS, seed, stride, mpi = [int(v) for v in g["meta"]]
+    w = [None if np.isnan(v) else float(v) for v in g["weights"]]
+    x = getattr(synth, gen)(B, K, R, R, R, seed=seed).to(dev).requires_grad_(True)
+    target = synth.pseudo_joints(B, K, seed=seed + 2).to(dev)
+    cams = {k: v.to(dev) for k, v in synth.cameras(B, seed=seed + 3, mpi=bool(mpi)).items()}
+    lp, ls, sel, kps, world, dmap, idx = ops.integral_reproj_min_loss(
+        x, target, cams, K, NH, NS, w_mse=w[0], w_bone=w[1], w_kp=w[2], w_kp2d=w[3], reduction="batch")
+    (lp + ls).backward()
+    assert rel_inf(kps.detach().cpu().numpy(), g["kps_f64"]) < TOL
+    assert rel_inf(world.detach().cpu().numpy(), g["world_f64"]) < 5 * TOL      # mm, Z/f amplification
+    np.testing.assert_allclose([lp.item(), ls.item()], g["loss_f64"], rtol=5 * TOL, atol=1e-9)
+    assert int(sel[0]) == int(np.argmin(g["pseudo_h_f64"]))                      # bit-exact slots
+    if any(v is not None for v in w[1:]):
+        assert int(sel[1]) == int(np.argmin(g["sym_h_f64"]))
+    else:
+        assert int(sel[1]) == -1
+    got = x.grad.flatten().cpu().numpy()
+    assert rel_inf(got[::stride], g["grad_sub_f64"]) < 2 * TOL
+    np.testing.assert_allclose(np.linalg.norm(got.astype(np.float64)), g["grad_norms_f64"][1], rtol=2 * TOL)
+
+
+# ------------------------------------------------------------------------------------------ oracle, larger sizes
+def _oracle_head(oracle, logits64, K, NH, NS, gw):
+    x = logits64.clone().requires_grad_(True)
+    kps, dmap, idx = oracle.integral_multi(x, K, NH, NS)
+    (kps * gw).sum().backward()
+    return kps.detach(), dmap, idx, x.grad
+
+
+@pytest.mark.parametrize("gen,B,K,R,NH,NS,seed", [
+    ("blob_logits", 3, 17, 64, 3, 15, 21),       # BASELINE shape: K=17, 64^3, NH=3, NS=15
+    ("iid_logits", 2, 18, 64, 3, 15, 22),        # reference's own num_kp
+    ("iid_logits", 2, 17, 32, 8, 15, 23),        # 32^3 (smem-small tiling), many hypotheses -> filler slots
+    ("blob_logits", 1, 5, 128, 4, 31, 24),       # 128^3: 16 tasks per depth slice
+    ("iid_logits", 2, 4, 16, 3, 5, 25),          # U=2 tiling
+    ("iid_logits", 3, 3, 8, 2, 3, 26),           # generic kernel (slice < 512 B)
+])
+def test_head_against_oracle(ops, oracle, synth, dev, gen, B, K, R, NH, NS, seed):
+    logits = getattr(synth, gen)(B, K, R, R, R, seed=seed)
+    gw = torch.randn(B, NH, K, 3, generator=torch.Generator().manual_seed(seed), dtype=torch.float64)
+    okps, odmap, oidx, ograd = _oracle_head(oracle, logits.double(), K, NH, NS, gw)
+    x = logits.to(dev).requires_grad_(True)
+    kps, dmap, idx = ops.integral_multi_head(x, K, NH, NS)
+    (kps * gw.float().to(dev)).sum().backward()
+
+    pz64 = oracle.marginals(oracle.softmax_volume(logits.double(), K))[2]
+    defined = _defined(_num_peaks(pz64), NH)
+    ties = _near_tie_rows(pz64, NH)
+    same = idx.cpu().numpy() == oidx.numpy()
+    # real mismatches (outside genuine near-ties) must be zero
+    assert same[~ties].all(), "peak index mismatch on a row that is not a near-tie"
+    ok_rows = same.all(-1)
+    assert rel_inf(dmap.cpu().numpy(), odmap.numpy()) < TOL
+    err = (kps.detach().cpu().double() - okps).abs().permute(0, 2, 1, 3)          # [B,K,NH,3]
+    assert err[..., :2].max().item() < TOL
+    assert err[torch.from_numpy(ok_rows)].max().item() < TOL
+    if ok_rows.all():
+        assert rel_inf(x.grad.cpu().numpy(), ograd.numpy()) < TOL
+        assert rel_l2(x.grad.cpu().numpy(), ograd.numpy()) < TOL
+
+
+def test_non_cubic_height_and_generic_shapes(ops, oracle, dev):
+    """H may differ from D=W (the reference runs); odd sizes take the generic kernels."""
+    for (K, D, H, NH, NS, seed) in [(3, 64, 32, 3, 15, 1), (2, 12, 5, 2, 3, 2), (2, 20, 7, 3, 5, 3)]:
+        g = torch.Generator().manual_seed(seed)
+        logits = torch.randn(2, K * D, H, D, generator=g) * 2
+        gw = torch.randn(2, NH, K, 3, generator=g, dtype=torch.float64)
+        okps, odmap, oidx, ograd = _oracle_head(oracle, logits.double(), K, NH, NS, gw)
+        x = logits.to(dev).requires_grad_(True)
+        kps, dmap, idx = ops.integral_multi_head(x, K, NH, NS)
+        (kps * gw.float().to(dev)).sum().backward()
+        assert torch.equal(idx.cpu(), oidx)
+        assert (kps.detach().cpu().double() - okps).abs().max().item() < TOL
+        assert rel_inf(x.grad.cpu().numpy(), ograd.numpy()) < TOL
+
+
+@pytest.mark.parametrize("R,K,NH", [(64, 17, 3), (32, 6, 3)])
+def test_bf16_head(ops, oracle, synth, dev, R, K, NH):
+    B, NS = 2, 15
+    logits = synth.blob_logits(B, K, R, R, R, seed=31).bfloat16()
+    gw = torch.randn(B, NH, K, 3, generator=torch.Generator().manual_seed(3), dtype=torch.float64)
+    okps, odmap, oidx, ograd = _oracle_head(oracle, logits.double(), K, NH, NS, gw)
+    x = logits.to(dev).requires_grad_(True)
+    kps, dmap, idx = ops.integral_multi_head(x, K, NH, NS)
+    (kps * gw.float().to(dev)).sum().backward()
+    assert x.grad.dtype == torch.bfloat16
+    assert torch.equal(idx.cpu(), oidx)
+    assert (kps.detach().cpu().double() - okps).abs().max().item() < TOL
+    assert rel_inf(dmap.cpu().numpy(), odmap.numpy()) < TOL
+    assert rel_inf(x.grad.float().cpu().numpy(), ograd.numpy()) < TOL_BF16_GRAD
+
+
+@pytest.mark.parametrize("reduction", ["batch", "sample", "joint"])
+@pytest.mark.parametrize("sym", [False, True])
+def test_fused_loss_against_oracle(ops, oracle, synth, dev, reduction, sym):
+    if reduction == "joint" and sym:
+        pytest.skip("symmetry terms are undefined per joint")
+    B, K, R, NH, NS = 6, 18, 32, 3, 15
+    logits = synth.iid_logits(B, K, R, R, R, seed=41)
+    target = synth.pseudo_joints(B, K, seed=42)
+    cams = synth.cameras(B, seed=43)
+    w = dict(w_mse=1.5, w_bone=0.1 if sym else None, w_kp=0.2 if sym else None, w_kp2d=0.3 if sym else None)
+    x64 = logits.double().requires_grad_(True)
+    olp, ols, osel, okps, oworld, _, _ = oracle.fused_forward(x64, K, NH, NS, target.double(),
+                                                               {k: v.double() for k, v in cams.items()}, reduction=reduction, **w)
+    (olp + 0.7 * ols).backward()
+    x = logits.to(dev).requires_grad_(True)
+    lp, ls, sel, kps, world, _, _ = ops.integral_reproj_min_loss(x, target.to(dev), {k: v.to(dev) for k, v in cams.items()},
+                                                                 K, NH, NS, reduction=reduction, **w)
+    (lp + 0.7 * ls).backward()
+    assert torch.equal(sel.cpu(), osel)                                           # bit-exact selection
+    np.testing.assert_allclose([lp.item(), ls.item()], [olp.item(), ols.item()], rtol=5 * TOL, atol=1e-9)
+    assert rel_inf(world.detach().cpu().numpy(), oworld.detach().numpy()) < 5 * TOL
+    assert rel_inf(x.grad.cpu().numpy(), x64.grad.numpy()) < 2 * TOL
+    assert rel_l2(x.grad.cpu().numpy(), x64.grad.numpy()) < 2 * TOL
+
+
+def test_downstream_gradients_through_kps_and_world(ops, oracle, synth, dev):
+    """The fused op's kps / kps_world outputs stay differentiable (draw_lines and the generator loss
+    consume them in the reference, model.py:91,128-138)."""
+    B, K, R, NH, NS = 3, 17, 16, 3, 5
+    logits = synth.iid_logits(B, K, R, R, R, seed=51)
+    target = synth.pseudo_joints(B, K, seed=52)
+    cams = synth.cameras(B, seed=53)
+    g = torch.Generator().manual_seed(5)
+    wk = torch.randn(B, NH, K, 3, generator=g, dtype=torch.float64)
+    ww = torch.randn(B, NH, K, 3, generator=g, dtype=torch.float64) * 1e-3
+    x64 = logits.double().requires_grad_(True)
+    olp, ols, _, okps, oworld, _, _ = oracle.fused_forward(x64, K, NH, NS, target.double(), {k: v.double() for k, v in cams.items()},
+                                                            w_mse=1.0, w_bone=0.1, w_kp=0.1, reduction="batch")
+    (olp + ols + (okps * wk).sum() + (oworld * ww).sum()).backward()
+    x = logits.to(dev).requires_grad_(True)
+    lp, ls, _, kps, world, _, _ = ops.integral_reproj_min_loss(x, target.to(dev), {k: v.to(dev) for k, v in cams.items()}, K, NH, NS,
+                                                               w_mse=1.0, w_bone=0.1, w_kp=0.1, reduction="batch")
+    (lp + ls + (kps * wk.float().to(dev)).sum() + (world * ww.float().to(dev)).sum()).backward()
+    assert rel_inf(x.grad.cpu().numpy(), x64.grad.numpy()) < 2 * TOL
+
+
+def test_patch_to_world_vjp(ops, oracle, synth, dev):
+    B, K = 5, 18
+    cams = synth.cameras(B, seed=61)
+    kps = synth.pseudo_joints(B, K, seed=62)
+    gw = torch.randn(B, K, 3, generator=torch.Generator().manual_seed(6), dtype=torch.float64)
+    k64 = kps.double().requires_grad_(True)
+    (oracle.patch_to_world(k64, {k: v.double() for k, v in cams.items()}) * gw).sum().backward()
+    k = kps.to(dev).requires_grad_(True)
+    params = synth.camera_dict({kk: v.to(dev) for kk, v in cams.items()}, "cam_3")
+    (ops.convert_patch_to_world(k, params, "cam_3") * gw.float().to(dev)).sum().backward()
+    assert rel_inf(k.grad.cpu().numpy(), k64.grad.numpy()) < TOL
+
+
+def test_detector_module_drop_in(ops, oracle, synth, dev):
+    det_mod = importlib.import_module("x-as-supervision_b200.detector")
+    K, R, NH, NS = 18, 16, 3, 5
+    det = det_mod.KPDetector3DMulti("resnet_multi", K, R, NH, NS, net=torch.nn.Identity()).to(dev)
+    logits = synth.iid_logits(2, K, R, R, R, seed=71)
+    kps, dmap = det(logits.to(dev))
+    okps, odmap, oidx = oracle.integral_multi(logits.double(), K, NH, NS)
+    assert kps.shape == (2, NH, K, 3) and dmap.shape == (K, R) and kps.is_contiguous()
+    assert (kps.cpu().double() - okps).abs().max().item() < TOL
+    p = oracle.softmax_volume(logits.double(), K)
+    assert torch.equal(det.find_peak(oracle.marginals(p)[2].float().to(dev)).cpu(), oidx)
+    x, y, z, dm = det.generate_3d_integral_preds_tensor(p.float().to(dev), R, R, R)
+    assert x.shape == (2, K, 1) and z.shape == (2, K, NH)
+    oz = oracle.window_depth(oracle.marginals(p)[2], oidx, NS)
+    assert (z.cpu().double() - oz).abs().max().item() < 1e-4
+    single = det_mod.KPDetector3D("resnet", K, R, net=torch.nn.Identity())
+    ks, _ = single(logits.to(dev))
+    assert (ks.cpu().double() - oracle.integral_single(logits.double(), K)[0]).abs().max().item() < TOL
+
+
+# ------------------------------------------------------------------------------------------ edge cases
+def test_edge_cases(ops, oracle, dev):
+    K, R, NH, NS = 2, 16, 3, 5
+    # empty batch
+    kps, dmap, idx = ops.integral_multi_head(torch.zeros(0, K * R, R, R, device=dev), K, NH, NS)
+    assert kps.shape == (0, NH, K, 3) and idx.shape == (0, K, NH)
+    # plateau: uniform logits -> every interior bin is a (tied) peak -> lowest bins first
+    kps, dmap, idx = ops.integral_multi_head(torch.zeros(1, K * R, R, R, device=dev), K, NH, NS)
+    assert idx.cpu().tolist() == [[[1, 2, 3]] * K]
+    assert torch.allclose(dmap.cpu(), torch.full((K, R), 1.0 / R), rtol=1e-6)
+    # overflow safety: huge logits and a single dominant spike
+    logits = torch.randn(1, K * R, R, R, generator=torch.Generator().manual_seed(1)) * 50 + 3000.0
+    logits[0, 5, 7, 9] = 1e4
+    okps, _, oidx = oracle.integral_multi(logits.double(), K, NH, NS)
+    x = logits.to(dev).requires_grad_(True)
+    kps, _, idx = ops.integral_multi_head(x, K, NH, NS)
+    kps.sum().backward()
+    assert torch.isfinite(kps).all() and torch.isfinite(x.grad).all()
+    assert (kps.detach().cpu().double()[..., :2] - okps[..., :2]).abs().max().item() < TOL
+    # -inf entries (masked logits) contribute nothing
+    logits = torch.randn(1, K * R, R, R, generator=torch.Generator().manual_seed(2))
+    logits[0, :, :, :4] = float("-inf")
+    okps, _, oidx = oracle.integral_multi(logits.double(), K, NH, NS)
+    kps, _, idx = ops.integral_multi_head(logits.to(dev), K, NH, NS)
+    assert torch.equal(idx.cpu(), oidx)
+    assert (kps.cpu().double() - okps).abs().max().item() < TOL
+    # rejected shapes raise with the library's message
+    with pytest.raises(RuntimeError, match="depth_dim"):
+        ops.integral_multi_head(torch.zeros(1, K * 8, 16, 16, device=dev), K, NH, NS)
+    with pytest.raises(RuntimeError, match="neighbor_size"):
+        ops.integral_multi_head(torch.zeros(1, K * R, R, R, device=dev), K, NH, 4)
+
+
+# ------------------------------------------------------------------------------------------ properties at BASELINE size
+def test_full_size_properties(ops, synth, dev):
+    """B=256, K=17, 64^3 fp32 (BASELINE configs[1]); the oracle cannot run this in seconds, so check
+    size-independent properties of the CUDA path itself."""
+    B, K, R, NH, NS = 256, 17, 64, 3, 15
+    g = torch.Generator(device="cpu").manual_seed(7)
+    x = torch.empty(B, K * R, R, R, device=dev)
+    chunk = 32
+    for i in range(0, B, chunk):                                               # same bits as CPU generation, bounded host memory
+        x[i:i + chunk] = torch.randn(chunk, K * R, R, R, generator=g).to(dev)
+    x.requires_grad_(True)
+    target = synth.pseudo_joints(B, K, seed=8).to(dev)
+    cams = {k: v.to(dev) for k, v in synth.cameras(B, seed=9).items()}
+    out = ops.integral_reproj_min_loss(x, target, cams, K, NH, NS, w_mse=3.0, reduction="batch")
+    lp, ls, sel, kps, world, dmap, idx = out
+    lp.backward()
+    grad = x.grad
+    # (1) softmax gradient sums to zero over every (b,k) volume
+    s = grad.view(B * K, -1).double().sum(-1).abs().max().item()
+    assert s < 1e-6 * grad.abs().max().item() * R ** 3
+    # (2) probabilities: depth marginal of sample 0 sums to one; coordinates inside [-1, 1)
+    assert torch.allclose(dmap.sum(-1).cpu(), torch.ones(K), atol=1e-5)
+    assert kps.min().item() >= -1.0 and kps.max().item() < 1.0
+    # (3) x,y are shared by all hypotheses; peak bins are distinct interior bins
+    assert torch.equal(kps[:, 0, :, :2], kps[:, 1, :, :2]) and torch.equal(kps[:, 0, :, :2], kps[:, 2, :, :2])
+    assert idx.min().item() >= 1 and idx.max().item() <= R - 2
+    srt = idx.sort(-1).values
+    assert (srt[..., 1:] != srt[..., :-1]).all()
+    # (4) determinism: a second run is bit-identical (fixed-order reductions, no float atomics)
+    x2 = x.detach().clone().requires_grad_(True)
+    out2 = ops.integral_reproj_min_loss(x2, target, cams, K, NH, NS, w_mse=3.0, reduction="batch")
+    out2[0].backward()
+    assert torch.equal(out2[0], lp) and torch.equal(out2[3], kps) and torch.equal(out2[2], sel) and torch.equal(x2.grad, grad)
+    # (5) shift invariance of the softmax: logits + c leave the outputs unchanged (up to fp32 rounding of l + c)
+    kps_s, _, idx_s = ops.integral_multi_head(x.detach()[:8] + 3.0, K, NH, NS)
+    assert (kps_s[..., :2] - kps[:8, ..., :2]).abs().max().item() < 5e-5
+    # (6) linearity of the backward in grad_kps
+    xs = x.detach()[:4].clone().requires_grad_(True)
+    k1, _, _ = ops.integral_multi_head(xs, K, NH, NS)
+    ga = torch.randn_like(k1)
+    gb = torch.randn_like(k1)
+    (g1,) = torch.autograd.grad(k1, xs, ga, retain_graph=True)
+    (g2,) = torch.autograd.grad(k1, xs, gb, retain_graph=True)
+    (g3,) = torch.autograd.grad(k1, xs, ga + 2 * gb)
+    assert (g3 - (g1 + 2 * g2)).abs().max().item() < 1e-5 * g3.abs().max().item()
+    # (7) the selected slot minimises the per-hypothesis batch MSE recomputed from kps
+    mse_h = ((kps - target[:, None]) ** 2).double().mean(dim=(0, 2, 3))
+    assert int(sel[0]) == int(mse_h.argmin()) and int(sel[1]) == -1
+    np.testing.assert_allclose(lp.item(), 3.0 * mse_h.min().item(), rtol=1e-5)
+
+
+def test_in_place_gradient(ops, synth, dev):
+    """g_logits may alias logits (halves memory for the sweep): same result as out-of-place."""
+    cabi = importlib.import_module("x-as-supervision_b200._cabi")
+    K, R, NH, NS, B = 4, 32, 3, 15, 2
+    x = synth.iid_logits(B, K, R, R, R, seed=81).to(dev).requires_grad_(True)
+    kps, _, _ = ops.integral_multi_head(x, K, NH, NS)
+    gk = torch.randn_like(kps)
+    (gref,) = torch.autograd.grad(kps, x, gk)
+    logits, shape, kps2, dmap, idx, stats = ops._head_forward(x.detach().clone(), K, NH, NS, cabi.HEAD_MULTI)
+    out = ops._head_backward(logits, stats, shape, gk, inplace=True)
+    assert out.data_ptr() == logits.data_ptr()
+    assert torch.equal(out, gref)

@@ -1,0 +1,117 @@
+"""ctypes binding of libxsup_b200.so (the C ABI declared in include/xsup_b200.h).
+
+There is no CPU or PyTorch fallback: if the shared library is missing the
+import of this module raises, and every compute call raises `RuntimeError`
+with the library's own message when a launch is rejected or fails.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "csrc", "libxsup_b200.so")
+
+F32, BF16 = 0, 1
+HEAD_MULTI, HEAD_SINGLE = 0, 1
+REDUCE = {"batch": 0, "sample": 1, "joint": 2}
+LOSS_TERMS = 4
+FLAG_NORM, FLAG_MONO, FLAG_PATCH = 1, 2, 4
+
+# every symbol include/xsup_b200.h declares (tests check the library exports all of them)
+SYMBOLS = (
+    "xsup_abi_version", "xsup_last_error", "xsup_launch_count", "xsup_stats_stride", "xsup_coef_stride",
+    "xsup_integral_fwd", "xsup_integral_bwd", "xsup_find_peak",
+    "xsup_patch_to_world_fwd", "xsup_patch_to_world_bwd", "xsup_world_to_patch_fwd",
+    "xsup_reproj_loss_fwd", "xsup_reproj_select", "xsup_reproj_loss_bwd",
+)
+
+
+class Shape(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in ("B", "K", "D", "H", "W", "NH", "NS", "dtype", "head")]
+
+
+class Cam(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("trans_image", "pelvis", "k_mat", "trans_world", "rot_world")]
+
+
+class LossCfg(C.Structure):
+    _fields_ = [("B", C.c_int32), ("K", C.c_int32), ("NH", C.c_int32), ("img_h", C.c_int32), ("img_w", C.c_int32),
+                ("rect_width", C.c_float), ("w_mse", C.c_float), ("w_bone", C.c_float), ("w_kp", C.c_float),
+                ("w_kp2d", C.c_float), ("use_sym", C.c_int32), ("reduction", C.c_int32), ("batch_total", C.c_int32)]
+
+
+def _load():
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            "libxsup_b200.so is not built (%s). Run `python -c 'import __graft_entry__ as g; g.build()'` "
+            "from the repository root; there is no CPU fallback." % LIB_PATH)
+    lib = C.CDLL(LIB_PATH)
+    vp, i32, f32 = C.c_void_p, C.c_int32, C.c_float
+    lib.xsup_abi_version.restype = C.c_int
+    lib.xsup_last_error.restype = C.c_char_p
+    lib.xsup_launch_count.restype = C.c_uint64
+    lib.xsup_stats_stride.restype = C.c_size_t
+    lib.xsup_stats_stride.argtypes = [C.POINTER(Shape)]
+    lib.xsup_coef_stride.restype = C.c_size_t
+    lib.xsup_coef_stride.argtypes = [C.POINTER(Shape)]
+    lib.xsup_integral_fwd.argtypes = [vp, vp, vp, vp, vp, C.POINTER(Shape), vp]
+    lib.xsup_integral_bwd.argtypes = [vp, vp, vp, vp, vp, C.POINTER(Shape), vp]
+    lib.xsup_find_peak.argtypes = [vp, vp, i32, i32, i32, vp]
+    lib.xsup_patch_to_world_fwd.argtypes = [vp, C.POINTER(Cam), vp, i32, i32, i32, i32, f32, i32, vp]
+    lib.xsup_patch_to_world_bwd.argtypes = [vp, vp, C.POINTER(Cam), vp, i32, i32, i32, i32, f32, i32, vp]
+    lib.xsup_world_to_patch_fwd.argtypes = [vp, C.POINTER(Cam), vp, i32, i32, i32, i32, f32, i32, vp]
+    lib.xsup_reproj_loss_fwd.argtypes = [vp, vp, C.POINTER(Cam), vp, vp, vp, C.POINTER(LossCfg), vp]
+    lib.xsup_reproj_select.argtypes = [vp, vp, vp, vp, vp, vp, C.POINTER(LossCfg), vp]
+    lib.xsup_reproj_loss_bwd.argtypes = [vp, vp, C.POINTER(Cam), vp, vp, vp, C.POINTER(LossCfg), vp]
+    for name in SYMBOLS:
+        fn = getattr(lib, name)
+        if name.startswith(("xsup_integral", "xsup_find", "xsup_patch", "xsup_world", "xsup_reproj")):
+            fn.restype = C.c_int
+    return lib
+
+
+lib = _load()
+if lib.xsup_abi_version() != 1:
+    raise ImportError("libxsup_b200.so ABI version %d, expected 1" % lib.xsup_abi_version())
+
+
+def check(rc: int, who: str) -> None:
+    if rc != 0:
+        raise RuntimeError("%s failed (code %d): %s" % (who, rc, lib.xsup_last_error().decode()))
+
+
+def launch_count() -> int:
+    return int(lib.xsup_launch_count())
+
+
+def stream_ptr(device) -> int:
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+def require_cuda(t: torch.Tensor, name: str) -> None:
+    if not t.is_cuda:
+        raise RuntimeError("%s must be a CUDA tensor: xsup_b200 has no CPU path (got device %s)" % (name, t.device))
+
+
+def make_shape(B, K, D, H, W, NH, NS, dtype, head=HEAD_MULTI) -> Shape:
+    if dtype == torch.float32:
+        dt = F32
+    elif dtype == torch.bfloat16:
+        dt = BF16
+    else:
+        raise TypeError("logits must be float32 or bfloat16, got %s" % dtype)
+    return Shape(B, K, D, H, W, NH, NS, dt, head)
+
+
+def make_cam(trans_image, pelvis, k_mat, trans_world, rot_world, B) -> Cam:
+    shapes = ((trans_image, (B, 2, 3)), (pelvis, (B, 3)), (k_mat, (B, 3, 3)), (trans_world, (B, 3)), (rot_world, (B, 3, 3)))
+    ptrs = []
+    for t, shp in shapes:
+        require_cuda(t, "camera tensor")
+        if tuple(t.shape) != shp or t.dtype != torch.float32 or not t.is_contiguous():
+            raise ValueError("camera tensor must be contiguous float32 of shape %s, got %s %s" % (shp, tuple(t.shape), t.dtype))
+        ptrs.append(t.data_ptr())
+    return Cam(*ptrs)

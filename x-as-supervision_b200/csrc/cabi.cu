@@ -1,0 +1,261 @@
+// extern "C" entry points of libxsup_b200.so (declared in include/xsup_b200.h).
+// Host-side validation happens here; nothing in this file computes on the CPU.
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+
+#include "xsup_internal.h"
+
+namespace xsup {
+
+static thread_local char t_err[512] = "";
+static std::atomic<uint64_t> g_launches{0};
+
+void count_launches(int n) { g_launches.fetch_add((uint64_t)n, std::memory_order_relaxed); }
+
+static int fail(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(t_err, sizeof(t_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+static int cuda_fail(cudaError_t e, const char* what) {
+    snprintf(t_err, sizeof(t_err), "%s: %s (%s)", what, cudaGetErrorString(e), cudaGetErrorName(e));
+    return (int)e;
+}
+
+static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+static bool is_pow2(int v) { return v > 0 && (v & (v - 1)) == 0; }
+
+// returns true when the TMA-ring kernels can cut this volume; false -> generic kernels
+static bool make_tiling(const xsup_shape_t& s, Tiling& t) {
+    t = Tiling{};
+    t.D = s.D; t.H = s.H; t.W = s.W;
+    t.esize = s.dtype == XSUP_F32 ? 4 : 2;
+    t.unit_bytes = (long long)s.D * s.H * s.W * t.esize;
+    const int vec = 16 / t.esize;
+    if (s.W % vec) return false;
+    t.lpr = s.W / vec;
+    if (!is_pow2(t.lpr) || t.lpr > 32) return false;
+    t.lpr_log2 = 0;
+    while ((1 << t.lpr_log2) < t.lpr) ++t.lpr_log2;
+    const long long slice_bytes = (long long)s.H * s.W * t.esize;
+    if (slice_bytes % 512) return false;
+    const long long per = slice_bytes / 512;
+    t.U = kMaxU;
+    while (per % t.U) t.U >>= 1;
+    t.task_bytes = 512 * t.U;
+    t.parts = (int)(slice_bytes / t.task_bytes);
+    t.rows_per_task = 32 * t.U / t.lpr;
+    const long long tu = (long long)s.D * t.parts;
+    if (tu > 4096) return false;
+    t.tasks_per_unit = (int)tu;
+    t.stages_per_unit = (t.tasks_per_unit + kTasksPerStage - 1) / kTasksPerStage;
+    t.stage_bytes = kTasksPerStage * t.task_bytes;
+    return true;
+}
+
+static int check_shape(const xsup_shape_t* s) {
+    if (!s) return fail(XSUP_E_NULL, "shape is NULL");
+    if (s->dtype != XSUP_F32 && s->dtype != XSUP_BF16) return fail(XSUP_E_DTYPE, "dtype must be XSUP_F32 or XSUP_BF16 (got %d)", s->dtype);
+    if (s->head != XSUP_HEAD_MULTI && s->head != XSUP_HEAD_SINGLE) return fail(XSUP_E_SHAPE, "unknown head mode %d", s->head);
+    if (s->B < 0 || s->K <= 0 || s->D <= 0 || s->H <= 0 || s->W <= 0) return fail(XSUP_E_SHAPE, "non-positive dimension");
+    if (s->D != s->W)
+        return fail(XSUP_E_SHAPE, "depth_dim (%d) must equal width (%d): the reference multiplies the depth marginal by arange(W)", s->D, s->W);
+    if (s->D > kMaxD) return fail(XSUP_E_SHAPE, "depth_dim %d > %d", s->D, kMaxD);
+    if ((long long)s->B * s->K > 0x7fffffffLL / 64) return fail(XSUP_E_SHAPE, "too many (b,k) units");
+    if (s->head == XSUP_HEAD_MULTI) {
+        if (s->NH < 1 || s->NH > s->D - 2) return fail(XSUP_E_SHAPE, "num_hypo %d must be in [1, D-2=%d] (topk over the interior bins)", s->NH, s->D - 2);
+        if (s->NS < 1 || !(s->NS & 1)) return fail(XSUP_E_SHAPE, "neighbor_size %d must be odd and positive", s->NS);
+    } else if (s->NH != 1) {
+        return fail(XSUP_E_SHAPE, "single-hypothesis head needs NH == 1");
+    }
+    return XSUP_OK;
+}
+
+static int device_info(int& num_sms) {
+    static thread_local int cached_dev = -1, cached_sms = 0, cached_major = 0;
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaGetDevice");
+    if (dev != cached_dev) {
+        cudaDeviceProp prop;
+        e = cudaGetDeviceProperties(&prop, dev);
+        if (e != cudaSuccess) return cuda_fail(e, "cudaGetDeviceProperties");
+        cached_dev = dev; cached_sms = prop.multiProcessorCount; cached_major = prop.major;
+    }
+    if (cached_major != 10) return fail(XSUP_E_DEVICE, "xsup_b200 kernels are built for sm_100a only (device is sm_%d*)", cached_major * 10);
+    num_sms = cached_sms;
+    return XSUP_OK;
+}
+
+static size_t stats_stride(const xsup_shape_t& s) { return (size_t)((4 + s.D + 3 * s.NH + 3) / 4 * 4); }
+static size_t coef_stride(const xsup_shape_t& s) { return (size_t)((4 + s.D + 3) / 4 * 4); }
+
+}  // namespace xsup
+
+using namespace xsup;
+
+extern "C" {
+
+int xsup_abi_version(void) { return XSUP_ABI_VERSION; }
+const char* xsup_last_error(void) { return t_err; }
+uint64_t xsup_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+size_t xsup_stats_stride(const xsup_shape_t* s) { return s ? stats_stride(*s) : 0; }
+size_t xsup_coef_stride(const xsup_shape_t* s) { return s ? coef_stride(*s) : 0; }
+
+int xsup_integral_fwd(const void* logits, float* kps, float* depth_prob_map, int64_t* peak_idx, float* stats,
+                      const xsup_shape_t* s, void* stream) {
+    if (int rc = check_shape(s)) return rc;
+    if (!logits || !kps || !depth_prob_map || !stats) return fail(XSUP_E_NULL, "xsup_integral_fwd: NULL pointer");
+    if (!aligned16(logits) || !aligned16(stats)) return fail(XSUP_E_ALIGN, "xsup_integral_fwd: logits/stats must be 16-byte aligned");
+    if (s->B == 0) return XSUP_OK;
+    int sms = 0;
+    if (int rc = device_info(sms)) return rc;
+    FwdParams p{};
+    p.logits = logits; p.kps = kps; p.dmap = depth_prob_map; p.peak_idx = peak_idx; p.stats = stats;
+    p.n_units = s->B * s->K; p.K = s->K; p.NH = s->NH; p.NS = s->NS; p.head = s->head;
+    p.stats_stride = (int)stats_stride(*s);
+    const bool fast = make_tiling(*s, p.t);
+    cudaError_t e = launch_integral_fwd(p, fast, s->dtype, sms, (cudaStream_t)stream);
+    if (e != cudaSuccess) return cuda_fail(e, "xsup_integral_fwd launch");
+    count_launches(1);
+    return XSUP_OK;
+}
+
+int xsup_integral_bwd(const void* logits, const float* stats, const float* g_kps, void* g_logits, float* coef_ws,
+                      const xsup_shape_t* s, void* stream) {
+    if (int rc = check_shape(s)) return rc;
+    if (!logits || !stats || !g_kps || !g_logits || !coef_ws) return fail(XSUP_E_NULL, "xsup_integral_bwd: NULL pointer");
+    if (!aligned16(logits) || !aligned16(g_logits) || !aligned16(coef_ws))
+        return fail(XSUP_E_ALIGN, "xsup_integral_bwd: logits/g_logits/coef_ws must be 16-byte aligned");
+    if (s->B == 0) return XSUP_OK;
+    int sms = 0;
+    if (int rc = device_info(sms)) return rc;
+    CoefParams c{};
+    c.stats = stats; c.g_kps = g_kps; c.coef = coef_ws;
+    c.n_units = s->B * s->K; c.K = s->K; c.D = s->D; c.H = s->H; c.W = s->W; c.NH = s->NH; c.NS = s->NS; c.head = s->head;
+    c.stats_stride = (int)stats_stride(*s); c.coef_stride = (int)coef_stride(*s);
+    cudaError_t e = launch_integral_coef(c, (cudaStream_t)stream);
+    if (e != cudaSuccess) return cuda_fail(e, "xsup_integral_bwd coefficient launch");
+    BwdParams p{};
+    p.logits = logits; p.coef = coef_ws; p.g_logits = g_logits;
+    p.n_units = c.n_units; p.coef_stride = c.coef_stride;
+    const bool fast = make_tiling(*s, p.t);
+    e = launch_integral_bwd(p, fast, s->dtype, sms, (cudaStream_t)stream);
+    if (e != cudaSuccess) return cuda_fail(e, "xsup_integral_bwd launch");
+    count_launches(2);
+    return XSUP_OK;
+}
+
+int xsup_find_peak(const float* pz, int64_t* idx, int32_t rows, int32_t D, int32_t NH, void* stream) {
+    if (!pz || !idx) return fail(XSUP_E_NULL, "xsup_find_peak: NULL pointer");
+    if (rows < 0 || D < 3 || D > kMaxD || NH < 1 || NH > D - 2) return fail(XSUP_E_SHAPE, "xsup_find_peak: need 3 <= D <= %d and 1 <= NH <= D-2", kMaxD);
+    if (rows == 0) return XSUP_OK;
+    cudaError_t e = launch_find_peak(pz, idx, rows, D, NH, (cudaStream_t)stream);
+    if (e != cudaSuccess) return cuda_fail(e, "xsup_find_peak launch");
+    count_launches(1);
+    return XSUP_OK;
+}
+
+static int check_cam(const xsup_cam_t* cam, const char* who) {
+    if (!cam) return fail(XSUP_E_NULL, "%s: cam is NULL", who);
+    if (!cam->trans_image || !cam->pelvis || !cam->k_mat || !cam->trans_world || !cam->rot_world)
+        return fail(XSUP_E_NULL, "%s: a camera tensor is NULL", who);
+    return XSUP_OK;
+}
+
+static int geom_params(GeomParams& g, const xsup_cam_t* cam, int B, int J, int img_h, int img_w, float rect_width, int flags,
+                       const char* who) {
+    if (int rc = check_cam(cam, who)) return rc;
+    if (B < 0 || J <= 0 || img_h <= 1 || img_w <= 1) return fail(XSUP_E_SHAPE, "%s: bad sizes", who);
+    g.cam = *cam; g.B = B; g.J = J; g.img_h = img_h; g.img_w = img_w; g.flags = flags; g.rect_width = rect_width;
+    return XSUP_OK;
+}
+
+int xsup_patch_to_world_fwd(const float* kps, const xsup_cam_t* cam, float* world, int32_t B, int32_t J, int32_t img_h,
+                            int32_t img_w, float rect_width, int32_t flags, void* stream) {
+    GeomParams g{};
+    if (int rc = geom_params(g, cam, B, J, img_h, img_w, rect_width, flags, "xsup_patch_to_world_fwd")) return rc;
+    if (!kps || !world) return fail(XSUP_E_NULL, "xsup_patch_to_world_fwd: NULL pointer");
+    if (B == 0) return XSUP_OK;
+    cudaError_t e = launch_patch_to_world_fwd(kps, world, g, (cudaStream_t)stream);
+    if (e != cudaSuccess) return cuda_fail(e, "xsup_patch_to_world_fwd launch");
+    count_launches(1);
+    return XSUP_OK;
+}
+
+int xsup_patch_to_world_bwd(const float* kps, const float* g_world, const xsup_cam_t* cam, float* g_kps, int32_t B, int32_t J,
+                            int32_t img_h, int32_t img_w, float rect_width, int32_t flags, void* stream) {
+    GeomParams g{};
+    if (int rc = geom_params(g, cam, B, J, img_h, img_w, rect_width, flags, "xsup_patch_to_world_bwd")) return rc;
+    if (!kps || !g_world || !g_kps) return fail(XSUP_E_NULL, "xsup_patch_to_world_bwd: NULL pointer");
+    if (B == 0) return XSUP_OK;
+    cudaError_t e = launch_patch_to_world_bwd(kps, g_world, g_kps, g, (cudaStream_t)stream);
+    if (e != cudaSuccess) return cuda_fail(e, "xsup_patch_to_world_bwd launch");
+    count_launches(1);
+    return XSUP_OK;
+}
+
+int xsup_world_to_patch_fwd(const float* world, const xsup_cam_t* cam, float* kps, int32_t B, int32_t J, int32_t img_h,
+                            int32_t img_w, float rect_width, int32_t flags, void* stream) {
+    GeomParams g{};
+    if (int rc = geom_params(g, cam, B, J, img_h, img_w, rect_width, flags, "xsup_world_to_patch_fwd")) return rc;
+    if (!kps || !world) return fail(XSUP_E_NULL, "xsup_world_to_patch_fwd: NULL pointer");
+    if (B == 0) return XSUP_OK;
+    cudaError_t e = launch_world_to_patch_fwd(world, kps, g, (cudaStream_t)stream);
+    if (e != cudaSuccess) return cuda_fail(e, "xsup_world_to_patch_fwd launch");
+    count_launches(1);
+    return XSUP_OK;
+}
+
+static int check_cfg(const xsup_loss_cfg_t* c, const char* who) {
+    if (!c) return fail(XSUP_E_NULL, "%s: cfg is NULL", who);
+    if (c->B < 0 || c->K <= 0 || c->NH <= 0) return fail(XSUP_E_SHAPE, "%s: bad sizes", who);
+    if (c->K > 32) return fail(XSUP_E_SHAPE, "%s: num_kp %d > 32 (one joint per lane)", who, c->K);
+    if (c->use_sym && c->K < 17) return fail(XSUP_E_SHAPE, "%s: symmetry terms index joints up to 16 (loss_func.py:20), num_kp is %d", who, c->K);
+    if (c->use_sym && c->reduction == XSUP_REDUCE_JOINT) return fail(XSUP_E_SHAPE, "%s: symmetry terms are undefined per joint", who);
+    if (c->reduction < XSUP_REDUCE_BATCH || c->reduction > XSUP_REDUCE_JOINT) return fail(XSUP_E_SHAPE, "%s: unknown reduction %d", who, c->reduction);
+    if (c->batch_total < c->B || c->img_h <= 1 || c->img_w <= 1) return fail(XSUP_E_SHAPE, "%s: batch_total < B or bad image size", who);
+    return XSUP_OK;
+}
+
+int xsup_reproj_loss_fwd(const float* kps, const float* target, const xsup_cam_t* cam, float* world, float* sample_terms,
+                         float* partial, const xsup_loss_cfg_t* cfg, void* stream) {
+    if (int rc = check_cfg(cfg, "xsup_reproj_loss_fwd")) return rc;
+    if (int rc = check_cam(cam, "xsup_reproj_loss_fwd")) return rc;
+    if (!kps || !target || !world || !sample_terms || !partial) return fail(XSUP_E_NULL, "xsup_reproj_loss_fwd: NULL pointer");
+    if (cfg->B == 0) return fail(XSUP_E_SHAPE, "xsup_reproj_loss_fwd: empty batch");
+    cudaError_t e = launch_reproj_loss_fwd(kps, target, *cam, world, sample_terms, partial, *cfg, (cudaStream_t)stream);
+    if (e != cudaSuccess) return cuda_fail(e, "xsup_reproj_loss_fwd launch");
+    count_launches(2);
+    return XSUP_OK;
+}
+
+int xsup_reproj_select(const float* kps, const float* target, const float* sample_terms, const float* partial, float* loss,
+                       int64_t* sel, const xsup_loss_cfg_t* cfg, void* stream) {
+    if (int rc = check_cfg(cfg, "xsup_reproj_select")) return rc;
+    if (!kps || !target || !sample_terms || !partial || !loss || !sel) return fail(XSUP_E_NULL, "xsup_reproj_select: NULL pointer");
+    cudaError_t e = launch_reproj_select(kps, target, sample_terms, partial, loss, sel, *cfg, (cudaStream_t)stream);
+    if (e != cudaSuccess) return cuda_fail(e, "xsup_reproj_select launch");
+    count_launches(1);
+    return XSUP_OK;
+}
+
+int xsup_reproj_loss_bwd(const float* kps, const float* target, const xsup_cam_t* cam, const int64_t* sel, const float* g_loss,
+                         float* g_kps, const xsup_loss_cfg_t* cfg, void* stream) {
+    if (int rc = check_cfg(cfg, "xsup_reproj_loss_bwd")) return rc;
+    if (int rc = check_cam(cam, "xsup_reproj_loss_bwd")) return rc;
+    if (!kps || !target || !sel || !g_loss || !g_kps) return fail(XSUP_E_NULL, "xsup_reproj_loss_bwd: NULL pointer");
+    if (cfg->B == 0) return XSUP_OK;
+    cudaError_t e = launch_reproj_loss_bwd(kps, target, *cam, sel, g_loss, g_kps, *cfg, (cudaStream_t)stream);
+    if (e != cudaSuccess) return cuda_fail(e, "xsup_reproj_loss_bwd launch");
+    count_launches(1);
+    return XSUP_OK;
+}
+
+}  // extern "C"

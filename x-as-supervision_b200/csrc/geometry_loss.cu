@@ -1,0 +1,440 @@
+// K2 — per-sample camera geometry, loss terms and min-over-hypotheses selection.
+//
+// Replaces, for one camera,
+//   modules/util.py:61-95,128-152     convert_patch_to_world (inverse crop affine, px->mm depth,
+//                                     pinhole back-projection, inverse extrinsics) and :98-125,155-168
+//                                     its inverse (forward perspective projection),
+//   modules/base_losses/loss_func.py:18-52   bone / keypoint symmetry and pseudo-GT MSE,
+//   modules/model.py:71-79,105-114,158-162   the per-hypothesis Python loops and torch.min(torch.stack()),
+//   eval.py:138-145 / loss_func.py:59        per-joint argmin / per-sample min.
+// The reference issues ~10^2 tiny kernels and two batched LU inversions per camera for this; here it is
+// three launches of a few microseconds.  All reductions are fixed-order (no float atomics), so the
+// selected hypothesis is reproducible run to run.
+#include "xsup_internal.h"
+
+namespace xsup {
+
+__constant__ int c_bone_child[8] = {16, 15, 13, 12, 3, 2, 6, 5};    // loss_func.py:20
+__constant__ int c_bone_parent[8] = {15, 14, 12, 11, 2, 1, 5, 4};
+__constant__ int c_mid_a[2] = {11, 1};                              // loss_func.py:28
+__constant__ int c_mid_b[2] = {14, 4};
+
+enum { F_NORM = 1, F_MONO = 2, F_PATCH = 4 };
+
+struct Cam {
+    float ai00, ai01, ai10, ai11;   // inverse of trans_image[:, :, :2]
+    float a00, a01, a10, a11, t0, t1;
+    float pz;                       // pelvis depth
+    float fx, fy, cx, cy;
+    float ri[9];                    // inverse of rot_world (general inverse, util.py:93)
+    float r[9], tw[3];
+};
+
+__device__ __forceinline__ Cam load_cam(const xsup_cam_t& c, int b) {
+    Cam m;
+    const float* A = c.trans_image + (size_t)b * 6;
+    m.a00 = A[0]; m.a01 = A[1]; m.t0 = A[2]; m.a10 = A[3]; m.a11 = A[4]; m.t1 = A[5];
+    const float idet = 1.0f / (m.a00 * m.a11 - m.a01 * m.a10);
+    m.ai00 = m.a11 * idet; m.ai01 = -m.a01 * idet; m.ai10 = -m.a10 * idet; m.ai11 = m.a00 * idet;
+    m.pz = c.pelvis[(size_t)b * 3 + 2];
+    const float* K = c.k_mat + (size_t)b * 9;
+    m.fx = K[0]; m.fy = K[4]; m.cx = K[2]; m.cy = K[5];
+    const float* R = c.rot_world + (size_t)b * 9;
+#pragma unroll
+    for (int i = 0; i < 9; ++i) m.r[i] = R[i];
+    const float c00 = R[4] * R[8] - R[5] * R[7], c01 = R[5] * R[6] - R[3] * R[8], c02 = R[3] * R[7] - R[4] * R[6];
+    const float rdet = 1.0f / (R[0] * c00 + R[1] * c01 + R[2] * c02);
+    m.ri[0] = c00 * rdet; m.ri[1] = (R[2] * R[7] - R[1] * R[8]) * rdet; m.ri[2] = (R[1] * R[5] - R[2] * R[4]) * rdet;
+    m.ri[3] = c01 * rdet; m.ri[4] = (R[0] * R[8] - R[2] * R[6]) * rdet; m.ri[5] = (R[2] * R[3] - R[0] * R[5]) * rdet;
+    m.ri[6] = c02 * rdet; m.ri[7] = (R[1] * R[6] - R[0] * R[7]) * rdet; m.ri[8] = (R[0] * R[4] - R[1] * R[3]) * rdet;
+    const float* T = c.trans_world + (size_t)b * 3;
+    m.tw[0] = T[0]; m.tw[1] = T[1]; m.tw[2] = T[2];
+    return m;
+}
+
+struct Img { float wm1, hm1, dm1, ds; };
+__device__ __forceinline__ Img make_img(int img_h, int img_w, float rect_width) {
+    // util.py:137-138: depth extent = image width, depth_scale = RECT_WIDTH / width
+    return Img{(float)(img_w - 1), (float)(img_h - 1), (float)(img_w - 1), 1.0f / (float)img_w * rect_width};
+}
+
+// (x,y,z) patch -> world; also returns the intermediates the VJP needs
+__device__ __forceinline__ void patch_to_world(const Cam& m, const Img& im, int flags, float x, float y, float z,
+                                               float (&w)[3], float& u, float& v, float& Z) {
+    if (flags & F_PATCH) {
+        if (flags & F_NORM) {
+            x = (x + 1.0f) / 2.0f * im.wm1;                       // util.py:70-72
+            y = (y + 1.0f) / 2.0f * im.hm1;
+            z = z * im.dm1;
+        }
+        const float du = x - m.t0, dv = y - m.t1;                 // util.py:65,76
+        u = m.ai00 * du + m.ai01 * dv;
+        v = m.ai10 * du + m.ai11 * dv;
+        Z = z * im.ds + m.pz;                                     // util.py:79-80
+    } else {
+        u = x; v = y; Z = z;
+    }
+    if (flags & F_MONO) {                                         // util.py:145-150
+        w[0] = -u; w[1] = -(Z + 128.0f); w[2] = -v;
+        return;
+    }
+    const float X = (u - m.cx) / m.fx * Z - m.tw[0];              // util.py:89-90,93
+    const float Y = (v - m.cy) / m.fy * Z - m.tw[1];
+    const float Zc = Z - m.tw[2];
+    w[0] = m.ri[0] * X + m.ri[1] * Y + m.ri[2] * Zc;
+    w[1] = m.ri[3] * X + m.ri[4] * Y + m.ri[5] * Zc;
+    w[2] = m.ri[6] * X + m.ri[7] * Y + m.ri[8] * Zc;
+}
+
+// vector-Jacobian product of patch_to_world: gw (d loss / d world) -> (gx, gy, gz)
+__device__ __forceinline__ void patch_to_world_vjp(const Cam& m, const Img& im, int flags, float u, float v, float Z,
+                                                   const float (&gw)[3], float (&g)[3]) {
+    float gu, gv, gZ;
+    if (flags & F_MONO) {
+        gu = -gw[0]; gZ = -gw[1]; gv = -gw[2];
+    } else {
+        const float gX = m.ri[0] * gw[0] + m.ri[3] * gw[1] + m.ri[6] * gw[2];
+        const float gY = m.ri[1] * gw[0] + m.ri[4] * gw[1] + m.ri[7] * gw[2];
+        const float gC = m.ri[2] * gw[0] + m.ri[5] * gw[1] + m.ri[8] * gw[2];
+        gu = gX * Z / m.fx;
+        gv = gY * Z / m.fy;
+        gZ = gC + gX * (u - m.cx) / m.fx + gY * (v - m.cy) / m.fy;
+    }
+    if (flags & F_PATCH) {
+        float gx = m.ai00 * gu + m.ai10 * gv, gy = m.ai01 * gu + m.ai11 * gv, gz = gZ * im.ds;
+        if (flags & F_NORM) { gx *= im.wm1 * 0.5f; gy *= im.hm1 * 0.5f; gz *= im.dm1; }
+        g[0] = gx; g[1] = gy; g[2] = gz;
+    } else {
+        g[0] = gu; g[1] = gv; g[2] = gZ;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------- standalone geometry
+__global__ void patch_to_world_fwd_kernel(const float* __restrict__ kps, float* __restrict__ world, const GeomParams g) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= g.B * g.J) return;
+    const Cam m = load_cam(g.cam, i / g.J);
+    const Img im = make_img(g.img_h, g.img_w, g.rect_width);
+    float w[3], u, v, Z;
+    patch_to_world(m, im, g.flags, kps[3 * i], kps[3 * i + 1], kps[3 * i + 2], w, u, v, Z);
+    world[3 * i] = w[0]; world[3 * i + 1] = w[1]; world[3 * i + 2] = w[2];
+}
+
+__global__ void patch_to_world_bwd_kernel(const float* __restrict__ kps, const float* __restrict__ g_world,
+                                          float* __restrict__ g_kps, const GeomParams g) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= g.B * g.J) return;
+    const Cam m = load_cam(g.cam, i / g.J);
+    const Img im = make_img(g.img_h, g.img_w, g.rect_width);
+    float w[3], u, v, Z;
+    patch_to_world(m, im, g.flags, kps[3 * i], kps[3 * i + 1], kps[3 * i + 2], w, u, v, Z);
+    const float gw[3] = {g_world[3 * i], g_world[3 * i + 1], g_world[3 * i + 2]};
+    float o[3];
+    patch_to_world_vjp(m, im, g.flags, u, v, Z, gw, o);
+    g_kps[3 * i] = o[0]; g_kps[3 * i + 1] = o[1]; g_kps[3 * i + 2] = o[2];
+}
+
+__global__ void world_to_patch_fwd_kernel(const float* __restrict__ world, float* __restrict__ kps, const GeomParams g) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= g.B * g.J) return;
+    const Cam m = load_cam(g.cam, i / g.J);
+    const Img im = make_img(g.img_h, g.img_w, g.rect_width);
+    const float wx = world[3 * i], wy = world[3 * i + 1], wz = world[3 * i + 2];
+    const float X = m.r[0] * wx + m.r[1] * wy + m.r[2] * wz + m.tw[0];      // util.py:120
+    const float Y = m.r[3] * wx + m.r[4] * wy + m.r[5] * wz + m.tw[1];
+    const float Z = m.r[6] * wx + m.r[7] * wy + m.r[8] * wz + m.tw[2];
+    const float u = X / Z * m.fx + m.cx, v = Y / Z * m.fy + m.cy;          // util.py:122-123
+    float z = (Z - m.pz) / im.ds;                                          // util.py:102-103
+    float x = m.a00 * u + m.a01 * v + m.t0, y = m.a10 * u + m.a11 * v + m.t1;
+    if (g.flags & F_NORM) {                                                // util.py:108-111
+        x = x / im.wm1 * 2.0f - 1.0f;
+        y = y / im.hm1 * 2.0f - 1.0f;
+        z = z / im.dm1;
+    }
+    kps[3 * i] = x; kps[3 * i + 1] = y; kps[3 * i + 2] = z;
+}
+
+cudaError_t launch_patch_to_world_fwd(const float* kps, float* world, const GeomParams& g, cudaStream_t st) {
+    const int n = g.B * g.J;
+    patch_to_world_fwd_kernel<<<(n + 127) / 128, 128, 0, st>>>(kps, world, g);
+    return cudaGetLastError();
+}
+cudaError_t launch_patch_to_world_bwd(const float* kps, const float* g_world, float* g_kps, const GeomParams& g,
+                                           cudaStream_t st) {
+    const int n = g.B * g.J;
+    patch_to_world_bwd_kernel<<<(n + 127) / 128, 128, 0, st>>>(kps, g_world, g_kps, g);
+    return cudaGetLastError();
+}
+cudaError_t launch_world_to_patch_fwd(const float* world, float* kps, const GeomParams& g, cudaStream_t st) {
+    const int n = g.B * g.J;
+    world_to_patch_fwd_kernel<<<(n + 127) / 128, 128, 0, st>>>(world, kps, g);
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------- loss forward
+// one warp per (sample, hypothesis); lane = joint (K <= 32)
+__global__ void __launch_bounds__(128) reproj_loss_fwd_kernel(const float* __restrict__ kps, const float* __restrict__ target,
+                                                              const xsup_cam_t cam, float* __restrict__ world,
+                                                              float* __restrict__ sample_terms, const xsup_loss_cfg_t c) {
+    const int wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (wid >= c.B * c.NH) return;
+    const int b = wid / c.NH, h = wid - b * c.NH, K = c.K;
+    const Cam m = load_cam(cam, b);
+    const Img im = make_img(c.img_h, c.img_w, c.rect_width);
+    float x = 0.f, y = 0.f, z = 0.f, w[3] = {0.f, 0.f, 0.f}, se = 0.f;
+    if (lane < K) {
+        const size_t o = (((size_t)b * c.NH + h) * K + lane) * 3;
+        x = kps[o]; y = kps[o + 1]; z = kps[o + 2];
+        const float* tg = target + ((size_t)b * K + lane) * 3;
+        const float dx = x - tg[0], dy = y - tg[1], dz = z - tg[2];
+        se = dx * dx + dy * dy + dz * dz;
+        float u, v, Z;
+        patch_to_world(m, im, F_NORM | F_PATCH, x, y, z, w, u, v, Z);
+        world[o] = w[0]; world[o + 1] = w[1]; world[o + 2] = w[2];
+    }
+    se = warp_sum(se);
+    float bone = 0.f, kp3 = 0.f, kp2 = 0.f;
+    if (c.use_sym) {
+        // bones: lane i < 8 owns bone i (loss_func.py:20-21)
+        const int ci = c_bone_child[lane & 7], pi = c_bone_parent[lane & 7];
+        const float vx = __shfl_sync(0xffffffffu, w[0], ci) - __shfl_sync(0xffffffffu, w[0], pi);
+        const float vy = __shfl_sync(0xffffffffu, w[1], ci) - __shfl_sync(0xffffffffu, w[1], pi);
+        const float vz = __shfl_sync(0xffffffffu, w[2], ci) - __shfl_sync(0xffffffffu, w[2], pi);
+        const float n = sqrtf(vx * vx + vy * vy + vz * vz) * 1e-3f;
+        const float nn = __shfl_down_sync(0xffffffffu, n, 1);
+        const float df = n - nn;
+        bone = warp_sum((lane < 8 && !(lane & 1)) ? df * df : 0.f);           // pairs (0,1),(2,3),(4,5),(6,7)
+        // midpoints: lane s < 2 owns pair s (loss_func.py:28-35)
+        const int ia = c_mid_a[lane & 1], ib = c_mid_b[lane & 1], ir = (lane & 1) ? 0 : K - 1;
+        float e3 = 0.f, e2 = 0.f;
+        {
+            const float a0 = __shfl_sync(0xffffffffu, w[0], ia), b0 = __shfl_sync(0xffffffffu, w[0], ib), r0 = __shfl_sync(0xffffffffu, w[0], ir);
+            const float a1 = __shfl_sync(0xffffffffu, w[1], ia), b1 = __shfl_sync(0xffffffffu, w[1], ib), r1 = __shfl_sync(0xffffffffu, w[1], ir);
+            const float a2 = __shfl_sync(0xffffffffu, w[2], ia), b2 = __shfl_sync(0xffffffffu, w[2], ib), r2 = __shfl_sync(0xffffffffu, w[2], ir);
+            const float d0 = (a0 + b0) / 2.0f * 1e-3f - r0 * 1e-3f, d1 = (a1 + b1) / 2.0f * 1e-3f - r1 * 1e-3f,
+                        d2 = (a2 + b2) / 2.0f * 1e-3f - r2 * 1e-3f;
+            e3 = d0 * d0 + d1 * d1 + d2 * d2;
+            const float xa = __shfl_sync(0xffffffffu, x, ia), xb = __shfl_sync(0xffffffffu, x, ib), xr = __shfl_sync(0xffffffffu, x, ir);
+            const float ya = __shfl_sync(0xffffffffu, y, ia), yb = __shfl_sync(0xffffffffu, y, ib), yr = __shfl_sync(0xffffffffu, y, ir);
+            const float q0 = (xa + xb) / 2.0f - xr, q1 = (ya + yb) / 2.0f - yr;
+            e2 = q0 * q0 + q1 * q1;
+        }
+        kp3 = warp_sum(lane < 2 ? e3 : 0.f);
+        kp2 = warp_sum(lane < 2 ? e2 : 0.f);
+    }
+    if (lane == 0) {
+        float* o = sample_terms + (size_t)b * XSUP_LOSS_TERMS * c.NH + h;
+        o[0] = se; o[c.NH] = bone; o[2 * c.NH] = kp3; o[3 * c.NH] = kp2;
+    }
+}
+
+// partial[term,h] = sum_b sample_terms[b,term,h]; one warp per (term,h), fixed order
+__global__ void __launch_bounds__(32) reproj_partial_kernel(const float* __restrict__ sample_terms, float* __restrict__ partial,
+                                                            int B, int NH) {
+    const int col = blockIdx.x, lane = threadIdx.x, stride = XSUP_LOSS_TERMS * NH;
+    float a = 0.f;
+    for (int b = lane; b < B; b += 32) a += sample_terms[(size_t)b * stride + col];
+    a = warp_sum(a);
+    if (lane == 0) partial[col] = a;
+}
+
+cudaError_t launch_reproj_loss_fwd(const float* kps, const float* target, const xsup_cam_t& cam, float* world,
+                                   float* sample_terms, float* partial, const xsup_loss_cfg_t& c, cudaStream_t st) {
+    const int warps = c.B * c.NH;
+    reproj_loss_fwd_kernel<<<(warps + 3) / 4, 128, 0, st>>>(kps, target, cam, world, sample_terms, c);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    reproj_partial_kernel<<<XSUP_LOSS_TERMS * c.NH, 32, 0, st>>>(sample_terms, partial, c.B, c.NH);
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------- selection
+__device__ __forceinline__ float sym_value(const xsup_loss_cfg_t& c, float bone, float kp3, float kp2, float n) {
+    // model.py:108-112: bone MSE over B*4, kp MSE over B*2*3, kp_2d MSE over B*2*2 (x 1e2)
+    return c.w_bone * bone / (n * 4.0f) + c.w_kp * kp3 / (n * 6.0f) + c.w_kp2d * 1e2f * kp2 / (n * 4.0f);
+}
+
+__device__ float block_sum_256(float v, float* scratch) {
+    v = warp_sum(v);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) scratch[threadIdx.x >> 5] = v;
+    __syncthreads();
+    float r = 0.f;
+    for (int i = 0; i < 8; ++i) r += scratch[i];
+    return r;
+}
+
+__global__ void __launch_bounds__(256) reproj_select_kernel(const float* __restrict__ kps, const float* __restrict__ target,
+                                                            const float* __restrict__ sample_terms, const float* __restrict__ partial,
+                                                            float* __restrict__ loss, int64_t* __restrict__ sel, const xsup_loss_cfg_t c) {
+    __shared__ float scratch[8];
+    const int NH = c.NH, K = c.K, B = c.B;
+    const float n = (float)c.batch_total;
+    if (c.reduction == XSUP_REDUCE_BATCH) {
+        if (threadIdx.x == 0) {
+            int sm = 0, ss = -1;
+            float vm = partial[0] / (n * (float)K * 3.0f), vs = 0.f;
+            for (int h = 1; h < NH; ++h) {
+                const float v = partial[h] / (n * (float)K * 3.0f);
+                if (v < vm) { vm = v; sm = h; }
+            }
+            if (c.use_sym) {
+                ss = 0;
+                vs = sym_value(c, partial[NH], partial[2 * NH], partial[3 * NH], n);
+                for (int h = 1; h < NH; ++h) {
+                    const float v = sym_value(c, partial[NH + h], partial[2 * NH + h], partial[3 * NH + h], n);
+                    if (v < vs) { vs = v; ss = h; }
+                }
+            }
+            loss[0] = c.w_mse * vm; loss[1] = vs;
+            sel[0] = sm; sel[1] = ss;
+        }
+        return;
+    }
+    if (c.reduction == XSUP_REDUCE_SAMPLE) {
+        float am = 0.f, as = 0.f;
+        for (int b = threadIdx.x; b < B; b += blockDim.x) {
+            const float* t = sample_terms + (size_t)b * XSUP_LOSS_TERMS * NH;
+            int sm = 0, ss = -1;
+            float vm = c.w_mse * t[0] / ((float)K * 3.0f), vs = 0.f;
+            for (int h = 1; h < NH; ++h) {
+                const float v = c.w_mse * t[h] / ((float)K * 3.0f);
+                if (v < vm) { vm = v; sm = h; }
+            }
+            if (c.use_sym) {
+                ss = 0;
+                vs = sym_value(c, t[NH], t[2 * NH], t[3 * NH], 1.0f);
+                for (int h = 1; h < NH; ++h) {
+                    const float v = sym_value(c, t[NH + h], t[2 * NH + h], t[3 * NH + h], 1.0f);
+                    if (v < vs) { vs = v; ss = h; }
+                }
+            }
+            sel[b] = sm; sel[B + b] = ss;
+            am += vm; as += vs;
+        }
+        am = block_sum_256(am, scratch);
+        as = block_sum_256(as, scratch);
+        if (threadIdx.x == 0) { loss[0] = am / n; loss[1] = as / n; }
+        return;
+    }
+    // joint: eval.py:138-145
+    float acc = 0.f;
+    for (int i = threadIdx.x; i < B * K; i += blockDim.x) {
+        const int b = i / K, k = i - b * K;
+        const float* tg = target + (size_t)i * 3;
+        int s = 0;
+        float best = 0.f;
+        for (int h = 0; h < NH; ++h) {
+            const float* p = kps + (((size_t)b * NH + h) * K + k) * 3;
+            const float dx = p[0] - tg[0], dy = p[1] - tg[1], dz = p[2] - tg[2];
+            const float e = dx * dx + dy * dy + dz * dz;
+            if (h == 0 || e < best) { best = e; s = h; }
+        }
+        sel[i] = s;
+        acc += best;
+    }
+    acc = block_sum_256(acc, scratch);
+    if (threadIdx.x == 0) { loss[0] = c.w_mse * acc / (n * (float)K * 3.0f); loss[1] = 0.f; }
+}
+
+cudaError_t launch_reproj_select(const float* kps, const float* target, const float* sample_terms, const float* partial,
+                                 float* loss, int64_t* sel, const xsup_loss_cfg_t& c, cudaStream_t st) {
+    reproj_select_kernel<<<1, 256, 0, st>>>(kps, target, sample_terms, partial, loss, sel, c);
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------- loss backward
+__global__ void __launch_bounds__(128) reproj_loss_bwd_kernel(const float* __restrict__ kps, const float* __restrict__ target,
+                                                              const xsup_cam_t cam, const int64_t* __restrict__ sel,
+                                                              const float* __restrict__ g_loss, float* __restrict__ g_kps,
+                                                              const xsup_loss_cfg_t c) {
+    const int wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (wid >= c.B * c.NH) return;
+    const int b = wid / c.NH, h = wid - b * c.NH, K = c.K;
+    const float n = (float)c.batch_total;
+    const float gl0 = g_loss[0], gl1 = g_loss[1];
+    bool on_sym = false;
+    if (c.use_sym) {
+        if (c.reduction == XSUP_REDUCE_BATCH) on_sym = (sel[1] == h);
+        else if (c.reduction == XSUP_REDUCE_SAMPLE) on_sym = (sel[c.B + b] == h);
+    }
+    float x = 0.f, y = 0.f, z = 0.f, g[3] = {0.f, 0.f, 0.f};
+    size_t o = 0;
+    if (lane < K) {
+        o = (((size_t)b * c.NH + h) * K + lane) * 3;
+        x = kps[o]; y = kps[o + 1]; z = kps[o + 2];
+        bool on_mse;
+        if (c.reduction == XSUP_REDUCE_BATCH) on_mse = (sel[0] == h);
+        else if (c.reduction == XSUP_REDUCE_SAMPLE) on_mse = (sel[b] == h);
+        else on_mse = (sel[(size_t)b * K + lane] == h);
+        if (on_mse) {
+            const float* tg = target + ((size_t)b * K + lane) * 3;
+            const float s = gl0 * c.w_mse * 2.0f / (n * (float)K * 3.0f);
+            g[0] = s * (x - tg[0]); g[1] = s * (y - tg[1]); g[2] = s * (z - tg[2]);
+        }
+    }
+    if (on_sym) {                                                            // warp-uniform
+        const Cam m = load_cam(cam, b);
+        const Img im = make_img(c.img_h, c.img_w, c.rect_width);
+        float w[3] = {0.f, 0.f, 0.f}, u = 0.f, v = 0.f, Z = 1.f;
+        if (lane < K) patch_to_world(m, im, F_NORM | F_PATCH, x, y, z, w, u, v, Z);
+        float gw[3] = {0.f, 0.f, 0.f};
+        // ---- bones
+        const int ci = c_bone_child[lane & 7], pi = c_bone_parent[lane & 7];
+        const float vx = __shfl_sync(0xffffffffu, w[0], ci) - __shfl_sync(0xffffffffu, w[0], pi);
+        const float vy = __shfl_sync(0xffffffffu, w[1], ci) - __shfl_sync(0xffffffffu, w[1], pi);
+        const float vz = __shfl_sync(0xffffffffu, w[2], ci) - __shfl_sync(0xffffffffu, w[2], pi);
+        const float len = sqrtf(vx * vx + vy * vy + vz * vz);
+        const float nrm = len * 1e-3f;
+        const float other = (lane & 1) ? __shfl_up_sync(0xffffffffu, nrm, 1) : __shfl_down_sync(0xffffffffu, nrm, 1);
+        // d bone_sum / d n_i = +2(n_i - n_partner) for even i, and the same expression for odd i
+        const float gn = gl1 * c.w_bone / (n * 4.0f) * 2.0f * (nrm - other) * 1e-3f;
+        const float il = len > 0.f ? 1.0f / len : 0.f;                        // torch.norm's backward is 0 at 0
+        const float bx = gn * vx * il, by = gn * vy * il, bz = gn * vz * il;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const float fx_ = __shfl_sync(0xffffffffu, bx, i), fy_ = __shfl_sync(0xffffffffu, by, i), fz_ = __shfl_sync(0xffffffffu, bz, i);
+            if (lane == c_bone_child[i]) { gw[0] += fx_; gw[1] += fy_; gw[2] += fz_; }
+            if (lane == c_bone_parent[i]) { gw[0] -= fx_; gw[1] -= fy_; gw[2] -= fz_; }
+        }
+        // ---- midpoints (3-D on world, 2-D on the patch x,y)
+        const int ia = c_mid_a[lane & 1], ib = c_mid_b[lane & 1], ir = (lane & 1) ? 0 : K - 1;
+        float e[3], q[2];
+#pragma unroll
+        for (int d = 0; d < 3; ++d)
+            e[d] = (__shfl_sync(0xffffffffu, w[d], ia) + __shfl_sync(0xffffffffu, w[d], ib)) / 2.0f * 1e-3f - __shfl_sync(0xffffffffu, w[d], ir) * 1e-3f;
+        q[0] = (__shfl_sync(0xffffffffu, x, ia) + __shfl_sync(0xffffffffu, x, ib)) / 2.0f - __shfl_sync(0xffffffffu, x, ir);
+        q[1] = (__shfl_sync(0xffffffffu, y, ia) + __shfl_sync(0xffffffffu, y, ib)) / 2.0f - __shfl_sync(0xffffffffu, y, ir);
+        const float s3 = gl1 * c.w_kp / (n * 6.0f) * 2.0f * 1e-3f;            // d/d(mid or ref), before the 1/2 of the midpoint
+        const float s2 = gl1 * c.w_kp2d * 1e2f / (n * 4.0f) * 2.0f;
+#pragma unroll
+        for (int s = 0; s < 2; ++s) {
+            const int ja = c_mid_a[s], jb = c_mid_b[s], jr = s ? 0 : K - 1;
+            float e0 = __shfl_sync(0xffffffffu, e[0], s), e1 = __shfl_sync(0xffffffffu, e[1], s), e2 = __shfl_sync(0xffffffffu, e[2], s);
+            float q0 = __shfl_sync(0xffffffffu, q[0], s), q1 = __shfl_sync(0xffffffffu, q[1], s);
+            if (lane == ja || lane == jb) {
+                gw[0] += 0.5f * s3 * e0; gw[1] += 0.5f * s3 * e1; gw[2] += 0.5f * s3 * e2;
+                g[0] += 0.5f * s2 * q0; g[1] += 0.5f * s2 * q1;
+            }
+            if (lane == jr) {
+                gw[0] -= s3 * e0; gw[1] -= s3 * e1; gw[2] -= s3 * e2;
+                g[0] -= s2 * q0; g[1] -= s2 * q1;
+            }
+        }
+        if (lane < K) {
+            float gk[3];
+            patch_to_world_vjp(m, im, F_NORM | F_PATCH, u, v, Z, gw, gk);
+            g[0] += gk[0]; g[1] += gk[1]; g[2] += gk[2];
+        }
+    }
+    if (lane < K) { g_kps[o] = g[0]; g_kps[o + 1] = g[1]; g_kps[o + 2] = g[2]; }
+}
+
+cudaError_t launch_reproj_loss_bwd(const float* kps, const float* target, const xsup_cam_t& cam, const int64_t* sel,
+                                   const float* g_loss, float* g_kps, const xsup_loss_cfg_t& c, cudaStream_t st) {
+    const int warps = c.B * c.NH;
+    reproj_loss_bwd_kernel<<<(warps + 3) / 4, 128, 0, st>>>(kps, target, cam, sel, g_loss, g_kps, c);
+    return cudaGetLastError();
+}
+
+}  // namespace xsup

@@ -1,0 +1,228 @@
+// K3 — backward of the integral multi-hypothesis head as ONE pass over the volume.
+//
+// The reference back-propagates through softmax + three expanded marginal sums + gathers
+// (autograd of keypoint_detector_integral_multi.py:69-88): ~4 reads and ~3 writes of the volume.
+// In closed form the gradient of every logit is
+//     dL/dl[d,h,w] = p[d,h,w] * (a*w + b*h + c[d] - gbar),   p = 2^(l*log2e - lse2)
+// with (a, b, c[0..D), gbar, lse2) per (b,k) unit — a (4+D)-float coefficient block that the tiny
+// `integral_coef_kernel` derives from grad_kps and the statistics saved by the forward.  The
+// streaming kernel then reads each logit once and writes each gradient once.
+//
+// Streaming kernel structure: persistent CTA per SM; warp 16 = TMA producer (bulk copy of the
+// stage and of its unit's coefficient block into the same ring slot), warps 0..15 = stateless
+// consumers (LDS.128 -> registers -> one MUFU.EX2 + 3 FP ops per element -> coalesced STG.128).
+#include "xsup_internal.h"
+
+namespace xsup {
+
+// ----------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) integral_coef_kernel(const CoefParams p) {
+    __shared__ float red[4];
+    const int unit = blockIdx.x, b = unit / p.K, k = unit - b * p.K;
+    const int D = p.D, NH = p.NH;
+    const float* st = p.stats + (size_t)unit * p.stats_stride;
+    float* cf = p.coef + (size_t)unit * p.coef_stride;
+    float gx = 0.f, gy = 0.f;
+    for (int h = 0; h < NH; ++h) {
+        const float* g = p.g_kps + (((size_t)b * NH + h) * p.K + k) * 3;
+        gx += g[0];
+        gy += g[1];
+    }
+    const float a = gx * (2.0f / (float)p.H);                // x was normalised by H (…_multi.py:78)
+    const float bb = gy * (2.0f / (float)p.W);               // y by W (…:79)
+    const float zs = 2.0f / (float)D;
+    const int half = p.NS >> 1;
+    float dot = 0.f;
+    for (int d = threadIdx.x; d < D; d += blockDim.x) {
+        float c = 0.f;
+        if (p.head == XSUP_HEAD_SINGLE) {
+            c = p.g_kps[((size_t)b * p.K + k) * 3 + 2] * zs * (float)d;
+        } else {
+            for (int h = 0; h < NH; ++h) {
+                const float* sh = st + 4 + D + 3 * h;
+                const int idx = (int)sh[0];
+                if (d >= idx - half && d <= idx + half) {
+                    const float gz = p.g_kps[(((size_t)b * NH + h) * p.K + k) * 3 + 2];
+                    c += gz * zs * ((float)d - sh[2]) / sh[1];
+                }
+            }
+        }
+        cf[4 + d] = c;
+        dot = fmaf(c, st[4 + d], dot);
+    }
+    dot = warp_sum(dot);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = dot;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        dot = (red[0] + red[1]) + (red[2] + red[3]);
+        cf[0] = st[0];
+        cf[1] = a;
+        cf[2] = bb;
+        cf[3] = fmaf(a, st[1], fmaf(bb, st[2], dot));         // gbar = a*xbar + b*ybar + sum_d c[d]*pz[d]
+    }
+}
+
+cudaError_t launch_integral_coef(const CoefParams& p, cudaStream_t st) {
+    integral_coef_kernel<<<p.n_units, 128, 0, st>>>(p);
+    return cudaGetLastError();
+}
+
+// ----------------------------------------------------------------------------------------------
+template <typename T, int U>
+__global__ void __launch_bounds__(kBwdThreads, 1) integral_bwd_kernel(const BwdParams p) {
+    constexpr int VEC = Vec<T>::N;
+    extern __shared__ __align__(128) uint8_t smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const Tiling& t = p.t;
+    const int nst = p.nst, TU = t.tasks_per_unit, SPU = t.stages_per_unit;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)nst * p.slot_bytes);
+    const uint32_t full0 = smem_u32(bars), empty0 = full0 + 8u * nst;
+    const uint32_t ring0 = smem_u32(smem);
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < nst; ++i) {
+            mbar_init(full0 + 8u * i, 1);
+            mbar_init(empty0 + 8u * i, kTasksPerStage);
+        }
+        mbar_fence_init();
+    }
+    __syncthreads();
+
+    const int n_iters = ((int)blockIdx.x < p.n_units) ? (p.n_units - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+    const uint32_t coef_bytes = (uint32_t)p.coef_stride * 4u;
+
+    if (warp == kConsumerWarps) {
+        if (lane == 0) {
+            const uint64_t pol = policy_evict_first();
+            int s = 0;
+            for (int it = 0; it < n_iters; ++it) {
+                const size_t unit = (size_t)blockIdx.x + (size_t)it * gridDim.x;
+                const uint8_t* src = static_cast<const uint8_t*>(p.logits) + unit * (size_t)t.unit_bytes;
+                const float* cf = p.coef + unit * (size_t)p.coef_stride;
+                for (int j = 0; j < SPU; ++j, ++s) {
+                    const int slot = s % nst;
+                    if (s >= nst) mbar_wait(empty0 + 8u * slot, ((s / nst) - 1) & 1);
+                    const long long off = (long long)j * t.stage_bytes;
+                    const uint32_t bytes = (uint32_t)min((long long)t.stage_bytes, t.unit_bytes - off);
+                    const uint32_t dst = ring0 + (uint32_t)slot * p.slot_bytes;
+                    mbar_arrive_expect_tx(full0 + 8u * slot, bytes + coef_bytes);
+                    bulk_g2s_hint(dst, src + off, bytes, full0 + 8u * slot, pol);
+                    bulk_g2s(dst + t.stage_bytes, cf, coef_bytes, full0 + 8u * slot);
+                }
+            }
+        }
+    } else {
+        const int g = warp / kTasksPerStage, q = warp % kTasksPerStage;
+        const int lr = lane >> t.lpr_log2;
+        const int w0 = (lane & (t.lpr - 1)) * VEC;
+        const float rpi = (float)(32 >> t.lpr_log2);
+        const int total = n_iters * SPU;
+        for (int s = g; s < total; s += kGroups) {
+            const int it = s / SPU, j = s - it * SPU;
+            const int task = j * kTasksPerStage + q;
+            const int slot = s % nst;
+            mbar_wait(full0 + 8u * slot, (s / nst) & 1);
+            if (task < TU) {
+                const uint32_t sbase = ring0 + (uint32_t)slot * p.slot_bytes;
+                const uint32_t addr = sbase + (uint32_t)q * t.task_bytes + lane * 16u;
+                const int d = task / t.parts, part = task - d * t.parts;
+                uint4 raw[U];
+#pragma unroll
+                for (int i = 0; i < U; ++i) raw[i] = lds128(addr + i * 512u);
+                const uint4 c4 = lds128(sbase + t.stage_bytes);
+                float cd;
+                asm volatile("ld.shared.f32 %0, [%1];" : "=f"(cd) : "r"(sbase + t.stage_bytes + 16u + 4u * d));
+                __syncwarp();
+                if (lane == 0) mbar_arrive(empty0 + 8u * slot);
+
+                const float nlse = -__uint_as_float(c4.x), a = __uint_as_float(c4.y), bb = __uint_as_float(c4.z);
+                const float base = cd - __uint_as_float(c4.w);
+                float aw[VEC];
+#pragma unroll
+                for (int v = 0; v < VEC; ++v) aw[v] = a * (float)(w0 + v);
+                float hf = (float)(part * t.rows_per_task + lr);
+                const size_t unit = (size_t)blockIdx.x + (size_t)it * gridDim.x;
+                uint8_t* out = static_cast<uint8_t*>(p.g_logits) + unit * (size_t)t.unit_bytes + (size_t)task * t.task_bytes + lane * 16u;
+#pragma unroll
+                for (int i = 0; i < U; ++i) {
+                    float f[VEC];
+                    Vec<T>::unpack(raw[i], f);
+                    const float rowv = fmaf(bb, hf, base);
+#pragma unroll
+                    for (int v = 0; v < VEC; ++v) f[v] = ex2(fmaf(f[v], kLog2e, nlse)) * (aw[v] + rowv);
+                    *reinterpret_cast<uint4*>(out + i * 512u) = Vec<T>::pack(f);
+                    hf += rpi;
+                }
+            } else {
+                __syncwarp();
+                if (lane == 0) mbar_arrive(empty0 + 8u * slot);
+            }
+        }
+    }
+}
+
+// Generic path (any shape): one CTA per unit, scalar accesses.
+template <typename T>
+__device__ __forceinline__ void store_elem(T* p, size_t i, float v);
+template <>
+__device__ __forceinline__ void store_elem<float>(float* p, size_t i, float v) { p[i] = v; }
+template <>
+__device__ __forceinline__ void store_elem<__nv_bfloat16>(__nv_bfloat16* p, size_t i, float v) { p[i] = __float2bfloat16_rn(v); }
+template <typename T>
+__device__ __forceinline__ float load_elem_b(const T* p, size_t i);
+template <>
+__device__ __forceinline__ float load_elem_b<float>(const float* p, size_t i) { return p[i]; }
+template <>
+__device__ __forceinline__ float load_elem_b<__nv_bfloat16>(const __nv_bfloat16* p, size_t i) { return __bfloat162float(p[i]); }
+
+template <typename T>
+__global__ void __launch_bounds__(256) integral_bwd_generic_kernel(const BwdParams p) {
+    const int D = p.t.D, H = p.t.H, W = p.t.W, HW = H * W;
+    const size_t unit = blockIdx.x;
+    const T* src = static_cast<const T*>(p.logits) + unit * D * HW;
+    T* dst = static_cast<T*>(p.g_logits) + unit * D * HW;
+    const float* cf = p.coef + unit * (size_t)p.coef_stride;
+    const float nlse = -cf[0], a = cf[1], bb = cf[2], gbar = cf[3];
+    for (int i = threadIdx.x; i < D * HW; i += blockDim.x) {
+        const int d = i / HW, r = i - d * HW, h = r / W, w = r - h * W;
+        const float pr = ex2(fmaf(load_elem_b(src, i), kLog2e, nlse));
+        store_elem(dst, i, pr * (fmaf(a, (float)w, fmaf(bb, (float)h, cf[4 + d] - gbar))));
+    }
+}
+
+template <typename T, int U>
+static cudaError_t launch_fast(const BwdParams& p, int grid, size_t smem, cudaStream_t st) {
+    auto kern = integral_bwd_kernel<T, U>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    kern<<<grid, kBwdThreads, smem, st>>>(p);
+    return cudaGetLastError();
+}
+template <typename T>
+static cudaError_t launch_fast_u(const BwdParams& p, int grid, size_t smem, cudaStream_t st) {
+    switch (p.t.U) {
+        case 8: return launch_fast<T, 8>(p, grid, smem, st);
+        case 4: return launch_fast<T, 4>(p, grid, smem, st);
+        case 2: return launch_fast<T, 2>(p, grid, smem, st);
+        default: return launch_fast<T, 1>(p, grid, smem, st);
+    }
+}
+
+cudaError_t launch_integral_bwd(BwdParams p, bool fast, int dtype, int num_sms, cudaStream_t st) {
+    if (!fast) {
+        if (dtype == XSUP_F32) integral_bwd_generic_kernel<float><<<p.n_units, 256, 0, st>>>(p);
+        else integral_bwd_generic_kernel<__nv_bfloat16><<<p.n_units, 256, 0, st>>>(p);
+        return cudaGetLastError();
+    }
+    const int coef_pad = ((p.coef_stride * 4 + 127) / 128) * 128;
+    p.slot_bytes = p.t.stage_bytes + coef_pad;
+    const size_t fixed = (size_t)(2 * kMaxStages) * 8;
+    int nst = (int)((kSmemBudget - fixed) / p.slot_bytes);
+    nst = nst > kMaxStages ? kMaxStages : nst;
+    p.nst = nst;
+    const size_t smem = (size_t)nst * p.slot_bytes + fixed;
+    const int grid = p.n_units < num_sms ? p.n_units : num_sms;
+    return dtype == XSUP_F32 ? launch_fast_u<float>(p, grid, smem, st) : launch_fast_u<__nv_bfloat16>(p, grid, smem, st);
+}
+
+}  // namespace xsup

@@ -1,0 +1,404 @@
+// K1 — fused integral (soft-argmax) multi-hypothesis head, forward.
+//
+// Replaces keypoint_detector_integral_multi.py:69-88 / keypoint_detector_integral.py:45-65 of the
+// reference: softmax over each joint's D*H*W volume, the three marginals, x/y expectations, depth
+// local-maxima + top-NH, windowed depth expectation, normalisation.  The reference makes ~6 passes
+// over the volume and materialises the probabilities; this kernel reads every logit from HBM
+// exactly once and writes O(D) floats per (b,k) unit.
+//
+// Structure (one persistent CTA per SM, 18 warps):
+//   warp 16      producer : 1-D bulk async copies (TMA, UBLKCP) global -> smem ring, mbarrier tx-count
+//   warps 0..15  consumers: 4 warps per ring stage, one 512*U-byte "task" each; LDS.128 into
+//                registers, early release of the slot, warp-uniform running max (CREDUX.MAX.F32),
+//                one MUFU.EX2 per element, per-lane column accumulators (x), row-weighted sum (y),
+//                per-task depth-slice sum (pz)
+//   warp 17      finaliser: log-sum-exp combine of the per-task/per-warp partials, peaks, top-NH,
+//                window depth, outputs + saved-for-backward stats; overlaps the next unit's stream
+#include "xsup_internal.h"
+
+namespace xsup {
+
+// ----------------------------------------------------------------------------------------------
+// find_peak (…_multi.py:24-34) on one depth row held in shared memory, by one warp.
+// cv[j] is the candidate value of bin lane+32j: pz if it is a non-strict interior local maximum,
+// 0 if it is an interior non-peak (the reference's masked value), -1 if it cannot be chosen.
+// ----------------------------------------------------------------------------------------------
+__device__ __forceinline__ void peak_candidates(const float* pz, int D, int lane, float (&cv)[kMaxD / 32]) {
+#pragma unroll
+    for (int j = 0; j < kMaxD / 32; ++j) {
+        const int d = lane + 32 * j;
+        float v = -1.0f;
+        if (d >= 1 && d <= D - 2) {
+            const float c = pz[d];
+            v = (c >= pz[d - 1] && c >= pz[d + 1]) ? c : 0.0f;
+        }
+        cv[j] = v;
+    }
+}
+// next entry of topk: largest candidate, lowest bin on ties; marks it taken.  Warp-uniform result.
+__device__ __forceinline__ int take_best_peak(float (&cv)[kMaxD / 32], int lane) {
+    float bv = -2.0f;
+    int bd = 0x7fffffff;
+#pragma unroll
+    for (int j = 0; j < kMaxD / 32; ++j)
+        if (cv[j] > bv) { bv = cv[j]; bd = lane + 32 * j; }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+        const int od = __shfl_xor_sync(0xffffffffu, bd, o);
+        if (ov > bv || (ov == bv && od < bd)) { bv = ov; bd = od; }
+    }
+#pragma unroll
+    for (int j = 0; j < kMaxD / 32; ++j)
+        if (lane + 32 * j == bd) cv[j] = -1.0f;
+    return bd;
+}
+
+// ----------------------------------------------------------------------------------------------
+// Unit epilogue, executed by one full warp.  On entry pz[0..D) in shared memory holds the raw
+// (un-normalised) depth marginal relative to the log2-domain reference `M`; sx, sy are the raw
+// w- and h-weighted sums relative to the same `M` (warp-uniform).
+// ----------------------------------------------------------------------------------------------
+__device__ void finalise_unit(const FwdParams& p, int unit, float* pz, float M, float sx, float sy, int lane) {
+    const int D = p.t.D, H = p.t.H, W = p.t.W, NH = p.NH;
+    const int b = unit / p.K, k = unit - b * p.K;
+    float ssum = 0.f;
+    for (int d = lane; d < D; d += 32) ssum += pz[d];
+    const float S = warp_sum(ssum);
+    const float invS = 1.0f / S;
+    float* st = p.stats + (size_t)unit * p.stats_stride;
+    for (int d = lane; d < D; d += 32) {
+        const float v = pz[d] * invS;
+        pz[d] = v;
+        st[4 + d] = v;
+        if (b == 0) p.dmap[k * D + d] = v;                      // depth_prob_map = accu_z[0] (…_multi.py:48)
+    }
+    __syncwarp();
+    const float xbar = sx * invS, ybar = sy * invS;
+    if (lane == 0) {
+        st[0] = M + log2f(S);                                   // log2-domain log-sum-exp: p = 2^(l*log2e - st[0])
+        st[1] = xbar;
+        st[2] = ybar;
+        st[3] = M;
+    }
+    // the reference normalises x by H and y by W (…_multi.py:78-79); kept literally
+    const float x = xbar / (float)H * 2.0f - 1.0f;
+    const float y = ybar / (float)W * 2.0f - 1.0f;
+
+    if (p.head == XSUP_HEAD_SINGLE) {                            // keypoint_detector_integral.py:37,41,59
+        float zs = 0.f;
+        for (int d = lane; d < D; d += 32) zs = fmaf((float)d, pz[d], zs);
+        zs = warp_sum(zs);
+        if (lane == 0) {
+            float* o = p.kps + ((size_t)b * p.K + k) * 3;
+            o[0] = x;
+            o[1] = y;
+            o[2] = zs / (float)D * 2.0f - 1.0f;
+            st[4 + D] = zs;
+        }
+        return;
+    }
+
+    // find_peak (…_multi.py:24-34): non-strict interior local maxima, value-descending top-NH.
+    // Candidates with value 0 (non-peaks) fill the remaining slots by ascending bin.
+    float cv[kMaxD / 32];
+    peak_candidates(pz, D, lane, cv);
+    const int half = p.NS >> 1;
+    const float fNS = (float)p.NS;
+    for (int h = 0; h < NH; ++h) {
+        const int bd = take_best_peak(cv, lane);
+        // windowed depth expectation (…_multi.py:57-62): zero-padded, count_include_pad average
+        // pools of d*pz and pz, gathered at the peak bin
+        const int lo = max(0, bd - half), hi = min(D - 1, bd + half);
+        float sw = 0.f, nw = 0.f;
+        for (int d = lo + lane; d <= hi; d += 32) {
+            const float v = pz[d];
+            sw += v;
+            nw = fmaf((float)d, v, nw);
+        }
+        sw = warp_sum(sw);
+        nw = warp_sum(nw);
+        const float zbar = (nw / fNS) / (sw / fNS);
+        if (lane == 0) {
+            float* o = p.kps + (((size_t)b * NH + h) * p.K + k) * 3;
+            o[0] = x;
+            o[1] = y;
+            o[2] = zbar / (float)D * 2.0f - 1.0f;
+            if (p.peak_idx) p.peak_idx[((size_t)b * p.K + k) * NH + h] = bd;
+            st[4 + D + 3 * h + 0] = (float)bd;
+            st[4 + D + 3 * h + 1] = sw;
+            st[4 + D + 3 * h + 2] = nw / sw;
+        }
+    }
+}
+
+// ----------------------------------------------------------------------------------------------
+// Fast path: TMA-fed ring, one pass over the volume.
+// ----------------------------------------------------------------------------------------------
+template <typename T, int U>
+__global__ void __launch_bounds__(kFwdThreads, 1) integral_fwd_kernel(const FwdParams p) {
+    constexpr int VEC = Vec<T>::N;
+    extern __shared__ __align__(128) uint8_t smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const Tiling& t = p.t;
+    const int nst = p.nst, TU = t.tasks_per_unit, SPU = t.stages_per_unit;
+
+    uint8_t* ring = smem;
+    float2* pz_table = reinterpret_cast<float2*>(smem + (size_t)nst * t.stage_bytes);   // [2][TU] (m, sum)
+    float4* unit_part = reinterpret_cast<float4*>(pz_table + 2 * TU);                   // [2][kConsumerWarps]
+    float* pz_final = reinterpret_cast<float*>(unit_part + 2 * kConsumerWarps);         // [kMaxD]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(pz_final + kMaxD);
+    const uint32_t full0 = smem_u32(bars), empty0 = full0 + 8u * nst;
+    const uint32_t pfull0 = empty0 + 8u * nst, pempty0 = pfull0 + 16u;
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < nst; ++i) {
+            mbar_init(full0 + 8u * i, 1);
+            mbar_init(empty0 + 8u * i, kTasksPerStage);
+        }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(pfull0 + 8u * i, kConsumerWarps);
+            mbar_init(pempty0 + 8u * i, 1);
+        }
+        mbar_fence_init();
+    }
+    __syncthreads();
+
+    const int n_iters = ((int)blockIdx.x < p.n_units) ? (p.n_units - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+
+    if (warp == kConsumerWarps) {
+        // ------------------------------------------------------------------ producer
+        if (lane == 0) {
+            const uint64_t pol = policy_evict_first();
+            const uint32_t ring0 = smem_u32(ring);
+            int s = 0;
+            for (int it = 0; it < n_iters; ++it) {
+                const size_t unit = (size_t)blockIdx.x + (size_t)it * gridDim.x;
+                const uint8_t* src = static_cast<const uint8_t*>(p.logits) + unit * (size_t)t.unit_bytes;
+                for (int j = 0; j < SPU; ++j, ++s) {
+                    const int slot = s % nst;
+                    if (s >= nst) mbar_wait(empty0 + 8u * slot, ((s / nst) - 1) & 1);
+                    const long long off = (long long)j * t.stage_bytes;
+                    const uint32_t bytes = (uint32_t)min((long long)t.stage_bytes, t.unit_bytes - off);
+                    mbar_arrive_expect_tx(full0 + 8u * slot, bytes);
+                    bulk_g2s_hint(ring0 + (uint32_t)slot * t.stage_bytes, src + off, bytes, full0 + 8u * slot, pol);
+                }
+            }
+        }
+    } else if (warp == kConsumerWarps + 1) {
+        // ------------------------------------------------------------------ finaliser
+        for (int it = 0; it < n_iters; ++it) {
+            const int unit = (int)blockIdx.x + it * (int)gridDim.x;
+            const int buf = it & 1;
+            mbar_wait(pfull0 + 8u * buf, (it >> 1) & 1);
+            float4 up = make_float4(kNegHuge, 0.f, 0.f, 0.f);
+            if (lane < kConsumerWarps) up = unit_part[buf * kConsumerWarps + lane];
+            const float M = warp_max(up.x);
+            const float wsc = ex2(up.x - M);
+            const float sx = warp_sum(up.y * wsc), sy = warp_sum(up.z * wsc);
+            const float2* tab = pz_table + buf * TU;
+            for (int d = lane; d < t.D; d += 32) {
+                float a = 0.f;
+                for (int q = 0; q < t.parts; ++q) {
+                    const float2 e = tab[d * t.parts + q];
+                    a = fmaf(e.y, ex2(e.x - M), a);
+                }
+                pz_final[d] = a;
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(pempty0 + 8u * buf);      // partial buffers may be refilled
+            finalise_unit(p, unit, pz_final, M, sx, sy, lane);
+            __syncwarp();
+        }
+    } else {
+        // ------------------------------------------------------------------ consumers
+        const int g = warp / kTasksPerStage, q = warp % kTasksPerStage;
+        const int lr = lane >> t.lpr_log2;
+        const int w0 = (lane & (t.lpr - 1)) * VEC;
+        const float rpi = (float)(32 >> t.lpr_log2);
+        const uint32_t ring0 = smem_u32(ring);
+        int s = g;
+        for (int it = 0; it < n_iters; ++it) {
+            const int base = it * SPU, buf = it & 1;
+            if (it >= 2) mbar_wait(pempty0 + 8u * buf, ((it >> 1) - 1) & 1);
+            float m_ref = kNegHuge, sy = 0.f;
+            float acc[VEC];
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) acc[v] = 0.f;
+
+            for (; s < base + SPU; s += kGroups) {
+                const int task = (s - base) * kTasksPerStage + q;
+                const int slot = s % nst;
+                mbar_wait(full0 + 8u * slot, (s / nst) & 1);
+                if (task < TU) {
+                    const uint32_t addr = ring0 + (uint32_t)slot * t.stage_bytes + (uint32_t)q * t.task_bytes + lane * 16u;
+                    uint4 raw[U];
+#pragma unroll
+                    for (int i = 0; i < U; ++i) raw[i] = lds128(addr + i * 512u);
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(empty0 + 8u * slot);   // data is in registers: free the slot early
+
+                    float lmax = kNegHuge;
+#pragma unroll
+                    for (int i = 0; i < U; ++i) {
+                        float f[VEC];
+                        Vec<T>::unpack(raw[i], f);
+#pragma unroll
+                        for (int v = 0; v < VEC; ++v) lmax = fmaxf(lmax, f[v]);
+                    }
+                    const float mt = warp_max(lmax) * kLog2e;
+                    if (mt > m_ref) {                                 // warp-uniform, rare after the first tasks
+                        const float sc = ex2(m_ref - mt);
+#pragma unroll
+                        for (int v = 0; v < VEC; ++v) acc[v] *= sc;
+                        sy *= sc;
+                        m_ref = mt;
+                    }
+                    const int d = task / t.parts, part = task - d * t.parts;
+                    float hf = (float)(part * t.rows_per_task + lr);
+                    float tsum = 0.f;
+                    const float nm = -m_ref;
+#pragma unroll
+                    for (int i = 0; i < U; ++i) {
+                        float f[VEC];
+                        Vec<T>::unpack(raw[i], f);
+                        float r = 0.f;
+#pragma unroll
+                        for (int v = 0; v < VEC; ++v) {
+                            const float e = ex2(fmaf(f[v], kLog2e, nm));
+                            acc[v] += e;
+                            r += e;
+                        }
+                        tsum += r;
+                        sy = fmaf(hf, r, sy);
+                        hf += rpi;
+                    }
+                    tsum = warp_sum(tsum);
+                    if (lane == 0) pz_table[buf * TU + task] = make_float2(m_ref, tsum);
+                } else {
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(empty0 + 8u * slot);
+                }
+            }
+            float sx = 0.f;
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) sx = fmaf((float)(w0 + v), acc[v], sx);
+            sx = warp_sum(sx);
+            sy = warp_sum(sy);
+            if (lane == 0) {
+                unit_part[buf * kConsumerWarps + warp] = make_float4(m_ref, sx, sy, 0.f);
+                mbar_arrive(pfull0 + 8u * buf);
+            }
+        }
+    }
+}
+
+// ----------------------------------------------------------------------------------------------
+// Generic path for shapes the tiling cannot cut (tiny or odd volumes): one CTA per unit, plain
+// loads, three passes.  Correctness net for edge cases, not a performance path.
+// ----------------------------------------------------------------------------------------------
+template <typename T>
+__device__ __forceinline__ float load_elem(const T* p, size_t i);
+template <>
+__device__ __forceinline__ float load_elem<float>(const float* p, size_t i) { return p[i]; }
+template <>
+__device__ __forceinline__ float load_elem<__nv_bfloat16>(const __nv_bfloat16* p, size_t i) { return __bfloat162float(p[i]); }
+
+__device__ float block_reduce(float v, float* scratch, bool is_max) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    v = is_max ? warp_max(v) : warp_sum(v);
+    __syncthreads();
+    if (lane == 0) scratch[warp] = v;
+    __syncthreads();
+    float r = is_max ? kNegHuge : 0.f;
+    for (int i = 0; i < nw; ++i) r = is_max ? fmaxf(r, scratch[i]) : r + scratch[i];
+    return r;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) integral_fwd_generic_kernel(const FwdParams p) {
+    __shared__ float pz[kMaxD];
+    __shared__ float scratch[8];
+    const int D = p.t.D, H = p.t.H, W = p.t.W, HW = H * W;
+    const int unit = blockIdx.x;
+    const T* src = static_cast<const T*>(p.logits) + (size_t)unit * D * HW;
+    float m = kNegHuge;
+    for (int i = threadIdx.x; i < D * HW; i += blockDim.x) m = fmaxf(m, load_elem(src, i));
+    const float M = block_reduce(m, scratch, true) * kLog2e;
+    float sx = 0.f, sy = 0.f;
+    for (int d = 0; d < D; ++d) {
+        float sd = 0.f;
+        for (int i = threadIdx.x; i < HW; i += blockDim.x) {
+            const float e = ex2(fmaf(load_elem(src, (size_t)d * HW + i), kLog2e, -M));
+            const int h = i / W, w = i - h * W;
+            sd += e;
+            sx = fmaf((float)w, e, sx);
+            sy = fmaf((float)h, e, sy);
+        }
+        sd = block_reduce(sd, scratch, false);
+        if (threadIdx.x == 0) pz[d] = sd;
+    }
+    sx = block_reduce(sx, scratch, false);
+    sy = block_reduce(sy, scratch, false);
+    __syncthreads();
+    if (threadIdx.x < 32) finalise_unit(p, unit, pz, M, sx, sy, threadIdx.x);
+}
+
+// ----------------------------------------------------------------------------------------------
+// Stand-alone find_peak on rows of a [rows, D] matrix (API parity with KPDetector3DMulti.find_peak).
+__global__ void __launch_bounds__(128) find_peak_kernel(const float* __restrict__ pz, int64_t* __restrict__ idx, int rows, int D, int NH) {
+    __shared__ float row[4][kMaxD];
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int r = blockIdx.x * 4 + w;
+    if (r >= rows) return;
+    for (int d = lane; d < D; d += 32) row[w][d] = pz[(size_t)r * D + d];
+    __syncwarp();
+    float cv[kMaxD / 32];
+    peak_candidates(row[w], D, lane, cv);
+    for (int h = 0; h < NH; ++h) {
+        const int bd = take_best_peak(cv, lane);
+        if (lane == 0) idx[(size_t)r * NH + h] = bd;
+    }
+}
+cudaError_t launch_find_peak(const float* pz, int64_t* idx, int rows, int D, int NH, cudaStream_t st) {
+    find_peak_kernel<<<(rows + 3) / 4, 128, 0, st>>>(pz, idx, rows, D, NH);
+    return cudaGetLastError();
+}
+
+// ----------------------------------------------------------------------------------------------
+template <typename T, int U>
+static cudaError_t launch_fast(const FwdParams& p, int grid, size_t smem, cudaStream_t st) {
+    auto kern = integral_fwd_kernel<T, U>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    kern<<<grid, kFwdThreads, smem, st>>>(p);
+    return cudaGetLastError();
+}
+
+template <typename T>
+static cudaError_t launch_fast_u(const FwdParams& p, int grid, size_t smem, cudaStream_t st) {
+    switch (p.t.U) {
+        case 8: return launch_fast<T, 8>(p, grid, smem, st);
+        case 4: return launch_fast<T, 4>(p, grid, smem, st);
+        case 2: return launch_fast<T, 2>(p, grid, smem, st);
+        default: return launch_fast<T, 1>(p, grid, smem, st);
+    }
+}
+
+cudaError_t launch_integral_fwd(FwdParams p, bool fast, int dtype, int num_sms, cudaStream_t st) {
+    if (!fast) {
+        if (dtype == XSUP_F32) integral_fwd_generic_kernel<float><<<p.n_units, 256, 0, st>>>(p);
+        else integral_fwd_generic_kernel<__nv_bfloat16><<<p.n_units, 256, 0, st>>>(p);
+        return cudaGetLastError();
+    }
+    const size_t fixed = (size_t)2 * p.t.tasks_per_unit * sizeof(float2) + 2 * kConsumerWarps * sizeof(float4) +
+                         kMaxD * sizeof(float) + (size_t)(2 * kMaxStages + 4) * 8;
+    int nst = (int)((kSmemBudget - fixed) / p.t.stage_bytes);
+    nst = nst > kMaxStages ? kMaxStages : nst;
+    p.nst = nst;
+    const size_t smem = (size_t)nst * p.t.stage_bytes + fixed;
+    const int grid = p.n_units < num_sms ? p.n_units : num_sms;
+    return dtype == XSUP_F32 ? launch_fast_u<float>(p, grid, smem, st) : launch_fast_u<__nv_bfloat16>(p, grid, smem, st);
+}
+
+}  // namespace xsup

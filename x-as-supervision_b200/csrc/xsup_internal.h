@@ -1,0 +1,62 @@
+// Host/device declarations shared by the xsup_b200 translation units (not part of the C ABI).
+#pragma once
+#include "xsup_common.cuh"
+
+namespace xsup {
+
+constexpr int kFwdThreads = (kConsumerWarps + 2) * 32;   // 16 consumers + producer + finaliser
+constexpr int kBwdThreads = (kConsumerWarps + 1) * 32;   // 16 consumers + producer
+constexpr size_t kSmemBudget = 227 * 1024;               // per-CTA opt-in maximum on sm_100
+constexpr int kMaxStages = 16;
+
+struct FwdParams {
+    const void* logits;
+    float* kps;
+    float* dmap;
+    int64_t* peak_idx;
+    float* stats;
+    int n_units, K, NH, NS, head, stats_stride;
+    int nst;
+    Tiling t;
+};
+
+struct BwdParams {
+    const void* logits;
+    const float* coef;
+    void* g_logits;
+    int n_units, coef_stride;
+    int nst, slot_bytes;
+    Tiling t;
+};
+
+struct CoefParams {
+    const float* stats;
+    const float* g_kps;
+    float* coef;
+    int n_units, K, D, H, W, NH, NS, head, stats_stride, coef_stride;
+};
+
+cudaError_t launch_integral_fwd(FwdParams p, bool fast, int dtype, int num_sms, cudaStream_t st);
+cudaError_t launch_find_peak(const float* pz, int64_t* idx, int rows, int D, int NH, cudaStream_t st);
+cudaError_t launch_integral_coef(const CoefParams& p, cudaStream_t st);
+cudaError_t launch_integral_bwd(BwdParams p, bool fast, int dtype, int num_sms, cudaStream_t st);
+
+struct GeomParams {
+    xsup_cam_t cam;
+    int B, J, img_h, img_w, flags;
+    float rect_width;
+};
+cudaError_t launch_patch_to_world_fwd(const float* kps, float* world, const GeomParams& g, cudaStream_t st);
+cudaError_t launch_patch_to_world_bwd(const float* kps, const float* g_world, float* g_kps, const GeomParams& g, cudaStream_t st);
+cudaError_t launch_world_to_patch_fwd(const float* world, float* kps, const GeomParams& g, cudaStream_t st);
+
+cudaError_t launch_reproj_loss_fwd(const float* kps, const float* target, const xsup_cam_t& cam, float* world,
+                                   float* sample_terms, float* partial, const xsup_loss_cfg_t& c, cudaStream_t st);
+cudaError_t launch_reproj_select(const float* kps, const float* target, const float* sample_terms, const float* partial,
+                                 float* loss, int64_t* sel, const xsup_loss_cfg_t& c, cudaStream_t st);
+cudaError_t launch_reproj_loss_bwd(const float* kps, const float* target, const xsup_cam_t& cam, const int64_t* sel,
+                                   const float* g_loss, float* g_kps, const xsup_loss_cfg_t& c, cudaStream_t st);
+
+void count_launches(int n);
+
+}  // namespace xsup

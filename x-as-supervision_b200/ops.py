@@ -1,0 +1,290 @@
+"""Drop-in `torch.autograd.Function`s over the C ABI (include/xsup_b200.h).
+
+Tensor signatures follow the reference so its detector, physique network, GCN
+discriminator and trainer can call these unchanged:
+
+* `IntegralMultiHead`      replaces modules/keypoint_detector_integral_multi.py:69-88
+* `IntegralSingleHead`     replaces modules/keypoint_detector_integral.py:45-65
+* `PatchToWorld` / `convert_patch_to_world` / `convert_world_to_patch`
+                           replace modules/util.py:128-152 / :155-168
+* `IntegralReprojMinLoss`  replaces, for one camera, modules/model.py:64,71-79,105-114,158-162
+                           (head + per-hypothesis world lift + loss terms + torch.min over slots)
+
+PyTorch is used for device memory, streams and `torch.distributed` only; all
+arithmetic happens in the CUDA kernels.  Nothing here falls back to the CPU.
+"""
+from __future__ import annotations
+
+from typing import Dict, Optional, Sequence, Tuple
+
+import torch
+
+from . import _cabi as cabi
+from . import dist as xdist
+
+__all__ = ["IntegralMultiHead", "IntegralSingleHead", "PatchToWorld", "IntegralReprojMinLoss", "integral_multi_head",
+           "integral_single_head", "convert_patch_to_world", "convert_world_to_patch", "find_peak",
+           "integral_reproj_min_loss", "launch_count"]
+
+launch_count = cabi.launch_count
+
+
+def _volume_dims(logits: torch.Tensor, num_kp: int) -> Tuple[int, int, int, int, int]:
+    if logits.dim() != 4:
+        raise ValueError("logits must be [B, K*D, H, W], got %s" % (tuple(logits.shape),))
+    B, C, H, W = logits.shape
+    if C % num_kp:
+        raise ValueError("channel count %d is not a multiple of num_kp %d" % (C, num_kp))
+    return B, C // num_kp, H, W, C
+
+
+def _head_forward(logits, num_kp, num_hypo, neighbor_size, head):
+    cabi.require_cuda(logits, "logits")
+    if not logits.is_contiguous():
+        logits = logits.contiguous()
+    B, D, H, W, _ = _volume_dims(logits, num_kp)
+    shape = cabi.make_shape(B, num_kp, D, H, W, num_hypo, neighbor_size, logits.dtype, head)
+    dev = logits.device
+    kps = torch.empty(B, num_hypo, num_kp, 3, dtype=torch.float32, device=dev)
+    dmap = torch.zeros(num_kp, D, dtype=torch.float32, device=dev) if B == 0 else \
+        torch.empty(num_kp, D, dtype=torch.float32, device=dev)
+    idx = torch.empty(B, num_kp, num_hypo, dtype=torch.int64, device=dev)
+    stride = cabi.lib.xsup_stats_stride(shape)
+    stats = torch.empty(max(B * num_kp * stride, 4), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        cabi.check(cabi.lib.xsup_integral_fwd(logits.data_ptr(), kps.data_ptr(), dmap.data_ptr(),
+                                              idx.data_ptr() if head == cabi.HEAD_MULTI else None,
+                                              stats.data_ptr(), shape, cabi.stream_ptr(dev)), "xsup_integral_fwd")
+    return logits, shape, kps, dmap, idx, stats
+
+
+def _head_backward(logits, stats, shape, g_kps, inplace=False):
+    dev = logits.device
+    g_kps = g_kps.to(torch.float32).contiguous()
+    g_logits = logits if inplace else torch.empty_like(logits)
+    coef = torch.empty(max(shape.B * shape.K * cabi.lib.xsup_coef_stride(shape), 4), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        cabi.check(cabi.lib.xsup_integral_bwd(logits.data_ptr(), stats.data_ptr(), g_kps.data_ptr(), g_logits.data_ptr(),
+                                              coef.data_ptr(), shape, cabi.stream_ptr(dev)), "xsup_integral_bwd")
+    return g_logits
+
+
+class IntegralMultiHead(torch.autograd.Function):
+    """logits `[B, K*D, H, W]` (fp32 | bf16) -> kps `[B,NH,K,3]` fp32, depth_prob_map `[K,D]` fp32,
+    peak_idx `[B,K,NH]` int64.  Only `kps` is differentiable (depth_prob_map is a TensorBoard
+    side output in the reference, train_util.py:296-299)."""
+
+    @staticmethod
+    def forward(ctx, logits, num_kp, num_hypo, neighbor_size):
+        logits, shape, kps, dmap, idx, stats = _head_forward(logits, num_kp, num_hypo, neighbor_size, cabi.HEAD_MULTI)
+        ctx.save_for_backward(logits, stats)
+        ctx.shape = shape
+        ctx.mark_non_differentiable(dmap, idx)
+        return kps, dmap, idx
+
+    @staticmethod
+    def backward(ctx, g_kps, _g_dmap, _g_idx):
+        logits, stats = ctx.saved_tensors
+        return _head_backward(logits, stats, ctx.shape, g_kps), None, None, None
+
+
+class IntegralSingleHead(torch.autograd.Function):
+    """Single-hypothesis variant: kps `[B,1,K,3]`, depth_prob_map `[K,D]`."""
+
+    @staticmethod
+    def forward(ctx, logits, num_kp):
+        logits, shape, kps, dmap, _, stats = _head_forward(logits, num_kp, 1, 1, cabi.HEAD_SINGLE)
+        ctx.save_for_backward(logits, stats)
+        ctx.shape = shape
+        ctx.mark_non_differentiable(dmap)
+        return kps, dmap
+
+    @staticmethod
+    def backward(ctx, g_kps, _g_dmap):
+        logits, stats = ctx.saved_tensors
+        return _head_backward(logits, stats, ctx.shape, g_kps), None
+
+
+def integral_multi_head(logits, num_kp, num_hypo, neighbor_size):
+    return IntegralMultiHead.apply(logits, num_kp, num_hypo, neighbor_size)
+
+
+def integral_single_head(logits, num_kp):
+    return IntegralSingleHead.apply(logits, num_kp)
+
+
+def find_peak(pz: torch.Tensor, num_hypo: int) -> torch.Tensor:
+    """KPDetector3DMulti.find_peak (…_multi.py:24-34) on `[..., D]` -> int64 `[..., NH]`."""
+    cabi.require_cuda(pz, "heatmap")
+    flat = pz.detach().to(torch.float32).contiguous().view(-1, pz.shape[-1])
+    idx = torch.empty(flat.shape[0], num_hypo, dtype=torch.int64, device=pz.device)
+    with torch.cuda.device(pz.device):
+        cabi.check(cabi.lib.xsup_find_peak(flat.data_ptr(), idx.data_ptr(), flat.shape[0], flat.shape[1], num_hypo,
+                                           cabi.stream_ptr(pz.device)), "xsup_find_peak")
+    return idx.view(*pz.shape[:-1], num_hypo)
+
+
+# --------------------------------------------------------------------------------------- geometry
+def _cam_args(cams: Dict[str, torch.Tensor], B: int):
+    t = [cams[k].to(torch.float32).contiguous() for k in ("trans_image", "pelvis", "k_mat", "trans_world", "rot_world")]
+    return t, cabi.make_cam(*t, B)
+
+
+def _flags(is_norm, mono, patch):
+    return (cabi.FLAG_NORM if is_norm else 0) | (cabi.FLAG_MONO if mono else 0) | (cabi.FLAG_PATCH if patch else 0)
+
+
+class PatchToWorld(torch.autograd.Function):
+    """kps `[B,J,3]` + per-sample camera tensors -> world `[B,J,3]` (util.py:128-152), differentiable in kps."""
+
+    @staticmethod
+    def forward(ctx, kps, trans_image, pelvis, k_mat, trans_world, rot_world, img_h, img_w, rect_width, flags):
+        cabi.require_cuda(kps, "keypoints")
+        kps = kps.to(torch.float32).contiguous()
+        B, J, _ = kps.shape
+        keep, cam = _cam_args(dict(trans_image=trans_image, pelvis=pelvis, k_mat=k_mat, trans_world=trans_world,
+                                   rot_world=rot_world), B)
+        world = torch.empty_like(kps)
+        with torch.cuda.device(kps.device):
+            cabi.check(cabi.lib.xsup_patch_to_world_fwd(kps.data_ptr(), cam, world.data_ptr(), B, J, img_h, img_w,
+                                                        float(rect_width), flags, cabi.stream_ptr(kps.device)),
+                       "xsup_patch_to_world_fwd")
+        ctx.save_for_backward(kps, *keep)
+        ctx.meta = (B, J, img_h, img_w, float(rect_width), flags)
+        return world
+
+    @staticmethod
+    def backward(ctx, g_world):
+        kps, *keep = ctx.saved_tensors
+        B, J, img_h, img_w, rect_width, flags = ctx.meta
+        cam = cabi.make_cam(*keep, B)
+        g_world = g_world.to(torch.float32).contiguous()
+        g_kps = torch.empty_like(kps)
+        with torch.cuda.device(kps.device):
+            cabi.check(cabi.lib.xsup_patch_to_world_bwd(kps.data_ptr(), g_world.data_ptr(), cam, g_kps.data_ptr(), B, J,
+                                                        img_h, img_w, rect_width, flags, cabi.stream_ptr(kps.device)),
+                       "xsup_patch_to_world_bwd")
+        return (g_kps,) + (None,) * 9
+
+
+def _unpack_params(params: Dict[str, torch.Tensor], mode: str):
+    cams = {k: params["{}_{}".format(mode, k)] for k in ("trans_image", "pelvis", "k_mat", "trans_world", "rot_world")}
+    shape_img = params["{}_img".format(mode)].shape
+    return cams, int(shape_img[-2]), int(shape_img[-1])
+
+
+def convert_patch_to_world(keypoints, params, mode, is_norm=True, RECT_WIDTH=2000, mono=False, patch=True):
+    """Same dict-keyed signature as modules/util.py:128 so model.py / eval.py can import this one."""
+    cams, img_h, img_w = _unpack_params(params, mode)
+    return PatchToWorld.apply(keypoints, cams["trans_image"], cams["pelvis"], cams["k_mat"], cams["trans_world"],
+                              cams["rot_world"], img_h, img_w, float(RECT_WIDTH), _flags(is_norm, mono, patch))
+
+
+def convert_world_to_patch(keypoints, params, mode, is_norm=True, RECT_WIDTH=2000):
+    """modules/util.py:155-168 (forward perspective projection).  Not differentiable here: the
+    reference never back-propagates through it (only `project_smpl_to_patch_kps` reaches it)."""
+    cams, img_h, img_w = _unpack_params(params, mode)
+    cabi.require_cuda(keypoints, "keypoints")
+    world = keypoints.detach().to(torch.float32).contiguous()
+    B, J, _ = world.shape
+    _, cam = _keep = _cam_args(cams, B)
+    out = torch.empty_like(world)
+    with torch.cuda.device(world.device):
+        cabi.check(cabi.lib.xsup_world_to_patch_fwd(world.data_ptr(), cam, out.data_ptr(), B, J, img_h, img_w,
+                                                    float(RECT_WIDTH), _flags(is_norm, False, True),
+                                                    cabi.stream_ptr(world.device)), "xsup_world_to_patch_fwd")
+    return out
+
+
+# --------------------------------------------------------------------------------------- fused head + loss
+class IntegralReprojMinLoss(torch.autograd.Function):
+    """Head + per-hypothesis world lift + loss terms + min over hypotheses for one camera.
+
+    forward(logits, target, trans_image, pelvis, k_mat, trans_world, rot_world,
+            num_kp, num_hypo, neighbor_size, img_hw, rect_width,
+            w_mse, w_bone, w_kp, w_kp2d, reduction, group)
+      -> loss_pseudo (0-d), loss_sym (0-d), sel_idx (int64), kps [B,NH,K,3], kps_world [B,NH,K,3],
+         depth_prob_map [K,D], peak_idx [B,K,NH]
+
+    `w_bone/w_kp/w_kp2d = None` means the symmetry term is absent (SurS1 configs).
+    `group`: a torch.distributed process group -> 'global' scope: the per-hypothesis partial sums
+    are all-reduced (one [4,NH] fp32 message) so every rank selects the slot the single-process
+    reference would select on the global batch.  `None` -> rank-local min, which is what the
+    reference does under DDP (model.py:114,162).
+    Gradients flow to `logits` from both losses and from anything downstream of `kps` / `kps_world`."""
+
+    @staticmethod
+    def forward(ctx, logits, target, trans_image, pelvis, k_mat, trans_world, rot_world, num_kp, num_hypo, neighbor_size,
+                img_hw, rect_width, w_mse, w_bone, w_kp, w_kp2d, reduction, group):
+        logits, shape, kps, dmap, idx, stats = _head_forward(logits, num_kp, num_hypo, neighbor_size, cabi.HEAD_MULTI)
+        dev = logits.device
+        B, K, NH = shape.B, num_kp, num_hypo
+        if B == 0:
+            raise ValueError("IntegralReprojMinLoss needs a non-empty batch")
+        target = target.to(device=dev, dtype=torch.float32).contiguous()
+        if tuple(target.shape) != (B, K, 3):
+            raise ValueError("target must be [B,K,3] = %s, got %s" % ((B, K, 3), tuple(target.shape)))
+        keep, cam = _cam_args(dict(trans_image=trans_image, pelvis=pelvis, k_mat=k_mat, trans_world=trans_world,
+                                   rot_world=rot_world), B)
+        use_sym = any(w is not None for w in (w_bone, w_kp, w_kp2d))
+        n_total = xdist.global_batch(B, group)
+        cfg = cabi.LossCfg(B, K, NH, int(img_hw[0]), int(img_hw[1]), float(rect_width), float(w_mse),
+                           float(w_bone or 0.0), float(w_kp or 0.0), float(w_kp2d or 0.0), int(use_sym),
+                           cabi.REDUCE[reduction], n_total)
+        world = torch.empty_like(kps)
+        sample_terms = torch.empty(B, cabi.LOSS_TERMS, NH, dtype=torch.float32, device=dev)
+        partial = torch.empty(cabi.LOSS_TERMS, NH, dtype=torch.float32, device=dev)
+        loss = torch.empty(2, dtype=torch.float32, device=dev)
+        sel_shape = {"batch": (2,), "sample": (2, B), "joint": (B, K)}[reduction]
+        sel = torch.empty(sel_shape, dtype=torch.int64, device=dev)
+        st = cabi.stream_ptr(dev)
+        with torch.cuda.device(dev):
+            cabi.check(cabi.lib.xsup_reproj_loss_fwd(kps.data_ptr(), target.data_ptr(), cam, world.data_ptr(),
+                                                     sample_terms.data_ptr(), partial.data_ptr(), cfg, st), "xsup_reproj_loss_fwd")
+            if reduction == "batch":
+                xdist.reduce_partials(partial, group)            # the one exchange step of the path
+            cabi.check(cabi.lib.xsup_reproj_select(kps.data_ptr(), target.data_ptr(), sample_terms.data_ptr(),
+                                                   partial.data_ptr(), loss.data_ptr(), sel.data_ptr(), cfg, st), "xsup_reproj_select")
+            if reduction != "batch":
+                xdist.reduce_partials(loss, group)               # reporting only: the gradient needs just n_total
+        ctx.save_for_backward(logits, stats, kps, target, sel, *keep)
+        ctx.shape, ctx.cfg = shape, cfg
+        ctx.mark_non_differentiable(sel, dmap, idx)
+        return loss[0], loss[1], sel, kps, world, dmap, idx
+
+    @staticmethod
+    def backward(ctx, g_lp, g_ls, _g_sel, g_kps_out, g_world, _g_dmap, _g_idx):
+        logits, stats, kps, target, sel, *keep = ctx.saved_tensors
+        shape, cfg = ctx.shape, ctx.cfg
+        dev = logits.device
+        cam = cabi.make_cam(*keep, shape.B)
+        zero = torch.zeros((), dtype=torch.float32, device=dev)
+        g_loss = torch.stack([(g_lp if g_lp is not None else zero).to(torch.float32),
+                              (g_ls if g_ls is not None else zero).to(torch.float32)]).contiguous()
+        g_kps = torch.empty_like(kps)
+        with torch.cuda.device(dev):
+            cabi.check(cabi.lib.xsup_reproj_loss_bwd(kps.data_ptr(), target.data_ptr(), cam, sel.data_ptr(), g_loss.data_ptr(),
+                                                     g_kps.data_ptr(), cfg, cabi.stream_ptr(dev)), "xsup_reproj_loss_bwd")
+            if g_world is not None:
+                # downstream use of kps_world (e.g. the generator loss with use_aug, model.py:138)
+                gw = g_world.to(torch.float32).contiguous().view(shape.B, -1, 3)
+                extra = torch.empty_like(gw)
+                cabi.check(cabi.lib.xsup_patch_to_world_bwd(kps.data_ptr(), gw.data_ptr(), cam, extra.data_ptr(), shape.B,
+                                                            shape.NH * shape.K, cfg.img_h, cfg.img_w, cfg.rect_width,
+                                                            cabi.FLAG_NORM | cabi.FLAG_PATCH, cabi.stream_ptr(dev)),
+                           "xsup_patch_to_world_bwd")
+                g_kps += extra.view_as(g_kps)
+        if g_kps_out is not None:
+            g_kps += g_kps_out                                   # downstream use of kps (draw_lines, model.py:91)
+        return (_head_backward(logits, stats, shape, g_kps),) + (None,) * 17
+
+
+def integral_reproj_min_loss(logits, target, cams: Dict[str, torch.Tensor], num_kp, num_hypo, neighbor_size,
+                             img_hw: Sequence[int] = (256, 256), rect_width: float = 2000.0, w_mse: float = 1.0,
+                             w_bone: Optional[float] = None, w_kp: Optional[float] = None, w_kp2d: Optional[float] = None,
+                             reduction: str = "batch", group=None):
+    """Functional form of `IntegralReprojMinLoss` taking the camera tensors as a dict keyed
+    trans_image / pelvis / k_mat / trans_world / rot_world."""
+    return IntegralReprojMinLoss.apply(logits, target, cams["trans_image"], cams["pelvis"], cams["k_mat"],
+                                       cams["trans_world"], cams["rot_world"], num_kp, num_hypo, neighbor_size,
+                                       tuple(img_hw), rect_width, w_mse, w_bone, w_kp, w_kp2d, reduction, group)
