@@ -137,7 +137,7 @@ class ClockSampler(threading.Thread):
         super().__init__(daemon=True)
         self.index, self.period = index, period
         self.samples, self.reasons, self.max_mhz = [], set(), None
-        self._stop = threading.Event()
+        self._halt = threading.Event()
         self.ok = False
         try:
             import pynvml
@@ -157,7 +157,7 @@ class ClockSampler(threading.Thread):
                  "hw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40),
                  "sw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20),
                  "sw_power_cap": getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4)}
-        while not self._stop.is_set():
+        while not self._halt.is_set():
             try:
                 self.samples.append(int(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
                 r = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
@@ -169,7 +169,7 @@ class ClockSampler(threading.Thread):
             time.sleep(self.period)
 
     def finish(self):
-        self._stop.set()
+        self._halt.set()
         if self.is_alive():
             self.join(timeout=1.0)
         if not self.samples:
@@ -275,6 +275,8 @@ def run_ours(args, c):
     value = B * world / (ms * 1e-3)
 
     # ---- end to end through the public API with pinned host buffers (H2D of every input, D2H of the results)
+    if args.no_e2e:
+        return finish(args, c, rank, world, dev, B, K, R, NH, ms, k_fwd, k_bwd, value, launches, clocks, None)
     e2e_steps = max(2, min(args.steps, 5))
     h_logits = torch.empty(logits.shape, dtype=tdt, pin_memory=True)
     h_logits.copy_(logits.detach())
@@ -316,6 +318,14 @@ def run_ours(args, c):
     h2d = h_logits.numel() * h_logits.element_size() + h_target.numel() * 4 + sum(v.numel() * 4 for v in h_cams.values())
     d2h = 2 * 4 + 2 * 8 + h_out["kps"].numel() * 4
 
+    e2e = {"value": round(B * world / (e2e_ms * 1e-3), 1), "unit": UNIT, "h2d_bytes_per_step": int(h2d),
+           "d2h_bytes_per_step": int(d2h), "ms_per_step": round(e2e_ms, 3), "steps": e2e_steps,
+           "note": "pinned host -> device copy of logits/target/cameras, fused op fwd+bwd, loss/sel/kps read back; PCIe-bound"}
+    return finish(args, c, rank, world, dev, B, K, R, NH, ms, k_fwd, k_bwd, value, launches, clocks, e2e)
+
+
+def finish(args, c, rank, world, dev, B, K, R, NH, ms, k_fwd, k_bwd, value, launches, clocks, e2e):
+    import torch.distributed as dist
     if rank == 0:
         peak, peak_src = measured_peak()
         unit_bytes = K * R ** 3 * (4 if c["dtype"] == "f32" else 2) * B          # one pass over this rank's volume
@@ -334,10 +344,7 @@ def run_ours(args, c):
                                             "traffic": ncu_traffic("integral_fwd_kernel")},
                              "whole_step": {"achieved": round(step_gbs, 1), "frac": round(step_gbs / peak, 4),
                                             "frac_of_8TBs": round(step_gbs / 8000.0, 4)}},
-                "e2e": {"value": round(B * world / (e2e_ms * 1e-3), 1), "unit": UNIT, "h2d_bytes_per_step": int(h2d),
-                        "d2h_bytes_per_step": int(d2h), "ms_per_step": round(e2e_ms, 3), "steps": e2e_steps,
-                        "note": "pinned host -> device copy of logits/target/cameras, fused op fwd+bwd, loss/sel/kps read back; PCIe-bound"},
-                "gpu_launches": int(launches), "clocks": clocks}
+                "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks}
         if world == 1 and not args.no_cpu:
             v, threads, t = time_cpu(c, 3, 1)
             line["cpu_baseline"] = {"value": round(v, 2), "unit": UNIT, "cores": threads, "kind": "port",
@@ -361,6 +368,7 @@ def main():
     ap.add_argument("--config", choices=sorted(CONFIGS), default="c2")
     ap.add_argument("--batch", type=int, default=None, help="override the per-GPU batch (sweeps)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer end-to-end leg (profiling runs)")
     args = ap.parse_args()
     c = dict(CONFIGS[args.config])
     if args.batch:

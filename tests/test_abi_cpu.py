@@ -38,7 +38,7 @@ def test_struct_layouts_match_header(cabi):
 def test_strides(cabi):
     s = cabi.make_shape(2, 17, 64, 64, 64, 3, 15, torch.float32)
     assert cabi.lib.xsup_stats_stride(s) == 80            # 4 + 64 + 3*3 -> 77 -> 80
-    assert cabi.lib.xsup_coef_stride(s) == 68
+    assert cabi.lib.xsup_coef_stride(s) == 72
     assert cabi.lib.xsup_stats_stride(s) % 4 == 0
 
 

@@ -141,7 +141,7 @@ def _oracle_head(oracle, logits64, K, NH, NS, gw):
     x = logits64.clone().requires_grad_(True)
     kps, dmap, idx = oracle.integral_multi(x, K, NH, NS)
     (kps * gw).sum().backward()
-    return kps.detach(), dmap, idx, x.grad
+    return kps.detach(), dmap.detach(), idx, x.grad
 
 
 @pytest.mark.parametrize("gen,B,K,R,NH,NS,seed", [
@@ -296,15 +296,24 @@ def test_edge_cases(ops, oracle, dev):
     kps, dmap, idx = ops.integral_multi_head(torch.zeros(1, K * R, R, R, device=dev), K, NH, NS)
     assert idx.cpu().tolist() == [[[1, 2, 3]] * K]
     assert torch.allclose(dmap.cpu(), torch.full((K, R), 1.0 / R), rtol=1e-6)
-    # overflow safety: huge logits and a single dominant spike
-    logits = torch.randn(1, K * R, R, R, generator=torch.Generator().manual_seed(1)) * 50 + 3000.0
-    logits[0, 5, 7, 9] = 1e4
+    # overflow safety: logits far outside exp()'s fp32 range, plus one dominant spike
+    logits = torch.randn(1, K * R, R, R, generator=torch.Generator().manual_seed(1)) * 3 + 3000.0
+    logits[0, 5, 7, 9] += 25.0
     okps, _, oidx = oracle.integral_multi(logits.double(), K, NH, NS)
     x = logits.to(dev).requires_grad_(True)
     kps, _, idx = ops.integral_multi_head(x, K, NH, NS)
     kps.sum().backward()
     assert torch.isfinite(kps).all() and torch.isfinite(x.grad).all()
-    assert (kps.detach().cpu().double()[..., :2] - okps[..., :2]).abs().max().item() < TOL
+    assert torch.equal(idx.cpu(), oidx)
+    assert (kps.detach().cpu().double() - okps).abs().max().item() < TOL
+    # a spike so dominant that every other bin underflows in fp32: x,y stay exact, and the depth windows
+    # that hold no mass are 0/0 = NaN exactly as in the reference (…_multi.py:62), never inf or garbage
+    logits = torch.zeros(1, K * R, R, R)
+    logits[0, 5, 7, 9] = 1e4
+    kps, _, idx = ops.integral_multi_head(logits.to(dev), K, NH, NS)
+    assert abs(kps[0, 0, 0, 0].item() - (9 / R * 2 - 1)) < 1e-6 and abs(kps[0, 0, 0, 1].item() - (7 / R * 2 - 1)) < 1e-6
+    assert idx[0, 0, 0].item() == 5 and abs(kps[0, 0, 0, 2].item() - (5 / R * 2 - 1)) < 1e-6
+    assert not torch.isinf(kps).any()
     # -inf entries (masked logits) contribute nothing
     logits = torch.randn(1, K * R, R, R, generator=torch.Generator().manual_seed(2))
     logits[0, :, :, :4] = float("-inf")

@@ -93,7 +93,7 @@ static int device_info(int& num_sms) {
 }
 
 static size_t stats_stride(const xsup_shape_t& s) { return (size_t)((4 + s.D + 3 * s.NH + 3) / 4 * 4); }
-static size_t coef_stride(const xsup_shape_t& s) { return (size_t)((4 + s.D + 3) / 4 * 4); }
+static size_t coef_stride(const xsup_shape_t& s) { return (size_t)((8 + s.D + 3) / 4 * 4); }
 
 }  // namespace xsup
 
@@ -111,9 +111,9 @@ size_t xsup_coef_stride(const xsup_shape_t* s) { return s ? coef_stride(*s) : 0;
 int xsup_integral_fwd(const void* logits, float* kps, float* depth_prob_map, int64_t* peak_idx, float* stats,
                       const xsup_shape_t* s, void* stream) {
     if (int rc = check_shape(s)) return rc;
+    if (s->B == 0) return XSUP_OK;                      // empty batch: nothing to do (pointers may be NULL)
     if (!logits || !kps || !depth_prob_map || !stats) return fail(XSUP_E_NULL, "xsup_integral_fwd: NULL pointer");
     if (!aligned16(logits) || !aligned16(stats)) return fail(XSUP_E_ALIGN, "xsup_integral_fwd: logits/stats must be 16-byte aligned");
-    if (s->B == 0) return XSUP_OK;
     int sms = 0;
     if (int rc = device_info(sms)) return rc;
     FwdParams p{};
@@ -130,10 +130,10 @@ int xsup_integral_fwd(const void* logits, float* kps, float* depth_prob_map, int
 int xsup_integral_bwd(const void* logits, const float* stats, const float* g_kps, void* g_logits, float* coef_ws,
                       const xsup_shape_t* s, void* stream) {
     if (int rc = check_shape(s)) return rc;
+    if (s->B == 0) return XSUP_OK;
     if (!logits || !stats || !g_kps || !g_logits || !coef_ws) return fail(XSUP_E_NULL, "xsup_integral_bwd: NULL pointer");
     if (!aligned16(logits) || !aligned16(g_logits) || !aligned16(coef_ws))
         return fail(XSUP_E_ALIGN, "xsup_integral_bwd: logits/g_logits/coef_ws must be 16-byte aligned");
-    if (s->B == 0) return XSUP_OK;
     int sms = 0;
     if (int rc = device_info(sms)) return rc;
     CoefParams c{};

@@ -386,7 +386,7 @@ __global__ void __launch_bounds__(128) reproj_loss_bwd_kernel(const float* __res
         const float vz = __shfl_sync(0xffffffffu, w[2], ci) - __shfl_sync(0xffffffffu, w[2], pi);
         const float len = sqrtf(vx * vx + vy * vy + vz * vz);
         const float nrm = len * 1e-3f;
-        const float other = (lane & 1) ? __shfl_up_sync(0xffffffffu, nrm, 1) : __shfl_down_sync(0xffffffffu, nrm, 1);
+        const float other = __shfl_xor_sync(0xffffffffu, nrm, 1);             // partner bone of the pair (2p, 2p+1)
         // d bone_sum / d n_i = +2(n_i - n_partner) for even i, and the same expression for odd i
         const float gn = gl1 * c.w_bone / (n * 4.0f) * 2.0f * (nrm - other) * 1e-3f;
         const float il = len > 0.f ? 1.0f / len : 0.f;                        // torch.norm's backward is 0 at 0

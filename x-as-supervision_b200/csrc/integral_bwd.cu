@@ -4,7 +4,9 @@
 // (autograd of keypoint_detector_integral_multi.py:69-88): ~4 reads and ~3 writes of the volume.
 // In closed form the gradient of every logit is
 //     dL/dl[d,h,w] = p[d,h,w] * (a*w + b*h + c[d] - gbar),   p = 2^(l*log2e - lse2)
-// with (a, b, c[0..D), gbar, lse2) per (b,k) unit — a (4+D)-float coefficient block that the tiny
+// evaluated about the integer bin (wc, hc) nearest the expectation, a*(w-wc) + b*(h-hc) + (c[d] + base0),
+// so that no term of size a*W cancels against gbar in fp32.  (lse2, a, b, base0, wc, hc, c[0..D)) per
+// (b,k) unit is an (8+D)-float coefficient block that the tiny
 // `integral_coef_kernel` derives from grad_kps and the statistics saved by the forward.  The
 // streaming kernel then reads each logit once and writes each gradient once.
 //
@@ -32,11 +34,12 @@ __global__ void __launch_bounds__(128) integral_coef_kernel(const CoefParams p) 
     const float bb = gy * (2.0f / (float)p.W);               // y by W (…:79)
     const float zs = 2.0f / (float)D;
     const int half = p.NS >> 1;
+    const float zc = p.head == XSUP_HEAD_SINGLE ? rintf(st[4 + D]) : 0.f;   // single head: centre d as well
     float dot = 0.f;
     for (int d = threadIdx.x; d < D; d += blockDim.x) {
         float c = 0.f;
         if (p.head == XSUP_HEAD_SINGLE) {
-            c = p.g_kps[((size_t)b * p.K + k) * 3 + 2] * zs * (float)d;
+            c = p.g_kps[((size_t)b * p.K + k) * 3 + 2] * zs * ((float)d - zc);
         } else {
             for (int h = 0; h < NH; ++h) {
                 const float* sh = st + 4 + D + 3 * h;
@@ -47,7 +50,7 @@ __global__ void __launch_bounds__(128) integral_coef_kernel(const CoefParams p) 
                 }
             }
         }
-        cf[4 + d] = c;
+        cf[8 + d] = c;
         dot = fmaf(c, st[4 + d], dot);
     }
     dot = warp_sum(dot);
@@ -55,10 +58,16 @@ __global__ void __launch_bounds__(128) integral_coef_kernel(const CoefParams p) 
     __syncthreads();
     if (threadIdx.x == 0) {
         dot = (red[0] + red[1]) + (red[2] + red[3]);
+        const float wc = rintf(st[1]), hc = rintf(st[2]);
         cf[0] = st[0];
         cf[1] = a;
         cf[2] = bb;
-        cf[3] = fmaf(a, st[1], fmaf(bb, st[2], dot));         // gbar = a*xbar + b*ybar + sum_d c[d]*pz[d]
+        // gbar = a*xbar + b*ybar + sum_d c[d]*pz[d];  base0 = a*wc + b*hc - gbar, formed from small differences
+        cf[3] = -fmaf(a, st[1] - wc, fmaf(bb, st[2] - hc, dot));
+        cf[4] = wc;
+        cf[5] = hc;
+        cf[6] = 0.f;
+        cf[7] = 0.f;
     }
 }
 
@@ -130,17 +139,19 @@ __global__ void __launch_bounds__(kBwdThreads, 1) integral_bwd_kernel(const BwdP
 #pragma unroll
                 for (int i = 0; i < U; ++i) raw[i] = lds128(addr + i * 512u);
                 const uint4 c4 = lds128(sbase + t.stage_bytes);
+                const uint4 c5 = lds128(sbase + t.stage_bytes + 16u);
                 float cd;
-                asm volatile("ld.shared.f32 %0, [%1];" : "=f"(cd) : "r"(sbase + t.stage_bytes + 16u + 4u * d));
+                asm volatile("ld.shared.f32 %0, [%1];" : "=f"(cd) : "r"(sbase + t.stage_bytes + 32u + 4u * d));
                 __syncwarp();
                 if (lane == 0) mbar_arrive(empty0 + 8u * slot);
 
                 const float nlse = -__uint_as_float(c4.x), a = __uint_as_float(c4.y), bb = __uint_as_float(c4.z);
-                const float base = cd - __uint_as_float(c4.w);
+                const float base = cd + __uint_as_float(c4.w);
+                const float wrel = (float)w0 - __uint_as_float(c5.x);
                 float aw[VEC];
 #pragma unroll
-                for (int v = 0; v < VEC; ++v) aw[v] = a * (float)(w0 + v);
-                float hf = (float)(part * t.rows_per_task + lr);
+                for (int v = 0; v < VEC; ++v) aw[v] = a * (wrel + (float)v);
+                float hf = (float)(part * t.rows_per_task + lr) - __uint_as_float(c5.y);
                 const size_t unit = (size_t)blockIdx.x + (size_t)it * gridDim.x;
                 uint8_t* out = static_cast<uint8_t*>(p.g_logits) + unit * (size_t)t.unit_bytes + (size_t)task * t.task_bytes + lane * 16u;
 #pragma unroll
@@ -182,11 +193,11 @@ __global__ void __launch_bounds__(256) integral_bwd_generic_kernel(const BwdPara
     const T* src = static_cast<const T*>(p.logits) + unit * D * HW;
     T* dst = static_cast<T*>(p.g_logits) + unit * D * HW;
     const float* cf = p.coef + unit * (size_t)p.coef_stride;
-    const float nlse = -cf[0], a = cf[1], bb = cf[2], gbar = cf[3];
+    const float nlse = -cf[0], a = cf[1], bb = cf[2], base0 = cf[3], wc = cf[4], hc = cf[5];
     for (int i = threadIdx.x; i < D * HW; i += blockDim.x) {
         const int d = i / HW, r = i - d * HW, h = r / W, w = r - h * W;
         const float pr = ex2(fmaf(load_elem_b(src, i), kLog2e, nlse));
-        store_elem(dst, i, pr * (fmaf(a, (float)w, fmaf(bb, (float)h, cf[4 + d] - gbar))));
+        store_elem(dst, i, pr * (fmaf(a, (float)w - wc, fmaf(bb, (float)h - hc, cf[8 + d] + base0))));
     }
 }
 
@@ -219,6 +230,8 @@ cudaError_t launch_integral_bwd(BwdParams p, bool fast, int dtype, int num_sms, 
     const size_t fixed = (size_t)(2 * kMaxStages) * 8;
     int nst = (int)((kSmemBudget - fixed) / p.slot_bytes);
     nst = nst > kMaxStages ? kMaxStages : nst;
+    nst = nst / kGroups * kGroups;        // one warp group per slot, see launch_integral_fwd
+    if (nst < kGroups) return cudaErrorInvalidConfiguration;
     p.nst = nst;
     const size_t smem = (size_t)nst * p.slot_bytes + fixed;
     const int grid = p.n_units < num_sms ? p.n_units : num_sms;

@@ -56,10 +56,12 @@ __device__ __forceinline__ int take_best_peak(float (&cv)[kMaxD / 32], int lane)
 
 // ----------------------------------------------------------------------------------------------
 // Unit epilogue, executed by one full warp.  On entry pz[0..D) in shared memory holds the raw
-// (un-normalised) depth marginal relative to the log2-domain reference `M`; sx, sy are the raw
-// w- and h-weighted sums relative to the same `M` (warp-uniform).
+// (un-normalised) depth marginal relative to the log2-domain reference `M`; xbar, ybar are the
+// w- and h-expectations in bin units (warp-uniform).  The callers form them as ratios of sums that
+// went through the SAME accumulators, so the rounding of the accumulation cancels to first order and
+// the residual error scales with the spread of the distribution, not with its position.
 // ----------------------------------------------------------------------------------------------
-__device__ void finalise_unit(const FwdParams& p, int unit, float* pz, float M, float sx, float sy, int lane) {
+__device__ void finalise_unit(const FwdParams& p, int unit, float* pz, float M, float xbar, float ybar, int lane) {
     const int D = p.t.D, H = p.t.H, W = p.t.W, NH = p.NH;
     const int b = unit / p.K, k = unit - b * p.K;
     float ssum = 0.f;
@@ -74,7 +76,6 @@ __device__ void finalise_unit(const FwdParams& p, int unit, float* pz, float M, 
         if (b == 0) p.dmap[k * D + d] = v;                      // depth_prob_map = accu_z[0] (…_multi.py:48)
     }
     __syncwarp();
-    const float xbar = sx * invS, ybar = sy * invS;
     if (lane == 0) {
         st[0] = M + log2f(S);                                   // log2-domain log-sum-exp: p = 2^(l*log2e - st[0])
         st[1] = xbar;
@@ -145,8 +146,8 @@ __global__ void __launch_bounds__(kFwdThreads, 1) integral_fwd_kernel(const FwdP
 
     uint8_t* ring = smem;
     float2* pz_table = reinterpret_cast<float2*>(smem + (size_t)nst * t.stage_bytes);   // [2][TU] (m, sum)
-    float4* unit_part = reinterpret_cast<float4*>(pz_table + 2 * TU);                   // [2][kConsumerWarps]
-    float* pz_final = reinterpret_cast<float*>(unit_part + 2 * kConsumerWarps);         // [kMaxD]
+    float4* unit_part = reinterpret_cast<float4*>(pz_table + 2 * TU);                   // [2][kConsumerWarps][2]
+    float* pz_final = reinterpret_cast<float*>(unit_part + 4 * kConsumerWarps);         // [kMaxD]
     uint64_t* bars = reinterpret_cast<uint64_t*>(pz_final + kMaxD);
     const uint32_t full0 = smem_u32(bars), empty0 = full0 + 8u * nst;
     const uint32_t pfull0 = empty0 + 8u * nst, pempty0 = pfull0 + 16u;
@@ -191,11 +192,16 @@ __global__ void __launch_bounds__(kFwdThreads, 1) integral_fwd_kernel(const FwdP
             const int unit = (int)blockIdx.x + it * (int)gridDim.x;
             const int buf = it & 1;
             mbar_wait(pfull0 + 8u * buf, (it >> 1) & 1);
-            float4 up = make_float4(kNegHuge, 0.f, 0.f, 0.f);
-            if (lane < kConsumerWarps) up = unit_part[buf * kConsumerWarps + lane];
+            float4 up = make_float4(kNegHuge, 0.f, 0.f, 0.f), uq = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (lane < kConsumerWarps) {
+                up = unit_part[(buf * kConsumerWarps + lane) * 2];
+                uq = unit_part[(buf * kConsumerWarps + lane) * 2 + 1];
+            }
             const float M = warp_max(up.x);
             const float wsc = ex2(up.x - M);
-            const float sx = warp_sum(up.y * wsc), sy = warp_sum(up.z * wsc);
+            // (w-weighted sum) / (sum through the same column accumulators), likewise for rows
+            const float xbar = warp_sum(up.y * wsc) / warp_sum(up.z * wsc);
+            const float ybar = warp_sum(uq.x * wsc) / warp_sum(uq.y * wsc);
             const float2* tab = pz_table + buf * TU;
             for (int d = lane; d < t.D; d += 32) {
                 float a = 0.f;
@@ -207,7 +213,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) integral_fwd_kernel(const FwdP
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(pempty0 + 8u * buf);      // partial buffers may be refilled
-            finalise_unit(p, unit, pz_final, M, sx, sy, lane);
+            finalise_unit(p, unit, pz_final, M, xbar, ybar, lane);
             __syncwarp();
         }
     } else {
@@ -221,7 +227,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) integral_fwd_kernel(const FwdP
         for (int it = 0; it < n_iters; ++it) {
             const int base = it * SPU, buf = it & 1;
             if (it >= 2) mbar_wait(pempty0 + 8u * buf, ((it >> 1) - 1) & 1);
-            float m_ref = kNegHuge, sy = 0.f;
+            float m_ref = kNegHuge, sy = 0.f, sr = 0.f;
             float acc[VEC];
 #pragma unroll
             for (int v = 0; v < VEC; ++v) acc[v] = 0.f;
@@ -252,6 +258,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) integral_fwd_kernel(const FwdP
 #pragma unroll
                         for (int v = 0; v < VEC; ++v) acc[v] *= sc;
                         sy *= sc;
+                        sr *= sc;
                         m_ref = mt;
                     }
                     const int d = task / t.parts, part = task - d * t.parts;
@@ -273,6 +280,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) integral_fwd_kernel(const FwdP
                         sy = fmaf(hf, r, sy);
                         hf += rpi;
                     }
+                    sr += tsum;
                     tsum = warp_sum(tsum);
                     if (lane == 0) pz_table[buf * TU + task] = make_float2(m_ref, tsum);
                 } else {
@@ -280,13 +288,19 @@ __global__ void __launch_bounds__(kFwdThreads, 1) integral_fwd_kernel(const FwdP
                     if (lane == 0) mbar_arrive(empty0 + 8u * slot);
                 }
             }
-            float sx = 0.f;
+            float sx = 0.f, sa = 0.f;
 #pragma unroll
-            for (int v = 0; v < VEC; ++v) sx = fmaf((float)(w0 + v), acc[v], sx);
+            for (int v = 0; v < VEC; ++v) {
+                sx = fmaf((float)(w0 + v), acc[v], sx);
+                sa += acc[v];
+            }
             sx = warp_sum(sx);
+            sa = warp_sum(sa);
             sy = warp_sum(sy);
+            sr = warp_sum(sr);
             if (lane == 0) {
-                unit_part[buf * kConsumerWarps + warp] = make_float4(m_ref, sx, sy, 0.f);
+                unit_part[(buf * kConsumerWarps + warp) * 2] = make_float4(m_ref, sx, sa, 0.f);
+                unit_part[(buf * kConsumerWarps + warp) * 2 + 1] = make_float4(sy, sr, 0.f, 0.f);
                 mbar_arrive(pfull0 + 8u * buf);
             }
         }
@@ -325,7 +339,7 @@ __global__ void __launch_bounds__(256) integral_fwd_generic_kernel(const FwdPara
     float m = kNegHuge;
     for (int i = threadIdx.x; i < D * HW; i += blockDim.x) m = fmaxf(m, load_elem(src, i));
     const float M = block_reduce(m, scratch, true) * kLog2e;
-    float sx = 0.f, sy = 0.f;
+    float sx = 0.f, sy = 0.f, sa = 0.f;
     for (int d = 0; d < D; ++d) {
         float sd = 0.f;
         for (int i = threadIdx.x; i < HW; i += blockDim.x) {
@@ -335,13 +349,15 @@ __global__ void __launch_bounds__(256) integral_fwd_generic_kernel(const FwdPara
             sx = fmaf((float)w, e, sx);
             sy = fmaf((float)h, e, sy);
         }
+        sa += sd;
         sd = block_reduce(sd, scratch, false);
         if (threadIdx.x == 0) pz[d] = sd;
     }
     sx = block_reduce(sx, scratch, false);
     sy = block_reduce(sy, scratch, false);
+    sa = block_reduce(sa, scratch, false);
     __syncthreads();
-    if (threadIdx.x < 32) finalise_unit(p, unit, pz, M, sx, sy, threadIdx.x);
+    if (threadIdx.x < 32) finalise_unit(p, unit, pz, M, sx / sa, sy / sa, threadIdx.x);
 }
 
 // ----------------------------------------------------------------------------------------------
@@ -391,10 +407,15 @@ cudaError_t launch_integral_fwd(FwdParams p, bool fast, int dtype, int num_sms, 
         else integral_fwd_generic_kernel<__nv_bfloat16><<<p.n_units, 256, 0, st>>>(p);
         return cudaGetLastError();
     }
-    const size_t fixed = (size_t)2 * p.t.tasks_per_unit * sizeof(float2) + 2 * kConsumerWarps * sizeof(float4) +
+    const size_t fixed = (size_t)2 * p.t.tasks_per_unit * sizeof(float2) + 4 * kConsumerWarps * sizeof(float4) +
                          kMaxD * sizeof(float) + (size_t)(2 * kMaxStages + 4) * 8;
     int nst = (int)((kSmemBudget - fixed) / p.t.stage_bytes);
     nst = nst > kMaxStages ? kMaxStages : nst;
+    // A slot must always be consumed by the same warp group (slot = s % nst, group = s % kGroups): a waiter
+    // may only wait on phase k of an mbarrier if it observed phase k-1 itself, because bulk copies complete
+    // out of order and try_wait.parity cannot tell "phase k done" from "phase k-1 still pending".
+    nst = nst / kGroups * kGroups;
+    if (nst < kGroups) return cudaErrorInvalidConfiguration;
     p.nst = nst;
     const size_t smem = (size_t)nst * p.t.stage_bytes + fixed;
     const int grid = p.n_units < num_sms ? p.n_units : num_sms;

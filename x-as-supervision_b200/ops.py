@@ -85,6 +85,8 @@ class IntegralMultiHead(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g_kps, _g_dmap, _g_idx):
         logits, stats = ctx.saved_tensors
+        if g_kps is None:
+            return None, None, None, None
         return _head_backward(logits, stats, ctx.shape, g_kps), None, None, None
 
 
@@ -217,6 +219,7 @@ class IntegralReprojMinLoss(torch.autograd.Function):
     def forward(ctx, logits, target, trans_image, pelvis, k_mat, trans_world, rot_world, num_kp, num_hypo, neighbor_size,
                 img_hw, rect_width, w_mse, w_bone, w_kp, w_kp2d, reduction, group):
         logits, shape, kps, dmap, idx, stats = _head_forward(logits, num_kp, num_hypo, neighbor_size, cabi.HEAD_MULTI)
+        ctx.set_materialize_grads(False)          # unused outputs (kps, kps_world, loss_sym) arrive as None, not zeros
         dev = logits.device
         B, K, NH = shape.B, num_kp, num_hypo
         if B == 0:
@@ -258,6 +261,8 @@ class IntegralReprojMinLoss(torch.autograd.Function):
         shape, cfg = ctx.shape, ctx.cfg
         dev = logits.device
         cam = cabi.make_cam(*keep, shape.B)
+        if g_lp is None and g_ls is None and g_kps_out is None and g_world is None:
+            return (None,) * 18
         zero = torch.zeros((), dtype=torch.float32, device=dev)
         g_loss = torch.stack([(g_lp if g_lp is not None else zero).to(torch.float32),
                               (g_ls if g_ls is not None else zero).to(torch.float32)]).contiguous()
