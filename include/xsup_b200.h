@@ -83,6 +83,10 @@ uint64_t xsup_launch_count(void);
 /* floats per (b,k) unit of the saved-for-backward block / of the backward coefficient block */
 size_t xsup_stats_stride(const xsup_shape_t* s);
 size_t xsup_coef_stride(const xsup_shape_t* s);
+/* total floats the caller must allocate for `stats` / `coef_ws`: B*K*stride plus a few words the kernels
+ * use as their work-claim counter (SMs of a B200 see different HBM bandwidth, so work is claimed, not dealt) */
+size_t xsup_stats_floats(const xsup_shape_t* s);
+size_t xsup_coef_floats(const xsup_shape_t* s);
 
 /* Replaces keypoint_detector_integral_multi.py:69-88 (softmax over D*H*W, the three marginals,
  * x/y expectations, find_peak + topk, windowed depth expectation, normalisation, assembly).
@@ -90,7 +94,7 @@ size_t xsup_coef_stride(const xsup_shape_t* s);
  *   kps             [B,NH,K,3]    fp32
  *   depth_prob_map  [K,D]         fp32, sample 0 (…:48)
  *   peak_idx        [B,K,NH]      int64 (…:24-34); NULL allowed
- *   stats           [B*K*xsup_stats_stride]  fp32, consumed by xsup_integral_bwd            */
+ *   stats           [xsup_stats_floats]      fp32, consumed by xsup_integral_bwd            */
 int xsup_integral_fwd(const void* logits, float* kps, float* depth_prob_map, int64_t* peak_idx,
                       float* stats, const xsup_shape_t* s, void* stream);
 
@@ -101,7 +105,7 @@ int xsup_find_peak(const float* pz, int64_t* idx, int32_t rows, int32_t D, int32
 /* The autograd of the above in one pass over the volume.
  *   g_kps    [B,NH,K,3] fp32  (d loss / d kps)
  *   g_logits [B,K*D,H,W]      (s->dtype); may alias `logits` for an in-place gradient
- *   coef_ws  [B*K*xsup_coef_stride] fp32 scratch                                           */
+ *   coef_ws  [xsup_coef_floats] fp32 scratch                                               */
 int xsup_integral_bwd(const void* logits, const float* stats, const float* g_kps, void* g_logits,
                       float* coef_ws, const xsup_shape_t* s, void* stream);
 

@@ -40,6 +40,7 @@ def test_strides(cabi):
     assert cabi.lib.xsup_stats_stride(s) == 80            # 4 + 64 + 3*3 -> 77 -> 80
     assert cabi.lib.xsup_coef_stride(s) == 72
     assert cabi.lib.xsup_stats_stride(s) % 4 == 0
+    assert cabi.lib.xsup_stats_floats(s) == 2 * 17 * 80 + 16 and cabi.lib.xsup_coef_floats(s) == 2 * 17 * 72 + 16
 
 
 @pytest.mark.parametrize("kw,code", [

@@ -23,6 +23,7 @@ FLAG_NORM, FLAG_MONO, FLAG_PATCH = 1, 2, 4
 # every symbol include/xsup_b200.h declares (tests check the library exports all of them)
 SYMBOLS = (
     "xsup_abi_version", "xsup_last_error", "xsup_launch_count", "xsup_stats_stride", "xsup_coef_stride",
+    "xsup_stats_floats", "xsup_coef_floats",
     "xsup_integral_fwd", "xsup_integral_bwd", "xsup_find_peak",
     "xsup_patch_to_world_fwd", "xsup_patch_to_world_bwd", "xsup_world_to_patch_fwd",
     "xsup_reproj_loss_fwd", "xsup_reproj_select", "xsup_reproj_loss_bwd",
@@ -57,6 +58,10 @@ def _load():
     lib.xsup_stats_stride.argtypes = [C.POINTER(Shape)]
     lib.xsup_coef_stride.restype = C.c_size_t
     lib.xsup_coef_stride.argtypes = [C.POINTER(Shape)]
+    lib.xsup_stats_floats.restype = C.c_size_t
+    lib.xsup_stats_floats.argtypes = [C.POINTER(Shape)]
+    lib.xsup_coef_floats.restype = C.c_size_t
+    lib.xsup_coef_floats.argtypes = [C.POINTER(Shape)]
     lib.xsup_integral_fwd.argtypes = [vp, vp, vp, vp, vp, C.POINTER(Shape), vp]
     lib.xsup_integral_bwd.argtypes = [vp, vp, vp, vp, vp, C.POINTER(Shape), vp]
     lib.xsup_find_peak.argtypes = [vp, vp, i32, i32, i32, vp]

@@ -107,6 +107,8 @@ uint64_t xsup_launch_count(void) { return g_launches.load(std::memory_order_rela
 
 size_t xsup_stats_stride(const xsup_shape_t* s) { return s ? stats_stride(*s) : 0; }
 size_t xsup_coef_stride(const xsup_shape_t* s) { return s ? coef_stride(*s) : 0; }
+size_t xsup_stats_floats(const xsup_shape_t* s) { return s ? (size_t)s->B * s->K * stats_stride(*s) + kSchedWords : 0; }
+size_t xsup_coef_floats(const xsup_shape_t* s) { return s ? (size_t)s->B * s->K * coef_stride(*s) + kSchedWords : 0; }
 
 int xsup_integral_fwd(const void* logits, float* kps, float* depth_prob_map, int64_t* peak_idx, float* stats,
                       const xsup_shape_t* s, void* stream) {
@@ -120,8 +122,12 @@ int xsup_integral_fwd(const void* logits, float* kps, float* depth_prob_map, int
     p.logits = logits; p.kps = kps; p.dmap = depth_prob_map; p.peak_idx = peak_idx; p.stats = stats;
     p.n_units = s->B * s->K; p.K = s->K; p.NH = s->NH; p.NS = s->NS; p.head = s->head;
     p.stats_stride = (int)stats_stride(*s);
+    p.counter = reinterpret_cast<int*>(stats + (size_t)p.n_units * p.stats_stride);
     const bool fast = make_tiling(*s, p.t);
-    cudaError_t e = launch_integral_fwd(p, fast, s->dtype, sms, (cudaStream_t)stream);
+    cudaError_t e = cudaSuccess;
+    if (fast) e = cudaMemsetAsync(p.counter, 0, sizeof(int), (cudaStream_t)stream);
+    if (e != cudaSuccess) return cuda_fail(e, "xsup_integral_fwd counter reset");
+    e = launch_integral_fwd(p, fast, s->dtype, sms, (cudaStream_t)stream);
     if (e != cudaSuccess) return cuda_fail(e, "xsup_integral_fwd launch");
     count_launches(1);
     return XSUP_OK;
@@ -140,11 +146,12 @@ int xsup_integral_bwd(const void* logits, const float* stats, const float* g_kps
     c.stats = stats; c.g_kps = g_kps; c.coef = coef_ws;
     c.n_units = s->B * s->K; c.K = s->K; c.D = s->D; c.H = s->H; c.W = s->W; c.NH = s->NH; c.NS = s->NS; c.head = s->head;
     c.stats_stride = (int)stats_stride(*s); c.coef_stride = (int)coef_stride(*s);
+    c.counter = reinterpret_cast<int*>(coef_ws + (size_t)c.n_units * c.coef_stride);
     cudaError_t e = launch_integral_coef(c, (cudaStream_t)stream);
     if (e != cudaSuccess) return cuda_fail(e, "xsup_integral_bwd coefficient launch");
     BwdParams p{};
     p.logits = logits; p.coef = coef_ws; p.g_logits = g_logits;
-    p.n_units = c.n_units; p.coef_stride = c.coef_stride;
+    p.n_units = c.n_units; p.coef_stride = c.coef_stride; p.counter = c.counter;
     const bool fast = make_tiling(*s, p.t);
     e = launch_integral_bwd(p, fast, s->dtype, sms, (cudaStream_t)stream);
     if (e != cudaSuccess) return cuda_fail(e, "xsup_integral_bwd launch");

@@ -19,8 +19,11 @@ namespace xsup {
 
 // ----------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128) integral_coef_kernel(const CoefParams p) {
-    __shared__ float red[4];
-    const int unit = blockIdx.x, b = unit / p.K, k = unit - b * p.K;
+    // one warp per (b,k) unit
+    const int unit = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (blockIdx.x == 0 && threadIdx.x == 0) *p.counter = 0;       // work-claim counter of the streaming kernel that follows
+    if (unit >= p.n_units) return;
+    const int b = unit / p.K, k = unit - b * p.K;
     const int D = p.D, NH = p.NH;
     const float* st = p.stats + (size_t)unit * p.stats_stride;
     float* cf = p.coef + (size_t)unit * p.coef_stride;
@@ -36,7 +39,7 @@ __global__ void __launch_bounds__(128) integral_coef_kernel(const CoefParams p) 
     const int half = p.NS >> 1;
     const float zc = p.head == XSUP_HEAD_SINGLE ? rintf(st[4 + D]) : 0.f;   // single head: centre d as well
     float dot = 0.f;
-    for (int d = threadIdx.x; d < D; d += blockDim.x) {
+    for (int d = lane; d < D; d += 32) {
         float c = 0.f;
         if (p.head == XSUP_HEAD_SINGLE) {
             c = p.g_kps[((size_t)b * p.K + k) * 3 + 2] * zs * ((float)d - zc);
@@ -54,10 +57,7 @@ __global__ void __launch_bounds__(128) integral_coef_kernel(const CoefParams p) 
         dot = fmaf(c, st[4 + d], dot);
     }
     dot = warp_sum(dot);
-    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = dot;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        dot = (red[0] + red[1]) + (red[2] + red[3]);
+    if (lane == 0) {
         const float wc = rintf(st[1]), hc = rintf(st[2]);
         cf[0] = st[0];
         cf[1] = a;
@@ -72,7 +72,7 @@ __global__ void __launch_bounds__(128) integral_coef_kernel(const CoefParams p) 
 }
 
 cudaError_t launch_integral_coef(const CoefParams& p, cudaStream_t st) {
-    integral_coef_kernel<<<p.n_units, 128, 0, st>>>(p);
+    integral_coef_kernel<<<(p.n_units + 3) / 4, 128, 0, st>>>(p);
     return cudaGetLastError();
 }
 
@@ -85,6 +85,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) integral_bwd_kernel(const BwdP
     const Tiling& t = p.t;
     const int nst = p.nst, TU = t.tasks_per_unit, SPU = t.stages_per_unit;
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)nst * p.slot_bytes);
+    volatile int2* hdr = reinterpret_cast<volatile int2*>(bars + 2 * kMaxStages);       // [nst] (unit, stage in unit)
     const uint32_t full0 = smem_u32(bars), empty0 = full0 + 8u * nst;
     const uint32_t ring0 = smem_u32(smem);
 
@@ -97,27 +98,44 @@ __global__ void __launch_bounds__(kBwdThreads, 1) integral_bwd_kernel(const BwdP
     }
     __syncthreads();
 
-    const int n_iters = ((int)blockIdx.x < p.n_units) ? (p.n_units - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
     const uint32_t coef_bytes = (uint32_t)p.coef_stride * 4u;
 
     if (warp == kConsumerWarps) {
+        // ------------------------------------------------------------------ producer + scheduler
+        // the consumers are stateless, so work is claimed in chunks of `p.chunk` ring stages of the
+        // global stage sequence (unit-major); chunks may straddle units
         if (lane == 0) {
             const uint64_t pol = policy_evict_first();
+            const int total = p.n_units * SPU;
+            const int n_chunks = (total + p.chunk - 1) / p.chunk;
             int s = 0;
-            for (int it = 0; it < n_iters; ++it) {
-                const size_t unit = (size_t)blockIdx.x + (size_t)it * gridDim.x;
-                const uint8_t* src = static_cast<const uint8_t*>(p.logits) + unit * (size_t)t.unit_bytes;
-                const float* cf = p.coef + unit * (size_t)p.coef_stride;
-                for (int j = 0; j < SPU; ++j, ++s) {
+            int cur = atomicAdd(p.counter, 1);
+            while (cur < n_chunks) {
+                const int nxt = atomicAdd(p.counter, 1);            // claim ahead
+                const int gs0 = cur * p.chunk, gs1 = min(gs0 + p.chunk, total);
+                int unit = gs0 / SPU, j = gs0 - unit * SPU;
+                for (int gs = gs0; gs < gs1; ++gs, ++s) {
                     const int slot = s % nst;
                     if (s >= nst) mbar_wait(empty0 + 8u * slot, ((s / nst) - 1) & 1);
+                    hdr[slot].x = unit;
+                    hdr[slot].y = j;
+                    const uint8_t* src = static_cast<const uint8_t*>(p.logits) + (size_t)unit * (size_t)t.unit_bytes;
                     const long long off = (long long)j * t.stage_bytes;
                     const uint32_t bytes = (uint32_t)min((long long)t.stage_bytes, t.unit_bytes - off);
                     const uint32_t dst = ring0 + (uint32_t)slot * p.slot_bytes;
                     mbar_arrive_expect_tx(full0 + 8u * slot, bytes + coef_bytes);
                     bulk_g2s_hint(dst, src + off, bytes, full0 + 8u * slot, pol);
-                    bulk_g2s(dst + t.stage_bytes, cf, coef_bytes, full0 + 8u * slot);
+                    bulk_g2s(dst + t.stage_bytes, p.coef + (size_t)unit * p.coef_stride, coef_bytes, full0 + 8u * slot);
+                    if (++j == SPU) { j = 0; ++unit; }
                 }
+                cur = nxt;
+            }
+            for (int g = 0; g < kGroups; ++g, ++s) {                // end-of-stream sentinel per consumer group
+                const int slot = s % nst;
+                if (s >= nst) mbar_wait(empty0 + 8u * slot, ((s / nst) - 1) & 1);
+                hdr[slot].x = -1;
+                hdr[slot].y = 0;
+                mbar_arrive(full0 + 8u * slot);
             }
         }
     } else {
@@ -125,12 +143,12 @@ __global__ void __launch_bounds__(kBwdThreads, 1) integral_bwd_kernel(const BwdP
         const int lr = lane >> t.lpr_log2;
         const int w0 = (lane & (t.lpr - 1)) * VEC;
         const float rpi = (float)(32 >> t.lpr_log2);
-        const int total = n_iters * SPU;
-        for (int s = g; s < total; s += kGroups) {
-            const int it = s / SPU, j = s - it * SPU;
-            const int task = j * kTasksPerStage + q;
+        for (int s = g;; s += kGroups) {
             const int slot = s % nst;
             mbar_wait(full0 + 8u * slot, (s / nst) & 1);
+            const int unit = hdr[slot].x, j = hdr[slot].y;
+            if (unit < 0) break;
+            const int task = j * kTasksPerStage + q;
             if (task < TU) {
                 const uint32_t sbase = ring0 + (uint32_t)slot * p.slot_bytes;
                 const uint32_t addr = sbase + (uint32_t)q * t.task_bytes + lane * 16u;
@@ -152,8 +170,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) integral_bwd_kernel(const BwdP
 #pragma unroll
                 for (int v = 0; v < VEC; ++v) aw[v] = a * (wrel + (float)v);
                 float hf = (float)(part * t.rows_per_task + lr) - __uint_as_float(c5.y);
-                const size_t unit = (size_t)blockIdx.x + (size_t)it * gridDim.x;
-                uint8_t* out = static_cast<uint8_t*>(p.g_logits) + unit * (size_t)t.unit_bytes + (size_t)task * t.task_bytes + lane * 16u;
+                uint8_t* out = static_cast<uint8_t*>(p.g_logits) + (size_t)unit * (size_t)t.unit_bytes + (size_t)task * t.task_bytes + lane * 16u;
 #pragma unroll
                 for (int i = 0; i < U; ++i) {
                     float f[VEC];
@@ -227,7 +244,8 @@ cudaError_t launch_integral_bwd(BwdParams p, bool fast, int dtype, int num_sms, 
     }
     const int coef_pad = ((p.coef_stride * 4 + 127) / 128) * 128;
     p.slot_bytes = p.t.stage_bytes + coef_pad;
-    const size_t fixed = (size_t)(2 * kMaxStages) * 8;
+    const size_t fixed = (size_t)(2 * kMaxStages) * 8 + (size_t)kMaxStages * sizeof(int2);
+    p.chunk = 16;
     int nst = (int)((kSmemBudget - fixed) / p.slot_bytes);
     nst = nst > kMaxStages ? kMaxStages : nst;
     nst = nst / kGroups * kGroups;        // one warp group per slot, see launch_integral_fwd

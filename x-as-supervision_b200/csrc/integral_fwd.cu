@@ -143,12 +143,16 @@ __global__ void __launch_bounds__(kFwdThreads, 1) integral_fwd_kernel(const FwdP
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const Tiling& t = p.t;
     const int nst = p.nst, TU = t.tasks_per_unit, SPU = t.stages_per_unit;
+    // every unit occupies a multiple of kGroups ring stages (the tail ones carry no data), so that every
+    // consumer group sees every unit and group g always handles the stages j = g (mod kGroups)
+    const int SPUP = (SPU + kGroups - 1) / kGroups * kGroups;
 
     uint8_t* ring = smem;
     float2* pz_table = reinterpret_cast<float2*>(smem + (size_t)nst * t.stage_bytes);   // [2][TU] (m, sum)
     float4* unit_part = reinterpret_cast<float4*>(pz_table + 2 * TU);                   // [2][kConsumerWarps][2]
     float* pz_final = reinterpret_cast<float*>(unit_part + 4 * kConsumerWarps);         // [kMaxD]
     uint64_t* bars = reinterpret_cast<uint64_t*>(pz_final + kMaxD);
+    volatile int2* hdr = reinterpret_cast<volatile int2*>(bars + 2 * kMaxStages + 4);   // [nst] (unit, stage in unit)
     const uint32_t full0 = smem_u32(bars), empty0 = full0 + 8u * nst;
     const uint32_t pfull0 = empty0 + 8u * nst, pempty0 = pfull0 + 16u;
 
@@ -165,31 +169,45 @@ __global__ void __launch_bounds__(kFwdThreads, 1) integral_fwd_kernel(const FwdP
     }
     __syncthreads();
 
-    const int n_iters = ((int)blockIdx.x < p.n_units) ? (p.n_units - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
-
     if (warp == kConsumerWarps) {
-        // ------------------------------------------------------------------ producer
+        // ------------------------------------------------------------------ producer + scheduler
+        // SMs see different HBM bandwidth (die / L2 distance), so units are claimed from a global counter
+        // instead of being dealt round-robin; the claim is published to the consumers in the slot header.
         if (lane == 0) {
             const uint64_t pol = policy_evict_first();
             const uint32_t ring0 = smem_u32(ring);
             int s = 0;
-            for (int it = 0; it < n_iters; ++it) {
-                const size_t unit = (size_t)blockIdx.x + (size_t)it * gridDim.x;
-                const uint8_t* src = static_cast<const uint8_t*>(p.logits) + unit * (size_t)t.unit_bytes;
-                for (int j = 0; j < SPU; ++j, ++s) {
+            int cur = atomicAdd(p.counter, 1);
+            while (cur < p.n_units) {
+                const int nxt = atomicAdd(p.counter, 1);            // claim ahead: the round trip overlaps this unit's copies
+                const uint8_t* src = static_cast<const uint8_t*>(p.logits) + (size_t)cur * (size_t)t.unit_bytes;
+                for (int j = 0; j < SPUP; ++j, ++s) {
                     const int slot = s % nst;
                     if (s >= nst) mbar_wait(empty0 + 8u * slot, ((s / nst) - 1) & 1);
-                    const long long off = (long long)j * t.stage_bytes;
-                    const uint32_t bytes = (uint32_t)min((long long)t.stage_bytes, t.unit_bytes - off);
-                    mbar_arrive_expect_tx(full0 + 8u * slot, bytes);
-                    bulk_g2s_hint(ring0 + (uint32_t)slot * t.stage_bytes, src + off, bytes, full0 + 8u * slot, pol);
+                    hdr[slot].x = cur;
+                    hdr[slot].y = j;
+                    if (j < SPU) {
+                        const long long off = (long long)j * t.stage_bytes;
+                        const uint32_t bytes = (uint32_t)min((long long)t.stage_bytes, t.unit_bytes - off);
+                        mbar_arrive_expect_tx(full0 + 8u * slot, bytes);
+                        bulk_g2s_hint(ring0 + (uint32_t)slot * t.stage_bytes, src + off, bytes, full0 + 8u * slot, pol);
+                    } else {
+                        mbar_arrive(full0 + 8u * slot);             // padding stage: header only
+                    }
                 }
+                cur = nxt;
+            }
+            for (int g = 0; g < kGroups; ++g, ++s) {                // one end-of-stream sentinel per consumer group
+                const int slot = s % nst;
+                if (s >= nst) mbar_wait(empty0 + 8u * slot, ((s / nst) - 1) & 1);
+                hdr[slot].x = -1;
+                hdr[slot].y = 0;
+                mbar_arrive(full0 + 8u * slot);
             }
         }
     } else if (warp == kConsumerWarps + 1) {
         // ------------------------------------------------------------------ finaliser
-        for (int it = 0; it < n_iters; ++it) {
-            const int unit = (int)blockIdx.x + it * (int)gridDim.x;
+        for (int it = 0;; ++it) {
             const int buf = it & 1;
             mbar_wait(pfull0 + 8u * buf, (it >> 1) & 1);
             float4 up = make_float4(kNegHuge, 0.f, 0.f, 0.f), uq = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -197,6 +215,8 @@ __global__ void __launch_bounds__(kFwdThreads, 1) integral_fwd_kernel(const FwdP
                 up = unit_part[(buf * kConsumerWarps + lane) * 2];
                 uq = unit_part[(buf * kConsumerWarps + lane) * 2 + 1];
             }
+            const int unit = __shfl_sync(0xffffffffu, __float_as_int(uq.z), 0);
+            if (unit < 0) break;                                     // consumers reached the sentinel
             const float M = warp_max(up.x);
             const float wsc = ex2(up.x - M);
             // (w-weighted sum) / (sum through the same column accumulators), likewise for rows
@@ -223,86 +243,107 @@ __global__ void __launch_bounds__(kFwdThreads, 1) integral_fwd_kernel(const FwdP
         const int w0 = (lane & (t.lpr - 1)) * VEC;
         const float rpi = (float)(32 >> t.lpr_log2);
         const uint32_t ring0 = smem_u32(ring);
-        int s = g;
-        for (int it = 0; it < n_iters; ++it) {
-            const int base = it * SPU, buf = it & 1;
-            if (it >= 2) mbar_wait(pempty0 + 8u * buf, ((it >> 1) - 1) & 1);
-            float m_ref = kNegHuge, sy = 0.f, sr = 0.f;
-            float acc[VEC];
+        int it = 0;                                                  // units this warp has flushed
+        bool fresh = true;                                           // first stage of a unit: claim the partial buffer
+        float m_ref = kNegHuge, sy = 0.f, sr = 0.f;
+        float acc[VEC];
 #pragma unroll
-            for (int v = 0; v < VEC; ++v) acc[v] = 0.f;
+        for (int v = 0; v < VEC; ++v) acc[v] = 0.f;
 
-            for (; s < base + SPU; s += kGroups) {
-                const int task = (s - base) * kTasksPerStage + q;
-                const int slot = s % nst;
-                mbar_wait(full0 + 8u * slot, (s / nst) & 1);
-                if (task < TU) {
-                    const uint32_t addr = ring0 + (uint32_t)slot * t.stage_bytes + (uint32_t)q * t.task_bytes + lane * 16u;
-                    uint4 raw[U];
+        for (int s = g;; s += kGroups) {
+            const int slot = s % nst;
+            mbar_wait(full0 + 8u * slot, (s / nst) & 1);
+            const int unit = hdr[slot].x, j = hdr[slot].y;
+            if (unit < 0) break;
+            const int buf = it & 1;
+            if (fresh) {
+                if (it >= 2) mbar_wait(pempty0 + 8u * buf, ((it >> 1) - 1) & 1);
+                fresh = false;
+            }
+            const int task = j * kTasksPerStage + q;
+            if (task < TU) {
+                const uint32_t addr = ring0 + (uint32_t)slot * t.stage_bytes + (uint32_t)q * t.task_bytes + lane * 16u;
+                uint4 raw[U];
 #pragma unroll
-                    for (int i = 0; i < U; ++i) raw[i] = lds128(addr + i * 512u);
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(empty0 + 8u * slot);   // data is in registers: free the slot early
+                for (int i = 0; i < U; ++i) raw[i] = lds128(addr + i * 512u);
+                __syncwarp();
+                if (lane == 0) mbar_arrive(empty0 + 8u * slot);   // data is in registers: free the slot early
 
-                    float lmax = kNegHuge;
+                float lmax = kNegHuge;
 #pragma unroll
-                    for (int i = 0; i < U; ++i) {
-                        float f[VEC];
-                        Vec<T>::unpack(raw[i], f);
+                for (int i = 0; i < U; ++i) {
+                    float f[VEC];
+                    Vec<T>::unpack(raw[i], f);
 #pragma unroll
-                        for (int v = 0; v < VEC; ++v) lmax = fmaxf(lmax, f[v]);
-                    }
-                    const float mt = warp_max(lmax) * kLog2e;
-                    if (mt > m_ref) {                                 // warp-uniform, rare after the first tasks
-                        const float sc = ex2(m_ref - mt);
-#pragma unroll
-                        for (int v = 0; v < VEC; ++v) acc[v] *= sc;
-                        sy *= sc;
-                        sr *= sc;
-                        m_ref = mt;
-                    }
-                    const int d = task / t.parts, part = task - d * t.parts;
-                    float hf = (float)(part * t.rows_per_task + lr);
-                    float tsum = 0.f;
-                    const float nm = -m_ref;
-#pragma unroll
-                    for (int i = 0; i < U; ++i) {
-                        float f[VEC];
-                        Vec<T>::unpack(raw[i], f);
-                        float r = 0.f;
-#pragma unroll
-                        for (int v = 0; v < VEC; ++v) {
-                            const float e = ex2(fmaf(f[v], kLog2e, nm));
-                            acc[v] += e;
-                            r += e;
-                        }
-                        tsum += r;
-                        sy = fmaf(hf, r, sy);
-                        hf += rpi;
-                    }
-                    sr += tsum;
-                    tsum = warp_sum(tsum);
-                    if (lane == 0) pz_table[buf * TU + task] = make_float2(m_ref, tsum);
-                } else {
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(empty0 + 8u * slot);
+                    for (int v = 0; v < VEC; ++v) lmax = fmaxf(lmax, f[v]);
                 }
-            }
-            float sx = 0.f, sa = 0.f;
+                const float mt = warp_max(lmax) * kLog2e;
+                if (mt > m_ref) {                                 // warp-uniform, rare after the first tasks
+                    const float sc = ex2(m_ref - mt);
 #pragma unroll
-            for (int v = 0; v < VEC; ++v) {
-                sx = fmaf((float)(w0 + v), acc[v], sx);
-                sa += acc[v];
+                    for (int v = 0; v < VEC; ++v) acc[v] *= sc;
+                    sy *= sc;
+                    sr *= sc;
+                    m_ref = mt;
+                }
+                const int d = task / t.parts, part = task - d * t.parts;
+                float hf = (float)(part * t.rows_per_task + lr);
+                float tsum = 0.f;
+                const float nm = -m_ref;
+#pragma unroll
+                for (int i = 0; i < U; ++i) {
+                    float f[VEC];
+                    Vec<T>::unpack(raw[i], f);
+                    float r = 0.f;
+#pragma unroll
+                    for (int v = 0; v < VEC; ++v) {
+                        const float e = ex2(fmaf(f[v], kLog2e, nm));
+                        acc[v] += e;
+                        r += e;
+                    }
+                    tsum += r;
+                    sy = fmaf(hf, r, sy);
+                    hf += rpi;
+                }
+                sr += tsum;
+                tsum = warp_sum(tsum);
+                if (lane == 0) pz_table[buf * TU + task] = make_float2(m_ref, tsum);
+            } else {
+                __syncwarp();
+                if (lane == 0) mbar_arrive(empty0 + 8u * slot);
             }
-            sx = warp_sum(sx);
-            sa = warp_sum(sa);
-            sy = warp_sum(sy);
-            sr = warp_sum(sr);
-            if (lane == 0) {
-                unit_part[(buf * kConsumerWarps + warp) * 2] = make_float4(m_ref, sx, sa, 0.f);
-                unit_part[(buf * kConsumerWarps + warp) * 2 + 1] = make_float4(sy, sr, 0.f, 0.f);
-                mbar_arrive(pfull0 + 8u * buf);
+            if (j + kGroups >= SPUP) {
+                // this warp's last stage of the unit: hand its partials to the finaliser
+                float sx = 0.f, sa = 0.f;
+#pragma unroll
+                for (int v = 0; v < VEC; ++v) {
+                    sx = fmaf((float)(w0 + v), acc[v], sx);
+                    sa += acc[v];
+                    acc[v] = 0.f;
+                }
+                sx = warp_sum(sx);
+                sa = warp_sum(sa);
+                sy = warp_sum(sy);
+                sr = warp_sum(sr);
+                if (lane == 0) {
+                    unit_part[(buf * kConsumerWarps + warp) * 2] = make_float4(m_ref, sx, sa, 0.f);
+                    unit_part[(buf * kConsumerWarps + warp) * 2 + 1] = make_float4(sy, sr, __int_as_float(unit), 0.f);
+                    mbar_arrive(pfull0 + 8u * buf);
+                }
+                m_ref = kNegHuge;
+                sy = 0.f;
+                sr = 0.f;
+                ++it;
+                fresh = true;
             }
+        }
+        // end of stream: pass the sentinel on to the finaliser
+        const int buf = it & 1;
+        if (it >= 2) mbar_wait(pempty0 + 8u * buf, ((it >> 1) - 1) & 1);
+        if (lane == 0) {
+            unit_part[(buf * kConsumerWarps + warp) * 2] = make_float4(kNegHuge, 0.f, 0.f, 0.f);
+            unit_part[(buf * kConsumerWarps + warp) * 2 + 1] = make_float4(0.f, 0.f, __int_as_float(-1), 0.f);
+            mbar_arrive(pfull0 + 8u * buf);
         }
     }
 }
@@ -408,7 +449,7 @@ cudaError_t launch_integral_fwd(FwdParams p, bool fast, int dtype, int num_sms, 
         return cudaGetLastError();
     }
     const size_t fixed = (size_t)2 * p.t.tasks_per_unit * sizeof(float2) + 4 * kConsumerWarps * sizeof(float4) +
-                         kMaxD * sizeof(float) + (size_t)(2 * kMaxStages + 4) * 8;
+                         kMaxD * sizeof(float) + (size_t)(2 * kMaxStages + 4) * 8 + (size_t)kMaxStages * sizeof(int2);
     int nst = (int)((kSmemBudget - fixed) / p.t.stage_bytes);
     nst = nst > kMaxStages ? kMaxStages : nst;
     // A slot must always be consumed by the same warp group (slot = s % nst, group = s % kGroups): a waiter

@@ -8,6 +8,7 @@ constexpr int kFwdThreads = (kConsumerWarps + 2) * 32;   // 16 consumers + produ
 constexpr int kBwdThreads = (kConsumerWarps + 1) * 32;   // 16 consumers + producer
 constexpr size_t kSmemBudget = 227 * 1024;               // per-CTA opt-in maximum on sm_100
 constexpr int kMaxStages = 16;
+constexpr int kSchedWords = 16;                          // ints reserved after stats / coef for the work-claim counter
 
 struct FwdParams {
     const void* logits;
@@ -17,6 +18,7 @@ struct FwdParams {
     float* stats;
     int n_units, K, NH, NS, head, stats_stride;
     int nst;
+    int* counter;      // work-claim counter (zeroed by the launcher), in the caller's stats buffer
     Tiling t;
 };
 
@@ -26,6 +28,8 @@ struct BwdParams {
     void* g_logits;
     int n_units, coef_stride;
     int nst, slot_bytes;
+    int chunk;         // ring stages per claim
+    int* counter;      // work-claim counter (zeroed by integral_coef_kernel), in the caller's coef buffer
     Tiling t;
 };
 
@@ -34,6 +38,7 @@ struct CoefParams {
     const float* g_kps;
     float* coef;
     int n_units, K, D, H, W, NH, NS, head, stats_stride, coef_stride;
+    int* counter;
 };
 
 cudaError_t launch_integral_fwd(FwdParams p, bool fast, int dtype, int num_sms, cudaStream_t st);

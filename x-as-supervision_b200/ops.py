@@ -49,8 +49,7 @@ def _head_forward(logits, num_kp, num_hypo, neighbor_size, head):
     dmap = torch.zeros(num_kp, D, dtype=torch.float32, device=dev) if B == 0 else \
         torch.empty(num_kp, D, dtype=torch.float32, device=dev)
     idx = torch.empty(B, num_kp, num_hypo, dtype=torch.int64, device=dev)
-    stride = cabi.lib.xsup_stats_stride(shape)
-    stats = torch.empty(max(B * num_kp * stride, 4), dtype=torch.float32, device=dev)
+    stats = torch.empty(cabi.lib.xsup_stats_floats(shape), dtype=torch.float32, device=dev)
     with torch.cuda.device(dev):
         cabi.check(cabi.lib.xsup_integral_fwd(logits.data_ptr(), kps.data_ptr(), dmap.data_ptr(),
                                               idx.data_ptr() if head == cabi.HEAD_MULTI else None,
@@ -62,7 +61,7 @@ def _head_backward(logits, stats, shape, g_kps, inplace=False):
     dev = logits.device
     g_kps = g_kps.to(torch.float32).contiguous()
     g_logits = logits if inplace else torch.empty_like(logits)
-    coef = torch.empty(max(shape.B * shape.K * cabi.lib.xsup_coef_stride(shape), 4), dtype=torch.float32, device=dev)
+    coef = torch.empty(cabi.lib.xsup_coef_floats(shape), dtype=torch.float32, device=dev)
     with torch.cuda.device(dev):
         cabi.check(cabi.lib.xsup_integral_bwd(logits.data_ptr(), stats.data_ptr(), g_kps.data_ptr(), g_logits.data_ptr(),
                                               coef.data_ptr(), shape, cabi.stream_ptr(dev)), "xsup_integral_bwd")
