@@ -122,11 +122,12 @@ def run_reference(args, c):
     return 0
 
 
-def config_block(c, n, cpu=False):
+def config_block(c, n, cpu=False, scope="global", exchange="none"):
     return {"workload": c["workload"], "batch_per_gpu": c["B"] if not cpu else CPU_SAMPLE_B, "global_batch": c["B"] * n if not cpu else CPU_SAMPLE_B,
             "num_kp": c["K"], "heatmap": [c["R"]] * 3, "num_hypo": c["NH"], "neighbor_size": c["NS"],
             "loss_weights": {"mse": c["w"][0], "bone": c["w"][1], "kp": c["w"][2], "kp_2d": c["w"][3]},
-            "reduction": "batch", "scope": "global" if n > 1 else "local", "parallelism": "sample-sharded x%d" % n,
+            "reduction": "batch", "scope": scope if n > 1 else "local", "exchange": exchange,
+            "parallelism": "sample-sharded x%d" % n,
             "l2": "inputs (%.2f GB of logits per GPU) exceed the 126 MB L2; no explicit flush" % (
                 (CPU_SAMPLE_B if cpu else c["B"]) * bytes_per_sample(c) / 3 / 1e9)}
 
@@ -192,8 +193,18 @@ def run_ours(args, c):
     dev = torch.device("cuda", local_rank)
     group = None
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
-        group = dist.group.WORLD
+        # keep stdout to the single JSON line: NCCL prints its version banner there at VERSION/INFO level
+        os.environ["NCCL_DEBUG"] = os.environ.get("XSUP_NCCL_DEBUG", "NONE")
+        sys.stdout.flush()
+        saved_stdout = os.dup(1)
+        os.dup2(2, 1)                                   # anything NCCL prints while connecting goes to stderr
+        try:
+            dist.init_process_group("nccl", device_id=dev)
+            dist.barrier()
+        finally:
+            os.dup2(saved_stdout, 1)
+            os.close(saved_stdout)
+        group = None
 
     import __graft_entry__ as ge
     if not os.path.exists(ge.LIB):
@@ -203,6 +214,18 @@ def run_ours(args, c):
             dist.barrier()
     pkg = importlib.import_module("x-as-supervision_b200")
     ops, synth = pkg.load_native(), pkg.synth
+    exchange = "none"
+    if world > 1 and args.scope == "global":
+        if args.exchange == "nvlink":
+            try:
+                group = pkg.dist.PeerExchange(dist.group.WORLD, dev)
+                exchange = "nvlink-p2p kernel (xsup_partial_allreduce)"
+            except Exception as e:                      # no peer mapping on this box: say so and use NCCL
+                sys.stderr.write("[bench] PeerExchange unavailable (%s); using NCCL all_reduce\n" % (e,))
+        if group is None:
+            group = dist.group.WORLD
+            exchange = "nccl all_reduce"
+    args.exchange_used = exchange
 
     B, K, R, NH, NS = c["B"], c["K"], c["R"], c["NH"], c["NS"]
     tdt = torch.float32 if c["dtype"] == "f32" else torch.bfloat16
@@ -216,7 +239,7 @@ def run_ours(args, c):
     cams = {k: v.to(dev) for k, v in synth.cameras(B, seed=3 + rank, mpi=c["mpi"]).items()}
 
     # per-kernel CUDA events on the launching stream (torch's current stream) around the two volume kernels
-    ev = {"fwd": [], "bwd": []}
+    ev = {"fwd": [], "bwd": [], "xchg": []}
     record = {"on": False}
     orig_fwd, orig_bwd = ops._head_forward, ops._head_backward
 
@@ -232,6 +255,8 @@ def run_ours(args, c):
             return out
         return wrap
     ops._head_forward, ops._head_backward = timed("fwd", orig_fwd), timed("bwd", orig_bwd)
+    if group is not None:
+        ops.xdist.reduce_partials = timed("xchg", ops.xdist.reduce_partials)
 
     def step():
         logits.grad = None
@@ -247,10 +272,12 @@ def run_ours(args, c):
 
     for _ in range(max(args.warmup, 3)):
         step()
-    sync_all()
+    # rank-0-only set-up goes BEFORE the barrier: every rank must enter the timed region together, otherwise the
+    # first exchange of the other ranks waits for rank 0 and that wait is charged to the max-over-ranks time
     sampler = ClockSampler(local_rank) if rank == 0 else None
     if sampler:
         sampler.start()
+    sync_all()
     record["on"] = True
     n0 = ops.launch_count()
     t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -265,6 +292,10 @@ def run_ours(args, c):
     ms = t0.elapsed_time(t1) / args.steps
     k_fwd = statistics.mean(a.elapsed_time(b) for a, b in ev["fwd"])
     k_bwd = statistics.mean(a.elapsed_time(b) for a, b in ev["bwd"])
+    k_x = [a.elapsed_time(b) for a, b in ev["xchg"]]
+    if k_x:
+        sys.stderr.write("[bench] rank %d: exchange (incl. waiting for peers) mean %.1f us, median %.1f us, max %.1f us; fwd %.4f ms bwd %.4f ms step %.4f ms\n"
+                         % (rank, 1e3 * statistics.mean(k_x), 1e3 * statistics.median(k_x), 1e3 * max(k_x), k_fwd, k_bwd, ms))
     if world > 1:
         t = torch.tensor([ms, k_fwd, k_bwd], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -334,7 +365,7 @@ def finish(args, c, rank, world, dev, B, K, R, NH, ms, k_fwd, k_bwd, value, laun
         step_gbs = 3 * unit_bytes / (ms * 1e-3) / 1e9
         line = {"metric": METRIC, "value": round(value, 1), "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": max(args.warmup, 3), "ms_per_step": round(ms, 4), "higher_is_better": True, "scaling": "weak",
-                "vs_baseline": None, "dtype": c["dtype"], "data": "synthetic", "config": config_block(c, world),
+                "vs_baseline": None, "dtype": c["dtype"], "data": "synthetic", "config": config_block(c, world, scope=args.scope, exchange=getattr(args, "exchange_used", "none")),
                 "roofline": {"bound": "hbm", "kernel": "integral_bwd_kernel (read logits + write grad, 2 passes)",
                              "achieved": round(bwd_gbs, 1), "peak": peak, "unit": "GB/s", "frac": round(bwd_gbs / peak, 4),
                              "traffic": ncu_traffic("integral_bwd_kernel"), "peak_source": peak_src,
@@ -367,6 +398,11 @@ def main():
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--config", choices=sorted(CONFIGS), default="c2")
     ap.add_argument("--batch", type=int, default=None, help="override the per-GPU batch (sweeps)")
+    ap.add_argument("--scope", choices=["global", "local"], default="global",
+                    help="N>1: 'global' all-reduces the [4,NH] partial sums (single-process semantics on the global batch); "
+                         "'local' selects per rank like the reference under DDP (no collective)")
+    ap.add_argument("--exchange", choices=["nvlink", "nccl"], default="nvlink",
+                    help="transport of the global-scope all-reduce: in-kernel NVLink peer-memory exchange, or torch NCCL")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer end-to-end leg (profiling runs)")
     args = ap.parse_args()

@@ -131,6 +131,25 @@ int xsup_world_to_patch_fwd(const float* world, const xsup_cam_t* cam, float* kp
 int xsup_reproj_loss_fwd(const float* kps, const float* target, const xsup_cam_t* cam, float* world,
                          float* sample_terms, float* partial, const xsup_loss_cfg_t* cfg, void* stream);
 
+/* The one exchange step of the path when the batch is sharded over GPUs and the winner is chosen on the
+ * GLOBAL batch: all-reduce(SUM) of `partial[n]` (n <= 48 floats) done by ONE kernel over NVLink peer memory.
+ * Every rank owns a zero-initialised mailbox of xsup_xchg_floats(world) floats that all peers have mapped
+ * (e.g. torch symmetric memory); `peer_bufs` is a DEVICE array of the `world` mailbox addresses as seen from
+ * this process (own included).  The kernel stores its partial sums into slot [step&1][rank] of every mailbox
+ * (P2P stores + st.release.sys flag), acquire-spins on the `world` flags of its own mailbox, and sums the slots
+ * in rank order, so all ranks end with bit-identical sums.  `step` is the call sequence number (1, 2, ...),
+ * identical on all ranks.  All ranks must make the call; a peer that never arrives turns the result into NaN
+ * after ~10 s instead of hanging the GPU.  Replaces nothing in the reference (it never reduces across ranks,
+ * model.py:114,162 run on the rank-local batch); it exists so that N GPUs reproduce the single-process result. */
+typedef struct {
+    void* const* peer_bufs;
+    int32_t rank, world;
+    uint32_t step;
+} xsup_xchg_t;
+#define XSUP_XCHG_SLOT 64
+size_t xsup_xchg_floats(int32_t world);
+int xsup_partial_allreduce(float* partial, int32_t n, const xsup_xchg_t* x, void* stream);
+
 /* min / argmin over hypotheses (model.py:114,162; loss_func.py:59; eval.py:138-145).
  *   loss [2] out: (pseudo term * w_mse, symmetry term)
  *   sel  out int64: batch -> [2] (slot or -1); sample -> [2,B]; joint -> [B,K]                 */

@@ -33,6 +33,7 @@ def test_struct_layouts_match_header(cabi):
     assert C.sizeof(cabi.Shape) == 9 * 4
     assert C.sizeof(cabi.Cam) == 5 * C.sizeof(C.c_void_p)
     assert C.sizeof(cabi.LossCfg) == 13 * 4
+    assert C.sizeof(cabi.Xchg) == 24 and cabi.lib.xsup_xchg_floats(8) == 2 * 8 * 64
 
 
 def test_strides(cabi):

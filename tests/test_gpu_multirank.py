@@ -1,0 +1,73 @@
+"""2-rank NCCL test (needs >= 2 GPUs, `-m gpu`): sample-sharded fused op in 'global' scope must select the
+slot, report the loss and produce the heat-map gradient of the single-GPU run on the whole batch."""
+import importlib
+import os
+import sys
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from conftest import ROOT
+
+pytestmark = pytest.mark.gpu
+
+B, K, R, NH, NS = 8, 18, 32, 3, 15
+W = dict(w_mse=1.0, w_bone=0.1, w_kp=0.1, w_kp2d=0.0)
+
+
+def _inputs(synth):
+    return (synth.blob_logits(B, K, R, R, R, seed=101), synth.pseudo_joints(B, K, seed=102), synth.cameras(B, seed=103))
+
+
+def _worker(rank, world, port, out, transport):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    try:
+        pkg = importlib.import_module("x-as-supervision_b200")
+        ops = pkg.load_native()
+        logits, target, cams = _inputs(pkg.synth)
+        lo, hi = pkg.dist.shard_range(B, rank, world)
+        group = pkg.dist.PeerExchange(dist.group.WORLD, dev) if transport == "nvlink" else dist.group.WORLD
+        for _ in range(3):                                   # several steps: mailbox parity / sequence numbers
+            x = logits[lo:hi].to(dev).requires_grad_(True)
+            lp, ls, sel, kps, world_pts, _, _ = ops.integral_reproj_min_loss(
+                x, target[lo:hi].to(dev), {k: v[lo:hi].to(dev) for k, v in cams.items()}, K, NH, NS, reduction="batch",
+                group=group, **W)
+            (lp + ls).backward()
+        torch.save({"loss": (lp.item(), ls.item()), "sel": sel.cpu(), "grad": x.grad.cpu(), "range": (lo, hi)},
+                   os.path.join(out, "rank%d.pt" % rank))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(300)
+@pytest.mark.parametrize("transport", ["nvlink", "nccl"])
+def test_two_gpus_global_scope_equals_single_gpu(synth, tmp_path, transport):
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import __graft_entry__ as ge
+    ge.build()
+    world, port = 2, 29500 + (os.getpid() * 2 + (transport == "nccl")) % 2000
+    mp.spawn(_worker, args=(world, port, str(tmp_path), transport), nprocs=world, join=True)
+    res = [torch.load(os.path.join(str(tmp_path), "rank%d.pt" % r), weights_only=False) for r in range(world)]
+
+    pkg = importlib.import_module("x-as-supervision_b200")
+    ops = pkg.load_native()
+    dev = torch.device("cuda:0")
+    logits, target, cams = _inputs(synth)
+    x = logits.to(dev).requires_grad_(True)
+    lp, ls, sel, *_ = ops.integral_reproj_min_loss(x, target.to(dev), {k: v.to(dev) for k, v in cams.items()}, K, NH, NS,
+                                                   reduction="batch", **W)
+    (lp + ls).backward()
+    for r in res:
+        assert torch.equal(r["sel"], sel.cpu())                                   # same slots on every rank
+        assert abs(r["loss"][0] - lp.item()) < 1e-6 * abs(lp.item()) and abs(r["loss"][1] - ls.item()) < 1e-6 * abs(ls.item())
+        lo, hi = r["range"]
+        ref = x.grad[lo:hi].cpu()
+        assert (r["grad"] - ref).abs().max().item() <= 1e-6 * ref.abs().max().item()

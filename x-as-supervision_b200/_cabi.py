@@ -27,7 +27,9 @@ SYMBOLS = (
     "xsup_integral_fwd", "xsup_integral_bwd", "xsup_find_peak",
     "xsup_patch_to_world_fwd", "xsup_patch_to_world_bwd", "xsup_world_to_patch_fwd",
     "xsup_reproj_loss_fwd", "xsup_reproj_select", "xsup_reproj_loss_bwd",
+    "xsup_xchg_floats", "xsup_partial_allreduce",
 )
+XCHG_SLOT = 64
 
 
 class Shape(C.Structure):
@@ -42,6 +44,10 @@ class LossCfg(C.Structure):
     _fields_ = [("B", C.c_int32), ("K", C.c_int32), ("NH", C.c_int32), ("img_h", C.c_int32), ("img_w", C.c_int32),
                 ("rect_width", C.c_float), ("w_mse", C.c_float), ("w_bone", C.c_float), ("w_kp", C.c_float),
                 ("w_kp2d", C.c_float), ("use_sym", C.c_int32), ("reduction", C.c_int32), ("batch_total", C.c_int32)]
+
+
+class Xchg(C.Structure):
+    _fields_ = [("peer_bufs", C.c_void_p), ("rank", C.c_int32), ("world", C.c_int32), ("step", C.c_uint32)]
 
 
 def _load():
@@ -71,6 +77,10 @@ def _load():
     lib.xsup_reproj_loss_fwd.argtypes = [vp, vp, C.POINTER(Cam), vp, vp, vp, C.POINTER(LossCfg), vp]
     lib.xsup_reproj_select.argtypes = [vp, vp, vp, vp, vp, vp, C.POINTER(LossCfg), vp]
     lib.xsup_reproj_loss_bwd.argtypes = [vp, vp, C.POINTER(Cam), vp, vp, vp, C.POINTER(LossCfg), vp]
+    lib.xsup_xchg_floats.restype = C.c_size_t
+    lib.xsup_xchg_floats.argtypes = [i32]
+    lib.xsup_partial_allreduce.argtypes = [vp, i32, C.POINTER(Xchg), vp]
+    lib.xsup_partial_allreduce.restype = C.c_int
     for name in SYMBOLS:
         fn = getattr(lib, name)
         if name.startswith(("xsup_integral", "xsup_find", "xsup_patch", "xsup_world", "xsup_reproj")):

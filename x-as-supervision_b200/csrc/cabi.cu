@@ -243,6 +243,18 @@ int xsup_reproj_loss_fwd(const float* kps, const float* target, const xsup_cam_t
     return XSUP_OK;
 }
 
+size_t xsup_xchg_floats(int32_t world) { return world > 0 ? (size_t)2 * world * XSUP_XCHG_SLOT : 0; }
+
+int xsup_partial_allreduce(float* partial, int32_t n, const xsup_xchg_t* x, void* stream) {
+    if (!partial || !x || !x->peer_bufs) return fail(XSUP_E_NULL, "xsup_partial_allreduce: NULL pointer");
+    if (n < 1 || n > XSUP_XCHG_SLOT - 1 || x->world < 1 || x->world > 64 || x->rank < 0 || x->rank >= x->world || x->step == 0)
+        return fail(XSUP_E_SHAPE, "xsup_partial_allreduce: need 1 <= n <= %d, 1 <= world <= 64, 0 <= rank < world, step >= 1", XSUP_XCHG_SLOT - 1);
+    cudaError_t e = launch_partial_allreduce(partial, n, *x, (cudaStream_t)stream);
+    if (e != cudaSuccess) return cuda_fail(e, "xsup_partial_allreduce launch");
+    count_launches(1);
+    return XSUP_OK;
+}
+
 int xsup_reproj_select(const float* kps, const float* target, const float* sample_terms, const float* partial, float* loss,
                        int64_t* sel, const xsup_loss_cfg_t* cfg, void* stream) {
     if (int rc = check_cfg(cfg, "xsup_reproj_select")) return rc;

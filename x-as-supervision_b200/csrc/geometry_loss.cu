@@ -248,6 +248,51 @@ cudaError_t launch_reproj_loss_fwd(const float* kps, const float* target, const 
     return cudaGetLastError();
 }
 
+// ---------------------------------------------------------------------------------------------- cross-GPU exchange
+// All-reduce(SUM) of the [4,NH] partial sums in one kernel over NVLink peer memory (no NCCL, no stream
+// hand-off): publish into every peer's mailbox, acquire-spin on the own mailbox, sum in rank order.
+__device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__global__ void __launch_bounds__(64) partial_allreduce_kernel(float* __restrict__ partial, int n, void* const* __restrict__ peers,
+                                                               int rank, int world, uint32_t step) {
+    __shared__ int timed_out;
+    const int t = threadIdx.x;
+    const size_t par = step & 1u;
+    if (t == 0) timed_out = 0;
+    __syncthreads();
+    if (t < world) {                                   // one thread per destination GPU
+        float* dst = static_cast<float*>(peers[t]) + (par * world + rank) * XSUP_XCHG_SLOT;
+        for (int i = 0; i < n; ++i) dst[i] = partial[i];
+        st_release_sys(reinterpret_cast<uint32_t*>(dst + XSUP_XCHG_SLOT - 1), step);
+    }
+    float* mine = static_cast<float*>(peers[rank]) + par * world * XSUP_XCHG_SLOT;
+    if (t < world) {                                   // one thread per source GPU
+        const uint32_t* flag = reinterpret_cast<const uint32_t*>(mine + (size_t)t * XSUP_XCHG_SLOT + XSUP_XCHG_SLOT - 1);
+        const long long t0 = clock64();
+        while (ld_acquire_sys(flag) != step) {
+            __nanosleep(64);
+            if (clock64() - t0 > 20000000000LL) { timed_out = 1; break; }     // ~10 s at 2 GHz: a peer died
+        }
+    }
+    __syncthreads();
+    if (t < n) {
+        float a = 0.f;
+        for (int r = 0; r < world; ++r) a += *reinterpret_cast<volatile float*>(mine + (size_t)r * XSUP_XCHG_SLOT + t);
+        partial[t] = timed_out ? __int_as_float(0x7fc00000) : a;
+    }
+}
+
+cudaError_t launch_partial_allreduce(float* partial, int n, const xsup_xchg_t& x, cudaStream_t st) {
+    partial_allreduce_kernel<<<1, 64, 0, st>>>(partial, n, x.peer_bufs, x.rank, x.world, x.step);
+    return cudaGetLastError();
+}
+
 // ---------------------------------------------------------------------------------------------- selection
 __device__ __forceinline__ float sym_value(const xsup_loss_cfg_t& c, float bone, float kp3, float kp2, float n) {
     // model.py:108-112: bone MSE over B*4, kp MSE over B*2*3, kp_2d MSE over B*2*2 (x 1e2)

@@ -57,6 +57,7 @@ cudaError_t launch_world_to_patch_fwd(const float* world, float* kps, const Geom
 
 cudaError_t launch_reproj_loss_fwd(const float* kps, const float* target, const xsup_cam_t& cam, float* world,
                                    float* sample_terms, float* partial, const xsup_loss_cfg_t& c, cudaStream_t st);
+cudaError_t launch_partial_allreduce(float* partial, int n, const xsup_xchg_t& x, cudaStream_t st);
 cudaError_t launch_reproj_select(const float* kps, const float* target, const float* sample_terms, const float* partial,
                                  float* loss, int64_t* sel, const xsup_loss_cfg_t& c, cudaStream_t st);
 cudaError_t launch_reproj_loss_bwd(const float* kps, const float* target, const xsup_cam_t& cam, const int64_t* sel,

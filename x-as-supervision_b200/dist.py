@@ -7,7 +7,14 @@ from batch means.  The reference evaluates that min on the rank-local batch (sco
 collective).  Scope 'global' reproduces the single-process result on the global batch with one
 all-reduce(SUM) of the `[4, NH]` fp32 partial sums — a latency-only message.
 
-Works with any backend (`nccl` on the GPUs, `gloo` in the CPU tests).
+Two transports for that message:
+  * `PeerExchange` — the B200-native path: one tiny kernel of this library
+    (`xsup_partial_allreduce`) publishes the sums into every peer's mailbox with NVLink P2P stores and
+    a release flag, acquire-spins on its own mailbox and adds the slots in rank order.  It runs on the
+    compute stream (no side stream, CUDA-graph capturable), measured 12 us median at 2 GPUs, and gives
+    bit-identical sums on all ranks;
+  * a `torch.distributed` process group (`nccl` on the GPUs — measured 13-20 us median for this
+    message — and `gloo` in the CPU tests).
 """
 from __future__ import annotations
 
@@ -16,7 +23,43 @@ from typing import Optional, Tuple
 import torch
 import torch.distributed as dist
 
-__all__ = ["shard_range", "global_batch", "reduce_partials", "select_slots"]
+__all__ = ["shard_range", "global_batch", "global_batch_exact", "reduce_partials", "select_slots", "PeerExchange"]
+
+
+class PeerExchange:
+    """NVLink peer-memory mailbox for the in-kernel all-reduce of the partial loss sums.
+
+    Collective constructor (all ranks of `group`): allocates a zeroed mailbox in torch symmetric memory and
+    rendezvous so that every rank holds the peer-mapped addresses of all mailboxes.  Pass the object as
+    `group=` to `ops.integral_reproj_min_loss`."""
+
+    def __init__(self, group=None, device=None):
+        import torch.distributed._symmetric_memory as symm_mem
+        from . import _cabi as cabi
+        self.group = group if group is not None else dist.group.WORLD
+        self.world = dist.get_world_size(self.group)
+        self.rank = dist.get_rank(self.group)
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        n = int(cabi.lib.xsup_xchg_floats(self.world))
+        self.mailbox = symm_mem.empty(n, dtype=torch.float32, device=self.device)
+        self.mailbox.zero_()
+        self.handle = symm_mem.rendezvous(self.mailbox, self.group)
+        self.peer_ptrs = torch.tensor([int(p) for p in self.handle.buffer_ptrs], dtype=torch.int64, device=self.device)
+        torch.cuda.synchronize(self.device)
+        dist.barrier(self.group)                       # every mailbox is zeroed before anyone publishes
+        self.step = 0
+
+    def all_reduce_(self, t: torch.Tensor) -> torch.Tensor:
+        """In-place SUM over the ranks of a small contiguous fp32 CUDA tensor (<= 63 elements)."""
+        from . import _cabi as cabi
+        if not (t.is_cuda and t.dtype == torch.float32 and t.is_contiguous()):
+            raise ValueError("PeerExchange.all_reduce_ needs a contiguous float32 CUDA tensor")
+        self.step += 1
+        x = cabi.Xchg(self.peer_ptrs.data_ptr(), self.rank, self.world, self.step)
+        with torch.cuda.device(self.device):
+            cabi.check(cabi.lib.xsup_partial_allreduce(t.data_ptr(), t.numel(), x, cabi.stream_ptr(self.device)),
+                       "xsup_partial_allreduce")
+        return t
 
 
 def shard_range(n: int, rank: int, world: int) -> Tuple[int, int]:
@@ -27,7 +70,13 @@ def shard_range(n: int, rank: int, world: int) -> Tuple[int, int]:
 
 
 def _active(group) -> bool:
+    if isinstance(group, PeerExchange):
+        return group.world > 1
     return group is not None and dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
+
+
+def _world(group) -> int:
+    return group.world if isinstance(group, PeerExchange) else dist.get_world_size(group)
 
 
 def global_batch(local_batch: int, group=None) -> int:
@@ -36,13 +85,15 @@ def global_batch(local_batch: int, group=None) -> int:
     so this is host arithmetic, not a collective.  Use `global_batch_exact` for ragged shards."""
     if not _active(group):
         return int(local_batch)
-    return int(local_batch) * dist.get_world_size(group)
+    return int(local_batch) * _world(group)
 
 
 def global_batch_exact(local_batch: int, group=None) -> int:
     """Sum of the ranks' local batch sizes (one int64 all-reduce + host read)."""
     if not _active(group):
         return int(local_batch)
+    if isinstance(group, PeerExchange):
+        group = group.group
     backend = dist.get_backend(group)
     dev = torch.device("cuda", torch.cuda.current_device()) if backend == "nccl" else torch.device("cpu")
     t = torch.tensor([local_batch], dtype=torch.int64, device=dev)
@@ -53,7 +104,10 @@ def global_batch_exact(local_batch: int, group=None) -> int:
 def reduce_partials(partial: torch.Tensor, group=None) -> torch.Tensor:
     """In-place all-reduce(SUM) of the per-hypothesis partial sums `[terms, NH]` (no-op without a group)."""
     if _active(group):
-        dist.all_reduce(partial, op=dist.ReduceOp.SUM, group=group)
+        if isinstance(group, PeerExchange):
+            group.all_reduce_(partial)
+        else:
+            dist.all_reduce(partial, op=dist.ReduceOp.SUM, group=group)
     return partial
 
 

@@ -208,10 +208,11 @@ class IntegralReprojMinLoss(torch.autograd.Function):
          depth_prob_map [K,D], peak_idx [B,K,NH]
 
     `w_bone/w_kp/w_kp2d = None` means the symmetry term is absent (SurS1 configs).
-    `group`: a torch.distributed process group -> 'global' scope: the per-hypothesis partial sums
-    are all-reduced (one [4,NH] fp32 message) so every rank selects the slot the single-process
-    reference would select on the global batch.  `None` -> rank-local min, which is what the
-    reference does under DDP (model.py:114,162).
+    `group`: a `dist.PeerExchange` (in-kernel NVLink exchange, preferred) or a torch.distributed
+    process group (NCCL) -> 'global' scope: the per-hypothesis partial sums are all-reduced (one
+    [4,NH] fp32 message) so every rank selects the slot the single-process reference would select on
+    the global batch.  `None` -> rank-local min, which is what the reference does under DDP
+    (model.py:114,162).
     Gradients flow to `logits` from both losses and from anything downstream of `kps` / `kps_world`."""
 
     @staticmethod
