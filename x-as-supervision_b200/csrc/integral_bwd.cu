@@ -163,22 +163,25 @@ __global__ void __launch_bounds__(kBwdThreads, 1) integral_bwd_kernel(const BwdP
                 __syncwarp();
                 if (lane == 0) mbar_arrive(empty0 + 8u * slot);
 
+                constexpr int P = Vec<T>::P;
                 const float nlse = -__uint_as_float(c4.x), a = __uint_as_float(c4.y), bb = __uint_as_float(c4.z);
                 const float base = cd + __uint_as_float(c4.w);
                 const float wrel = (float)w0 - __uint_as_float(c5.x);
-                float aw[VEC];
+                f32x2 aw[P];                                       // a*(w - wc) for this lane's columns, as pairs
 #pragma unroll
-                for (int v = 0; v < VEC; ++v) aw[v] = a * (wrel + (float)v);
+                for (int v = 0; v < P; ++v) aw[v] = pk2(a * (wrel + (float)(2 * v)), a * (wrel + (float)(2 * v + 1)));
+                const f32x2 l2e2 = pk2(kLog2e, kLog2e), nlse2 = pk2(nlse, nlse);
                 float hf = (float)(part * t.rows_per_task + lr) - __uint_as_float(c5.y);
                 uint8_t* out = static_cast<uint8_t*>(p.g_logits) + (size_t)unit * (size_t)t.unit_bytes + (size_t)task * t.task_bytes + lane * 16u;
 #pragma unroll
                 for (int i = 0; i < U; ++i) {
-                    float f[VEC];
-                    Vec<T>::unpack(raw[i], f);
+                    f32x2 x[P];
+                    Vec<T>::unpack2(raw[i], x);
                     const float rowv = fmaf(bb, hf, base);
+                    const f32x2 rowv2 = pk2(rowv, rowv);
 #pragma unroll
-                    for (int v = 0; v < VEC; ++v) f[v] = ex2(fmaf(f[v], kLog2e, nlse)) * (aw[v] + rowv);
-                    *reinterpret_cast<uint4*>(out + i * 512u) = Vec<T>::pack(f);
+                    for (int v = 0; v < P; ++v) x[v] = fmul2(ex2_2(ffma2(x[v], l2e2, nlse2)), fadd2(aw[v], rowv2));
+                    *reinterpret_cast<uint4*>(out + i * 512u) = Vec<T>::pack2(x);
                     hf += rpi;
                 }
             } else {

@@ -245,10 +245,12 @@ __global__ void __launch_bounds__(kFwdThreads, 1) integral_fwd_kernel(const FwdP
         const uint32_t ring0 = smem_u32(ring);
         int it = 0;                                                  // units this warp has flushed
         bool fresh = true;                                           // first stage of a unit: claim the partial buffer
+        constexpr int P = Vec<T>::P;
         float m_ref = kNegHuge, sy = 0.f, sr = 0.f;
-        float acc[VEC];
+        f32x2 acc[P];                                                // column accumulators, as fp32 pairs
 #pragma unroll
-        for (int v = 0; v < VEC; ++v) acc[v] = 0.f;
+        for (int v = 0; v < P; ++v) acc[v] = pk2(0.f, 0.f);
+        const f32x2 l2e2 = pk2(kLog2e, kLog2e);
 
         for (int s = g;; s += kGroups) {
             const int slot = s % nst;
@@ -269,19 +271,12 @@ __global__ void __launch_bounds__(kFwdThreads, 1) integral_fwd_kernel(const FwdP
                 __syncwarp();
                 if (lane == 0) mbar_arrive(empty0 + 8u * slot);   // data is in registers: free the slot early
 
-                float lmax = kNegHuge;
-#pragma unroll
-                for (int i = 0; i < U; ++i) {
-                    float f[VEC];
-                    Vec<T>::unpack(raw[i], f);
-#pragma unroll
-                    for (int v = 0; v < VEC; ++v) lmax = fmaxf(lmax, f[v]);
-                }
-                const float mt = warp_max(lmax) * kLog2e;
+                const float mt = warp_max(Vec<T>::template vmax<U>(raw)) * kLog2e;
                 if (mt > m_ref) {                                 // warp-uniform, rare after the first tasks
                     const float sc = ex2(m_ref - mt);
+                    const f32x2 sc2 = pk2(sc, sc);
 #pragma unroll
-                    for (int v = 0; v < VEC; ++v) acc[v] *= sc;
+                    for (int v = 0; v < P; ++v) acc[v] = fmul2(acc[v], sc2);
                     sy *= sc;
                     sr *= sc;
                     m_ref = mt;
@@ -289,18 +284,22 @@ __global__ void __launch_bounds__(kFwdThreads, 1) integral_fwd_kernel(const FwdP
                 const int d = task / t.parts, part = task - d * t.parts;
                 float hf = (float)(part * t.rows_per_task + lr);
                 float tsum = 0.f;
-                const float nm = -m_ref;
+                const f32x2 nm2 = pk2(-m_ref, -m_ref);
 #pragma unroll
                 for (int i = 0; i < U; ++i) {
-                    float f[VEC];
-                    Vec<T>::unpack(raw[i], f);
-                    float r = 0.f;
+                    f32x2 x[P];
+                    Vec<T>::unpack2(raw[i], x);
 #pragma unroll
-                    for (int v = 0; v < VEC; ++v) {
-                        const float e = ex2(fmaf(f[v], kLog2e, nm));
-                        acc[v] += e;
-                        r += e;
+                    for (int v = 0; v < P; ++v) {
+                        x[v] = ex2_2(ffma2(x[v], l2e2, nm2));     // e = 2^(l*log2e - m_ref)
+                        acc[v] = fadd2(acc[v], x[v]);
                     }
+                    f32x2 rs = fadd2(x[0], x[1]);
+#pragma unroll
+                    for (int v = 2; v < P; ++v) rs = fadd2(rs, x[v]);
+                    float r0, r1;
+                    upk2(rs, r0, r1);
+                    const float r = r0 + r1;                      // sum of this row fragment
                     tsum += r;
                     sy = fmaf(hf, r, sy);
                     hf += rpi;
@@ -316,10 +315,13 @@ __global__ void __launch_bounds__(kFwdThreads, 1) integral_fwd_kernel(const FwdP
                 // this warp's last stage of the unit: hand its partials to the finaliser
                 float sx = 0.f, sa = 0.f;
 #pragma unroll
-                for (int v = 0; v < VEC; ++v) {
-                    sx = fmaf((float)(w0 + v), acc[v], sx);
-                    sa += acc[v];
-                    acc[v] = 0.f;
+                for (int v = 0; v < P; ++v) {
+                    float a0, a1;
+                    upk2(acc[v], a0, a1);
+                    sx = fmaf((float)(w0 + 2 * v), a0, sx);
+                    sx = fmaf((float)(w0 + 2 * v + 1), a1, sx);
+                    sa += a0 + a1;
+                    acc[v] = pk2(0.f, 0.f);
                 }
                 sx = warp_sum(sx);
                 sa = warp_sum(sa);

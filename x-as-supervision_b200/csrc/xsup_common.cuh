@@ -95,43 +95,107 @@ __device__ __forceinline__ uint4 ldg128_stream(const void* p) {
     return v;
 }
 
-// ------------------------------------------------------------------ 16-byte vector <-> fp32 lanes
+// ------------------------------------------------------------------ packed fp32x2 arithmetic (sm_100: FFMA2 / FADD2 / FMUL2)
+// Two independent round-to-nearest fp32 operations per instruction: same results as the scalar forms,
+// half the issue slots.  A pair lives in one 64-bit register (even/odd 32-bit register pair).
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pk2(float lo, float hi) {
+    f32x2 r;
+    asm("mov.b64 %0, {%1,%2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ f32x2 pk2u(uint32_t lo, uint32_t hi) {
+    f32x2 r;
+    asm("mov.b64 %0, {%1,%2};" : "=l"(r) : "r"(lo), "r"(hi));
+    return r;
+}
+__device__ __forceinline__ void upk2(f32x2 v, float& lo, float& hi) {
+    asm("mov.b64 {%0,%1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ f32x2 ffma2(f32x2 a, f32x2 b, f32x2 c) {
+    f32x2 d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+__device__ __forceinline__ f32x2 fadd2(f32x2 a, f32x2 b) {
+    f32x2 d;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ f32x2 fmul2(f32x2 a, f32x2 b) {
+    f32x2 d;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ f32x2 ex2_2(f32x2 a) {                 // MUFU has no packed form
+    float lo, hi;
+    upk2(a, lo, hi);
+    return pk2(ex2(lo), ex2(hi));
+}
+
+// ------------------------------------------------------------------ 16-byte vector <-> fp32 pairs
 template <typename T>
 struct Vec;
 template <>
 struct Vec<float> {
-    static constexpr int N = 4;
-    __device__ __forceinline__ static void unpack(const uint4& u, float (&f)[4]) {
-        f[0] = __uint_as_float(u.x);
-        f[1] = __uint_as_float(u.y);
-        f[2] = __uint_as_float(u.z);
-        f[3] = __uint_as_float(u.w);
+    static constexpr int N = 4;       // elements per 16-byte vector
+    static constexpr int P = 2;       // fp32 pairs per vector
+    __device__ __forceinline__ static void unpack2(const uint4& u, f32x2 (&x)[2]) {
+        x[0] = pk2u(u.x, u.y);
+        x[1] = pk2u(u.z, u.w);
     }
-    __device__ __forceinline__ static uint4 pack(const float (&f)[4]) {
-        return make_uint4(__float_as_uint(f[0]), __float_as_uint(f[1]), __float_as_uint(f[2]), __float_as_uint(f[3]));
+    __device__ __forceinline__ static uint4 pack2(const f32x2 (&x)[2]) {
+        uint4 u;
+        asm("mov.b64 {%0,%1}, %2;" : "=r"(u.x), "=r"(u.y) : "l"(x[0]));
+        asm("mov.b64 {%0,%1}, %2;" : "=r"(u.z), "=r"(u.w) : "l"(x[1]));
+        return u;
+    }
+    // lane-local max of U vectors
+    template <int U>
+    __device__ __forceinline__ static float vmax(const uint4 (&raw)[U]) {
+        float m = kNegHuge;
+#pragma unroll
+        for (int i = 0; i < U; ++i) {
+            m = fmaxf(m, fmaxf(__uint_as_float(raw[i].x), __uint_as_float(raw[i].y)));
+            m = fmaxf(m, fmaxf(__uint_as_float(raw[i].z), __uint_as_float(raw[i].w)));
+        }
+        return m;
     }
 };
 template <>
 struct Vec<__nv_bfloat16> {
     static constexpr int N = 8;
-    __device__ __forceinline__ static void unpack(const uint4& u, float (&f)[8]) {
-        // bf16 -> fp32 is a 16-bit left shift; element 2i is the low half of word i
-        f[0] = __uint_as_float(u.x << 16);
-        f[1] = __uint_as_float(u.x & 0xffff0000u);
-        f[2] = __uint_as_float(u.y << 16);
-        f[3] = __uint_as_float(u.y & 0xffff0000u);
-        f[4] = __uint_as_float(u.z << 16);
-        f[5] = __uint_as_float(u.z & 0xffff0000u);
-        f[6] = __uint_as_float(u.w << 16);
-        f[7] = __uint_as_float(u.w & 0xffff0000u);
+    static constexpr int P = 4;
+    // bf16 -> fp32 is a 16-bit left shift; element 2i is the low half of word i
+    __device__ __forceinline__ static f32x2 widen(uint32_t w) { return pk2u(w << 16, w & 0xffff0000u); }
+    __device__ __forceinline__ static void unpack2(const uint4& u, f32x2 (&x)[4]) {
+        x[0] = widen(u.x);
+        x[1] = widen(u.y);
+        x[2] = widen(u.z);
+        x[3] = widen(u.w);
     }
-    __device__ __forceinline__ static uint32_t pack2(float lo, float hi) {
+    __device__ __forceinline__ static uint32_t narrow(f32x2 v) {
+        float lo, hi;
+        upk2(v, lo, hi);
         uint32_t r;
         asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
         return r;
     }
-    __device__ __forceinline__ static uint4 pack(const float (&f)[8]) {
-        return make_uint4(pack2(f[0], f[1]), pack2(f[2], f[3]), pack2(f[4], f[5]), pack2(f[6], f[7]));
+    __device__ __forceinline__ static uint4 pack2(const f32x2 (&x)[4]) {
+        return make_uint4(narrow(x[0]), narrow(x[1]), narrow(x[2]), narrow(x[3]));
+    }
+    // max on the packed bf16 pairs (HMNMX2.BF16_V2): no widening needed for the max pass
+    template <int U>
+    __device__ __forceinline__ static float vmax(const uint4 (&raw)[U]) {
+        uint32_t m = 0xff7fff7fu;     // (-bf16 max, -bf16 max)
+#pragma unroll
+        for (int i = 0; i < U; ++i) {
+            asm("max.bf16x2 %0, %0, %1;" : "+r"(m) : "r"(raw[i].x));
+            asm("max.bf16x2 %0, %0, %1;" : "+r"(m) : "r"(raw[i].y));
+            asm("max.bf16x2 %0, %0, %1;" : "+r"(m) : "r"(raw[i].z));
+            asm("max.bf16x2 %0, %0, %1;" : "+r"(m) : "r"(raw[i].w));
+        }
+        return fmaxf(__uint_as_float(m << 16), __uint_as_float(m & 0xffff0000u));
     }
 };
 
