@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define XSUP_ABI_VERSION 1
+#define XSUP_ABI_VERSION 2
 
 enum { XSUP_F32 = 0, XSUP_BF16 = 1 };
 enum { XSUP_HEAD_MULTI = 0, XSUP_HEAD_SINGLE = 1 };
@@ -160,6 +160,71 @@ int xsup_reproj_select(const float* kps, const float* target, const float* sampl
  * receive gradient (torch.min semantics; exact ties resolve to the lowest slot).              */
 int xsup_reproj_loss_bwd(const float* kps, const float* target, const xsup_cam_t* cam, const int64_t* sel,
                          const float* g_loss, float* g_kps, const xsup_loss_cfg_t* cfg, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Skeleton rasteriser + mask-reconstruction loss.
+ *
+ * Lines run from joint child[l] (start) to joint parent[l] (end), as built by cal_links
+ * (modules/model.py:8-22).  `kps` holds the 2-D patch coordinates in [-1,1]: element (b, j) is at
+ * kps[b*kp_batch_stride + j*kp_joint_stride + {0,1}], so the reference's strided view
+ * kps_ori[cam][:, 0, :, :2] of the [B,NH,K,3] head output (model.py:91) is passed without a copy
+ * (kp_batch_stride = NH*K*3, kp_joint_stride = 3). */
+#define XSUP_MAX_LINES 32
+typedef struct {
+    int32_t B, K;              /* samples, joints */
+    int32_t S;                 /* image_size: the heat-maps are S x S (x['{cam}_img'].shape[-1]); S % 4 == 0 */
+    int32_t L;                 /* number of lines, 1..XSUP_MAX_LINES; L >= 21 halves the width of lines 11,12,14,15 (util.py:50-53) */
+    int32_t kp_batch_stride, kp_joint_stride;
+    float body_width;          /* cfg body_width * 1e-3 (model.py:31-32) */
+    int32_t parent[XSUP_MAX_LINES];
+    int32_t child[XSUP_MAX_LINES];
+} xsup_skel_t;
+
+/* compute_mask_reconstruction_loss (modules/base_losses/loss_func.py:4-16) over n = numel(mask) elements:
+ *   XSUP_MASK_MSE        weight=None, use_clip=False : mean((m-gt)^2)
+ *   XSUP_MASK_CLIP_MEAN  weight=None, use_clip=True  : the reference returns the TENSOR mean((m-gt)^2) * (m>0.1),
+ *                        which the trainer reduces with .mean() (train.py:182); this mode is that mean
+ *   XSUP_MASK_WEIGHTED   weight given               : mean((m-gt)^2 * [m>0.1 if use_clip] * weight)          */
+enum { XSUP_MASK_MSE = 0, XSUP_MASK_CLIP_MEAN = 1, XSUP_MASK_WEIGHTED = 2 };
+typedef struct {
+    int64_t n;
+    int32_t mode;
+    int32_t use_clip;          /* XSUP_MASK_WEIGHTED only; CLIP_MEAN implies the filter, MSE ignores it */
+} xsup_mask_loss_t;
+#define XSUP_MASK_SUMS 4      /* loss_sums: sum (m-gt)^2, sum filter, sum (m-gt)^2*filter*weight, loss */
+
+/* floats of scratch the calls below need (per-CTA partial sums; nothing is kept between calls) */
+size_t xsup_skel_ws_floats(const xsup_skel_t* s);
+size_t xsup_draw_lines_ws_floats(const xsup_skel_t* s);
+size_t xsup_mask_loss_ws_floats(int64_t n);
+
+/* Replaces draw_lines (modules/util.py:21-59): heat [B,L,S,S] fp32 = exp(-c_l * dist^2(pixel, segment l) / body_width).
+ * `_bwd`: g_kps [B,K,2] (contiguous) = vector-Jacobian product with g_heat [B,L,S,S]. */
+int xsup_draw_lines_fwd(const float* kps, const xsup_skel_t* s, float* heat, void* stream);
+int xsup_draw_lines_bwd(const float* kps, const xsup_skel_t* s, const float* heat, const float* g_heat, float* g_kps,
+                        float* ws, void* stream);
+
+/* Replaces draw_lines + torch.max(heatmaps, dim=1, keepdim=True)[0] (modules/model.py:91-96) without
+ * materialising the L heat-maps, optionally fused with compute_mask_reconstruction_loss of the result
+ * against `gt` / `weight` [B,1,S,S] (model.py:185-188).
+ *   recon     [B,1,S,S] fp32 out
+ *   line_idx  [B,S,S]   uint8 out: winning line per pixel (lowest index on exact ties), consumed by _bwd
+ *   loss      NULL -> no loss (gt, weight, loss_sums ignored); else loss_sums[XSUP_MASK_SUMS] out
+ * `_bwd`: g_kps [B,K,2] = d( <g_recon, recon> + g_loss * loss ) / d kps; g_recon may be NULL (no other consumer
+ * of recon), loss may be NULL (then gt, weight, loss_sums, g_loss are ignored); g_loss is a DEVICE scalar. */
+int xsup_skeleton_mask_fwd(const float* kps, const xsup_skel_t* s, float* recon, uint8_t* line_idx, const float* gt,
+                           const float* weight, const xsup_mask_loss_t* loss, float* loss_sums, float* ws, void* stream);
+int xsup_skeleton_mask_bwd(const float* kps, const xsup_skel_t* s, const float* recon, const uint8_t* line_idx,
+                           const float* g_recon, const float* gt, const float* weight, const xsup_mask_loss_t* loss,
+                           const float* loss_sums, const float* g_loss, float* g_kps, float* ws, void* stream);
+
+/* compute_mask_reconstruction_loss on an arbitrary mask tensor (the physique network's output, model.py:176).
+ * filter_out (nullable): the (m > 0.1) map as floats, for callers that need the reference's tensor-valued result.
+ * `_bwd`: g_mask[n] = g_loss * d loss / d mask. */
+int xsup_mask_loss_fwd(const float* mask, const float* gt, const float* weight, float* filter_out,
+                       const xsup_mask_loss_t* cfg, float* loss_sums, float* ws, void* stream);
+int xsup_mask_loss_bwd(const float* mask, const float* gt, const float* weight, const xsup_mask_loss_t* cfg,
+                       const float* loss_sums, const float* g_loss, float* g_mask, void* stream);
 
 #ifdef __cplusplus
 }

@@ -337,3 +337,81 @@ def best_hypothesis(kps, gt):
     idx = (kps - gt[:, None]).pow(2).sum(-1).argmin(dim=1)             # [B,K]
     best = torch.gather(kps, 1, idx[:, None, :, None].expand(-1, -1, -1, kps.shape[-1])).squeeze(1)
     return idx, best
+
+
+# --------------------------------------------------------------------------- skeleton rasteriser + mask loss
+ARM_LINES = (11, 12, 14, 15)      # util.py:53: lines drawn with half the body width when there are >= 21 of them
+
+
+def skeleton_links(parent_ids: Sequence[int], line_select_ids: Optional[Sequence[int]] = None,
+                   use_root: bool = False, extension: bool = True):
+    """cal_links (model.py:8-22): (parent, child) joint pairs of the drawn lines; the eight
+    extension links are the torso/limb cross braces appended at model.py:19-20."""
+    parent_ids = list(parent_ids)
+    if use_root:
+        child = list(range(len(parent_ids)))
+        parent = parent_ids
+    else:
+        child = list(range(1, len(parent_ids)))
+        parent = parent_ids[1:]
+    if line_select_ids is None:
+        line_select_ids = range(len(parent))
+    parent = [parent[i] for i in line_select_ids]
+    child = [child[i] for i in line_select_ids]
+    if extension:
+        parent += [7, 7, 7, 7, 0, 0, 1, 4]
+        child += [1, 4, 11, 14, 2, 5, 14, 11]
+    return parent, child
+
+
+def pixel_grid(size: int, dtype) -> torch.Tensor:
+    """make_coordinate_grid (util.py:3-19) flattened to `[size*size, 2]`, x fastest."""
+    c = 2 * (torch.arange(size).to(dtype) / (size - 1)) - 1
+    return torch.stack((c.repeat(size), c.repeat_interleave(size)), dim=-1)
+
+
+def segment_sqdist(kp2d: torch.Tensor, size: int, parent_ids, child_ids) -> torch.Tensor:
+    """Squared distance of every pixel centre to every line segment, `[B, L, size*size]`
+    (util.py:34-47).  The segment runs from the child joint (`start`) to the parent joint (`end`)."""
+    s = kp2d[:, list(child_ids), :]                       # [B,L,2]
+    e = kp2d[:, list(parent_ids), :]
+    d = e - s
+    g = pixel_grid(size, kp2d.dtype).to(kp2d.device)      # [P,2]
+    a = g[None, None] - s[:, :, None]                     # [B,L,P,2]
+    t = (a * d[:, :, None]).sum(-1) / (1e-8 + (d * d).sum(-1, keepdim=True))
+    to_end = g[None, None] - e[:, :, None]
+    foot = g[None, None] - (s[:, :, None] + t[..., None] * d[:, :, None])
+    zero = torch.zeros((), dtype=kp2d.dtype)
+    q = torch.where(t <= 0, (a * a).sum(-1), zero) + torch.where(t >= 1, (to_end * to_end).sum(-1), zero) \
+        + torch.where((t > 0) & (t < 1), (foot * foot).sum(-1), zero)
+    return q
+
+
+def draw_lines(kp2d: torch.Tensor, size: int, parent_ids, child_ids, body_width: float) -> torch.Tensor:
+    """draw_lines (util.py:21-59): Gaussian-profile line heat-maps `[B, L, size, size]`."""
+    B = kp2d.shape[0]
+    u = -segment_sqdist(kp2d, size, parent_ids, child_ids) / body_width
+    if u.shape[1] >= 21:
+        scale = torch.ones(u.shape[1], dtype=u.dtype)
+        scale[list(ARM_LINES)] = 2
+        u = u * scale[None, :, None]
+    return torch.exp(u).reshape(B, -1, size, size)
+
+
+def skeleton_mask(kp2d, size, parent_ids, child_ids, body_width):
+    """model.py:91-94: channel-max of the line heat-maps, `[B, 1, size, size]`."""
+    return draw_lines(kp2d, size, parent_ids, child_ids, body_width).max(dim=1, keepdim=True)[0]
+
+
+def mask_recon_loss(mask, gt, weight=None, use_clip=False):
+    """compute_mask_reconstruction_loss (loss_func.py:4-16).  Note the reference's asymmetry: without a
+    weight map the MSE is reduced to a scalar *before* the clip filter multiplies it, so with
+    `use_clip` and no weight the result is a tensor shaped like `mask` (the trainer `.mean()`s it,
+    train.py:182)."""
+    sq = (mask - gt) ** 2
+    loss = sq.mean() if weight is None else sq
+    if use_clip:
+        loss = loss * (mask > 0.1).to(mask.dtype)
+    if weight is not None:
+        loss = (loss * weight).mean()
+    return loss

@@ -198,10 +198,58 @@ def loss_case(multi, util, lf, name, gen, B, K, R, NH, NS, seed, weights, grad_s
     print("wrote", name, "loss", out["loss_f64"], "pseudo_h", out["pseudo_h_f64"], "sym_h", out["sym_h_f64"])
 
 
+LOSS_VARIANTS = (("mse", False, False), ("clip", False, True), ("w", True, False), ("wclip", True, True))
+
+
+def skeleton_case(util, lf, model, name, B, K, S, seed, extension, sub):
+    """draw_lines (util.py:21-59) -> channel max (model.py:94) -> compute_mask_reconstruction_loss
+    (loss_func.py:4-16) in its four (weight, use_clip) variants, reduced with .mean() as train.py:182 does,
+    fwd + bwd to the 2-D keypoints; plus the VJP of the max-map and of the un-maxed heat-maps with seeded
+    cotangents."""
+    parent, child = model.cal_links(list(synth.H36M_PARENTS), line_select_ids=list(synth.LINE_SELECT), use_root=False,
+                                    extension=extension)
+    pose = synth.skeleton_pose2d(B, K, seed=seed)
+    gt = synth.silhouette_mask(synth.skeleton_pose2d(B, K, seed=seed + 1, jitter=0.03), S)
+    wmap = synth.geodesic_weight(gt, seed=seed + 2)
+    gen = torch.Generator().manual_seed(300 + seed)
+    G = torch.randn(B, 1, S, S, generator=gen, dtype=torch.float64)
+    GH = torch.randn(B, len(parent), S, S, generator=gen, dtype=torch.float64)
+    out = {"meta": np.array([B, K, S, seed, int(extension), sub, len(parent)]), "parent": np.array(parent), "child": np.array(child),
+           "in_checksum": checksum(pose), "gt_checksum": checksum(gt), "w_checksum": checksum(wmap)}
+    for tag, dt in (("f32", torch.float32), ("f64", torch.float64)):
+        def go():
+            kp = pose.to(dt).clone().requires_grad_(True)
+            heat = util.draw_lines(kp, S, parent, child, synth.BODY_WIDTH)
+            recon = torch.max(heat.clone(), dim=1, keepdim=True)[0]
+            res = {"heat_sub": heat.detach()[:, :, ::sub, ::sub], "recon": recon.detach()}
+            res["g_recon"], = torch.autograd.grad((recon * G.to(dt)).sum(), kp, retain_graph=True)
+            res["g_heat"], = torch.autograd.grad((heat * GH.to(dt)).sum(), kp, retain_graph=True)
+            for vname, use_w, clip in LOSS_VARIANTS:
+                loss = lf.compute_mask_reconstruction_loss(recon, gt.to(dt), weight=wmap.to(dt) if use_w else None, use_clip=clip)
+                res["loss_shape_" + vname] = torch.tensor(list(loss.shape) or [0])
+                res["loss_" + vname] = loss.mean().detach()
+                res["g_loss_" + vname], = torch.autograd.grad(loss.mean(), kp, retain_graph=True)
+            return res
+        for k, v in run_in(dt, go).items():
+            out[k + "_" + tag] = v.numpy()
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
+    print("wrote", name, {k: float(out["loss_%s_f64" % k]) for k, _, _ in LOSS_VARIANTS}, "lines", len(parent))
+
+
 def main():
     torch.manual_seed(0)
     torch.set_num_threads(8)
     multi, single, util, lf = load_reference()
+    model = importlib.import_module("modules.model")
+    if "--only-skeleton" not in sys.argv:
+        main_head_and_loss(multi, single, util, lf)
+    # skeleton rasteriser + mask loss: 25 lines (17 tree links + 8 braces, arm lines at half width) and the
+    # 17-line variant without the braces (below the 21-line threshold of util.py:50)
+    skeleton_case(util, lf, model, "skel_h36m_s128", B=2, K=18, S=128, seed=30, extension=True, sub=8)
+    skeleton_case(util, lf, model, "skel_l17_s64", B=3, K=18, S=64, seed=33, extension=False, sub=4)
+
+
+def main_head_and_loss(multi, single, util, lf):
     head_case(multi, "head_iid_k18_r16", synth.iid_logits, B=2, K=18, R=16, NH=3, NS=5, seed=0, grad_stride=7)
     head_case(multi, "head_blob_k17_r32", synth.blob_logits, B=2, K=17, R=32, NH=3, NS=15, seed=1, grad_stride=61)
     head_case(multi, "head_blob_k18_r64", synth.blob_logits, B=1, K=18, R=64, NH=3, NS=15, seed=4, grad_stride=997)

@@ -26,7 +26,7 @@ def test_library_exports_every_declared_symbol(cabi):
     assert declared == set(cabi.SYMBOLS)
     for name in declared:
         assert hasattr(cabi.lib, name), name
-    assert cabi.lib.xsup_abi_version() == 1
+    assert cabi.lib.xsup_abi_version() == cabi.ABI_VERSION == 2
 
 
 def test_struct_layouts_match_header(cabi):
@@ -34,6 +34,42 @@ def test_struct_layouts_match_header(cabi):
     assert C.sizeof(cabi.Cam) == 5 * C.sizeof(C.c_void_p)
     assert C.sizeof(cabi.LossCfg) == 13 * 4
     assert C.sizeof(cabi.Xchg) == 24 and cabi.lib.xsup_xchg_floats(8) == 2 * 8 * 64
+
+
+def test_skeleton_structs_and_validation(cabi):
+    assert C.sizeof(cabi.Skel) == (7 + 2 * cabi.MAX_LINES) * 4
+    assert C.sizeof(cabi.MaskLoss) == 16
+    buf = (C.c_float * 64)()
+    p = (C.addressof(buf) + 15) // 16 * 16
+
+    def skel(**kw):
+        f = dict(B=2, K=18, S=256, L=25, bs=36, js=2, bw=0.003)
+        f.update(kw)
+        s = cabi.Skel(f["B"], f["K"], f["S"], f["L"], f["bs"], f["js"], f["bw"])
+        for i in range(min(f["L"], cabi.MAX_LINES)):
+            s.parent[i], s.child[i] = i % f["K"], (i + 1) % f["K"]
+        return s
+    s = skel()
+    # 256x256: 16x32 tiles of 16x8 pixels, 64 tiles per CTA -> 8 CTAs per sample, (32 lines x 4 + 4) floats each
+    assert cabi.lib.xsup_skel_ws_floats(s) == 2 * 8 * (32 * 4 + 4)
+    assert cabi.lib.xsup_draw_lines_ws_floats(s) == 2 * 64 * 32 * 4
+    assert cabi.lib.xsup_mask_loss_ws_floats(2 * 256 * 256) == 128 * 4
+    assert cabi.lib.xsup_draw_lines_fwd(p, skel(S=250), p, None) == -1          # S % 4
+    assert cabi.lib.xsup_draw_lines_fwd(p, skel(L=33), p, None) == -1           # too many lines
+    assert cabi.lib.xsup_draw_lines_fwd(p, skel(L=0), p, None) == -1
+    assert cabi.lib.xsup_draw_lines_fwd(p, skel(bw=0.0), p, None) == -1
+    assert cabi.lib.xsup_draw_lines_fwd(p, skel(js=1), p, None) == -1           # x and y of one joint must be adjacent
+    bad = skel()
+    bad.parent[3] = 18
+    assert cabi.lib.xsup_draw_lines_fwd(p, bad, p, None) == -1                  # joint index outside [0, K)
+    assert cabi.lib.xsup_draw_lines_fwd(None, s, p, None) == -3
+    assert cabi.lib.xsup_draw_lines_fwd(p, s, p + 4, None) == -2
+    assert cabi.lib.xsup_skeleton_mask_fwd(p, s, p, p, p, None, cabi.MaskLoss(7, 0, 0), p, p, None) == -1     # n != B*S*S
+    assert cabi.lib.xsup_skeleton_mask_fwd(p, s, p, p, p, None, cabi.MaskLoss(2 * 256 * 256, 2, 1), p, p, None) == -3   # weighted, no map
+    assert cabi.lib.xsup_skeleton_mask_fwd(p, s, p, p, p, None, cabi.MaskLoss(2 * 256 * 256, 5, 0), p, p, None) == -1   # unknown mode
+    assert cabi.lib.xsup_mask_loss_fwd(p, p, None, None, cabi.MaskLoss(0, 0, 0), p, p, None) == -1            # empty mask
+    assert cabi.lib.xsup_mask_loss_fwd(p, p, None, None, cabi.MaskLoss(64, 2, 0), p, p, None) == -3
+    assert cabi.lib.xsup_skeleton_mask_fwd(p, skel(B=0), None, None, None, None, None, None, None, None) == 0  # empty batch: no-op
 
 
 def test_strides(cabi):
@@ -91,6 +127,22 @@ def test_no_cpu_fallback(cabi):
         ops.integral_multi_head(torch.zeros(1, 18 * 16, 16, 16), 18, 3, 5)
     with pytest.raises(RuntimeError, match="no CPU path"):
         ops.find_peak(torch.rand(2, 3, 16), 3)
+    sk = importlib.import_module("x-as-supervision_b200.skeleton")
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        sk.skeleton_mask(torch.zeros(1, 18, 2), 64, [0, 1], [1, 2], 0.003)
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        sk.compute_mask_reconstruction_loss(torch.zeros(1, 1, 8, 8), torch.zeros(1, 1, 8, 8))
+
+
+def test_cal_links_matches_the_reference_tables(cabi):
+    sk = importlib.import_module("x-as-supervision_b200.skeleton")
+    synth = importlib.import_module("x-as-supervision_b200.synth")
+    parent, child = sk.cal_links(synth.H36M_PARENTS, synth.LINE_SELECT)
+    # model.py:8-22 on config/HM36_Multi_SurS1.yaml:56,60: 17 tree links then the 8 braces of model.py:19-20
+    assert child[:17] == list(range(1, 18)) and parent[:17] == list(synth.H36M_PARENTS[1:])
+    assert parent[17:] == [7, 7, 7, 7, 0, 0, 1, 4] and child[17:] == [1, 4, 11, 14, 2, 5, 14, 11]
+    p2, c2 = sk.cal_links(synth.H36M_PARENTS, [0, 2], use_root=True, extension=False)
+    assert (p2, c2) == ([0, 1], [0, 2])
 
 
 def test_product_never_imports_oracle():

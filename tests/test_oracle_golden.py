@@ -137,3 +137,50 @@ def test_filler_slots_are_deterministic(oracle):
     assert idx.tolist() == [[[2, 6, 1, 3]]]
     flat = torch.full((1, 1, 8), 0.125, dtype=torch.float64)          # plateau: every interior bin is a peak
     assert oracle.depth_peaks(flat, 3).tolist() == [[[1, 2, 3]]]
+
+
+# --------------------------------------------------------------------------- skeleton rasteriser + mask loss
+SKEL_VARIANTS = (("mse", False, False), ("clip", False, True), ("w", True, False), ("wclip", True, True))
+
+
+def skeleton_inputs(synth, g):
+    B, K, S, seed = (int(v) for v in g["meta"][:4])
+    pose = synth.skeleton_pose2d(B, K, seed=seed)
+    gt = synth.silhouette_mask(synth.skeleton_pose2d(B, K, seed=seed + 1, jitter=0.03), S)
+    wmap = synth.geodesic_weight(gt, seed=seed + 2)
+    np.testing.assert_allclose(input_checksum(pose), g["in_checksum"], rtol=1e-12)
+    np.testing.assert_allclose(input_checksum(gt), g["gt_checksum"], rtol=1e-12)
+    np.testing.assert_allclose(input_checksum(wmap), g["w_checksum"], rtol=1e-12)
+    gen = torch.Generator().manual_seed(300 + seed)
+    G = torch.randn(B, 1, S, S, generator=gen, dtype=torch.float64)
+    GH = torch.randn(B, int(g["meta"][6]), S, S, generator=gen, dtype=torch.float64)
+    return pose, gt, wmap, G, GH, S
+
+
+@pytest.mark.parametrize("name", ["skel_h36m_s128", "skel_l17_s64"])
+@pytest.mark.parametrize("tag,dtype,tol", [("f64", torch.float64, 1e-11), ("f32", torch.float32, 2e-5)])
+def test_skeleton_rasteriser_matches_reference(oracle, synth, name, tag, dtype, tol):
+    g = load_golden(name)
+    pose, gt, wmap, G, GH, S = skeleton_inputs(synth, g)
+    parent, child = oracle.skeleton_links(synth.H36M_PARENTS, synth.LINE_SELECT, extension=bool(g["meta"][4]))
+    assert parent == g["parent"].tolist() and child == g["child"].tolist()
+    sub = int(g["meta"][5])
+    kp = pose.to(dtype).requires_grad_(True)
+    heat = oracle.draw_lines(kp, S, parent, child, synth.BODY_WIDTH)
+    recon = oracle.skeleton_mask(kp, S, parent, child, synth.BODY_WIDTH)
+    assert np.abs(heat.detach().numpy()[:, :, ::sub, ::sub] - g["heat_sub_" + tag]).max() < tol
+    assert np.abs(recon.detach().numpy() - g["recon_" + tag]).max() < tol
+    gr, = torch.autograd.grad((recon * G.to(dtype)).sum(), kp, retain_graph=True)
+    gh, = torch.autograd.grad((heat * GH.to(dtype)).sum(), kp, retain_graph=True)
+    assert rel_inf(gr.numpy(), g["g_recon_" + tag]) < tol * 10
+    assert rel_inf(gh.numpy(), g["g_heat_" + tag]) < tol * 10
+    for vname, use_w, clip in SKEL_VARIANTS:
+        loss = oracle.mask_recon_loss(recon, gt.to(dtype), weight=wmap.to(dtype) if use_w else None, use_clip=clip)
+        assert (list(loss.shape) or [0]) == g["loss_shape_%s_%s" % (vname, tag)].tolist(), vname   # the tensor-valued quirk
+        # weight=None + use_clip: the reference multiplies its 0-d fp64 MSE by `(mask > 0.1).float()`, an fp32
+        # tensor, so even its fp64 run carries this variant in fp32 (loss_func.py:9-10)
+        vtol = max(tol, 2e-6) if vname == "clip" else tol
+        ref = float(g["loss_%s_%s" % (vname, tag)])
+        assert abs(float(loss.mean().detach()) - ref) < vtol * 10 * abs(ref), vname
+        gl, = torch.autograd.grad(loss.mean(), kp, retain_graph=True)
+        assert rel_inf(gl.numpy(), g["g_loss_%s_%s" % (vname, tag)]) < vtol * 50, vname

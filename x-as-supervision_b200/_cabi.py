@@ -28,7 +28,13 @@ SYMBOLS = (
     "xsup_patch_to_world_fwd", "xsup_patch_to_world_bwd", "xsup_world_to_patch_fwd",
     "xsup_reproj_loss_fwd", "xsup_reproj_select", "xsup_reproj_loss_bwd",
     "xsup_xchg_floats", "xsup_partial_allreduce",
+    "xsup_skel_ws_floats", "xsup_draw_lines_ws_floats", "xsup_mask_loss_ws_floats",
+    "xsup_draw_lines_fwd", "xsup_draw_lines_bwd", "xsup_skeleton_mask_fwd", "xsup_skeleton_mask_bwd",
+    "xsup_mask_loss_fwd", "xsup_mask_loss_bwd",
 )
+MAX_LINES = 32
+MASK_MSE, MASK_CLIP_MEAN, MASK_WEIGHTED = 0, 1, 2
+MASK_SUMS = 4
 XCHG_SLOT = 64
 
 
@@ -44,6 +50,16 @@ class LossCfg(C.Structure):
     _fields_ = [("B", C.c_int32), ("K", C.c_int32), ("NH", C.c_int32), ("img_h", C.c_int32), ("img_w", C.c_int32),
                 ("rect_width", C.c_float), ("w_mse", C.c_float), ("w_bone", C.c_float), ("w_kp", C.c_float),
                 ("w_kp2d", C.c_float), ("use_sym", C.c_int32), ("reduction", C.c_int32), ("batch_total", C.c_int32)]
+
+
+class Skel(C.Structure):
+    _fields_ = [("B", C.c_int32), ("K", C.c_int32), ("S", C.c_int32), ("L", C.c_int32), ("kp_batch_stride", C.c_int32),
+                ("kp_joint_stride", C.c_int32), ("body_width", C.c_float), ("parent", C.c_int32 * MAX_LINES),
+                ("child", C.c_int32 * MAX_LINES)]
+
+
+class MaskLoss(C.Structure):
+    _fields_ = [("n", C.c_int64), ("mode", C.c_int32), ("use_clip", C.c_int32)]
 
 
 class Xchg(C.Structure):
@@ -81,16 +97,31 @@ def _load():
     lib.xsup_xchg_floats.argtypes = [i32]
     lib.xsup_partial_allreduce.argtypes = [vp, i32, C.POINTER(Xchg), vp]
     lib.xsup_partial_allreduce.restype = C.c_int
+    for name in ("xsup_skel_ws_floats", "xsup_draw_lines_ws_floats"):
+        getattr(lib, name).restype = C.c_size_t
+        getattr(lib, name).argtypes = [C.POINTER(Skel)]
+    lib.xsup_mask_loss_ws_floats.restype = C.c_size_t
+    lib.xsup_mask_loss_ws_floats.argtypes = [C.c_int64]
+    sk, ml = C.POINTER(Skel), C.POINTER(MaskLoss)
+    lib.xsup_draw_lines_fwd.argtypes = [vp, sk, vp, vp]
+    lib.xsup_draw_lines_bwd.argtypes = [vp, sk, vp, vp, vp, vp, vp]
+    lib.xsup_skeleton_mask_fwd.argtypes = [vp, sk, vp, vp, vp, vp, ml, vp, vp, vp]
+    lib.xsup_skeleton_mask_bwd.argtypes = [vp, sk, vp, vp, vp, vp, vp, ml, vp, vp, vp, vp, vp]
+    lib.xsup_mask_loss_fwd.argtypes = [vp, vp, vp, vp, ml, vp, vp, vp]
+    lib.xsup_mask_loss_bwd.argtypes = [vp, vp, vp, ml, vp, vp, vp, vp]
     for name in SYMBOLS:
         fn = getattr(lib, name)
-        if name.startswith(("xsup_integral", "xsup_find", "xsup_patch", "xsup_world", "xsup_reproj")):
+        if name.startswith(("xsup_integral", "xsup_find", "xsup_patch", "xsup_world", "xsup_reproj", "xsup_draw_lines_f",
+                            "xsup_draw_lines_b", "xsup_skeleton", "xsup_mask_loss_f", "xsup_mask_loss_b")):
             fn.restype = C.c_int
     return lib
 
 
 lib = _load()
-if lib.xsup_abi_version() != 1:
-    raise ImportError("libxsup_b200.so ABI version %d, expected 1" % lib.xsup_abi_version())
+ABI_VERSION = 2
+if lib.xsup_abi_version() != ABI_VERSION:
+    raise ImportError("libxsup_b200.so ABI version %d, expected %d: rebuild with __graft_entry__.build()"
+                      % (lib.xsup_abi_version(), ABI_VERSION))
 
 
 def check(rc: int, who: str) -> None:

@@ -277,4 +277,141 @@ int xsup_reproj_loss_bwd(const float* kps, const float* target, const xsup_cam_t
     return XSUP_OK;
 }
 
+// ------------------------------------------------------------------------------------------------ skeleton rasteriser + mask loss
+static int skel_params(SkelParams& p, const float* kps, const xsup_skel_t* s, const char* who) {
+    if (!s) return fail(XSUP_E_NULL, "%s: skeleton description is NULL", who);
+    if (s->B < 0 || s->K <= 0 || s->S < 4) return fail(XSUP_E_SHAPE, "%s: bad sizes (B=%d K=%d S=%d)", who, s->B, s->K, s->S);
+    if (s->S % 4 || s->S > 16384) return fail(XSUP_E_SHAPE, "%s: image_size %d must be a multiple of 4 (128-bit rows) and <= 16384", who, s->S);
+    if (s->L < 1 || s->L > XSUP_MAX_LINES) return fail(XSUP_E_SHAPE, "%s: %d lines, need 1..%d", who, s->L, XSUP_MAX_LINES);
+    if (!(s->body_width > 0.0f)) return fail(XSUP_E_SHAPE, "%s: body_width must be positive", who);
+    if (s->kp_joint_stride < 2 || s->kp_batch_stride < 0) return fail(XSUP_E_SHAPE, "%s: bad keypoint strides", who);
+    for (int l = 0; l < s->L; ++l)
+        if (s->parent[l] < 0 || s->parent[l] >= s->K || s->child[l] < 0 || s->child[l] >= s->K)
+            return fail(XSUP_E_SHAPE, "%s: line %d joins joints (%d,%d) outside [0,%d)", who, l, s->parent[l], s->child[l], s->K);
+    if (s->B > 0 && !kps) return fail(XSUP_E_NULL, "%s: kps is NULL", who);
+    p = SkelParams{};
+    p.kps = kps; p.kbs = s->kp_batch_stride; p.kjs = s->kp_joint_stride;
+    p.B = s->B; p.K = s->K; p.S = s->S; p.L = s->L; p.bw = s->body_width;
+    for (int l = 0; l < s->L; ++l) { p.parent[l] = s->parent[l]; p.child[l] = s->child[l]; }
+    return XSUP_OK;
+}
+
+static int check_mask_cfg(const xsup_mask_loss_t* c, const char* who) {
+    if (!c) return fail(XSUP_E_NULL, "%s: loss cfg is NULL", who);
+    if (c->n <= 0) return fail(XSUP_E_SHAPE, "%s: empty mask", who);
+    if (c->mode < XSUP_MASK_MSE || c->mode > XSUP_MASK_WEIGHTED) return fail(XSUP_E_SHAPE, "%s: unknown loss mode %d", who, c->mode);
+    return XSUP_OK;
+}
+
+size_t xsup_skel_ws_floats(const xsup_skel_t* s) {
+    if (!s || s->S < 4 || s->B < 0) return 0;
+    return (size_t)s->B * skel_chunks(s->S) * (XSUP_MAX_LINES * 4 + 4);
+}
+size_t xsup_draw_lines_ws_floats(const xsup_skel_t* s) {
+    if (!s || s->S < 4 || s->B < 0) return 0;
+    return (size_t)s->B * draw_lines_chunks(s->S) * XSUP_MAX_LINES * 4;
+}
+size_t xsup_mask_loss_ws_floats(int64_t n) { return n > 0 ? (size_t)mask_loss_ctas(n) * 4 : 0; }
+
+int xsup_draw_lines_fwd(const float* kps, const xsup_skel_t* s, float* heat, void* stream) {
+    SkelParams p;
+    if (int rc = skel_params(p, kps, s, "xsup_draw_lines_fwd")) return rc;
+    if (p.B == 0) return XSUP_OK;
+    if (!heat) return fail(XSUP_E_NULL, "xsup_draw_lines_fwd: NULL pointer");
+    if (!aligned16(heat)) return fail(XSUP_E_ALIGN, "xsup_draw_lines_fwd: heat must be 16-byte aligned");
+    if (p.B > 65535) return fail(XSUP_E_SHAPE, "xsup_draw_lines_fwd: B > 65535");
+    cudaError_t e = launch_draw_lines_fwd(p, heat, (cudaStream_t)stream);
+    if (e != cudaSuccess) return cuda_fail(e, "xsup_draw_lines_fwd launch");
+    count_launches(1);
+    return XSUP_OK;
+}
+
+int xsup_draw_lines_bwd(const float* kps, const xsup_skel_t* s, const float* heat, const float* g_heat, float* g_kps, float* ws,
+                        void* stream) {
+    SkelParams p;
+    if (int rc = skel_params(p, kps, s, "xsup_draw_lines_bwd")) return rc;
+    if (p.B == 0) return XSUP_OK;
+    if (!heat || !g_heat || !g_kps || !ws) return fail(XSUP_E_NULL, "xsup_draw_lines_bwd: NULL pointer");
+    if (!aligned16(heat) || !aligned16(g_heat) || !aligned16(ws)) return fail(XSUP_E_ALIGN, "xsup_draw_lines_bwd: heat/g_heat/ws must be 16-byte aligned");
+    if (p.B > 65535) return fail(XSUP_E_SHAPE, "xsup_draw_lines_bwd: B > 65535");
+    cudaError_t e = launch_draw_lines_bwd(p, heat, g_heat, g_kps, ws, (cudaStream_t)stream);
+    if (e != cudaSuccess) return cuda_fail(e, "xsup_draw_lines_bwd launch");
+    count_launches(2);
+    return XSUP_OK;
+}
+
+int xsup_skeleton_mask_fwd(const float* kps, const xsup_skel_t* s, float* recon, uint8_t* line_idx, const float* gt,
+                           const float* weight, const xsup_mask_loss_t* loss, float* loss_sums, float* ws, void* stream) {
+    SkelParams p;
+    if (int rc = skel_params(p, kps, s, "xsup_skeleton_mask_fwd")) return rc;
+    if (loss) {
+        if (int rc = check_mask_cfg(loss, "xsup_skeleton_mask_fwd")) return rc;
+        if (loss->n != (int64_t)p.B * p.S * p.S) return fail(XSUP_E_SHAPE, "xsup_skeleton_mask_fwd: loss n must be B*S*S");
+        if (!gt || !loss_sums || !ws) return fail(XSUP_E_NULL, "xsup_skeleton_mask_fwd: gt/loss_sums/ws is NULL");
+        if (loss->mode == XSUP_MASK_WEIGHTED && !weight) return fail(XSUP_E_NULL, "xsup_skeleton_mask_fwd: weighted mode without a weight map");
+        if (!aligned16(gt) || !aligned16(weight) || !aligned16(ws)) return fail(XSUP_E_ALIGN, "xsup_skeleton_mask_fwd: gt/weight/ws must be 16-byte aligned");
+    }
+    if (p.B == 0) return XSUP_OK;
+    if (!recon || !line_idx) return fail(XSUP_E_NULL, "xsup_skeleton_mask_fwd: NULL pointer");
+    if (!aligned16(recon) || (reinterpret_cast<uintptr_t>(line_idx) & 3u)) return fail(XSUP_E_ALIGN, "xsup_skeleton_mask_fwd: recon (16 B) / line_idx (4 B) misaligned");
+    if (p.B > 65535) return fail(XSUP_E_SHAPE, "xsup_skeleton_mask_fwd: B > 65535");
+    cudaError_t e = launch_skeleton_mask_fwd(p, recon, line_idx, gt, loss && loss->mode == XSUP_MASK_WEIGHTED ? weight : nullptr, loss,
+                                             loss_sums, ws, (cudaStream_t)stream);
+    if (e != cudaSuccess) return cuda_fail(e, "xsup_skeleton_mask_fwd launch");
+    count_launches(loss ? 2 : 1);
+    return XSUP_OK;
+}
+
+int xsup_skeleton_mask_bwd(const float* kps, const xsup_skel_t* s, const float* recon, const uint8_t* line_idx, const float* g_recon,
+                           const float* gt, const float* weight, const xsup_mask_loss_t* loss, const float* loss_sums,
+                           const float* g_loss, float* g_kps, float* ws, void* stream) {
+    SkelParams p;
+    if (int rc = skel_params(p, kps, s, "xsup_skeleton_mask_bwd")) return rc;
+    if (loss) {
+        if (int rc = check_mask_cfg(loss, "xsup_skeleton_mask_bwd")) return rc;
+        if (loss->n != (int64_t)p.B * p.S * p.S) return fail(XSUP_E_SHAPE, "xsup_skeleton_mask_bwd: loss n must be B*S*S");
+        if (!gt || !loss_sums || !g_loss) return fail(XSUP_E_NULL, "xsup_skeleton_mask_bwd: gt/loss_sums/g_loss is NULL");
+        if (loss->mode == XSUP_MASK_WEIGHTED && !weight) return fail(XSUP_E_NULL, "xsup_skeleton_mask_bwd: weighted mode without a weight map");
+        if (!aligned16(gt) || !aligned16(weight)) return fail(XSUP_E_ALIGN, "xsup_skeleton_mask_bwd: gt/weight must be 16-byte aligned");
+    }
+    if (p.B == 0) return XSUP_OK;
+    if (!recon || !line_idx || !g_kps || !ws) return fail(XSUP_E_NULL, "xsup_skeleton_mask_bwd: NULL pointer");
+    if (!aligned16(recon) || !aligned16(g_recon) || !aligned16(ws) || (reinterpret_cast<uintptr_t>(line_idx) & 3u))
+        return fail(XSUP_E_ALIGN, "xsup_skeleton_mask_bwd: recon/g_recon/ws (16 B) / line_idx (4 B) misaligned");
+    if (p.B > 65535) return fail(XSUP_E_SHAPE, "xsup_skeleton_mask_bwd: B > 65535");
+    cudaError_t e = launch_skeleton_mask_bwd(p, recon, line_idx, g_recon, gt, loss && loss->mode == XSUP_MASK_WEIGHTED ? weight : nullptr,
+                                             loss, loss_sums, g_loss, g_kps, ws, (cudaStream_t)stream);
+    if (e != cudaSuccess) return cuda_fail(e, "xsup_skeleton_mask_bwd launch");
+    count_launches(2);
+    return XSUP_OK;
+}
+
+int xsup_mask_loss_fwd(const float* mask, const float* gt, const float* weight, float* filter_out, const xsup_mask_loss_t* cfg,
+                       float* loss_sums, float* ws, void* stream) {
+    if (int rc = check_mask_cfg(cfg, "xsup_mask_loss_fwd")) return rc;
+    if (!mask || !gt || !loss_sums || !ws) return fail(XSUP_E_NULL, "xsup_mask_loss_fwd: NULL pointer");
+    if (cfg->mode == XSUP_MASK_WEIGHTED && !weight) return fail(XSUP_E_NULL, "xsup_mask_loss_fwd: weighted mode without a weight map");
+    if (!aligned16(mask) || !aligned16(gt) || !aligned16(weight) || !aligned16(filter_out))
+        return fail(XSUP_E_ALIGN, "xsup_mask_loss_fwd: tensors must be 16-byte aligned");
+    cudaError_t e = launch_mask_loss_fwd(mask, gt, cfg->mode == XSUP_MASK_WEIGHTED ? weight : nullptr, filter_out, *cfg, loss_sums, ws,
+                                         (cudaStream_t)stream);
+    if (e != cudaSuccess) return cuda_fail(e, "xsup_mask_loss_fwd launch");
+    count_launches(2);
+    return XSUP_OK;
+}
+
+int xsup_mask_loss_bwd(const float* mask, const float* gt, const float* weight, const xsup_mask_loss_t* cfg, const float* loss_sums,
+                       const float* g_loss, float* g_mask, void* stream) {
+    if (int rc = check_mask_cfg(cfg, "xsup_mask_loss_bwd")) return rc;
+    if (!mask || !gt || !loss_sums || !g_loss || !g_mask) return fail(XSUP_E_NULL, "xsup_mask_loss_bwd: NULL pointer");
+    if (cfg->mode == XSUP_MASK_WEIGHTED && !weight) return fail(XSUP_E_NULL, "xsup_mask_loss_bwd: weighted mode without a weight map");
+    int sms = 0;
+    if (int rc = device_info(sms)) return rc;
+    cudaError_t e = launch_mask_loss_bwd(mask, gt, cfg->mode == XSUP_MASK_WEIGHTED ? weight : nullptr, *cfg, loss_sums, g_loss, g_mask, sms,
+                                         (cudaStream_t)stream);
+    if (e != cudaSuccess) return cuda_fail(e, "xsup_mask_loss_bwd launch");
+    count_launches(1);
+    return XSUP_OK;
+}
+
 }  // extern "C"

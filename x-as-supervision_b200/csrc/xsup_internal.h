@@ -63,6 +63,30 @@ cudaError_t launch_reproj_select(const float* kps, const float* target, const fl
 cudaError_t launch_reproj_loss_bwd(const float* kps, const float* target, const xsup_cam_t& cam, const int64_t* sel,
                                    const float* g_loss, float* g_kps, const xsup_loss_cfg_t& c, cudaStream_t st);
 
+// skeleton rasteriser + mask loss (skeleton_mask.cu)
+struct SkelParams {
+    const float* kps;
+    int kbs, kjs;              // batch / joint strides of `kps` in floats (x at +0, y at +1)
+    int B, K, S, L;
+    float bw;                  // body_width (model.py:31-32)
+    int tiles_x, tiles, NC;    // 16x8 pixel tiles per row / per sample, CTAs per sample
+    int parent[XSUP_MAX_LINES], child[XSUP_MAX_LINES];
+};
+int skel_chunks(int S);
+int draw_lines_chunks(int S);
+int mask_loss_ctas(long long n);
+cudaError_t launch_skeleton_mask_fwd(SkelParams p, float* recon, uint8_t* line_idx, const float* gt, const float* weight,
+                                     const xsup_mask_loss_t* loss, float* loss_sums, float* ws, cudaStream_t st);
+cudaError_t launch_skeleton_mask_bwd(SkelParams p, const float* recon, const uint8_t* line_idx, const float* g_recon,
+                                     const float* gt, const float* weight, const xsup_mask_loss_t* loss, const float* loss_sums,
+                                     const float* g_loss, float* g_kps, float* ws, cudaStream_t st);
+cudaError_t launch_draw_lines_fwd(SkelParams p, float* heat, cudaStream_t st);
+cudaError_t launch_draw_lines_bwd(SkelParams p, const float* heat, const float* g_heat, float* g_kps, float* ws, cudaStream_t st);
+cudaError_t launch_mask_loss_fwd(const float* mask, const float* gt, const float* weight, float* filter_out,
+                                 const xsup_mask_loss_t& c, float* loss_sums, float* ws, cudaStream_t st);
+cudaError_t launch_mask_loss_bwd(const float* mask, const float* gt, const float* weight, const xsup_mask_loss_t& c,
+                                 const float* loss_sums, const float* g_loss, float* g_mask, int num_sms, cudaStream_t st);
+
 void count_launches(int n);
 
 }  // namespace xsup

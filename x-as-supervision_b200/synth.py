@@ -16,7 +16,8 @@ from typing import Dict
 
 import torch
 
-__all__ = ["iid_logits", "blob_logits", "pseudo_joints", "cameras", "camera_dict", "CAM_FIELDS"]
+__all__ = ["iid_logits", "blob_logits", "pseudo_joints", "cameras", "camera_dict", "CAM_FIELDS",
+           "H36M_PARENTS", "LINE_SELECT", "BODY_WIDTH", "skeleton_pose2d", "silhouette_mask", "geodesic_weight"]
 
 # order of the per-sample camera tensors everywhere in this package
 CAM_FIELDS = ("trans_image", "pelvis", "k_mat", "trans_world", "rot_world")
@@ -122,3 +123,69 @@ def camera_dict(cams: Dict[str, torch.Tensor], mode: str = "cam_0", img: int = 2
     # a zero-stride view: only the shape is ever read (util.py:130,137-138)
     out["{}_img".format(mode)] = torch.zeros(1, dtype=cams["pelvis"].dtype, device=cams["pelvis"].device).expand(B, 3, img, img)
     return out
+
+
+# --------------------------------------------------------------------------------------- skeleton rasteriser inputs
+# config/HM36_Multi_SurS1.yaml:56,60,61: 18-joint H36M tree (joint 17 = thorax), the 17 drawn child->parent
+# links and the body width (x 1e-3 at model.py:32)
+H36M_PARENTS = (0, 0, 1, 2, 0, 4, 5, 0, 17, 8, 9, 17, 11, 12, 17, 14, 15, 7)
+LINE_SELECT = tuple(range(17))
+BODY_WIDTH = 3.0e-3
+
+# a standing figure in patch coordinates (x right, y down, [-1,1]); joint order as H36M_PARENTS
+_TEMPLATE = ((0.0, 0.05), (-0.12, 0.05), (-0.13, 0.40), (-0.14, 0.75), (0.12, 0.05), (0.13, 0.40), (0.14, 0.75),
+             (0.0, -0.20), (0.0, -0.50), (0.0, -0.60), (0.0, -0.72), (0.20, -0.45), (0.30, -0.20), (0.33, 0.05),
+             (-0.20, -0.45), (-0.30, -0.20), (-0.33, 0.05), (0.0, -0.45))
+
+
+def skeleton_pose2d(B: int, K: int = 18, seed: int = 20, jitter: float = 0.06) -> torch.Tensor:
+    """2-D patch poses `[B, K, 2]`: the template figure with per-joint jitter, a global scale U(0.7,1.1)
+    and a shift N(0, 0.08).  Joints beyond the 18 of the template are placed uniformly in [-0.8, 0.8]."""
+    g = _gen(seed)
+    base = torch.tensor(_TEMPLATE, dtype=torch.float32)
+    if K <= base.shape[0]:
+        base = base[:K].expand(B, K, 2)
+    else:
+        extra = torch.rand(K - base.shape[0], 2, generator=g) * 1.6 - 0.8
+        base = torch.cat((base, extra)).expand(B, K, 2)
+    pose = base + jitter * torch.randn(B, K, 2, generator=g)
+    scale = 0.7 + 0.4 * torch.rand(B, 1, 1, generator=g)
+    shift = 0.08 * torch.randn(B, 1, 2, generator=g)
+    return (pose * scale + shift).contiguous()
+
+
+def _pixel_centres(size: int) -> torch.Tensor:
+    c = 2 * (torch.arange(size, dtype=torch.float32) / (size - 1)) - 1
+    return torch.stack((c.view(1, size).expand(size, size), c.view(size, 1).expand(size, size)), dim=-1)   # [S,S,2] (x,y)
+
+
+def silhouette_mask(pose: torch.Tensor, size: int = 256, radius: float = 0.075) -> torch.Tensor:
+    """Binary person mask `[B,1,S,S]` (floats 0/1, like `mask_patch / 255`, dataloader.py:184): the union of
+    discs around the joints and the points at 1/3 and 2/3 of every tree edge of `pose`."""
+    B, K, _ = pose.shape
+    par = torch.tensor([H36M_PARENTS[k] if k < len(H36M_PARENTS) else 0 for k in range(K)])
+    pts = torch.cat((pose, pose + (pose[:, par] - pose) / 3, pose + (pose[:, par] - pose) * 2 / 3), dim=1)   # [B,3K,2]
+    g = _pixel_centres(size).view(1, 1, size * size, 2)
+    out = torch.zeros(B, size * size, dtype=torch.bool)
+    for i in range(0, pts.shape[1], 6):                                       # bounded temporaries
+        d2 = (g - pts[:, i:i + 6, None, :]).pow(2).sum(-1)
+        out |= (d2 < radius * radius).any(dim=1)
+    return out.view(B, 1, size, size).to(torch.float32)
+
+
+def geodesic_weight(mask: torch.Tensor, seed: int = 21) -> torch.Tensor:
+    """A positive per-pixel weight map `[B,1,S,S]` standing in for `geodesic_dis` (geodesic.py:14-53:
+    exp of a normalised in-mask distance plus a scaled background distance): larger inside the mask and
+    growing away from its centroid, plus a background ramp."""
+    B, _, S, _ = mask.shape
+    g = _pixel_centres(S)
+    gen = _gen(seed)
+    a = 0.5 + torch.rand(B, 1, 1, 1, generator=gen)
+    m = mask[:, 0]
+    cnt = m.sum(dim=(1, 2)).clamp_min(1.0)
+    cx = (m * g[..., 0]).sum(dim=(1, 2)) / cnt
+    cy = (m * g[..., 1]).sum(dim=(1, 2)) / cnt
+    r = ((g[None, ..., 0] - cx.view(B, 1, 1)) ** 2 + (g[None, ..., 1] - cy.view(B, 1, 1)) ** 2).sqrt()
+    r = r / r.amax(dim=(1, 2), keepdim=True)
+    w = mask * torch.exp(a * r[:, None]) + 0.3 + 0.7 * r[:, None]
+    return w.contiguous()
