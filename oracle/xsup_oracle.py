@@ -93,8 +93,8 @@ def integral_multi(logits: torch.Tensor, num_kp: int, num_hypo: int, neighbor_si
         raise ValueError("reference semantics need depth_dim == width (got D=%d, W=%d)" % (D, W))
     p = softmax_volume(logits, num_kp)
     ax, ay, pz = marginals(p)
-    xbar = (ax * torch.arange(W, dtype=p.dtype)).sum(-1, keepdim=True)
-    ybar = (ay * torch.arange(H, dtype=p.dtype)).sum(-1, keepdim=True)
+    xbar = (ax * torch.arange(W, dtype=p.dtype, device=p.device)).sum(-1, keepdim=True)
+    ybar = (ay * torch.arange(H, dtype=p.dtype, device=p.device)).sum(-1, keepdim=True)
     idx = depth_peaks(pz, num_hypo)
     zwin = window_depth(pz, idx, neighbor_size)                      # [B,K,NH]
     x = xbar / H * 2 - 1
@@ -113,9 +113,9 @@ def integral_single(logits: torch.Tensor, num_kp: int) -> Tuple[torch.Tensor, to
         raise ValueError("reference semantics need depth_dim == width")
     p = softmax_volume(logits, num_kp)
     ax, ay, pz = marginals(p)
-    x = (ax * torch.arange(W, dtype=p.dtype)).sum(-1) / H * 2 - 1
-    y = (ay * torch.arange(H, dtype=p.dtype)).sum(-1) / W * 2 - 1
-    z = (pz * torch.arange(D, dtype=p.dtype)).sum(-1) / D * 2 - 1
+    x = (ax * torch.arange(W, dtype=p.dtype, device=p.device)).sum(-1) / H * 2 - 1
+    y = (ay * torch.arange(H, dtype=p.dtype, device=p.device)).sum(-1) / W * 2 - 1
+    z = (pz * torch.arange(D, dtype=p.dtype, device=p.device)).sum(-1) / D * 2 - 1
     return torch.stack((x, y, z), dim=-1).unsqueeze(1), pz[0].clone()
 
 
@@ -131,7 +131,7 @@ def integral_multi_backward(logits: torch.Tensor, g_kps: torch.Tensor, num_kp: i
     ax, ay, pz = marginals(p)
     idx = depth_peaks(pz, num_hypo)                                   # [B,K,NH]
     dt = p.dtype
-    bins = torch.arange(D, dtype=dt)
+    bins = torch.arange(D, dtype=dt, device=logits.device)
     g = g_kps.to(dt).permute(0, 2, 1, 3)                              # [B,K,NH,3]
     a = g[..., 0].sum(-1) * (2.0 / H)                                 # on w
     b = g[..., 1].sum(-1) * (2.0 / W)                                 # on h
@@ -140,11 +140,11 @@ def integral_multi_backward(logits: torch.Tensor, g_kps: torch.Tensor, num_kp: i
     zbar = (inwin * (pz * bins).unsqueeze(2)).sum(-1) / swin
     c = (g[..., 2].unsqueeze(-1) * (2.0 / D) * inwin * (bins.view(1, 1, 1, D) - zbar.unsqueeze(-1))
          / swin.unsqueeze(-1)).sum(2)                                 # [B,K,D]
-    xbar = (ax * torch.arange(W, dtype=dt)).sum(-1)
-    ybar = (ay * torch.arange(H, dtype=dt)).sum(-1)
+    xbar = (ax * torch.arange(W, dtype=dt, device=logits.device)).sum(-1)
+    ybar = (ay * torch.arange(H, dtype=dt, device=logits.device)).sum(-1)
     gbar = a * xbar + b * ybar + (c * pz).sum(-1)
-    field = (a.view(B, num_kp, 1, 1, 1) * torch.arange(W, dtype=dt).view(1, 1, 1, 1, W)
-             + b.view(B, num_kp, 1, 1, 1) * torch.arange(H, dtype=dt).view(1, 1, 1, H, 1)
+    field = (a.view(B, num_kp, 1, 1, 1) * torch.arange(W, dtype=dt, device=logits.device).view(1, 1, 1, 1, W)
+             + b.view(B, num_kp, 1, 1, 1) * torch.arange(H, dtype=dt, device=logits.device).view(1, 1, 1, H, 1)
              + c.view(B, num_kp, D, 1, 1) - gbar.view(B, num_kp, 1, 1, 1))
     return (p * field).reshape(B, C, H, W)
 
@@ -312,7 +312,7 @@ def reproj_min_loss(kps, target, cams, img_hw=(256, 256), rect_width=2000.0, w_m
         mse_bh = w_mse * mse / (K * 3)
         vm, im = mse_bh.min(dim=1)
         loss_p = vm.sum() / n
-        loss_s, isym = zero, torch.full((B,), -1, dtype=torch.long)
+        loss_s, isym = zero, torch.full((B,), -1, dtype=torch.long, device=kps.device)
         if use_sym:
             sym_bh = wb * bone / 4 + wk * kp3 / 6 + wk2 * 1e2 * kp2 / 4
             vs, isym = sym_bh.min(dim=1)
@@ -381,7 +381,7 @@ def segment_sqdist(kp2d: torch.Tensor, size: int, parent_ids, child_ids) -> torc
     t = (a * d[:, :, None]).sum(-1) / (1e-8 + (d * d).sum(-1, keepdim=True))
     to_end = g[None, None] - e[:, :, None]
     foot = g[None, None] - (s[:, :, None] + t[..., None] * d[:, :, None])
-    zero = torch.zeros((), dtype=kp2d.dtype)
+    zero = torch.zeros((), dtype=kp2d.dtype, device=kp2d.device)
     q = torch.where(t <= 0, (a * a).sum(-1), zero) + torch.where(t >= 1, (to_end * to_end).sum(-1), zero) \
         + torch.where((t > 0) & (t < 1), (foot * foot).sum(-1), zero)
     return q
@@ -392,7 +392,7 @@ def draw_lines(kp2d: torch.Tensor, size: int, parent_ids, child_ids, body_width:
     B = kp2d.shape[0]
     u = -segment_sqdist(kp2d, size, parent_ids, child_ids) / body_width
     if u.shape[1] >= 21:
-        scale = torch.ones(u.shape[1], dtype=u.dtype)
+        scale = torch.ones(u.shape[1], dtype=u.dtype, device=u.device)
         scale[list(ARM_LINES)] = 2
         u = u * scale[None, :, None]
     return torch.exp(u).reshape(B, -1, size, size)

@@ -5,8 +5,8 @@
 
 Tolerances: heat-map values within 1e-5 absolute (they live in [0,1]); losses 1e-5 relative; keypoint
 gradients 1e-5 norm-wise.  Pixels whose value sits within 1e-5 of the 0.1 clip threshold (loss_func.py:9)
-may fall on either side in fp32 — the reference's own fp32 run flips them too — so the clipped losses are
-compared against the oracle evaluated with OUR filter decisions for those pixels."""
+may fall on either side in fp32 — the reference's own fp32 run flips them too — so the clipped-loss
+comparisons are only made on cases without such pixels (checked on the fp64 oracle's map)."""
 import importlib
 
 import numpy as np
@@ -89,6 +89,21 @@ def _oracle_all(oracle, pose64, S, parent, child, bw, G64, gt64, w64, clip):
 
 
 POSES = ["template", "uniform", "tiny", "off_image", "coincident", "huge"]
+COINCIDENT = ((1, 2), (11, 12, 13))
+
+
+def _grad_err(ours, ref64, kind):
+    """max |ours - ref| / max |ref|.  Where several joints sit on the same point, the pixels nearest to that point
+    are at exactly the same distance from every line touching it, and which of the coincident joints receives their
+    gradient is `torch.max`'s tie-break - unspecified in the reference; only the sum over the group is defined."""
+    a, b = ours.detach().cpu().double().clone(), ref64.clone()
+    if kind == "coincident":
+        for grp in COINCIDENT:
+            a[:, grp[0]] = a[:, list(grp)].sum(1)
+            b[:, grp[0]] = b[:, list(grp)].sum(1)
+            a[:, list(grp[1:])] = 0
+            b[:, list(grp[1:])] = 0
+    return float((a - b).abs().max()) / max(float(b.abs().max()), 1e-30)
 
 
 @pytest.mark.parametrize("kind", POSES)
@@ -120,16 +135,14 @@ def test_rasteriser_against_oracle(sk, oracle, synth, dev, kind, S):
     o = _oracle_all(oracle, pose.double(), S, parent, child, synth.BODY_WIDTH, G.double(), gt.double(), wmap.double(), True)
     assert (recon.detach().cpu().double() - o["recon"]).abs().max() < TOL
     gr, = torch.autograd.grad((recon * G.to(dev)).sum(), kp)
-    scale = max(float(o["g_recon"].abs().max()), 1e-30)
-    assert float((gr.cpu().double() - o["g_recon"]).abs().max()) <= TOL * scale
+    assert _grad_err(gr, o["g_recon"], kind) <= TOL
     # fused loss (SurS1 configuration: weight map + clip), skipping cases with pixels on the clip threshold
     if int(((o["recon"] - 0.1).abs() < 1e-5).sum()) == 0:
         kp2 = pose.to(dev).requires_grad_(True)
         _, loss = sk.skeleton_mask_loss(kp2, gt.to(dev), wmap.to(dev), S, parent, child, synth.BODY_WIDTH, use_clip=True)
         assert abs(float(loss) - o["loss"]) <= TOL * max(abs(o["loss"]), 1e-30)
         loss.backward()
-        gs = max(float(o["g_loss"].abs().max()), 1e-30)
-        assert float((kp2.grad.cpu().double() - o["g_loss"]).abs().max()) <= TOL * gs
+        assert _grad_err(kp2.grad, o["g_loss"], kind) <= TOL
     # un-maxed heat-maps
     heat = sk.draw_lines(pose.to(dev), S, parent, child, synth.BODY_WIDTH)
     oh = oracle.draw_lines(pose.double(), S, parent, child, synth.BODY_WIDTH)

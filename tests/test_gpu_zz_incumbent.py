@@ -1,0 +1,86 @@
+"""The on-box incumbent: the reference's op sequence (the oracle restatement, plain torch ops) run eagerly in
+fp32 ON THE SAME B200, timed beside our kernels.  SURVEY.md 8d asks for this number next to ours; it is a
+reported baseline, not a parity gate (parity is test_gpu_parity.py / test_gpu_skeleton.py).  Results go to
+gpurun_out/incumbent.json when that directory exists."""
+import importlib
+import json
+import os
+
+import pytest
+import torch
+
+from conftest import ROOT
+
+pytestmark = pytest.mark.gpu
+
+
+def _time(fn, steps=5, warmup=2):
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0.record()
+    for _ in range(steps):
+        fn()
+    t1.record()
+    torch.cuda.synchronize()
+    return t0.elapsed_time(t1) / steps
+
+
+def test_incumbent_eager_timings(oracle, synth):
+    import __graft_entry__ as ge
+    ge.build()
+    pkg = importlib.import_module("x-as-supervision_b200")
+    ops = pkg.load_native()
+    sk = pkg.skeleton
+    dev = torch.device("cuda:0")
+    out = {}
+
+    # ---- integral head + reprojection min-loss, BASELINE configs[1] shapes at a batch the eager graph fits easily
+    B, K, R, NH, NS = 64, 17, 64, 3, 15
+    logits = torch.randn(B, K * R, R, R, device=dev)
+    target = synth.pseudo_joints(B, K, seed=2).to(dev)
+    cams = {k: v.to(dev) for k, v in synth.cameras(B, seed=3).items()}
+
+    def eager():
+        x = logits.clone().requires_grad_(True)
+        lp, ls, *_ = oracle.fused_forward(x, K, NH, NS, target, cams, w_mse=3.0, reduction="batch")
+        (lp + ls).backward()
+
+    def ours():
+        x = logits.clone().requires_grad_(True)
+        lp, ls, *_ = ops.integral_reproj_min_loss(x, target, cams, K, NH, NS, w_mse=3.0, reduction="batch")
+        (lp + ls).backward()
+
+    te, to = _time(eager), _time(ours, steps=20, warmup=3)
+    out["integral_reproj"] = {"batch": B, "eager_ms": round(te, 3), "ours_ms": round(to, 3),
+                              "eager_samples_per_s": round(B / te * 1e3, 1), "ours_samples_per_s": round(B / to * 1e3, 1),
+                              "note": "both include one clone of the logits per step"}
+    assert to < te
+
+    # ---- skeleton rasteriser + max + weighted clipped mask loss
+    B2, S = 16, 256
+    parent, child = sk.cal_links(synth.H36M_PARENTS, synth.LINE_SELECT)
+    pose = synth.skeleton_pose2d(B2, 18, seed=60).to(dev)
+    gt = synth.silhouette_mask(synth.skeleton_pose2d(B2, 18, seed=61), S).to(dev)
+    wmap = synth.geodesic_weight(gt.cpu(), seed=62).to(dev)
+
+    def eager2():
+        kp = pose.clone().requires_grad_(True)
+        recon = oracle.skeleton_mask(kp, S, parent, child, synth.BODY_WIDTH)
+        oracle.mask_recon_loss(recon, gt, weight=wmap, use_clip=True).backward()
+
+    def ours2():
+        kp = pose.clone().requires_grad_(True)
+        _, loss = sk.skeleton_mask_loss(kp, gt, wmap, S, parent, child, synth.BODY_WIDTH, use_clip=True)
+        loss.backward()
+
+    te2, to2 = _time(eager2), _time(ours2, steps=20, warmup=3)
+    out["skeleton_mask_loss"] = {"batch": B2, "eager_ms": round(te2, 3), "ours_ms": round(to2, 3),
+                                 "eager_samples_per_s": round(B2 / te2 * 1e3, 1), "ours_samples_per_s": round(B2 / to2 * 1e3, 1)}
+    assert to2 < te2
+    print("\n[incumbent]", json.dumps(out))
+    d = os.path.join(ROOT, "gpurun_out")
+    if os.path.isdir(d):
+        with open(os.path.join(d, "incumbent.json"), "w") as f:
+            json.dump(out, f, indent=1)

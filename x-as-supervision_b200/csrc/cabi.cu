@@ -281,7 +281,7 @@ int xsup_reproj_loss_bwd(const float* kps, const float* target, const xsup_cam_t
 static int skel_params(SkelParams& p, const float* kps, const xsup_skel_t* s, const char* who) {
     if (!s) return fail(XSUP_E_NULL, "%s: skeleton description is NULL", who);
     if (s->B < 0 || s->K <= 0 || s->S < 4) return fail(XSUP_E_SHAPE, "%s: bad sizes (B=%d K=%d S=%d)", who, s->B, s->K, s->S);
-    if (s->S % 4 || s->S > 16384) return fail(XSUP_E_SHAPE, "%s: image_size %d must be a multiple of 4 (128-bit rows) and <= 16384", who, s->S);
+    if (s->S % 4 || s->S > 8192) return fail(XSUP_E_SHAPE, "%s: image_size %d must be a multiple of 4 (128-bit rows) and <= 8192", who, s->S);
     if (s->L < 1 || s->L > XSUP_MAX_LINES) return fail(XSUP_E_SHAPE, "%s: %d lines, need 1..%d", who, s->L, XSUP_MAX_LINES);
     if (!(s->body_width > 0.0f)) return fail(XSUP_E_SHAPE, "%s: body_width must be positive", who);
     if (s->kp_joint_stride < 2 || s->kp_batch_stride < 0) return fail(XSUP_E_SHAPE, "%s: bad keypoint strides", who);

@@ -31,7 +31,7 @@ constexpr int kTilesPerCta = kSkelWarps * kTilesPerWarp;
 
 // segment `l` of sample `b`: A = (start.x, start.y, d.x, d.y), Bv = (1/(1e-8+|d|^2), end.x, end.y, c)
 // start = child joint, end = parent joint (util.py:34-36); c = 2 for the arm lines when L >= 21 (util.py:50-53)
-__device__ __forceinline__ void load_lines(const SkelParams& p, int b, float4* sA, float4* sB) {
+__device__ __forceinline__ void load_lines(const SkelParams& p, int b, float4* sA, float4* sB, float4* sC = nullptr) {
     const int l = threadIdx.x;
     if (l < p.L) {
         const float* s = p.kps + (size_t)b * p.kbs + (size_t)p.child[l] * p.kjs;
@@ -40,53 +40,70 @@ __device__ __forceinline__ void load_lines(const SkelParams& p, int b, float4* s
         const float dx = ex - sx, dy = ey - sy;
         const float den = 1e-8f + __fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy));
         const float c = (p.L >= 21 && (l == 11 || l == 12 || l == 14 || l == 15)) ? 2.0f : 1.0f;
+        const float inv = 1.0f / den;
         sA[l] = make_float4(sx, sy, dx, dy);
-        sB[l] = make_float4(1.0f / den, ex, ey, c);
+        sB[l] = make_float4(inv, ex, ey, c);
+        if (sC) sC[l] = make_float4(dx * inv, dy * inv, c, 0.0f);       // forward form: t = a . (d/den)
     }
 }
 
 // pixel-centre coordinate of make_coordinate_grid (util.py:8-12): 2*(i/(S-1)) - 1
 __device__ __forceinline__ float grid_coord(int i, float fS1) { return fmaf(2.0f, __fdiv_rn((float)i, fS1), -1.0f); }
 
-// squared distance from (gx, gy) to the segment; ay = gy - start.y, aydy = ay*d.y, gey = gy - end.y
-__device__ __forceinline__ float seg_sqdist(float gx, float ay, float aydy, float gey, const float4& A, const float4& Bv) {
-    const float ax = gx - A.x;
-    const float t = fmaf(ax, A.z, aydy) * Bv.x;
-    float rx, ry;
-    if (t >= 1.0f) {                                   // after_end (util.py:45)
-        rx = gx - Bv.y;
-        ry = gey;
-    } else {                                           // before_start (t <= 0, :44) or the foot of the perpendicular (:46)
-        const float tc = fmaxf(t, 0.0f);
-        rx = fmaf(-tc, A.z, ax);
-        ry = fmaf(-tc, A.w, ay);
-    }
-    return __fadd_rn(__fmul_rn(rx, rx), __fmul_rn(ry, ry));
+// the S coordinates once per CTA (true divisions), padded to a multiple of 4 so rows can be fetched as float4
+__device__ __forceinline__ void load_coord_table(float* tab, int S) {
+    const float fS1 = (float)(S - 1);
+    for (int i = threadIdx.x; i < S; i += blockDim.x) tab[i] = grid_coord(i, fS1);
+}
+
+// q / bw with one Newton correction of the reciprocal product (within 1 ulp of the IEEE quotient, 3 instructions)
+__device__ __forceinline__ float div_by(float q, float bw, float rbw) {
+    const float y = q * rbw;
+    return fmaf(fmaf(-y, bw, q), rbw, y);
+}
+
+// Squared distance from the pixel centre to the segment.  ax, ay = g - start; aydyi = ay * d.y/den; C = (d.x/den, d.y/den, c).
+// t = a.d/den clamped to [0,1] (one FFMA.SAT) selects the three cases of util.py:44-46 at once: t <= 0 -> |g - start|^2,
+// t >= 1 -> |a - d|^2 = |g - end|^2, else the foot of the perpendicular.  6 instructions per pixel and line.
+__device__ __forceinline__ float seg_sqdist(float ax, float ay, float aydyi, const float4& A, const float4& C) {
+    const float t = __saturatef(fmaf(ax, C.x, aydyi));
+    const float rx = fmaf(-t, A.z, ax), ry = fmaf(-t, A.w, ay);
+    return fmaf(rx, rx, ry * ry);
 }
 
 __device__ __forceinline__ float warp_min(float v) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v = fminf(v, __shfl_xor_sync(0xffffffffu, v, o));
-    return v;
+    float r;
+    asm volatile("redux.sync.min.f32 %0, %1, 0xffffffff;" : "=f"(r) : "f"(v));   // CREDUX.MIN.F32 (sm_100a)
+    return r;
+}
+__device__ __forceinline__ float sqrt_approx(float x) {
+    float r;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
 }
 
 // lines that can be the winner somewhere in the tile whose first pixel is (x0, y0); lane = line
-__device__ __forceinline__ unsigned cull_lines(const SkelParams& p, const float4* sA, const float4* sB, int x0, int y0,
-                                               float fS1, float rho, int lane) {
+// Returns 0 when every pixel of the tile is exactly 0 (so far from all lines that exp underflows: u < -105).
+__device__ __forceinline__ unsigned cull_lines(int L, const float4* sA, const float4* sC, int x0, int y0, float two_over, float rho,
+                                               float rbw, int lane) {
     float lo = kInf, up = kInf;
-    if (lane < p.L) {
-        const float cx = fmaf(2.0f, ((float)x0 + 0.5f * (kTileW - 1)) / fS1, -1.0f);
-        const float cy = fmaf(2.0f, ((float)y0 + 0.5f * (kTileH - 1)) / fS1, -1.0f);
-        const float4 A = sA[lane], Bv = sB[lane];
+    if (lane < L) {
+        const float cx = fmaf((float)x0 + 0.5f * (kTileW - 1), two_over, -1.0f);
+        const float cy = fmaf((float)y0 + 0.5f * (kTileH - 1), two_over, -1.0f);
+        const float4 A = sA[lane], C = sC[lane];
         const float ay = cy - A.y;
-        const float dist = sqrtf(seg_sqdist(cx, ay, ay * A.w, cy - Bv.z, A, Bv));
-        const float wl = Bv.w == 2.0f ? 1.41421356f : 1.0f;     // sqrt(c): the quantity minimised is c*q = (sqrt(c)*dist)^2
+        const float dist = sqrt_approx(seg_sqdist(cx - A.x, ay, ay * C.y, A, C));
+        const float wl = C.z == 2.0f ? 1.41421356f : 1.0f;      // sqrt(c): the quantity minimised is c*q = (sqrt(c)*dist)^2
         lo = wl * fmaxf(dist - rho, 0.0f);
         up = wl * (dist + rho);
     }
     const float U = warp_min(up);
-    // slack: rounding of the few fp32 operations above is ~1e-6 on values <= 4; 1e-4 only keeps a few more lines
-    return __ballot_sync(0xffffffffu, lo <= U + 1e-4f);
+    // slack: the fp32 operations above (incl. the approximate sqrt) err by ~1e-6 on values <= 4; 1e-4 only keeps a few more lines
+    const unsigned keep = __ballot_sync(0xffffffffu, lo <= U + 1e-4f);
+    // min over the lines of the lower bound of c*q/bw: beyond 105 every exp() in the tile is exactly 0 in fp32
+    // (exp(-103.98) is already below half the smallest denormal), for the reference as well
+    const float lmin = warp_min(lo);
+    return (lmin * lmin * rbw > 105.0f) ? 0u : keep;
 }
 
 // ---------------------------------------------------------------------------------------------- fused forward
@@ -96,51 +113,68 @@ __global__ void __launch_bounds__(kSkelThreads) skeleton_mask_fwd_kernel(const S
                                                                          const float* __restrict__ gt,
                                                                          const float* __restrict__ weight, int use_clip,
                                                                          float* __restrict__ ws_loss) {
-    __shared__ float4 sA[XSUP_MAX_LINES], sB[XSUP_MAX_LINES];
+    __shared__ float4 sA[XSUP_MAX_LINES], sB[XSUP_MAX_LINES], sC[XSUP_MAX_LINES];
     __shared__ float red[kSkelWarps][3];
+    extern __shared__ __align__(16) float tab[];                  // [S] pixel-centre coordinates
     const int b = blockIdx.y, chunk = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    load_lines(p, b, sA, sB);
+    load_lines(p, b, sA, sB, sC);
+    load_coord_table(tab, p.S);
     __syncthreads();
-    const float fS1 = (float)(p.S - 1);
-    const float rho = 8.27648f * 2.0f / fS1 * 1.0001f;           // half diagonal of the tile's pixel centres
-    const int S = p.S;
+    const float two_over = 2.0f / (float)(p.S - 1);
+    const float rho = 8.27648f * two_over * 1.0001f;             // half diagonal of the tile's pixel centres
+    const float rbw = 1.0f / p.bw;
+    const int S = p.S, L = p.L;
+    const size_t sample = (size_t)b * S * S;
+    recon += sample;
+    line_idx += sample;
+    if (LOSS) {
+        gt += sample;
+        if (weight) weight += sample;
+    }
     float s_sq = 0.f, s_f = 0.f, s_w = 0.f;
     const int t_end = min(p.tiles, (chunk + 1) * kTilesPerCta);
     for (int tile = chunk * kTilesPerCta + warp; tile < t_end; tile += kSkelWarps) {
-        const int ty = tile / p.tiles_x, tx = tile - ty * p.tiles_x;
+        int ty = (int)__umulhi((unsigned)tile, p.tiles_x_magic);   // tile / tiles_x without the integer-division sequence
+        int tx = tile - ty * p.tiles_x;
+        if (tx >= p.tiles_x) { tx -= p.tiles_x; ++ty; }
         const int x0 = tx * kTileW, y0 = ty * kTileH;
-        const unsigned keep = cull_lines(p, sA, sB, x0, y0, fS1, rho, lane);
         const int py = y0 + (lane >> 2), px = x0 + (lane & 3) * 4;
-        const float gy = grid_coord(py, fS1);
-        float gx[4], best[4], bq[4], bc[4];
-        int bl[4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            gx[i] = grid_coord(px + i, fS1);
-            best[i] = kInf; bq[i] = kInf; bc[i] = 1.0f; bl[i] = 0;
+        const bool in = py < S && px < S;                         // ragged edge tiles: lanes outside the image idle
+        const int o = py * S + px;
+        float4 g4 = make_float4(0.f, 0.f, 0.f, 0.f), w4 = make_float4(1.f, 1.f, 1.f, 1.f);
+        if (LOSS && in) {                                         // issued before the line loop: their latency hides behind it
+            g4 = *reinterpret_cast<const float4*>(gt + o);
+            if (weight) w4 = *reinterpret_cast<const float4*>(weight + o);
         }
-        for (unsigned m = keep; m; m &= m - 1) {
-            const int l = __ffs(m) - 1;
-            const float4 A = sA[l], Bv = sB[l];
-            const float ay = gy - A.y, aydy = ay * A.w, gey = gy - Bv.z;
+        const unsigned keep = cull_lines(L, sA, sC, x0, y0, two_over, rho, rbw, lane);
+        if (in) {
+            float h[4] = {0.f, 0.f, 0.f, 0.f};
+            int bl[4] = {0, 0, 0, 0};
+            if (keep) {
+                const float gy = tab[py];
+                const float4 gx4 = *reinterpret_cast<const float4*>(tab + px);
+                const float gx[4] = {gx4.x, gx4.y, gx4.z, gx4.w};
+                float best[4] = {kInf, kInf, kInf, kInf};
+                for (unsigned m = keep; m; m &= m - 1) {
+                    const int l = __ffs(m) - 1;
+                    const float4 A = sA[l], C = sC[l];
+                    const float ay = gy - A.y, aydyi = ay * C.y;
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const float q = seg_sqdist(gx[i], ay, aydy, gey, A, Bv);
-                const float cq = q * Bv.w;
-                if (cq < best[i]) { best[i] = cq; bq[i] = q; bc[i] = Bv.w; bl[i] = l; }   // ties: lowest line index
+                    for (int i = 0; i < 4; ++i) {
+                        const float cq = seg_sqdist(gx[i] - A.x, ay, aydyi, A, C) * C.z;
+                        if (cq < best[i]) { best[i] = cq; bl[i] = l; }                     // ties: lowest line index
+                    }
+                }
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const float c = sC[bl[i]].z;
+                    const float q = c == 2.0f ? 0.5f * best[i] : best[i];                   // exact
+                    h[i] = expf(-div_by(q, p.bw, rbw) * c);                                 // util.py:52-55
+                }
             }
-        }
-        if (py < S && px < S) {
-            float h[4];
-#pragma unroll
-            for (int i = 0; i < 4; ++i) h[i] = expf(__fdiv_rn(-bq[i], p.bw) * bc[i]);       // util.py:52-55
-            const size_t o = ((size_t)b * S + py) * S + px;
             *reinterpret_cast<float4*>(recon + o) = make_float4(h[0], h[1], h[2], h[3]);
             *reinterpret_cast<uchar4*>(line_idx + o) = make_uchar4((uint8_t)bl[0], (uint8_t)bl[1], (uint8_t)bl[2], (uint8_t)bl[3]);
             if (LOSS) {
-                const float4 g4 = *reinterpret_cast<const float4*>(gt + o);
-                float4 w4 = make_float4(1.f, 1.f, 1.f, 1.f);
-                if (weight) w4 = *reinterpret_cast<const float4*>(weight + o);
                 const float g[4] = {g4.x, g4.y, g4.z, g4.w}, w[4] = {w4.x, w4.y, w4.z, w4.w};
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
@@ -228,35 +262,63 @@ __global__ void __launch_bounds__(kSkelThreads) skeleton_mask_bwd_kernel(const S
                                                                          float* __restrict__ ws_grad) {
     __shared__ float4 sA[XSUP_MAX_LINES], sB[XSUP_MAX_LINES];
     __shared__ float4 acc[kSkelWarps][XSUP_MAX_LINES];
+    extern __shared__ __align__(16) float tab[];                  // [S] pixel-centre coordinates
     const int b = blockIdx.y, chunk = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     load_lines(p, b, sA, sB);
+    load_coord_table(tab, p.S);
     acc[warp][lane] = make_float4(0.f, 0.f, 0.f, 0.f);
     __syncthreads();
-    const float fS1 = (float)(p.S - 1);
     const int S = p.S;
     const float lscale = LOSS ? loss_grad_scale(mode, n, sums, g_loss) : 0.f;
     const float nibw = -1.0f / p.bw;
+    const size_t sample = (size_t)b * S * S;
+    recon += sample;
+    line_idx += sample;
+    if (g_ext) g_ext += sample;
+    if (LOSS) {
+        gt += sample;
+        if (weight) weight += sample;
+    }
+    struct TileIn {
+        float4 m4, e4, g4, w4;
+        uchar4 l4;
+        int px, py;
+        bool in;
+    };
+    auto fetch = [&](int tile, TileIn& t) {
+        int ty = (int)__umulhi((unsigned)tile, p.tiles_x_magic);
+        int tx = tile - ty * p.tiles_x;
+        if (tx >= p.tiles_x) { tx -= p.tiles_x; ++ty; }
+        t.py = ty * kTileH + (lane >> 2);
+        t.px = tx * kTileW + (lane & 3) * 4;
+        t.in = t.py < S && t.px < S;
+        t.e4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        t.w4 = make_float4(1.f, 1.f, 1.f, 1.f);
+        if (t.in) {
+            const int o = t.py * S + t.px;
+            t.m4 = *reinterpret_cast<const float4*>(recon + o);
+            t.l4 = *reinterpret_cast<const uchar4*>(line_idx + o);
+            if (g_ext) t.e4 = *reinterpret_cast<const float4*>(g_ext + o);
+            if (LOSS) {
+                t.g4 = *reinterpret_cast<const float4*>(gt + o);
+                if (weight) t.w4 = *reinterpret_cast<const float4*>(weight + o);
+            }
+        }
+    };
+    // (prefetching the next tile's inputs was measured: 80 registers, 3 CTAs/SM, 64 -> 76 us; not kept)
     const int t_end = min(p.tiles, (chunk + 1) * kTilesPerCta);
     for (int tile = chunk * kTilesPerCta + warp; tile < t_end; tile += kSkelWarps) {
-        const int ty = tile / p.tiles_x, tx = tile - ty * p.tiles_x;
-        const int py = ty * kTileH + (lane >> 2), px = tx * kTileW + (lane & 3) * 4;
+        TileIn cur;
+        fetch(tile, cur);
         float4 c[4];
         int li[4] = {-1, -1, -1, -1};
         unsigned bits = 0;
-        if (py < S && px < S) {
-            const size_t o = ((size_t)b * S + py) * S + px;
-            const float4 m4 = *reinterpret_cast<const float4*>(recon + o);
-            const uchar4 l4 = *reinterpret_cast<const uchar4*>(line_idx + o);
-            float4 e4 = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (g_ext) e4 = *reinterpret_cast<const float4*>(g_ext + o);
-            float G[4] = {e4.x, e4.y, e4.z, e4.w};
-            const float m[4] = {m4.x, m4.y, m4.z, m4.w};
-            const int ls[4] = {l4.x & 31, l4.y & 31, l4.z & 31, l4.w & 31};
+        if (cur.in) {
+            float G[4] = {cur.e4.x, cur.e4.y, cur.e4.z, cur.e4.w};
+            const float m[4] = {cur.m4.x, cur.m4.y, cur.m4.z, cur.m4.w};
+            const int ls[4] = {cur.l4.x & 31, cur.l4.y & 31, cur.l4.z & 31, cur.l4.w & 31};
             if (LOSS) {
-                const float4 g4 = *reinterpret_cast<const float4*>(gt + o);
-                float4 w4 = make_float4(1.f, 1.f, 1.f, 1.f);
-                if (weight) w4 = *reinterpret_cast<const float4*>(weight + o);
-                const float g[4] = {g4.x, g4.y, g4.z, g4.w}, w[4] = {w4.x, w4.y, w4.z, w4.w};
+                const float g[4] = {cur.g4.x, cur.g4.y, cur.g4.z, cur.g4.w}, w[4] = {cur.w4.x, cur.w4.y, cur.w4.z, cur.w4.w};
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
                     float s = lscale * (m[i] - g[i]);
@@ -264,14 +326,16 @@ __global__ void __launch_bounds__(kSkelThreads) skeleton_mask_bwd_kernel(const S
                     G[i] += s;
                 }
             }
-            const float gy = grid_coord(py, fS1);
+            const float gy = tab[cur.py];
+            const float4 gx4 = *reinterpret_cast<const float4*>(tab + cur.px);
+            const float gx[4] = {gx4.x, gx4.y, gx4.z, gx4.w};
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
                 const float4 Bv = sB[ls[i]];
                 const float wq = G[i] * m[i] * (Bv.w * nibw);            // dL/dq = G * heat * (-c / body_width)
                 if (wq != 0.0f) {
                     float dsx, dsy, dex, dey;
-                    seg_sqdist_grad(grid_coord(px + i, fS1), gy, sA[ls[i]], Bv, dsx, dsy, dex, dey);
+                    seg_sqdist_grad(gx[i], gy, sA[ls[i]], Bv, dsx, dsy, dex, dey);
                     c[i] = make_float4(wq * dsx, wq * dsy, wq * dex, wq * dey);
                     li[i] = ls[i];
                     bits |= 1u << ls[i];
@@ -330,19 +394,21 @@ __global__ void __launch_bounds__(128) skeleton_scatter_kernel(const SkelParams 
 
 // ---------------------------------------------------------------------------------------------- un-maxed heat-maps (util.draw_lines)
 __global__ void __launch_bounds__(256) draw_lines_fwd_kernel(const SkelParams p, float* __restrict__ heat) {
-    __shared__ float4 sA[XSUP_MAX_LINES], sB[XSUP_MAX_LINES];
+    __shared__ float4 sA[XSUP_MAX_LINES], sB[XSUP_MAX_LINES], sC[XSUP_MAX_LINES];
     const int b = blockIdx.z, l = blockIdx.y;
-    load_lines(p, b, sA, sB);
+    load_lines(p, b, sA, sB, sC);
     __syncthreads();
     const int S = p.S, quad = blockIdx.x * 256 + threadIdx.x;          // 4 consecutive pixels of one row
     if (quad * 4 >= S * S) return;
     const int py = (quad * 4) / S, px = quad * 4 - py * S;
     const float fS1 = (float)(S - 1);
-    const float4 A = sA[l], Bv = sB[l];
-    const float gy = grid_coord(py, fS1), ay = gy - A.y, aydy = ay * A.w, gey = gy - Bv.z;
+    const float4 A = sA[l], C = sC[l];
+    const float gy = grid_coord(py, fS1), ay = gy - A.y, aydyi = ay * C.y;
+    const float rbw = 1.0f / p.bw;
     float h[4];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) h[i] = expf(__fdiv_rn(-seg_sqdist(grid_coord(px + i, fS1), ay, aydy, gey, A, Bv), p.bw) * Bv.w);
+    for (int i = 0; i < 4; ++i)          // same operation sequence as the fused kernel: max over l of these == its output, bit for bit
+        h[i] = expf(-div_by(seg_sqdist(grid_coord(px + i, fS1) - A.x, ay, aydyi, A, C), p.bw, rbw) * C.z);
     *reinterpret_cast<float4*>(heat + (((size_t)b * p.L + l) * S + py) * S + px) = make_float4(h[0], h[1], h[2], h[3]);
 }
 
@@ -447,6 +513,7 @@ int mask_loss_ctas(long long n) {
 
 static void fill_tiles(SkelParams& p) {
     p.tiles_x = (p.S + kTileW - 1) / kTileW;
+    p.tiles_x_magic = p.tiles_x == 1 ? 0xffffffffu : (unsigned)(0x100000000ULL / (unsigned)p.tiles_x);   // floor: __umulhi may be one short, fixed up in the kernel
     p.tiles = p.tiles_x * ((p.S + kTileH - 1) / kTileH);
     p.NC = skel_chunks(p.S);
 }
@@ -455,13 +522,14 @@ cudaError_t launch_skeleton_mask_fwd(SkelParams p, float* recon, uint8_t* line_i
                                      const xsup_mask_loss_t* loss, float* loss_sums, float* ws, cudaStream_t st) {
     fill_tiles(p);
     const dim3 grid(p.NC, p.B);
+    const size_t tab_bytes = (size_t)p.S * sizeof(float);
     float* ws_loss = ws + (size_t)p.B * p.NC * XSUP_MAX_LINES * 4;
     if (loss) {
-        skeleton_mask_fwd_kernel<true><<<grid, kSkelThreads, 0, st>>>(p, recon, line_idx, gt, weight,
+        skeleton_mask_fwd_kernel<true><<<grid, kSkelThreads, tab_bytes, st>>>(p, recon, line_idx, gt, weight,
                                                                       loss->use_clip || loss->mode == XSUP_MASK_CLIP_MEAN, ws_loss);
         mask_loss_finalize_kernel<<<1, 256, 0, st>>>(ws_loss, p.B * p.NC, (double)loss->n, loss->mode, loss_sums);
     } else {
-        skeleton_mask_fwd_kernel<false><<<grid, kSkelThreads, 0, st>>>(p, recon, line_idx, nullptr, nullptr, 0, nullptr);
+        skeleton_mask_fwd_kernel<false><<<grid, kSkelThreads, tab_bytes, st>>>(p, recon, line_idx, nullptr, nullptr, 0, nullptr);
     }
     return cudaGetLastError();
 }
@@ -471,12 +539,13 @@ cudaError_t launch_skeleton_mask_bwd(SkelParams p, const float* recon, const uin
                                      const float* g_loss, float* g_kps, float* ws, cudaStream_t st) {
     fill_tiles(p);
     const dim3 grid(p.NC, p.B);
+    const size_t tab_bytes = (size_t)p.S * sizeof(float);
     if (loss)
-        skeleton_mask_bwd_kernel<true><<<grid, kSkelThreads, 0, st>>>(p, recon, line_idx, g_recon, gt, weight, loss->mode,
+        skeleton_mask_bwd_kernel<true><<<grid, kSkelThreads, tab_bytes, st>>>(p, recon, line_idx, g_recon, gt, weight, loss->mode,
                                                                      loss->use_clip || loss->mode == XSUP_MASK_CLIP_MEAN,
                                                                      (double)loss->n, loss_sums, g_loss, ws);
     else
-        skeleton_mask_bwd_kernel<false><<<grid, kSkelThreads, 0, st>>>(p, recon, line_idx, g_recon, nullptr, nullptr, 0, 0, 1.0,
+        skeleton_mask_bwd_kernel<false><<<grid, kSkelThreads, tab_bytes, st>>>(p, recon, line_idx, g_recon, nullptr, nullptr, 0, 0, 1.0,
                                                                       nullptr, nullptr, ws);
     skeleton_scatter_kernel<<<p.B, 128, 0, st>>>(p, p.NC, ws, g_kps);
     return cudaGetLastError();

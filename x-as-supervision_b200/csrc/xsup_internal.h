@@ -70,6 +70,7 @@ struct SkelParams {
     int B, K, S, L;
     float bw;                  // body_width (model.py:31-32)
     int tiles_x, tiles, NC;    // 16x8 pixel tiles per row / per sample, CTAs per sample
+    unsigned tiles_x_magic;    // floor(2^32 / tiles_x)
     int parent[XSUP_MAX_LINES], child[XSUP_MAX_LINES];
 };
 int skel_chunks(int S);
