@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define XSUP_ABI_VERSION 2
+#define XSUP_ABI_VERSION 3
 
 enum { XSUP_F32 = 0, XSUP_BF16 = 1 };
 enum { XSUP_HEAD_MULTI = 0, XSUP_HEAD_SINGLE = 1 };
@@ -225,6 +225,51 @@ int xsup_mask_loss_fwd(const float* mask, const float* gt, const float* weight, 
                        const xsup_mask_loss_t* cfg, float* loss_sums, float* ws, void* stream);
 int xsup_mask_loss_bwd(const float* mask, const float* gt, const float* weight, const xsup_mask_loss_t* cfg,
                        const float* loss_sums, const float* g_loss, float* g_mask, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Eval-side selection + triangulation, discriminator-side glue. */
+
+/* Replaces eval.py:122-148 + eval_utils.py:7-41 for one camera: normalise the pixel-space ground truth
+ * `joints_px [B,K,3]` (x,y -> [-1,1], z -> [0,1] by img_size-1), undo left/right swaps per hypothesis
+ * (`switch_points`, per joint, decided on the L1 error in x,y; perm[k] = the joint k swaps with), and per joint keep
+ * the hypothesis with the smallest squared error (best != 0, eval mode 'best') or hypothesis 0 ('confident').
+ *   kps [B,NH,K,3] -> kp3d [B,K,3], kp2d [B,K,2] (selected on the 2-D error), is_trans [B,K] uint8 (of the LAST
+ *   hypothesis, as the reference's loop leaves it), err2d [B] (`per_act_mse`), best_idx / best_2d_idx [B,K] int64,
+ *   gt_norm [B,K,3].  is_trans, err2d, best_idx, best_2d_idx, gt_norm may be NULL.  K <= 32. */
+typedef struct {
+    int32_t B, NH, K;
+    float img_size;            /* Eval.img_size (eval.py:72), 256 */
+    int32_t best;              /* 1: mode 'best', 0: 'confident' */
+    int32_t perm[32];
+} xsup_eval_t;
+int xsup_eval_select(const float* kps, const float* joints_px, const xsup_eval_t* cfg, float* kp3d, float* kp2d,
+                     uint8_t* is_trans, float* err2d, int64_t* best_idx, int64_t* best_2d_idx, float* gt_norm, void* stream);
+
+/* Replaces triangulation / batch_triangulate (modules/util.py:171-230): V <= 8 cameras, each with its patch
+ * keypoints kps[v] [B,K,3] and camera tensors; world [B,K,3] out = the DLT solution (right singular vector of
+ * the smallest singular value of the [2V,4] system, rows weighted by the metric depth as in the reference). */
+#define XSUP_MAX_VIEWS 8
+typedef struct {
+    int32_t V, B, K;
+    int32_t img_h, img_w, is_norm;
+    float rect_width;
+    const float* kps[XSUP_MAX_VIEWS];
+    xsup_cam_t cam[XSUP_MAX_VIEWS];
+} xsup_tri_t;
+int xsup_triangulate(const xsup_tri_t* t, float* world, void* stream);
+
+/* modules/model.py:123-124: out [N,K,dim] = (world [N,K,3] - world[:, 0]) / 1000, first `dim` coordinates
+ * (DISC_SUP_DIMENSION); `_bwd` is its vector-Jacobian product (g_world [N,K,3]). */
+int xsup_root_centre_fwd(const float* world, float* out, int32_t N, int32_t K, int32_t dim, void* stream);
+int xsup_root_centre_bwd(const float* g_out, float* g_world, int32_t N, int32_t K, int32_t dim, void* stream);
+
+/* One term of compute_disc_loss (modules/base_losses/loss_func.py:54-76) on logits [B,NH,C]:
+ * loss = mean over (b,c) of min over h of (x - target)^2; sel [B,C] int64 = the argmin (first minimum).  NH = 1
+ * is the 2-D-input case.  `_bwd`: g_logits [B,NH,C] = g_loss * d loss / d logits (only the selected slot). */
+int xsup_disc_min_loss_fwd(const float* logits, int32_t B, int32_t NH, int32_t C, float target, float* loss, int64_t* sel,
+                           void* stream);
+int xsup_disc_min_loss_bwd(const float* logits, const int64_t* sel, const float* g_loss, int32_t B, int32_t NH, int32_t C,
+                           float target, float* g_logits, void* stream);
 
 #ifdef __cplusplus
 }

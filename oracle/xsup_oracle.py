@@ -415,3 +415,96 @@ def mask_recon_loss(mask, gt, weight=None, use_clip=False):
     if weight is not None:
         loss = (loss * weight).mean()
     return loss
+
+
+# --------------------------------------------------------------------------- eval-side selection + triangulation
+SWITCH_LIST = ((1, 4), (2, 5), (3, 6), (14, 11), (15, 12), (16, 13))     # left/right pairs, eval_utils.py:8
+
+
+def switch_points(points, gt, switch_all=False, switch_list=SWITCH_LIST):
+    """eval_utils.py:7-29: left/right-swapped copy of `points [B,K,C]`, kept wherever its L1 error in
+    (x, y) against `gt` is strictly smaller - per joint, or per sample with `switch_all`."""
+    perm = list(range(points.shape[1]))
+    for a, b in switch_list:
+        perm[a], perm[b] = b, a
+    swapped = points[:, perm, :]
+    e_sw = (swapped - gt).abs()[..., :2]
+    e = (points - gt).abs()[..., :2]
+    dims = (1, 2) if switch_all else (2,)
+    is_trans = e_sw.sum(dim=dims, keepdim=True) < e.sum(dim=dims, keepdim=True)
+    return torch.where(is_trans, swapped, points), is_trans
+
+
+def per_act_mse(pred, gt):
+    """eval_utils.py:31-41: mean over joints of the 2-D Euclidean error in [0,1] patch units -> `[B]`."""
+    return ((((pred + 1) / 2 - (gt + 1) / 2) ** 2).sum(dim=2)).sqrt().mean(dim=1)
+
+
+def eval_select(kps, joints_px, img_size=256.0, mode="best"):
+    """eval.py:117-148 for one camera: normalise the pixel-space ground truth, undo left/right swaps per
+    hypothesis (2-D copy and 3-D prediction separately), then per joint keep the hypothesis closest to the
+    ground truth ('best') or hypothesis 0 ('confident').
+    Returns (kp3d [B,K,3], kp2d [B,K,2], is_trans [B,K,1] of the LAST hypothesis (the reference overwrites
+    `trans_dict[cam_key]` in its loop), err2d [B], best_idx [B,K], best_2d_idx [B,K], gt_norm [B,K,3])."""
+    B, NH, K, _ = kps.shape
+    gt = joints_px.clone()
+    gt[..., :2] = gt[..., :2] / (img_size - 1) * 2 - 1
+    gt[..., 2] = gt[..., 2] / (img_size - 1)
+    k3 = kps.clone()
+    k2 = kps[..., :2].clone()
+    is_trans = None
+    for h in range(NH):
+        k2[:, h], _ = switch_points(k2[:, h], gt[..., :2])
+        k3[:, h], is_trans = switch_points(k3[:, h], gt, switch_all=False)
+    if mode == "best" and NH > 1:
+        bi = (k3 - gt[:, None]).pow(2).sum(-1).argmin(dim=1)
+        k3 = torch.gather(k3, 1, bi[:, None, :, None].expand(-1, -1, -1, 3)).squeeze(1)
+        b2 = (k2 - gt[:, None, :, :2]).pow(2).sum(-1).argmin(dim=1)
+        k2 = torch.gather(k2, 1, b2[:, None, :, None].expand(-1, -1, -1, 2)).squeeze(1)
+    else:
+        bi = torch.zeros(B, K, dtype=torch.long, device=kps.device)
+        b2 = bi
+        k3, k2 = k3[:, 0], k2[:, 0]
+    return k3, k2, is_trans, per_act_mse(k2, gt[..., :2]), bi, b2, gt
+
+
+def triangulate(kps_by_cam, cams_by_cam, img_hw=(256, 256), is_norm=True, rect_width=2000.0):
+    """triangulation + batch_triangulate (util.py:171-230): every camera's patch keypoints `[B,K,3]` to image
+    pixels (+ metric depth, which the reference then uses as the per-point confidence weight), P = K [R|T],
+    the two DLT rows per view, and the right singular vector of the smallest singular value, dehomogenised."""
+    img_h, img_w = img_hw
+    pts, Ps = [], []
+    for kps, cams in zip(kps_by_cam, cams_by_cam):
+        pts.append(patch_to_image(kps, cams["trans_image"], img_w, img_h, img_w, 1.0 / img_w * rect_width,
+                                  cams["pelvis"], is_norm=is_norm))
+        Ps.append(cams["k_mat"] @ torch.cat((cams["rot_world"], cams["trans_world"].unsqueeze(-1)), dim=-1))
+    pts = torch.stack(pts, dim=1)                                    # [B,V,K,3]
+    P = torch.stack(Ps, dim=1)                                       # [B,V,3,4]
+    u = pts[..., 0].permute(0, 2, 1)[..., None]                      # [B,K,V,1]
+    v = pts[..., 1].permute(0, 2, 1)[..., None]
+    conf = pts[..., 2].permute(0, 2, 1)[..., None]
+    P0, P1, P2 = (P[:, None, :, i, :] for i in range(3))             # [B,1,V,4]
+    A = torch.cat((conf * (u * P2 - P0), conf * (v * P2 - P1)), dim=2)   # [B,K,2V,4]
+    X = torch.linalg.svd(A)[2][:, :, -1, :]
+    return (X / X[..., 3:])[..., :3]
+
+
+# --------------------------------------------------------------------------- discriminator-side glue (SURVEY §8f row 4)
+def root_centre(world, dim=3):
+    """model.py:123-124: world joints relative to joint 0, in metres, first `dim` coordinates."""
+    return ((world - world[..., [0], :]) / 1000)[..., :dim]
+
+
+def disc_loss(pred_logits, gt_logits=None):
+    """compute_disc_loss (loss_func.py:54-76): least-squares GAN terms; a `[B,NH,1]` input takes the
+    per-sample min over hypotheses before the batch mean."""
+    def term(x, target):
+        e = (x - target).pow(2)
+        if x.dim() == 3:
+            e = e.min(dim=1)[0]
+        elif x.dim() != 2:
+            raise ValueError("Invalid dimension of logits")
+        return e.mean()
+    if gt_logits is None:
+        return term(pred_logits, 1.0)
+    return 0.5 * term(gt_logits, 1.0) + 0.5 * term(pred_logits, 0.0)

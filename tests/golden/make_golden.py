@@ -236,13 +236,74 @@ def skeleton_case(util, lf, model, name, B, K, S, seed, extension, sub):
     print("wrote", name, {k: float(out["loss_%s_f64" % k]) for k, _, _ in LOSS_VARIANTS}, "lines", len(parent))
 
 
+def load_eval_utils():
+    """eval_utils.py imports matplotlib and train_util at module level only for plotting helpers: stub them."""
+    for m in ("matplotlib", "matplotlib.gridspec", "matplotlib.pyplot"):
+        sys.modules.setdefault(m, types.ModuleType(m))
+    tu = types.ModuleType("train_util")
+    tu.pose_vis = None
+    sys.modules.setdefault("train_util", tu)
+    return importlib.import_module("eval_utils")
+
+
+def eval_case(util, lf, eu, name, B, NH, K, V, seed):
+    """eval.py:122-148 (its own lines, driven with eval_utils.switch_points / per_act_mse), util.triangulation on V
+    synthetic cameras, and loss_func.compute_disc_loss in its four input-shape combinations."""
+    kps32, jp32 = synth.eval_predictions(B, NH, K, seed=seed)
+    gen = torch.Generator().manual_seed(400 + seed)
+    world = torch.randn(B, K, 3, generator=gen) * 300
+    cams = [synth.cameras(B, seed=seed + 10 + i) for i in range(V)]
+    noise = [0.002 * torch.randn(B, K, 3, generator=gen) for _ in range(V)]
+    logits = {"p2": torch.randn(B, 1, generator=gen), "g2": torch.randn(B, 1, generator=gen),
+              "p3": torch.randn(B, NH, 1, generator=gen), "g3": torch.randn(B, NH, 1, generator=gen)}
+    out = {"meta": np.array([B, NH, K, V, seed]), "in_checksum": checksum(kps32), "jp_checksum": checksum(jp32),
+           "world_checksum": checksum(world)}
+    for tag, dt in (("f32", torch.float32), ("f64", torch.float64)):
+        kps, jp = kps32.to(dt), jp32.to(dt)
+        kp_gt = jp.clone()
+        kp_gt[..., :2] = kp_gt[..., :2] / (256.0 - 1) * 2 - 1
+        kp_gt[..., 2] = kp_gt[..., 2] / (256.0 - 1)
+        kd, k2 = kps.clone(), kps.clone()[..., :2]
+        tr = None
+        for h in range(NH):
+            k2[:, h, ...], _ = eu.switch_points(k2[:, h, ...], kp_gt[..., :2])
+            kd[:, h, ...], tr = eu.switch_points(kd[:, h, ...], kp_gt, switch_all=False)
+        best_idx = (kd - kp_gt[:, None, ...]).pow(2).sum(dim=-1).argmin(dim=1)
+        kbest = torch.gather(kd, 1, best_idx[:, None, :, None].expand(-1, -1, -1, 3)).squeeze(1)
+        best_2d_idx = (k2 - kp_gt[:, None, ..., :2]).pow(2).sum(dim=-1).argmin(dim=1)
+        k2best = torch.gather(k2, 1, best_2d_idx[:, None, :, None].expand(-1, -1, -1, 2)).squeeze(1)
+        out["kp3d_" + tag], out["kp2d_" + tag] = kbest.numpy(), k2best.numpy()
+        out["is_trans_" + tag], out["best_idx_" + tag], out["best_2d_idx_" + tag] = tr.numpy(), best_idx.numpy(), best_2d_idx.numpy()
+        out["err2d_" + tag] = eu.per_act_mse(k2best, kp_gt[..., :2]).numpy()
+        out["err2d_h0_" + tag] = eu.per_act_mse(k2[:, 0], kp_gt[..., :2]).numpy()          # mode 'confident'
+        # triangulation: each camera observes the same world points (projected with the reference's own inverse), + noise
+        params, kd3 = {}, {}
+        for i, c in enumerate(cams):
+            cd = {k: v.to(dt) for k, v in c.items()}
+            params.update(synth.camera_dict(cd, "cam_%d" % i))
+            kd3["cam_%d" % i] = util.convert_world_to_patch(world.to(dt), params, "cam_%d" % i, is_norm=True) + noise[i].to(dt)
+        out["tri_" + tag] = util.triangulation(kd3, params, list(range(V))).numpy()
+        if tag == "f32":
+            out["tri_inputs_f32"] = torch.stack([kd3["cam_%d" % i] for i in range(V)]).numpy()
+        L = {k: v.to(dt) for k, v in logits.items()}
+        out["disc_" + tag] = np.array([lf.compute_disc_loss(L["p2"], None).item(), lf.compute_disc_loss(L["p3"], None).item(),
+                                       lf.compute_disc_loss(L["p2"], L["g2"]).item(), lf.compute_disc_loss(L["p3"], L["g3"]).item(),
+                                       lf.compute_disc_loss(L["p3"], L["g2"]).item()])
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
+    print("wrote", name, "swapped joints", int(out["is_trans_f64"].sum()), "disc", out["disc_f64"])
+
+
 def main():
     torch.manual_seed(0)
     torch.set_num_threads(8)
     multi, single, util, lf = load_reference()
     model = importlib.import_module("modules.model")
+    if "--only-eval" in sys.argv:
+        eval_case(util, lf, load_eval_utils(), "eval_k18_nh3_v4", B=6, NH=3, K=18, V=4, seed=80)
+        return
     if "--only-skeleton" not in sys.argv:
         main_head_and_loss(multi, single, util, lf)
+        eval_case(util, lf, load_eval_utils(), "eval_k18_nh3_v4", B=6, NH=3, K=18, V=4, seed=80)
     # skeleton rasteriser + mask loss: 25 lines (17 tree links + 8 braces, arm lines at half width) and the
     # 17-line variant without the braces (below the 21-line threshold of util.py:50)
     skeleton_case(util, lf, model, "skel_h36m_s128", B=2, K=18, S=128, seed=30, extension=True, sub=8)

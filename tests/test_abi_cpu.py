@@ -26,7 +26,7 @@ def test_library_exports_every_declared_symbol(cabi):
     assert declared == set(cabi.SYMBOLS)
     for name in declared:
         assert hasattr(cabi.lib, name), name
-    assert cabi.lib.xsup_abi_version() == cabi.ABI_VERSION == 2
+    assert cabi.lib.xsup_abi_version() == cabi.ABI_VERSION == 3
 
 
 def test_struct_layouts_match_header(cabi):
@@ -70,6 +70,26 @@ def test_skeleton_structs_and_validation(cabi):
     assert cabi.lib.xsup_mask_loss_fwd(p, p, None, None, cabi.MaskLoss(0, 0, 0), p, p, None) == -1            # empty mask
     assert cabi.lib.xsup_mask_loss_fwd(p, p, None, None, cabi.MaskLoss(64, 2, 0), p, p, None) == -3
     assert cabi.lib.xsup_skeleton_mask_fwd(p, skel(B=0), None, None, None, None, None, None, None, None) == 0  # empty batch: no-op
+
+
+def test_eval_structs_and_validation(cabi):
+    assert C.sizeof(cabi.Eval) == (5 + 32) * 4
+    assert C.sizeof(cabi.Tri) == 8 * 4 + 8 * 8 + 8 * C.sizeof(cabi.Cam)      # 7 words + padding, 8 pointers, 8 cameras
+    buf = (C.c_float * 64)()
+    p = C.addressof(buf)
+    cfg = cabi.Eval(4, 3, 40, 256.0, 1)
+    assert cabi.lib.xsup_eval_select(p, p, cfg, p, p, None, None, None, None, None, None) == -1           # K > 32
+    cfg = cabi.Eval(4, 3, 18, 256.0, 1)
+    cfg.perm[2] = 18
+    assert cabi.lib.xsup_eval_select(p, p, cfg, p, p, None, None, None, None, None, None) == -1           # perm outside [0,K)
+    cfg = cabi.Eval(4, 3, 18, 256.0, 1)
+    assert cabi.lib.xsup_eval_select(None, p, cfg, p, p, None, None, None, None, None, None) == -3
+    t = cabi.Tri(1, 4, 18, 256, 256, 1, 2000.0)
+    assert cabi.lib.xsup_triangulate(t, p, None) == -1                                                    # one view
+    t = cabi.Tri(2, 4, 18, 256, 256, 1, 2000.0)
+    assert cabi.lib.xsup_triangulate(t, p, None) == -3                                                    # NULL keypoints
+    assert cabi.lib.xsup_root_centre_fwd(p, p, 4, 18, 4, None) == -1                                      # dim > 3
+    assert cabi.lib.xsup_disc_min_loss_fwd(p, 0, 3, 1, 1.0, p, p, None) == -1                             # empty batch
 
 
 def test_strides(cabi):

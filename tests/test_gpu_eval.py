@@ -1,0 +1,129 @@
+"""GPU parity tests (`-m gpu`, through the C ABI) of the eval-side selection + triangulation and the
+discriminator-side glue against the CPU oracle (itself checked against the reference's eval_utils / util /
+loss_func in test_oracle_golden.py).  Index outputs (best hypothesis, swap decisions, argmin slots) are
+bit-exact; coordinates 1e-6 absolute (pure selection, no arithmetic); triangulated points 1e-5 relative to
+the scene scale against the fp64 oracle; losses and gradients 1e-6 relative."""
+import importlib
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_golden
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ev():
+    import __graft_entry__ as ge
+    ge.build()
+    pkg = importlib.import_module("x-as-supervision_b200")
+    pkg.load_native()
+    return pkg.evalops
+
+
+@pytest.fixture(scope="module")
+def dev():
+    return torch.device("cuda:0")
+
+
+@pytest.mark.parametrize("B,NH,K,mode", [(7, 3, 18, "best"), (64, 3, 17, "best"), (5, 1, 18, "best"), (9, 4, 18, "confident"),
+                                         (256, 8, 17, "best")])
+def test_eval_select_matches_oracle(ev, oracle, synth, dev, B, NH, K, mode):
+    kps, jp = synth.eval_predictions(B, NH, K, seed=B + NH)
+    out = ev.eval_select(kps.to(dev), jp.to(dev), 256.0, mode)
+    k3, k2, tr, err, bi, b2, gt = oracle.eval_select(kps, jp, 256.0, mode)
+    assert torch.equal(out["best_idx"].cpu(), bi) and torch.equal(out["best_2d_idx"].cpu(), b2)
+    assert torch.equal(out["is_trans"].cpu(), tr)
+    assert torch.equal(out["kp3d"].cpu(), k3) and torch.equal(out["kp2d"].cpu(), k2)       # pure selection: bit-exact
+    assert torch.equal(out["gt"].cpu(), gt)
+    assert float((out["err2d"].cpu() - err).abs().max()) < 1e-6
+    # fp64 oracle makes the same decisions (no near-ties in these inputs)
+    k3d, _, trd, errd, bid, b2d, _ = oracle.eval_select(kps.double(), jp.double(), 256.0, mode)
+    assert torch.equal(bid, bi) and torch.equal(b2d, b2) and torch.equal(trd, tr)
+
+
+def test_switch_points_drop_in(ev, oracle, synth, dev):
+    kps, jp = synth.eval_predictions(11, 1, 18, seed=3)
+    gt = jp.clone()
+    gt[..., :2] = gt[..., :2] / 255 * 2 - 1
+    gt[..., 2] = gt[..., 2] / 255
+    for C in (3, 2):
+        res, tr = ev.switch_points(kps[:, 0, :, :C].to(dev), gt[..., :C].to(dev))
+        ores, otr = oracle.switch_points(kps[:, 0, :, :C], gt[..., :C])
+        assert torch.equal(tr.cpu(), otr) and torch.equal(res.cpu(), ores)
+
+
+def test_eval_side_against_reference_golden(ev, synth, dev):
+    g = load_golden("eval_k18_nh3_v4")
+    B, NH, K, V, seed = (int(v) for v in g["meta"])
+    kps, jp = synth.eval_predictions(B, NH, K, seed=seed)
+    out = ev.eval_select(kps.to(dev), jp.to(dev), 256.0, "best")
+    assert np.array_equal(out["best_idx"].cpu().numpy(), g["best_idx_f64"])
+    assert np.array_equal(out["best_2d_idx"].cpu().numpy(), g["best_2d_idx_f64"])
+    assert np.array_equal(out["is_trans"].cpu().numpy(), g["is_trans_f64"])
+    assert np.array_equal(out["kp3d"].cpu().numpy(), g["kp3d_f32"]) and np.array_equal(out["kp2d"].cpu().numpy(), g["kp2d_f32"])
+    assert np.abs(out["err2d"].cpu().numpy() - g["err2d_f64"]).max() < 1e-6
+    cams = [{k: v.to(dev) for k, v in synth.cameras(B, seed=seed + 10 + i).items()} for i in range(V)]
+    tri = ev.triangulate([torch.from_numpy(g["tri_inputs_f32"][i]).to(dev) for i in range(V)], cams)
+    # fp32 inputs (the reference's fp32 projections), fp64 solve: within 0.05 mm of the reference's fp64 run on 10^3 mm scenes
+    assert np.abs(tri.cpu().numpy() - g["tri_f64"]).max() < 0.05
+
+
+@pytest.mark.parametrize("V,B,K", [(4, 6, 18), (2, 33, 17), (8, 3, 18)])
+def test_triangulation_matches_oracle(ev, oracle, synth, dev, V, B, K):
+    g = torch.Generator().manual_seed(V * 100 + B)
+    world = torch.randn(B, K, 3, generator=g) * 300
+    cams = [synth.cameras(B, seed=70 + i) for i in range(V)]
+    kpc = [oracle.world_to_patch(world.double(), {k: v.double() for k, v in c.items()}).float()
+           + 0.002 * torch.randn(B, K, 3, generator=g) for c in cams]
+    ref = oracle.triangulate([k.double() for k in kpc], [{k: v.double() for k, v in c.items()} for c in cams])
+    out = ev.triangulate([k.to(dev) for k in kpc], [{k: v.to(dev) for k, v in c.items()} for c in cams])
+    scale = float(ref.abs().max())
+    assert float((out.cpu().double() - ref).abs().max()) < 1e-5 * scale
+    assert float((out.cpu() - world).abs().max()) < 25.0            # and it is a sensible reconstruction (mm)
+    # dict-keyed drop-in signature (util.py:171)
+    params, kd = {}, {}
+    for i, c in enumerate(cams):
+        params.update({k: v.to(dev) for k, v in synth.camera_dict(c, "cam_%d" % i).items()})
+        kd["cam_%d" % i] = kpc[i].to(dev)
+    out2 = ev.triangulation(kd, params, list(range(V)))
+    assert torch.equal(out2, out)
+
+
+@pytest.mark.parametrize("dim", [3, 2])
+def test_root_centre_and_batched_scoring(ev, oracle, dev, dim):
+    g = torch.Generator().manual_seed(9)
+    world = torch.randn(6, 3, 18, 3, generator=g) * 400
+    w = world.to(dev).requires_grad_(True)
+    out = ev.root_centre(w, dim)
+    w64 = world.double().requires_grad_(True)
+    ref = oracle.root_centre(w64, dim)
+    assert float((out.detach().cpu().double() - ref.detach()).abs().max()) < 1e-6 * float(ref.abs().max())
+    G = torch.randn(out.shape, generator=g)
+    out.backward(G.to(dev))
+    ref.backward(G.double())
+    assert float((w.grad.cpu().double() - w64.grad).abs().max()) < 1e-6 * float(w64.grad.abs().max())
+    assert float(out.detach()[..., 0, :].abs().max()) == 0.0        # the root is exactly the origin
+
+
+@pytest.mark.parametrize("shape", [(16, 1), (16, 3, 1), (5, 4, 2), (256, 3, 1)])
+def test_disc_loss_matches_oracle(ev, oracle, dev, shape):
+    g = torch.Generator().manual_seed(sum(shape))
+    p, q = torch.randn(shape, generator=g), torch.randn(shape, generator=g)
+    for gt in (None, q):
+        x = p.to(dev).requires_grad_(True)
+        y = gt.to(dev).requires_grad_(True) if gt is not None else None
+        loss = ev.compute_disc_loss(x, y)
+        x64 = p.double().requires_grad_(True)
+        y64 = gt.double().requires_grad_(True) if gt is not None else None
+        ref = oracle.disc_loss(x64, y64)
+        assert abs(float(loss) - float(ref)) < 1e-6 * abs(float(ref))
+        loss.backward()
+        ref.backward()
+        assert float((x.grad.cpu().double() - x64.grad).abs().max()) < 1e-6 * float(x64.grad.abs().max())
+        if gt is not None:
+            assert float((y.grad.cpu().double() - y64.grad).abs().max()) < 1e-6 * float(y64.grad.abs().max())
+    with pytest.raises(ValueError, match="Invalid dimension"):
+        ev.compute_disc_loss(torch.zeros(3, device=dev), None)

@@ -184,3 +184,37 @@ def test_skeleton_rasteriser_matches_reference(oracle, synth, name, tag, dtype, 
         assert abs(float(loss.mean().detach()) - ref) < vtol * 10 * abs(ref), vname
         gl, = torch.autograd.grad(loss.mean(), kp, retain_graph=True)
         assert rel_inf(gl.numpy(), g["g_loss_%s_%s" % (vname, tag)]) < vtol * 50, vname
+
+
+# --------------------------------------------------------------------------- eval selection, triangulation, discriminator loss
+@pytest.mark.parametrize("tag,dtype,tol", [("f64", torch.float64, 1e-9), ("f32", torch.float32, 1e-6)])
+def test_eval_side_matches_reference(oracle, synth, tag, dtype, tol):
+    g = load_golden("eval_k18_nh3_v4")
+    B, NH, K, V, seed = (int(v) for v in g["meta"])
+    kps, jp = synth.eval_predictions(B, NH, K, seed=seed)
+    np.testing.assert_allclose(input_checksum(kps), g["in_checksum"], rtol=1e-12)
+    np.testing.assert_allclose(input_checksum(jp), g["jp_checksum"], rtol=1e-12)
+    k3, k2, tr, err, bi, b2, gt = oracle.eval_select(kps.to(dtype), jp.to(dtype), 256.0, "best")
+    assert np.array_equal(bi.numpy(), g["best_idx_" + tag]) and np.array_equal(b2.numpy(), g["best_2d_idx_" + tag])
+    assert np.array_equal(tr.numpy(), g["is_trans_" + tag]) and g["is_trans_" + tag].sum() > 0
+    assert np.array_equal(k3.numpy(), g["kp3d_" + tag]) and np.array_equal(k2.numpy(), g["kp2d_" + tag])
+    assert np.abs(err.numpy() - g["err2d_" + tag]).max() < tol
+    _, _, _, err0, bi0, _, _ = oracle.eval_select(kps.to(dtype), jp.to(dtype), 256.0, "confident")
+    assert np.abs(err0.numpy() - g["err2d_h0_" + tag]).max() < tol and int(bi0.abs().max()) == 0
+    # triangulation on the reference's own camera inputs
+    gen = torch.Generator().manual_seed(400 + seed)
+    world = torch.randn(B, K, 3, generator=gen) * 300
+    np.testing.assert_allclose(input_checksum(world), g["world_checksum"], rtol=1e-12)
+    cams = [{k: v.to(dtype) for k, v in synth.cameras(B, seed=seed + 10 + i).items()} for i in range(V)]
+    noise = [0.002 * torch.randn(B, K, 3, generator=gen) for _ in range(V)]
+    kpc = [oracle.world_to_patch(world.to(dtype), c) + n.to(dtype) for c, n in zip(cams, noise)]
+    tri = oracle.triangulate(kpc, cams)
+    # the reference writes its result through a float32 buffer (util.py:226) and its fp32 SVD of the badly scaled
+    # DLT matrix is itself only ~1e-3 mm accurate, so: fp64 run to 1e-3 mm of 10^3 mm, fp32 run to 0.5 mm
+    assert np.abs(tri.numpy() - g["tri_" + tag]).max() < (1e-3 if tag == "f64" else 0.5)
+    logits = {"p2": torch.randn(B, 1, generator=gen), "g2": torch.randn(B, 1, generator=gen),
+              "p3": torch.randn(B, NH, 1, generator=gen), "g3": torch.randn(B, NH, 1, generator=gen)}
+    L = {k: v.to(dtype) for k, v in logits.items()}
+    ours = [oracle.disc_loss(L["p2"], None), oracle.disc_loss(L["p3"], None), oracle.disc_loss(L["p2"], L["g2"]),
+            oracle.disc_loss(L["p3"], L["g3"]), oracle.disc_loss(L["p3"], L["g2"])]
+    np.testing.assert_allclose(np.array([float(v) for v in ours]), g["disc_" + tag], rtol=tol * 10)

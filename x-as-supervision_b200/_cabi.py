@@ -31,7 +31,10 @@ SYMBOLS = (
     "xsup_skel_ws_floats", "xsup_draw_lines_ws_floats", "xsup_mask_loss_ws_floats",
     "xsup_draw_lines_fwd", "xsup_draw_lines_bwd", "xsup_skeleton_mask_fwd", "xsup_skeleton_mask_bwd",
     "xsup_mask_loss_fwd", "xsup_mask_loss_bwd",
+    "xsup_eval_select", "xsup_triangulate", "xsup_root_centre_fwd", "xsup_root_centre_bwd",
+    "xsup_disc_min_loss_fwd", "xsup_disc_min_loss_bwd",
 )
+MAX_VIEWS = 8
 MAX_LINES = 32
 MASK_MSE, MASK_CLIP_MEAN, MASK_WEIGHTED = 0, 1, 2
 MASK_SUMS = 4
@@ -60,6 +63,16 @@ class Skel(C.Structure):
 
 class MaskLoss(C.Structure):
     _fields_ = [("n", C.c_int64), ("mode", C.c_int32), ("use_clip", C.c_int32)]
+
+
+class Eval(C.Structure):
+    _fields_ = [("B", C.c_int32), ("NH", C.c_int32), ("K", C.c_int32), ("img_size", C.c_float), ("best", C.c_int32),
+                ("perm", C.c_int32 * 32)]
+
+
+class Tri(C.Structure):
+    _fields_ = [("V", C.c_int32), ("B", C.c_int32), ("K", C.c_int32), ("img_h", C.c_int32), ("img_w", C.c_int32),
+                ("is_norm", C.c_int32), ("rect_width", C.c_float), ("kps", C.c_void_p * MAX_VIEWS), ("cam", Cam * MAX_VIEWS)]
 
 
 class Xchg(C.Structure):
@@ -109,8 +122,16 @@ def _load():
     lib.xsup_skeleton_mask_bwd.argtypes = [vp, sk, vp, vp, vp, vp, vp, ml, vp, vp, vp, vp, vp]
     lib.xsup_mask_loss_fwd.argtypes = [vp, vp, vp, vp, ml, vp, vp, vp]
     lib.xsup_mask_loss_bwd.argtypes = [vp, vp, vp, ml, vp, vp, vp, vp]
+    lib.xsup_eval_select.argtypes = [vp, vp, C.POINTER(Eval), vp, vp, vp, vp, vp, vp, vp, vp]
+    lib.xsup_triangulate.argtypes = [C.POINTER(Tri), vp, vp]
+    lib.xsup_root_centre_fwd.argtypes = [vp, vp, i32, i32, i32, vp]
+    lib.xsup_root_centre_bwd.argtypes = [vp, vp, i32, i32, i32, vp]
+    lib.xsup_disc_min_loss_fwd.argtypes = [vp, i32, i32, i32, f32, vp, vp, vp]
+    lib.xsup_disc_min_loss_bwd.argtypes = [vp, vp, vp, i32, i32, i32, f32, vp, vp]
     for name in SYMBOLS:
         fn = getattr(lib, name)
+        if name.startswith(("xsup_eval", "xsup_triangulate", "xsup_root", "xsup_disc")):
+            fn.restype = C.c_int
         if name.startswith(("xsup_integral", "xsup_find", "xsup_patch", "xsup_world", "xsup_reproj", "xsup_draw_lines_f",
                             "xsup_draw_lines_b", "xsup_skeleton", "xsup_mask_loss_f", "xsup_mask_loss_b")):
             fn.restype = C.c_int
@@ -118,7 +139,7 @@ def _load():
 
 
 lib = _load()
-ABI_VERSION = 2
+ABI_VERSION = 3
 if lib.xsup_abi_version() != ABI_VERSION:
     raise ImportError("libxsup_b200.so ABI version %d, expected %d: rebuild with __graft_entry__.build()"
                       % (lib.xsup_abi_version(), ABI_VERSION))

@@ -414,4 +414,80 @@ int xsup_mask_loss_bwd(const float* mask, const float* gt, const float* weight, 
     return XSUP_OK;
 }
 
+// ------------------------------------------------------------------------------------------------ eval selection, triangulation, discriminator glue
+int xsup_eval_select(const float* kps, const float* joints_px, const xsup_eval_t* cfg, float* kp3d, float* kp2d, uint8_t* is_trans,
+                     float* err2d, int64_t* best_idx, int64_t* best_2d_idx, float* gt_norm, void* stream) {
+    if (!cfg) return fail(XSUP_E_NULL, "xsup_eval_select: cfg is NULL");
+    if (cfg->B < 0 || cfg->NH < 1 || cfg->K < 1 || cfg->K > 32) return fail(XSUP_E_SHAPE, "xsup_eval_select: need B >= 0, NH >= 1, 1 <= K <= 32 (one joint per lane)");
+    if (!(cfg->img_size > 1.0f)) return fail(XSUP_E_SHAPE, "xsup_eval_select: img_size must exceed 1");
+    for (int k = 0; k < cfg->K; ++k)
+        if (cfg->perm[k] < 0 || cfg->perm[k] >= cfg->K) return fail(XSUP_E_SHAPE, "xsup_eval_select: perm[%d] = %d outside [0,%d)", k, cfg->perm[k], cfg->K);
+    if (cfg->B == 0) return XSUP_OK;
+    if (!kps || !joints_px || !kp3d || !kp2d) return fail(XSUP_E_NULL, "xsup_eval_select: NULL pointer");
+    EvalParams p{};
+    p.kps = kps; p.joints_px = joints_px; p.img_size = cfg->img_size; p.B = cfg->B; p.NH = cfg->NH; p.K = cfg->K; p.best = cfg->best;
+    p.kp3d = kp3d; p.kp2d = kp2d; p.is_trans = is_trans; p.err2d = err2d; p.best_idx = best_idx; p.best_2d_idx = best_2d_idx; p.gt_norm = gt_norm;
+    for (int k = 0; k < 32; ++k) p.perm[k] = k < cfg->K ? cfg->perm[k] : k;
+    cudaError_t e = launch_eval_select(p, (cudaStream_t)stream);
+    if (e != cudaSuccess) return cuda_fail(e, "xsup_eval_select launch");
+    count_launches(1);
+    return XSUP_OK;
+}
+
+int xsup_triangulate(const xsup_tri_t* t, float* world, void* stream) {
+    if (!t) return fail(XSUP_E_NULL, "xsup_triangulate: description is NULL");
+    if (t->V < 2 || t->V > XSUP_MAX_VIEWS) return fail(XSUP_E_SHAPE, "xsup_triangulate: %d views, need 2..%d", t->V, XSUP_MAX_VIEWS);
+    if (t->B < 0 || t->K < 1 || t->img_h <= 1 || t->img_w <= 1) return fail(XSUP_E_SHAPE, "xsup_triangulate: bad sizes");
+    if (t->B == 0) return XSUP_OK;
+    if (!world) return fail(XSUP_E_NULL, "xsup_triangulate: world is NULL");
+    for (int v = 0; v < t->V; ++v) {
+        if (!t->kps[v]) return fail(XSUP_E_NULL, "xsup_triangulate: kps[%d] is NULL", v);
+        if (int rc = check_cam(&t->cam[v], "xsup_triangulate")) return rc;
+    }
+    cudaError_t e = launch_triangulate(*t, world, (cudaStream_t)stream);
+    if (e != cudaSuccess) return cuda_fail(e, "xsup_triangulate launch");
+    count_launches(1);
+    return XSUP_OK;
+}
+
+static int check_root(const void* a, const void* b, int N, int K, int dim, const char* who) {
+    if (N < 0 || K < 1 || dim < 1 || dim > 3) return fail(XSUP_E_SHAPE, "%s: need N >= 0, K >= 1, 1 <= dim <= 3", who);
+    if (N > 0 && (!a || !b)) return fail(XSUP_E_NULL, "%s: NULL pointer", who);
+    return XSUP_OK;
+}
+int xsup_root_centre_fwd(const float* world, float* out, int32_t N, int32_t K, int32_t dim, void* stream) {
+    if (int rc = check_root(world, out, N, K, dim, "xsup_root_centre_fwd")) return rc;
+    if (N == 0) return XSUP_OK;
+    cudaError_t e = launch_root_centre_fwd(world, out, N, K, dim, (cudaStream_t)stream);
+    if (e != cudaSuccess) return cuda_fail(e, "xsup_root_centre_fwd launch");
+    count_launches(1);
+    return XSUP_OK;
+}
+int xsup_root_centre_bwd(const float* g_out, float* g_world, int32_t N, int32_t K, int32_t dim, void* stream) {
+    if (int rc = check_root(g_out, g_world, N, K, dim, "xsup_root_centre_bwd")) return rc;
+    if (N == 0) return XSUP_OK;
+    cudaError_t e = launch_root_centre_bwd(g_out, g_world, N, K, dim, (cudaStream_t)stream);
+    if (e != cudaSuccess) return cuda_fail(e, "xsup_root_centre_bwd launch");
+    count_launches(1);
+    return XSUP_OK;
+}
+
+int xsup_disc_min_loss_fwd(const float* logits, int32_t B, int32_t NH, int32_t C, float target, float* loss, int64_t* sel, void* stream) {
+    if (B < 1 || NH < 1 || C < 1) return fail(XSUP_E_SHAPE, "xsup_disc_min_loss_fwd: need B, NH, C >= 1 (mean of an empty batch is undefined)");
+    if (!logits || !loss || !sel) return fail(XSUP_E_NULL, "xsup_disc_min_loss_fwd: NULL pointer");
+    cudaError_t e = launch_disc_min_loss_fwd(logits, B, NH, C, target, loss, sel, (cudaStream_t)stream);
+    if (e != cudaSuccess) return cuda_fail(e, "xsup_disc_min_loss_fwd launch");
+    count_launches(1);
+    return XSUP_OK;
+}
+int xsup_disc_min_loss_bwd(const float* logits, const int64_t* sel, const float* g_loss, int32_t B, int32_t NH, int32_t C, float target,
+                           float* g_logits, void* stream) {
+    if (B < 1 || NH < 1 || C < 1) return fail(XSUP_E_SHAPE, "xsup_disc_min_loss_bwd: need B, NH, C >= 1");
+    if (!logits || !sel || !g_loss || !g_logits) return fail(XSUP_E_NULL, "xsup_disc_min_loss_bwd: NULL pointer");
+    cudaError_t e = launch_disc_min_loss_bwd(logits, sel, g_loss, B, NH, C, target, g_logits, (cudaStream_t)stream);
+    if (e != cudaSuccess) return cuda_fail(e, "xsup_disc_min_loss_bwd launch");
+    count_launches(1);
+    return XSUP_OK;
+}
+
 }  // extern "C"

@@ -88,6 +88,30 @@ cudaError_t launch_mask_loss_fwd(const float* mask, const float* gt, const float
 cudaError_t launch_mask_loss_bwd(const float* mask, const float* gt, const float* weight, const xsup_mask_loss_t& c,
                                  const float* loss_sums, const float* g_loss, float* g_mask, int num_sms, cudaStream_t st);
 
+// eval selection, triangulation, discriminator glue (eval_disc.cu)
+struct EvalParams {
+    const float* kps;
+    const float* joints_px;
+    float img_size;
+    int B, NH, K, best;
+    float* kp3d;
+    float* kp2d;
+    uint8_t* is_trans;
+    float* err2d;
+    int64_t* best_idx;
+    int64_t* best_2d_idx;
+    float* gt_norm;
+    int perm[32];
+};
+typedef xsup_tri_t TriParams;
+cudaError_t launch_eval_select(const EvalParams& p, cudaStream_t st);
+cudaError_t launch_triangulate(const TriParams& p, float* world, cudaStream_t st);
+cudaError_t launch_root_centre_fwd(const float* world, float* out, int N, int K, int dim, cudaStream_t st);
+cudaError_t launch_root_centre_bwd(const float* g_out, float* g_world, int N, int K, int dim, cudaStream_t st);
+cudaError_t launch_disc_min_loss_fwd(const float* logits, int B, int NH, int C, float target, float* loss, int64_t* sel, cudaStream_t st);
+cudaError_t launch_disc_min_loss_bwd(const float* logits, const int64_t* sel, const float* g_loss, int B, int NH, int C, float target,
+                                     float* g_logits, cudaStream_t st);
+
 void count_launches(int n);
 
 }  // namespace xsup

@@ -17,7 +17,8 @@ from typing import Dict
 import torch
 
 __all__ = ["iid_logits", "blob_logits", "pseudo_joints", "cameras", "camera_dict", "CAM_FIELDS",
-           "H36M_PARENTS", "LINE_SELECT", "BODY_WIDTH", "skeleton_pose2d", "silhouette_mask", "geodesic_weight"]
+           "H36M_PARENTS", "LINE_SELECT", "BODY_WIDTH", "skeleton_pose2d", "silhouette_mask", "geodesic_weight",
+           "eval_predictions", "SWITCH_LIST"]
 
 # order of the per-sample camera tensors everywhere in this package
 CAM_FIELDS = ("trans_image", "pelvis", "k_mat", "trans_world", "rot_world")
@@ -189,3 +190,25 @@ def geodesic_weight(mask: torch.Tensor, seed: int = 21) -> torch.Tensor:
     r = r / r.amax(dim=(1, 2), keepdim=True)
     w = mask * torch.exp(a * r[:, None]) + 0.3 + 0.7 * r[:, None]
     return w.contiguous()
+
+
+# --------------------------------------------------------------------------------------- eval-side inputs
+SWITCH_LIST = ((1, 4), (2, 5), (3, 6), (14, 11), (15, 12), (16, 13))      # eval_utils.py:8
+
+
+def eval_predictions(B: int, NH: int, K: int, seed: int = 80, img_size: float = 256.0, noise: float = 0.05):
+    """(kps [B,NH,K,3], joints_px [B,K,3]): pixel-space ground-truth joints (`{cam}_joints`, dataloader.py:166) and
+    multi-hypothesis predictions scattered around their normalised positions; every other sample predicts the
+    left/right-swapped skeleton, the case `switch_points` exists for."""
+    g = _gen(seed)
+    jp = torch.rand(B, K, 3, generator=g) * (img_size - 1)
+    gt = jp.clone()
+    gt[..., :2] = gt[..., :2] / (img_size - 1) * 2 - 1
+    gt[..., 2] = gt[..., 2] / (img_size - 1)
+    kps = gt[:, None] + noise * (torch.rand(B, NH, K, 3, generator=g) * 2 - 1)
+    perm = list(range(K))
+    for a, b in SWITCH_LIST:
+        if a < K and b < K:
+            perm[a], perm[b] = b, a
+    kps[1::2] = kps[1::2][:, :, perm]
+    return kps.contiguous(), jp.contiguous()
