@@ -122,12 +122,12 @@ def run_reference(args, c):
     return 0
 
 
-def config_block(c, n, cpu=False, scope="global", exchange="none"):
+def config_block(c, n, cpu=False, scope="global", exchange="none", launch="eager (one C-ABI call per kernel)"):
     return {"workload": c["workload"], "batch_per_gpu": c["B"] if not cpu else CPU_SAMPLE_B, "global_batch": c["B"] * n if not cpu else CPU_SAMPLE_B,
             "num_kp": c["K"], "heatmap": [c["R"]] * 3, "num_hypo": c["NH"], "neighbor_size": c["NS"],
             "loss_weights": {"mse": c["w"][0], "bone": c["w"][1], "kp": c["w"][2], "kp_2d": c["w"][3]},
             "reduction": "batch", "scope": scope if n > 1 else "local", "exchange": exchange,
-            "parallelism": "sample-sharded x%d" % n,
+            "parallelism": "sample-sharded x%d" % n, "launch": launch,
             "l2": "inputs (%.2f GB of logits per GPU) exceed the 126 MB L2; no explicit flush" % (
                 (CPU_SAMPLE_B if cpu else c["B"]) * bytes_per_sample(c) / 3 / 1e9)}
 
@@ -265,6 +265,26 @@ def run_ours(args, c):
         (lp + ls).backward()
         return lp, ls, sel, kps
 
+    graphed = None
+    if args.graph:
+        if group is not None:
+            raise SystemExit("--graph needs --scope local (or one GPU): the NVLink exchange carries a per-call sequence number")
+        for _ in range(3):
+            step()                                          # per-kernel events of the eager path (roofline block)
+        torch.cuda.synchronize()
+        record["on"] = True
+        for _ in range(5):
+            step()
+        torch.cuda.synchronize()
+        record["on"] = False
+        graphed = ops.GraphedReprojStep(logits, target, cams, K, NH, NS, w_mse=w[0], w_bone=w[1], w_kp=w[2], w_kp2d=w[3],
+                                        reduction="batch")
+        eager_step, launches_per_step = step, None
+        n_a = ops.launch_count()
+        eager_step()
+        launches_per_step = ops.launch_count() - n_a
+        step = graphed.__call__
+
     def sync_all():
         if world > 1:
             dist.barrier()
@@ -278,7 +298,7 @@ def run_ours(args, c):
     if sampler:
         sampler.start()
     sync_all()
-    record["on"] = True
+    record["on"] = graphed is None
     n0 = ops.launch_count()
     t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t0.record()
@@ -287,6 +307,8 @@ def run_ours(args, c):
     t1.record()
     sync_all()
     launches = ops.launch_count() - n0
+    if graphed is not None:
+        launches = launches_per_step * args.steps            # replayed through cudaGraphLaunch: the same kernels, counted per eager step
     record["on"] = False
     clocks = sampler.finish() if sampler else None
     ms = t0.elapsed_time(t1) / args.steps
@@ -365,7 +387,8 @@ def finish(args, c, rank, world, dev, B, K, R, NH, ms, k_fwd, k_bwd, value, laun
         step_gbs = 3 * unit_bytes / (ms * 1e-3) / 1e9
         line = {"metric": METRIC, "value": round(value, 1), "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": max(args.warmup, 3), "ms_per_step": round(ms, 4), "higher_is_better": True, "scaling": "weak",
-                "vs_baseline": None, "dtype": c["dtype"], "data": "synthetic", "config": config_block(c, world, scope=args.scope, exchange=getattr(args, "exchange_used", "none")),
+                "vs_baseline": None, "dtype": c["dtype"], "data": "synthetic", "config": config_block(c, world, scope=args.scope, exchange=getattr(args, "exchange_used", "none"),
+                                                                                   launch="cuda graph replay" if args.graph else "eager (one C-ABI call per kernel)"),
                 "roofline": {"bound": "hbm", "kernel": "integral_bwd_kernel (read logits + write grad, 2 passes)",
                              "achieved": round(bwd_gbs, 1), "peak": peak, "unit": "GB/s", "frac": round(bwd_gbs / peak, 4),
                              "traffic": ncu_traffic("integral_bwd_kernel"), "peak_source": peak_src,
@@ -403,6 +426,9 @@ def main():
                          "'local' selects per rank like the reference under DDP (no collective)")
     ap.add_argument("--exchange", choices=["nvlink", "nccl"], default="nvlink",
                     help="transport of the global-scope all-reduce: in-kernel NVLink peer-memory exchange, or torch NCCL")
+    ap.add_argument("--graph", action="store_true",
+                    help="replay the step as one CUDA graph (rank-local selection only); per-kernel events are then unavailable, "
+                         "the roofline block reports the whole step")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer end-to-end leg (profiling runs)")
     args = ap.parse_args()

@@ -391,3 +391,27 @@ def test_in_place_gradient(ops, synth, dev):
     out = ops._head_backward(logits, stats, shape, gk, inplace=True)
     assert out.data_ptr() == logits.data_ptr()
     assert torch.equal(out, gref)
+
+
+def test_cuda_graph_replay_equals_eager(ops, synth, dev):
+    """The whole fwd+bwd step is CUDA-graph capturable (C ABI contract: caller's stream, no allocation, no sync);
+    a replay on fresh inputs is bit-identical to the eager step."""
+    B, K, R, NH, NS = 6, 17, 32, 3, 15
+    kw = dict(w_mse=1.0, w_bone=0.1, w_kp=0.1, w_kp2d=0.0, reduction="batch")
+    l0 = synth.blob_logits(B, K, R, R, R, seed=90).to(dev)
+    l1 = synth.iid_logits(B, K, R, R, R, seed=91).to(dev)
+    t0, t1 = synth.pseudo_joints(B, K, seed=92).to(dev), synth.pseudo_joints(B, K, seed=93).to(dev)
+    cams = {k: v.to(dev) for k, v in synth.cameras(B, seed=94).items()}
+    step = ops.GraphedReprojStep(l0, t0, cams, K, NH, NS, **kw)
+    for logits, target in ((l0, t0), (l1, t1), (l0, t1)):
+        step.logits.detach().copy_(logits)
+        step.target.copy_(target)
+        n0 = ops.launch_count()
+        lp, ls, sel = step()
+        assert ops.launch_count() == n0, "a replay goes through cudaGraphLaunch, not through the C-ABI entry points"
+        x = logits.clone().requires_grad_(True)
+        elp, els, esel, ekps, eworld, *_ = ops.integral_reproj_min_loss(x, target, cams, K, NH, NS, **kw)
+        (elp + els).backward()
+        assert torch.equal(lp, elp.detach()) and torch.equal(ls, els.detach()) and torch.equal(sel, esel)
+        assert torch.equal(step.kps, ekps.detach()) and torch.equal(step.kps_world, eworld.detach())
+        assert torch.equal(step.grad, x.grad)

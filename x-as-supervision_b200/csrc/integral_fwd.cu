@@ -61,7 +61,7 @@ __device__ __forceinline__ int take_best_peak(float (&cv)[kMaxD / 32], int lane)
 // went through the SAME accumulators, so the rounding of the accumulation cancels to first order and
 // the residual error scales with the spread of the distribution, not with its position.
 // ----------------------------------------------------------------------------------------------
-__device__ void finalise_unit(const FwdParams& p, int unit, float* pz, float M, float xbar, float ybar, int lane) {
+__device__ void finalise_unit(const FwdParams& p, int unit, float* pz, int* bins, float M, float xbar, float ybar, int lane) {
     const int D = p.t.D, H = p.t.H, W = p.t.W, NH = p.NH;
     const int b = unit / p.K, k = unit - b * p.K;
     float ssum = 0.f;
@@ -102,34 +102,37 @@ __device__ void finalise_unit(const FwdParams& p, int unit, float* pz, float M, 
 
     // find_peak (…_multi.py:24-34): non-strict interior local maxima, value-descending top-NH.
     // Candidates with value 0 (non-peaks) fill the remaining slots by ascending bin.
+    // Phase 1 (serial in h, the selection is a dependency chain): the NH peak bins into shared memory.
     float cv[kMaxD / 32];
     peak_candidates(pz, D, lane, cv);
-    const int half = p.NS >> 1;
-    const float fNS = (float)p.NS;
     for (int h = 0; h < NH; ++h) {
         const int bd = take_best_peak(cv, lane);
-        // windowed depth expectation (…_multi.py:57-62): zero-padded, count_include_pad average
-        // pools of d*pz and pz, gathered at the peak bin
+        if (lane == 0) bins[h] = bd;
+    }
+    __syncwarp();
+    // Phase 2 (one lane per hypothesis, no shuffles): windowed depth expectation (…_multi.py:57-62): zero-padded,
+    // count_include_pad average pools of d*pz and pz, gathered at the peak bin.  With the per-hypothesis warp
+    // reductions this used to be the bottleneck of small volumes / many hypotheses (32^3, NH = 16: 9 us per unit).
+    const int half = p.NS >> 1;
+    const float fNS = (float)p.NS;
+    for (int h = lane; h < NH; h += 32) {
+        const int bd = bins[h];
         const int lo = max(0, bd - half), hi = min(D - 1, bd + half);
         float sw = 0.f, nw = 0.f;
-        for (int d = lo + lane; d <= hi; d += 32) {
+        for (int d = lo; d <= hi; ++d) {
             const float v = pz[d];
             sw += v;
             nw = fmaf((float)d, v, nw);
         }
-        sw = warp_sum(sw);
-        nw = warp_sum(nw);
         const float zbar = (nw / fNS) / (sw / fNS);
-        if (lane == 0) {
-            float* o = p.kps + (((size_t)b * NH + h) * p.K + k) * 3;
-            o[0] = x;
-            o[1] = y;
-            o[2] = zbar / (float)D * 2.0f - 1.0f;
-            if (p.peak_idx) p.peak_idx[((size_t)b * p.K + k) * NH + h] = bd;
-            st[4 + D + 3 * h + 0] = (float)bd;
-            st[4 + D + 3 * h + 1] = sw;
-            st[4 + D + 3 * h + 2] = nw / sw;
-        }
+        float* o = p.kps + (((size_t)b * NH + h) * p.K + k) * 3;
+        o[0] = x;
+        o[1] = y;
+        o[2] = zbar / (float)D * 2.0f - 1.0f;
+        if (p.peak_idx) p.peak_idx[((size_t)b * p.K + k) * NH + h] = bd;
+        st[4 + D + 3 * h + 0] = (float)bd;
+        st[4 + D + 3 * h + 1] = sw;
+        st[4 + D + 3 * h + 2] = nw / sw;
     }
 }
 
@@ -151,7 +154,8 @@ __global__ void __launch_bounds__(kFwdThreads, 1) integral_fwd_kernel(const FwdP
     float2* pz_table = reinterpret_cast<float2*>(smem + (size_t)nst * t.stage_bytes);   // [2][TU] (m, sum)
     float4* unit_part = reinterpret_cast<float4*>(pz_table + 2 * TU);                   // [2][kConsumerWarps][2]
     float* pz_final = reinterpret_cast<float*>(unit_part + 4 * kConsumerWarps);         // [kMaxD]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(pz_final + kMaxD);
+    int* peak_bins = reinterpret_cast<int*>(pz_final + kMaxD);                          // [kMaxD]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(peak_bins + kMaxD);
     volatile int2* hdr = reinterpret_cast<volatile int2*>(bars + 2 * kMaxStages + 4);   // [nst] (unit, stage in unit)
     const uint32_t full0 = smem_u32(bars), empty0 = full0 + 8u * nst;
     const uint32_t pfull0 = empty0 + 8u * nst, pempty0 = pfull0 + 16u;
@@ -233,7 +237,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) integral_fwd_kernel(const FwdP
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(pempty0 + 8u * buf);      // partial buffers may be refilled
-            finalise_unit(p, unit, pz_final, M, xbar, ybar, lane);
+            finalise_unit(p, unit, pz_final, peak_bins, M, xbar, ybar, lane);
             __syncwarp();
         }
     } else {
@@ -375,6 +379,7 @@ __device__ float block_reduce(float v, float* scratch, bool is_max) {
 template <typename T>
 __global__ void __launch_bounds__(256) integral_fwd_generic_kernel(const FwdParams p) {
     __shared__ float pz[kMaxD];
+    __shared__ int peak_bins[kMaxD];
     __shared__ float scratch[8];
     const int D = p.t.D, H = p.t.H, W = p.t.W, HW = H * W;
     const int unit = blockIdx.x;
@@ -400,7 +405,7 @@ __global__ void __launch_bounds__(256) integral_fwd_generic_kernel(const FwdPara
     sy = block_reduce(sy, scratch, false);
     sa = block_reduce(sa, scratch, false);
     __syncthreads();
-    if (threadIdx.x < 32) finalise_unit(p, unit, pz, M, sx / sa, sy / sa, threadIdx.x);
+    if (threadIdx.x < 32) finalise_unit(p, unit, pz, peak_bins, M, sx / sa, sy / sa, threadIdx.x);
 }
 
 // ----------------------------------------------------------------------------------------------
@@ -451,7 +456,7 @@ cudaError_t launch_integral_fwd(FwdParams p, bool fast, int dtype, int num_sms, 
         return cudaGetLastError();
     }
     const size_t fixed = (size_t)2 * p.t.tasks_per_unit * sizeof(float2) + 4 * kConsumerWarps * sizeof(float4) +
-                         kMaxD * sizeof(float) + (size_t)(2 * kMaxStages + 4) * 8 + (size_t)kMaxStages * sizeof(int2);
+                         2 * kMaxD * sizeof(float) + (size_t)(2 * kMaxStages + 4) * 8 + (size_t)kMaxStages * sizeof(int2);
     int nst = (int)((kSmemBudget - fixed) / p.t.stage_bytes);
     nst = nst > kMaxStages ? kMaxStages : nst;
     // A slot must always be consumed by the same warp group (slot = s % nst, group = s % kGroups): a waiter

@@ -24,7 +24,7 @@ from . import dist as xdist
 
 __all__ = ["IntegralMultiHead", "IntegralSingleHead", "PatchToWorld", "IntegralReprojMinLoss", "integral_multi_head",
            "integral_single_head", "convert_patch_to_world", "convert_world_to_patch", "find_peak",
-           "integral_reproj_min_loss", "launch_count"]
+           "integral_reproj_min_loss", "launch_count", "GraphedReprojStep"]
 
 launch_count = cabi.launch_count
 
@@ -293,3 +293,51 @@ def integral_reproj_min_loss(logits, target, cams: Dict[str, torch.Tensor], num_
     return IntegralReprojMinLoss.apply(logits, target, cams["trans_image"], cams["pelvis"], cams["k_mat"],
                                        cams["trans_world"], cams["rot_world"], num_kp, num_hypo, neighbor_size,
                                        tuple(img_hw), rect_width, w_mse, w_bone, w_kp, w_kp2d, reduction, group)
+
+
+class GraphedReprojStep:
+    """The fused head + reprojection min-loss forward AND backward captured once into a CUDA graph.
+
+    Every C-ABI call is capture-safe (caller's stream, no allocation, no synchronisation), so for fixed shapes the
+    ~10 launches and the Python/autograd bookkeeping of a step collapse into one `cudaGraphLaunch`: this is what
+    removes the host-side floor (~0.3 ms) that small batches / small volumes otherwise sit on.
+
+        step = GraphedReprojStep(logits, target, cams, num_kp, num_hypo, neighbor_size, **loss_kwargs)
+        step.logits.copy_(new_logits); ...                # or produce the inputs directly into the static buffers
+        loss_pseudo, loss_sym, sel = step()               # replays; step.grad holds d(loss_pseudo + loss_sym)/d logits
+
+    Static tensors: `logits`, `target`, `cams[...]` (inputs), `grad`, `kps`, `kps_world`, `loss_pseudo`, `loss_sym`,
+    `sel` (outputs).  Rank-local only (`group=None`): the NVLink exchange carries a per-call sequence number that a
+    replayed graph would repeat."""
+
+    def __init__(self, logits, target, cams, num_kp, num_hypo, neighbor_size, warmup: int = 3, **kw):
+        if kw.get("group") is not None:
+            raise ValueError("GraphedReprojStep is rank-local: pass group=None")
+        cabi.require_cuda(logits, "logits")
+        dev = logits.device
+        self.logits = logits.detach().clone().requires_grad_(True)
+        self.target = target.detach().to(dev).clone()
+        self.cams = {k: v.detach().to(dev).clone() for k, v in cams.items()}
+        args = (num_kp, num_hypo, neighbor_size)
+
+        def run():
+            self.logits.grad = None
+            out = integral_reproj_min_loss(self.logits, self.target, self.cams, *args, **kw)
+            (out[0] + out[1]).backward()
+            return out
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):                       # warm-up off the capture stream, as torch.cuda.graph requires
+            for _ in range(max(1, warmup)):
+                run()
+        torch.cuda.current_stream(dev).wait_stream(side)
+        self.graph = torch.cuda.CUDAGraph()
+        self.logits.grad = None
+        with torch.cuda.graph(self.graph):
+            out = run()
+        self.loss_pseudo, self.loss_sym, self.sel, self.kps, self.kps_world = (o.detach() for o in out[:5])
+        self.grad = self.logits.grad
+
+    def __call__(self):
+        self.graph.replay()
+        return self.loss_pseudo, self.loss_sym, self.sel
