@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define XSUP_ABI_VERSION 3
+#define XSUP_ABI_VERSION 4
 
 enum { XSUP_F32 = 0, XSUP_BF16 = 1 };
 enum { XSUP_HEAD_MULTI = 0, XSUP_HEAD_SINGLE = 1 };
@@ -270,6 +270,19 @@ int xsup_disc_min_loss_fwd(const float* logits, int32_t B, int32_t NH, int32_t C
                            void* stream);
 int xsup_disc_min_loss_bwd(const float* logits, const int64_t* sel, const float* g_loss, int32_t B, int32_t NH, int32_t C,
                            float target, float* g_logits, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * The head's final 1x1 convolution fused into the integral head, forward only.
+ * Replaces `Conv2d(C, K*D, 1)` (modules/integral_base_modules/deconv_head.py:33-35, the last layer of `self.net`)
+ * followed by keypoint_detector_integral_multi.py:69-88 on the eval path (eval.py:120): the logits never touch HBM.
+ *   x_nhwc  [B, H, W, C]  bf16, channels-last (torch.channels_last storage of a [B,C,H,W] tensor)
+ *   weight  [K*D, C]      bf16 (the conv weight [K*D, C, 1, 1])
+ *   bias    [K*D]         fp32 or NULL
+ *   kps, depth_prob_map, peak_idx, stats: as xsup_integral_fwd (s->dtype is ignored: the operands are bf16, the
+ *   accumulation and all statistics are fp32); logits_out: NULL, or [B, K*D, H, W] fp32 to also materialise the
+ *   logits (validation).  Constraints: 128 % D == 0, (H*W) % 128 == 0, W % 32 == 0, C % 64 == 0, C <= 256. */
+int xsup_conv_head_fwd(const void* x_nhwc, const void* weight, const float* bias, float* kps, float* depth_prob_map,
+                       int64_t* peak_idx, float* stats, float* logits_out, const xsup_shape_t* s, int32_t C, void* stream);
 
 #ifdef __cplusplus
 }

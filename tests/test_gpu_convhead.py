@@ -1,0 +1,63 @@
+"""GPU parity tests (`-m gpu`) of the conv-fused forward: the tcgen05 GEMM's logits against a plain
+PyTorch fp32 reference of the same op on the same bf16-rounded operands, and the head outputs against the streaming
+kernel run on those logits and against the fp64 oracle.  Tolerances: logits 1e-5 relative to their scale (exact bf16
+products, fp32 accumulation in a different order), peak indices bit-exact, coordinates 1e-5."""
+import importlib
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ops():
+    import __graft_entry__ as ge
+    ge.build()
+    return importlib.import_module("x-as-supervision_b200").load_native()
+
+
+def _case(B, K, D, C, seed, peaked=True):
+    g = torch.Generator().manual_seed(seed)
+    x = torch.randn(B, C, D, D, generator=g)
+    w = torch.randn(K * D, C, generator=g) / C ** 0.5
+    if peaked:                                   # give the logits structure: a few strong rows / pixels
+        w[::7] *= 3.0
+        x[:, :, D // 3, D // 2] += 2.0
+    bias = torch.randn(K * D, generator=g)
+    return x, w, bias
+
+
+@pytest.mark.parametrize("B,K,D,C,NH,NS", [(2, 2, 64, 64, 3, 15), (2, 3, 64, 256, 3, 15), (3, 17, 64, 256, 3, 15), (2, 4, 32, 128, 2, 5),
+                                           (1, 18, 64, 256, 3, 15), (2, 1, 128, 64, 3, 15)])
+def test_conv_head_matches_reference(ops, oracle, B, K, D, C, NH, NS):
+    dev = torch.device("cuda:0")
+    x, w, bias = _case(B, K, D, C, seed=B * 100 + K)
+    xb, wb = x.bfloat16().float(), w.bfloat16().float()
+    kps, dmap, idx, logits = ops.conv_integral_head(x.to(dev), w.to(dev), bias.to(dev), K, NH, NS, return_logits=True)
+    ref = torch.einsum("oc,bchw->bohw", wb.double(), xb.double()) + bias.double().view(1, -1, 1, 1)
+    err = float((logits.cpu().double() - ref).abs().max()) / float(ref.abs().max())
+    assert err < 1e-5, err
+    # head outputs: the streaming kernel on the materialised logits, and the fp64 oracle on the exact logits
+    k2, d2, i2 = ops.integral_multi_head(logits, K, NH, NS)
+    assert torch.equal(idx, i2)
+    assert float((kps - k2).abs().max()) < 1e-5 and float((dmap - d2).abs().max()) < 1e-5
+    okps, odmap, oidx = oracle.integral_multi(ref, K, NH, NS)
+    assert torch.equal(idx.cpu(), oidx)
+    assert float((kps.cpu().double() - okps).abs().max()) < 1e-5
+    assert float((dmap.cpu().double() - odmap).abs().max()) < 1e-5 * float(odmap.abs().max())
+    # without the validation output, from a channels-last bf16 tensor used in place, and without a bias
+    xcl = x.to(dev).to(dtype=torch.bfloat16, memory_format=torch.channels_last)
+    k3, d3, i3 = ops.conv_integral_head(xcl, w.to(dev).view(K * D, C, 1, 1), bias.to(dev), K, NH, NS)
+    assert torch.equal(k3, kps) and torch.equal(i3, idx) and torch.equal(d3, dmap)
+    k4, _, _, l4 = ops.conv_integral_head(xcl, w.to(dev), None, K, NH, NS, return_logits=True)
+    ref0 = ref - bias.double().view(1, -1, 1, 1)
+    assert float((l4.cpu().double() - ref0).abs().max()) / float(ref0.abs().max()) < 1e-5
+
+
+def test_conv_head_shape_errors(ops):
+    dev = torch.device("cuda:0")
+    with pytest.raises(RuntimeError, match="divide 128"):
+        ops.conv_integral_head(torch.zeros(1, 64, 48, 48, device=dev), torch.zeros(2 * 48, 64, device=dev), None, 2, 3, 15)
+    with pytest.raises(RuntimeError, match="channels"):
+        ops.conv_integral_head(torch.zeros(1, 96, 64, 64, device=dev), torch.zeros(2 * 64, 96, device=dev), None, 2, 3, 15)

@@ -33,6 +33,7 @@ SYMBOLS = (
     "xsup_mask_loss_fwd", "xsup_mask_loss_bwd",
     "xsup_eval_select", "xsup_triangulate", "xsup_root_centre_fwd", "xsup_root_centre_bwd",
     "xsup_disc_min_loss_fwd", "xsup_disc_min_loss_bwd",
+    "xsup_conv_head_fwd",
 )
 MAX_VIEWS = 8
 MAX_LINES = 32
@@ -122,6 +123,8 @@ def _load():
     lib.xsup_skeleton_mask_bwd.argtypes = [vp, sk, vp, vp, vp, vp, vp, ml, vp, vp, vp, vp, vp]
     lib.xsup_mask_loss_fwd.argtypes = [vp, vp, vp, vp, ml, vp, vp, vp]
     lib.xsup_mask_loss_bwd.argtypes = [vp, vp, vp, ml, vp, vp, vp, vp]
+    lib.xsup_conv_head_fwd.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, C.POINTER(Shape), i32, vp]
+    lib.xsup_conv_head_fwd.restype = C.c_int
     lib.xsup_eval_select.argtypes = [vp, vp, C.POINTER(Eval), vp, vp, vp, vp, vp, vp, vp, vp]
     lib.xsup_triangulate.argtypes = [C.POINTER(Tri), vp, vp]
     lib.xsup_root_centre_fwd.argtypes = [vp, vp, i32, i32, i32, vp]
@@ -139,7 +142,7 @@ def _load():
 
 
 lib = _load()
-ABI_VERSION = 3
+ABI_VERSION = 4
 if lib.xsup_abi_version() != ABI_VERSION:
     raise ImportError("libxsup_b200.so ABI version %d, expected %d: rebuild with __graft_entry__.build()"
                       % (lib.xsup_abi_version(), ABI_VERSION))

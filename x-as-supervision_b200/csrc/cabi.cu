@@ -490,4 +490,29 @@ int xsup_disc_min_loss_bwd(const float* logits, const int64_t* sel, const float*
     return XSUP_OK;
 }
 
+// ------------------------------------------------------------------------------------------------ conv-fused forward
+int xsup_conv_head_fwd(const void* x_nhwc, const void* weight, const float* bias, float* kps, float* depth_prob_map, int64_t* peak_idx,
+                       float* stats, float* logits_out, const xsup_shape_t* s, int32_t C, void* stream) {
+    if (int rc = check_shape(s)) return rc;
+    if (128 % s->D) return fail(XSUP_E_SHAPE, "xsup_conv_head_fwd: depth_dim %d must divide 128 (output rows per CTA)", s->D);
+    if ((s->H * s->W) % 128 || s->W % 32) return fail(XSUP_E_SHAPE, "xsup_conv_head_fwd: H*W must be a multiple of 128 and W of 32");
+    if (C < 64 || C % 64 || C > 256) return fail(XSUP_E_SHAPE, "xsup_conv_head_fwd: channels %d must be 64, 128, 192 or 256", C);
+    if ((long long)s->B * s->H * s->W > 0x7fffffffLL) return fail(XSUP_E_SHAPE, "xsup_conv_head_fwd: too many pixels");
+    if (s->B == 0) return XSUP_OK;
+    if (!x_nhwc || !weight || !kps || !depth_prob_map || !stats) return fail(XSUP_E_NULL, "xsup_conv_head_fwd: NULL pointer");
+    if (!aligned16(x_nhwc) || !aligned16(weight) || !aligned16(logits_out)) return fail(XSUP_E_ALIGN, "xsup_conv_head_fwd: x/weight/logits_out must be 16-byte aligned");
+    int sms = 0;
+    if (int rc = device_info(sms)) return rc;
+    FwdParams f{};
+    f.kps = kps; f.dmap = depth_prob_map; f.peak_idx = peak_idx; f.stats = stats;
+    f.n_units = s->B * s->K; f.K = s->K; f.NH = s->NH; f.NS = s->NS; f.head = s->head;
+    f.stats_stride = (int)stats_stride(*s);
+    f.t.D = s->D; f.t.H = s->H; f.t.W = s->W;
+    cudaError_t e = launch_conv_head_fwd(x_nhwc, weight, bias, logits_out, f, s->B, C, (cudaStream_t)stream);
+    if (e == cudaErrorNotSupported) return fail(XSUP_E_DEVICE, "xsup_conv_head_fwd: cuTensorMapEncodeTiled unavailable or rejected the tensors");
+    if (e != cudaSuccess) return cuda_fail(e, "xsup_conv_head_fwd launch");
+    count_launches(1);
+    return XSUP_OK;
+}
+
 }  // extern "C"

@@ -1,0 +1,310 @@
+// K7 — the head's final 1x1 convolution FUSED into the integral head, forward.
+//
+// Replaces modules/integral_base_modules/deconv_head.py:33-35 (`Conv2d(C, K*D, 1)`, the last layer of
+// `self.net`) followed by modules/keypoint_detector_integral_multi.py:69-88 for the forward / eval path
+// (eval.py:120): the logits `[B, K*D, H, W]` (4.56 GB at B=256) are never written to or read from HBM.
+// This is the one dense contraction next to the path, so it runs on the 5th-generation tensor cores:
+//
+//   logits[b, k*D+d, p] = sum_c Wt[k*D+d, c] * X[b, p, c] + bias[k*D+d]        p = h*W+w, C = 256
+//
+// One CTA per (sample b, group of 128 output rows = 128/D joints):
+//   warp 4      TMA producer: the 128 x C weight slab once (bf16, K-major, SWIZZLE_128B), then the sample's
+//               activations as 128-pixel tiles (channels-last bf16, K-major) through a 2-stage ring
+//   warp 5      MMA issuer: one elected thread, tcgen05.mma.cta_group::1.kind::f16 M=128 N=128 K=16, 16 per tile,
+//               accumulators in TMEM (4 x 128 columns, so the epilogue of tile t overlaps the MMAs of t+1..t+3);
+//               tcgen05.commit releases the smem stage and publishes the accumulator
+//   warps 0..3  epilogue: thread = TMEM lane = output row (joint, d); tcgen05.ld 32 columns at a time; the softmax
+//               statistics of the row (running max, sum e, sum w*e, sum h*e) stay in FOUR registers per thread -
+//               rows are depth bins, so the depth marginal pz[d] is simply the row sum; no shuffles per tile
+//   unit end    rows of a joint are merged through shared memory (log-sum-exp) and handed to the same finaliser as
+//               the streaming kernel (find_peak, top-NH, window depth, outputs, saved statistics)
+// Roofline: tensor (2*K*D*C flops per pixel = 584 GFLOP at B=256) with MUFU.EX2 of the epilogue at the same
+// order (one exp per logit); HBM traffic is the activations only (0.54 GB).
+#include <cuda.h>
+
+#include "xsup_finalise.cuh"
+
+namespace xsup {
+
+constexpr int kCvThreads = 192;
+constexpr int kCvRows = 128;           // UMMA M: output rows per CTA
+constexpr int kCvPix = 128;            // UMMA N: pixels per tile
+constexpr int kCvKB = 64;              // channels per swizzle-128B k-block (bf16)
+constexpr int kCvStages = 2;
+constexpr int kCvAcc = 4;              // TMEM accumulator buffers (4 x 128 columns = all 512)
+constexpr int kCvKBBytes = kCvRows * kCvKB * 2;   // 16 KB: one [128 x 64] bf16 k-block (same for W and X tiles)
+
+struct ConvHeadParams {
+    FwdParams f;                // kps, dmap, peak_idx, stats, K, NH, NS, head, stats_stride, t.{D,H,W}
+    const float* bias;          // [K*D] or nullptr
+    float* logits_out;          // optional [B, K*D, H*W] fp32 (validation); nullptr in production
+    int C, HW, rows_total;      // channels, pixels per sample, K*D
+    int groups;                 // CTAs per sample = ceil(K*D / 128)
+    int n_tiles;                // HW / 128
+    int kblocks;                // C / 64
+};
+
+// ------------------------------------------------------------------ PTX wrappers (sm_100a)
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(dst),
+                 "l"(map), "r"(c0), "r"(c1), "r"(bar)
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_alloc(uint32_t smem_dst, uint32_t cols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst), "r"(cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(tmem_d),
+        "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// arrives on the mbarrier when all previously issued tcgen05.mma of this thread have completed
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+          "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+          "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+          "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start address >> 4 in [0,14),
+// stride byte offset (8 rows x 128 B = 1024 B) >> 4 in [32,46), descriptor version 1 in [46,48), layout type 2 in [61,64).
+// The leading byte offset is unused for swizzled K-major operands.  Stepping K by 16 bf16 (32 B) inside the 128-byte
+// swizzle atom adds 2 to the start-address field; the hardware applies the XOR pattern on the absolute address, which
+// is why every k-block sits on a 1024-byte boundary.
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
+    return (uint64_t)((smem_addr & 0x3ffffu) >> 4) | ((uint64_t)(1024u >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+// instruction descriptor (cute::UMMA::InstrDescriptor): D = f32 (bit 4), A = B = bf16 (bits 7, 10), both K-major,
+// N >> 3 in [17,23), M >> 4 in [24,29)
+constexpr uint32_t kCvIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(kCvPix >> 3) << 17) | ((uint32_t)(kCvRows >> 4) << 24);
+
+// ------------------------------------------------------------------ kernel
+__global__ void __launch_bounds__(kCvThreads, 1) conv_head_fwd_kernel(const __grid_constant__ CUtensorMap map_w,
+                                                                      const __grid_constant__ CUtensorMap map_x,
+                                                                      const ConvHeadParams p) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    // the dynamic shared window is only 16-byte aligned by contract: round up to the 1024 B the swizzle needs
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int KBn = p.kblocks;
+    uint8_t* sW = smem;                                             // [KBn][128 x 64] bf16
+    uint8_t* sX = sW + (size_t)KBn * kCvKBBytes;                    // [stages][KBn][128 x 64] bf16
+    float4* row_stat = reinterpret_cast<float4*>(sX + (size_t)kCvStages * KBn * kCvKBBytes);   // [128] (m, s, sx, sy)
+    float* pz_s = reinterpret_cast<float*>(row_stat + kCvRows);     // [2][kMaxD]
+    int* bins_s = reinterpret_cast<int*>(pz_s + 2 * kMaxD);         // [2][kMaxD]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(bins_s + 2 * kMaxD);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
+    const uint32_t b_wfull = smem_u32(bars), b_xfull = b_wfull + 8, b_xempty = b_xfull + 8 * kCvStages,
+                   b_afull = b_xempty + 8 * kCvStages, b_aempty = b_afull + 8 * kCvAcc;
+
+    if (threadIdx.x == 0) {
+        mbar_init(b_wfull, 1);
+        for (int i = 0; i < kCvStages; ++i) {
+            mbar_init(b_xfull + 8 * i, 1);
+            mbar_init(b_xempty + 8 * i, 1);
+        }
+        for (int i = 0; i < kCvAcc; ++i) {
+            mbar_init(b_afull + 8 * i, 1);
+            mbar_init(b_aempty + 8 * i, 4);                          // one elected lane per epilogue warp
+        }
+        mbar_fence_init();
+    }
+    if (warp == 5) tmem_alloc(smem_u32(tmem_slot), 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    const int b = blockIdx.x / p.groups, grp = blockIdx.x - b * p.groups;
+    const int row0 = grp * kCvRows;                                  // first output row of this CTA
+    const int T = p.n_tiles;
+
+    if (warp == 4) {
+        // ------------------------------------------------------------ TMA producer
+        if (lane == 0) {
+            mbar_arrive_expect_tx(b_wfull, (uint32_t)KBn * kCvKBBytes);
+            for (int kb = 0; kb < KBn; ++kb) tma_load_2d(smem_u32(sW) + kb * kCvKBBytes, &map_w, kb * kCvKB, row0, b_wfull);
+            for (int t = 0; t < T; ++t) {
+                const int s = t % kCvStages, it = t / kCvStages;
+                mbar_wait(b_xempty + 8 * s, (it & 1) ^ 1);
+                mbar_arrive_expect_tx(b_xfull + 8 * s, (uint32_t)KBn * kCvKBBytes);
+                const uint32_t dst = smem_u32(sX) + (uint32_t)s * KBn * kCvKBBytes;
+                for (int kb = 0; kb < KBn; ++kb) tma_load_2d(dst + kb * kCvKBBytes, &map_x, kb * kCvKB, b * p.HW + t * kCvPix, b_xfull + 8 * s);
+            }
+        }
+        __syncwarp();
+    } else if (warp == 5) {
+        // ------------------------------------------------------------ MMA issuer
+        mbar_wait(b_wfull, 0);
+        for (int t = 0; t < T; ++t) {
+            const int s = t % kCvStages, it = t / kCvStages, a = t % kCvAcc, ia = t / kCvAcc;
+            mbar_wait(b_aempty + 8 * a, (ia & 1) ^ 1);               // the epilogue has drained this accumulator
+            mbar_wait(b_xfull + 8 * s, it & 1);                      // the tile has landed
+            tc_fence_after();
+            if (lane == 0) {
+                const uint32_t xs = smem_u32(sX) + (uint32_t)s * KBn * kCvKBBytes, ws = smem_u32(sW);
+                for (int kb = 0; kb < KBn; ++kb) {
+                    const uint64_t da = umma_desc_sw128(ws + kb * kCvKBBytes), db = umma_desc_sw128(xs + kb * kCvKBBytes);
+#pragma unroll
+                    for (int k = 0; k < kCvKB / 16; ++k)             // +32 B per K step of 16 bf16: +2 in the address field
+                        umma_f16(tmem_base + (uint32_t)a * kCvPix, da + 2 * k, db + 2 * k, kCvIdesc, (kb | k) != 0);
+                }
+                umma_commit(b_xempty + 8 * s);                       // smem stage reusable once these MMAs have read it
+                umma_commit(b_afull + 8 * a);                        // accumulator complete
+            }
+            __syncwarp();
+        }
+    } else {
+        // ------------------------------------------------------------ epilogue: thread = output row
+        const int row = warp * 32 + lane, grow = row0 + row;         // TMEM lane = row; warp w may only touch lanes 32w..32w+31
+        const bool live = grow < p.rows_total;
+        const float bl = (live && p.bias) ? p.bias[grow] * kLog2e : 0.f;
+        const int Wd = p.f.t.W;
+        float m = kNegHuge, s = 0.f, sx = 0.f, sy = 0.f;
+        float* lrow = p.logits_out ? p.logits_out + ((size_t)b * p.rows_total + grow) * p.HW : nullptr;
+        for (int t = 0; t < T; ++t) {
+            const int a = t % kCvAcc, ia = t / kCvAcc;
+            mbar_wait(b_afull + 8 * a, ia & 1);
+            tc_fence_after();
+#pragma unroll 1
+            for (int c0 = 0; c0 < kCvPix; c0 += 32) {
+                uint32_t r[32];
+                tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(a * kCvPix + c0), r);
+                const int pix = t * kCvPix + c0;                     // 32 consecutive pixels of one image row (W >= 32)
+                const int hh = pix / Wd, w0 = pix - hh * Wd;
+                if (lrow && live) {
+                    const float bb = p.bias ? p.bias[grow] : 0.f;
+#pragma unroll
+                    for (int i = 0; i < 32; i += 4)
+                        *reinterpret_cast<float4*>(lrow + pix + i) = make_float4(__uint_as_float(r[i]) + bb, __uint_as_float(r[i + 1]) + bb,
+                                                                                 __uint_as_float(r[i + 2]) + bb, __uint_as_float(r[i + 3]) + bb);
+                }
+                float cm = __uint_as_float(r[0]);
+#pragma unroll
+                for (int i = 1; i < 32; ++i) cm = fmaxf(cm, __uint_as_float(r[i]));
+                cm = fmaf(cm, kLog2e, bl);                           // chunk max in the log2 domain (bias included)
+                if (cm > m) {                                        // per-row running max: rescale four registers
+                    const float sc = ex2(m - cm);
+                    s *= sc; sx *= sc; sy *= sc;
+                    m = cm;
+                }
+                const float sh = bl - m;
+                float cs = 0.f, cx = 0.f;
+#pragma unroll
+                for (int i = 0; i < 32; ++i) {
+                    const float e = ex2(fmaf(__uint_as_float(r[i]), kLog2e, sh));
+                    cs += e;
+                    cx = fmaf((float)i, e, cx);
+                }
+                s += cs;
+                sx += fmaf((float)w0, cs, cx);
+                sy = fmaf((float)hh, cs, sy);
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(b_aempty + 8 * a);
+        }
+        // ---- merge the rows of each joint and finalise (warps 0 and 1 take one joint each per round)
+        row_stat[row] = make_float4(m, s, sx, sy);
+        asm volatile("bar.sync 1, 128;" ::: "memory");               // the four epilogue warps only
+        const int D = p.f.t.D, jpc = kCvRows / D;                    // joints per CTA
+        for (int jl = warp; jl < jpc; jl += 4) {
+            const int k = row0 / D + jl;
+            if (k >= p.f.K) continue;
+            float* pz = pz_s + (jl & 1) * kMaxD;
+            float M = kNegHuge;
+            for (int d = lane; d < D; d += 32) M = fmaxf(M, row_stat[jl * D + d].x);
+            M = warp_max(M);
+            float ax = 0.f, ay = 0.f, as = 0.f;
+            for (int d = lane; d < D; d += 32) {
+                const float4 q = row_stat[jl * D + d];
+                const float sc = ex2(q.x - M);
+                pz[d] = q.y * sc;
+                as = fmaf(q.y, sc, as);
+                ax = fmaf(q.z, sc, ax);
+                ay = fmaf(q.w, sc, ay);
+            }
+            as = warp_sum(as); ax = warp_sum(ax); ay = warp_sum(ay);
+            __syncwarp();
+            finalise_unit(p.f, b * p.f.K + k, pz, bins_s + (jl & 1) * kMaxD, M, ax / as, ay / as, lane);
+            __syncwarp();
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 5) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, 512);
+    }
+}
+
+// ------------------------------------------------------------------ host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_tiled() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* ptr = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(ptr);
+    }
+    return fn;
+}
+
+// [rows, C] bf16 row-major (C contiguous) -> boxes of [128 rows x 64 channels], 128-byte swizzle, zero fill out of bounds
+static bool make_map(CUtensorMap* map, const void* base, long long rows, int C) {
+    EncodeTiledFn enc = encode_tiled();
+    if (!enc) return false;
+    const cuuint64_t dims[2] = {(cuuint64_t)C, (cuuint64_t)rows};
+    const cuuint64_t strides[1] = {(cuuint64_t)C * 2};
+    const cuuint32_t box[2] = {(cuuint32_t)kCvKB, (cuuint32_t)kCvRows};
+    const cuuint32_t estr[2] = {1, 1};
+    return enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+               CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+cudaError_t launch_conv_head_fwd(const void* x_nhwc, const void* w, const float* bias, float* logits_out, FwdParams f, int B, int C,
+                                 cudaStream_t st) {
+    ConvHeadParams p{};
+    p.f = f;
+    p.bias = bias;
+    p.logits_out = logits_out;
+    p.C = C;
+    p.HW = f.t.H * f.t.W;
+    p.rows_total = f.K * f.t.D;
+    p.groups = (p.rows_total + kCvRows - 1) / kCvRows;
+    p.n_tiles = p.HW / kCvPix;
+    p.kblocks = C / kCvKB;
+    CUtensorMap map_w, map_x;
+    if (!make_map(&map_w, w, p.rows_total, C) || !make_map(&map_x, x_nhwc, (long long)B * p.HW, C)) return cudaErrorNotSupported;
+    const size_t smem = 1024 + (size_t)(1 + kCvStages) * p.kblocks * kCvKBBytes + kCvRows * sizeof(float4) + 4 * kMaxD * 4 + 16 * 8 + 16;
+    cudaError_t e = cudaFuncSetAttribute(conv_head_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    conv_head_fwd_kernel<<<B * p.groups, kCvThreads, smem, st>>>(map_w, map_x, p);
+    return cudaGetLastError();
+}
+
+}  // namespace xsup

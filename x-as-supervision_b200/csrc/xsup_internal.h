@@ -112,6 +112,10 @@ cudaError_t launch_disc_min_loss_fwd(const float* logits, int B, int NH, int C, 
 cudaError_t launch_disc_min_loss_bwd(const float* logits, const int64_t* sel, const float* g_loss, int B, int NH, int C, float target,
                                      float* g_logits, cudaStream_t st);
 
+// conv-fused forward (conv_head_fwd.cu)
+cudaError_t launch_conv_head_fwd(const void* x_nhwc, const void* w, const float* bias, float* logits_out, FwdParams f, int B, int C,
+                                 cudaStream_t st);
+
 void count_launches(int n);
 
 }  // namespace xsup

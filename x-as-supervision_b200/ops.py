@@ -24,7 +24,7 @@ from . import dist as xdist
 
 __all__ = ["IntegralMultiHead", "IntegralSingleHead", "PatchToWorld", "IntegralReprojMinLoss", "integral_multi_head",
            "integral_single_head", "convert_patch_to_world", "convert_world_to_patch", "find_peak",
-           "integral_reproj_min_loss", "launch_count", "GraphedReprojStep"]
+           "integral_reproj_min_loss", "launch_count", "GraphedReprojStep", "conv_integral_head"]
 
 launch_count = cabi.launch_count
 
@@ -341,3 +341,42 @@ class GraphedReprojStep:
     def __call__(self):
         self.graph.replay()
         return self.loss_pseudo, self.loss_sym, self.sel
+
+
+def conv_integral_head(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor], num_kp: int, num_hypo: int,
+                       neighbor_size: int, return_logits: bool = False):
+    """The head's final `Conv2d(C, K*D, 1)` (deconv_head.py:33-35) fused with the integral multi-hypothesis head
+    (…_multi.py:69-88), forward only (the eval path, eval.py:120): tcgen05 tensor-core GEMM with the softmax statistics
+    taken from the TMEM accumulators, so the `[B, K*D, H, W]` logits are never written to HBM.
+
+    x `[B, C, H, W]`: used in place when it is bf16 with channels-last storage (what `autocast` + `channels_last`
+    backbones produce); anything else is converted once (one extra pass over the activations).
+    weight `[K*D, C]` or `[K*D, C, 1, 1]`, bias `[K*D]` or None.  Operands are rounded to bf16, accumulation and all
+    statistics are fp32 - the reference's own conv runs in TF32 on the same hardware.
+    Returns (kps [B,NH,K,3], depth_prob_map [K,D], peak_idx [B,K,NH]) and, with `return_logits`, the fp32 logits."""
+    cabi.require_cuda(x, "x")
+    B, C, H, W = x.shape
+    w2 = weight.detach().reshape(weight.shape[0], -1)
+    if w2.shape[1] != C:
+        raise ValueError("weight is %s, expected [K*D, %d]" % (tuple(weight.shape), C))
+    D = w2.shape[0] // num_kp
+    if D * num_kp != w2.shape[0]:
+        raise ValueError("weight rows %d are not a multiple of num_kp %d" % (w2.shape[0], num_kp))
+    dev = x.device
+    xb = x.detach()
+    if xb.dtype != torch.bfloat16 or not xb.is_contiguous(memory_format=torch.channels_last):
+        xb = xb.to(dtype=torch.bfloat16, memory_format=torch.channels_last)
+    wb = w2.to(device=dev, dtype=torch.bfloat16).contiguous()
+    bf = bias.detach().to(device=dev, dtype=torch.float32).contiguous() if bias is not None else None
+    shape = cabi.make_shape(B, num_kp, D, H, W, num_hypo, neighbor_size, torch.bfloat16, cabi.HEAD_MULTI)
+    kps = torch.empty(B, num_hypo, num_kp, 3, dtype=torch.float32, device=dev)
+    dmap = torch.empty(num_kp, D, dtype=torch.float32, device=dev)
+    idx = torch.empty(B, num_kp, num_hypo, dtype=torch.int64, device=dev)
+    stats = torch.empty(cabi.lib.xsup_stats_floats(shape), dtype=torch.float32, device=dev)
+    logits = torch.empty(B, num_kp * D, H, W, dtype=torch.float32, device=dev) if return_logits else None
+    with torch.cuda.device(dev):
+        cabi.check(cabi.lib.xsup_conv_head_fwd(xb.data_ptr(), wb.data_ptr(), bf.data_ptr() if bf is not None else None,
+                                               kps.data_ptr(), dmap.data_ptr(), idx.data_ptr(), stats.data_ptr(),
+                                               logits.data_ptr() if return_logits else None, shape, C, cabi.stream_ptr(dev)),
+                   "xsup_conv_head_fwd")
+    return (kps, dmap, idx, logits) if return_logits else (kps, dmap, idx)
