@@ -1,0 +1,90 @@
+#!/usr/bin/env python
+"""Device timing of the conv-fused forward against the unfused path on one B200.
+
+    python tools/bench_convhead.py [--batch 256] [--steps 20]
+
+fused     : xsup_conv_head_fwd on channels-last bf16 activations resident in HBM (logits never materialised)
+fused+cvt : the same, from the NCHW fp32 tensor a plain backbone produces (one conversion pass added)
+unfused   : torch 1x1 conv (cuDNN/cuBLAS; fp32 with TF32 allowed as PyTorch's default, and bf16) writing the
+            [B, K*D, H, W] logits, then the streaming kernel xsup_integral_fwd reading them
+Roofline of the fused kernel: tensor - algorithmic flops = 2 * K*D * C per pixel over the launch time, against
+the measured dense bf16 peak of MEASURED_PEAKS.json (burst figure: the kernel is timed alone).
+"""
+import argparse
+import importlib
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--batch", type=int, default=256)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--fused-only", action="store_true")
+    args = ap.parse_args()
+    import torch
+    import torch.nn.functional as F
+    pkg = importlib.import_module("x-as-supervision_b200")
+    ops = pkg.load_native()
+    dev = torch.device("cuda:0")
+    B, K, D, C, NH, NS = args.batch, 17, 64, 256, 3, 15
+    g = torch.Generator(device=dev).manual_seed(3)
+    x = torch.randn(B, C, D, D, device=dev, generator=g)
+    w = torch.randn(K * D, C, device=dev, generator=g) / 16
+    bias = torch.randn(K * D, device=dev, generator=g)
+    xcl = x.to(dtype=torch.bfloat16, memory_format=torch.channels_last)
+    wb = w.bfloat16()
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+
+    def timeit(fn, n=args.steps):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        t0.record()
+        for _ in range(n):
+            fn()
+        t1.record()
+        torch.cuda.synchronize()
+        return t0.elapsed_time(t1) / n
+
+    n0 = ops.launch_count()
+    ms_fused = timeit(lambda: ops.conv_integral_head(xcl, wb, bias, K, NH, NS))
+    launches = ops.launch_count() - n0
+    flops = 2.0 * K * D * C * B * D * D
+    try:
+        peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["bf16_tflops"])
+    except Exception:
+        peak = 1590.0
+    out = {"metric": "conv1x1 + integral head forward samples/sec", "config": {"workload": "B=%d, C=%d -> K*D=%d, %dx%d, NH=%d" % (B, C, K * D, D, D, NH)},
+           "fused": {"ms": round(ms_fused, 4), "samples_per_s": round(B / ms_fused * 1e3, 1)},
+           "roofline": {"bound": "tensor", "kernel": "conv_head_fwd_kernel", "achieved": round(flops / (ms_fused * 1e-3) / 1e12, 1), "peak": peak,
+                        "unit": "TFLOP/s", "frac": round(flops / (ms_fused * 1e-3) / 1e12 / peak, 4),
+                        "hbm_traffic_algorithmic_gb": round(xcl.numel() * 2 / 1e9, 3)},
+           "gpu_launches": int(launches)}
+    if not args.fused_only:
+        ms_cvt = timeit(lambda: ops.conv_integral_head(x, wb, bias, K, NH, NS))
+        w4, wb4 = w.view(K * D, C, 1, 1), wb.view(K * D, C, 1, 1)
+
+        def unfused32():
+            logits = F.conv2d(x, w4, bias)
+            return ops.integral_multi_head(logits, K, NH, NS)
+
+        def unfused16():
+            logits = F.conv2d(xcl, wb4, bias.bfloat16())
+            return ops.integral_multi_head(logits.contiguous(), K, NH, NS)
+        ms_u32 = timeit(unfused32)
+        ms_conv32 = timeit(lambda: F.conv2d(x, w4, bias))
+        ms_u16 = timeit(unfused16)
+        out["fused_from_nchw_fp32"] = {"ms": round(ms_cvt, 4), "samples_per_s": round(B / ms_cvt * 1e3, 1)}
+        out["unfused_fp32_tf32conv"] = {"ms": round(ms_u32, 4), "conv_ms": round(ms_conv32, 4), "samples_per_s": round(B / ms_u32 * 1e3, 1)}
+        out["unfused_bf16_conv_bf16_logits"] = {"ms": round(ms_u16, 4), "samples_per_s": round(B / ms_u16 * 1e3, 1)}
+        out["speedup_vs_unfused_fp32"] = round(ms_u32 / ms_fused, 2)
+    print(json.dumps(out), flush=True)
+
+
+if __name__ == "__main__":
+    main()

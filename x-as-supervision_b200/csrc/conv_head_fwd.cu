@@ -110,9 +110,9 @@ __global__ void __launch_bounds__(kCvThreads, 1) conv_head_fwd_kernel(const __gr
     uint8_t* sW = smem;                                             // [KBn][128 x 64] bf16
     uint8_t* sX = sW + (size_t)KBn * kCvKBBytes;                    // [stages][KBn][128 x 64] bf16
     float4* row_stat = reinterpret_cast<float4*>(sX + (size_t)kCvStages * KBn * kCvKBBytes);   // [128] (m, s, sx, sy)
-    float* pz_s = reinterpret_cast<float*>(row_stat + kCvRows);     // [2][kMaxD]
-    int* bins_s = reinterpret_cast<int*>(pz_s + 2 * kMaxD);         // [2][kMaxD]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(bins_s + 2 * kMaxD);
+    float* pz_s = reinterpret_cast<float*>(row_stat + kCvRows);     // [4 epilogue warps][kMaxD]
+    int* bins_s = reinterpret_cast<int*>(pz_s + 4 * kMaxD);         // [4][kMaxD]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(bins_s + 4 * kMaxD);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
     const uint32_t b_wfull = smem_u32(bars), b_xfull = b_wfull + 8, b_xempty = b_xfull + 8 * kCvStages,
                    b_afull = b_xempty + 8 * kCvStages, b_aempty = b_afull + 8 * kCvAcc;
@@ -224,14 +224,14 @@ __global__ void __launch_bounds__(kCvThreads, 1) conv_head_fwd_kernel(const __gr
             __syncwarp();
             if (lane == 0) mbar_arrive(b_aempty + 8 * a);
         }
-        // ---- merge the rows of each joint and finalise (warps 0 and 1 take one joint each per round)
+        // ---- merge the rows of each joint and finalise (one joint per epilogue warp and round)
         row_stat[row] = make_float4(m, s, sx, sy);
         asm volatile("bar.sync 1, 128;" ::: "memory");               // the four epilogue warps only
         const int D = p.f.t.D, jpc = kCvRows / D;                    // joints per CTA
         for (int jl = warp; jl < jpc; jl += 4) {
             const int k = row0 / D + jl;
             if (k >= p.f.K) continue;
-            float* pz = pz_s + (jl & 1) * kMaxD;
+            float* pz = pz_s + warp * kMaxD;                         // one scratch row per finalising warp
             float M = kNegHuge;
             for (int d = lane; d < D; d += 32) M = fmaxf(M, row_stat[jl * D + d].x);
             M = warp_max(M);
@@ -246,7 +246,7 @@ __global__ void __launch_bounds__(kCvThreads, 1) conv_head_fwd_kernel(const __gr
             }
             as = warp_sum(as); ax = warp_sum(ax); ay = warp_sum(ay);
             __syncwarp();
-            finalise_unit(p.f, b * p.f.K + k, pz, bins_s + (jl & 1) * kMaxD, M, ax / as, ay / as, lane);
+            finalise_unit(p.f, b * p.f.K + k, pz, bins_s + warp * kMaxD, M, ax / as, ay / as, lane);
             __syncwarp();
         }
     }
@@ -300,7 +300,7 @@ cudaError_t launch_conv_head_fwd(const void* x_nhwc, const void* w, const float*
     p.kblocks = C / kCvKB;
     CUtensorMap map_w, map_x;
     if (!make_map(&map_w, w, p.rows_total, C) || !make_map(&map_x, x_nhwc, (long long)B * p.HW, C)) return cudaErrorNotSupported;
-    const size_t smem = 1024 + (size_t)(1 + kCvStages) * p.kblocks * kCvKBBytes + kCvRows * sizeof(float4) + 4 * kMaxD * 4 + 16 * 8 + 16;
+    const size_t smem = 1024 + (size_t)(1 + kCvStages) * p.kblocks * kCvKBBytes + kCvRows * sizeof(float4) + 8 * kMaxD * 4 + 16 * 8 + 16;
     cudaError_t e = cudaFuncSetAttribute(conv_head_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     conv_head_fwd_kernel<<<B * p.groups, kCvThreads, smem, st>>>(map_w, map_x, p);
