@@ -8,14 +8,16 @@
 //   logits[b, k*D+d, p] = sum_c Wt[k*D+d, c] * X[b, p, c] + bias[k*D+d]        p = h*W+w, C = 256
 //
 // One CTA per (sample b, group of 128 output rows = 128/D joints):
-//   warp 4      TMA producer: the 128 x C weight slab once (bf16, K-major, SWIZZLE_128B), then the sample's
+//   warp 16     TMA producer: the 128 x C weight slab once (bf16, K-major, SWIZZLE_128B), then the sample's
 //               activations as 128-pixel tiles (channels-last bf16, K-major) through a 2-stage ring
-//   warp 5      MMA issuer: one elected thread, tcgen05.mma.cta_group::1.kind::f16 M=128 N=128 K=16, 16 per tile,
+//   warp 17     MMA issuer: one elected thread, tcgen05.mma.cta_group::1.kind::f16 M=128 N=128 K=16, 16 per tile,
 //               accumulators in TMEM (4 x 128 columns, so the epilogue of tile t overlaps the MMAs of t+1..t+3);
 //               tcgen05.commit releases the smem stage and publishes the accumulator
-//   warps 0..3  epilogue: thread = TMEM lane = output row (joint, d); tcgen05.ld 32 columns at a time; the softmax
-//               statistics of the row (running max, sum e, sum w*e, sum h*e) stay in FOUR registers per thread -
-//               rows are depth bins, so the depth marginal pz[d] is simply the row sum; no shuffles per tile
+//   warps 0..15 epilogue: thread = TMEM lane = output row (joint, d), warps w, w+4, w+8, w+12 share a lane quarter and
+//               split the tile's columns (four warps per scheduler: one's tcgen05.ld / reduction chains hide behind the
+//               others' MUFU work - with one warp per scheduler the kernel ran at 2.4x the MUFU floor); tcgen05.ld 32 columns at a time; the softmax statistics of the row (running max, sum e,
+//               sum w*e, sum h*e) stay in FOUR registers per thread - rows are depth bins, so the depth marginal pz[d]
+//               is simply the row sum; no shuffles per tile
 //   unit end    rows of a joint are merged through shared memory (log-sum-exp) and handed to the same finaliser as
 //               the streaming kernel (find_peak, top-NH, window depth, outputs, saved statistics)
 // Roofline: tensor (2*K*D*C flops per pixel = 584 GFLOP at B=256) with MUFU.EX2 of the epilogue at the same
@@ -26,7 +28,9 @@
 
 namespace xsup {
 
-constexpr int kCvThreads = 192;
+constexpr int kCvEpiWarps = 16;         // four per TMEM lane quarter: each takes 32 of a tile's 128 columns
+constexpr int kCvParts = kCvEpiWarps / 4;
+constexpr int kCvThreads = (kCvEpiWarps + 2) * 32;
 constexpr int kCvRows = 128;           // UMMA M: output rows per CTA
 constexpr int kCvPix = 128;            // UMMA N: pixels per tile
 constexpr int kCvKB = 64;              // channels per swizzle-128B k-block (bf16)
@@ -109,8 +113,8 @@ __global__ void __launch_bounds__(kCvThreads, 1) conv_head_fwd_kernel(const __gr
     const int KBn = p.kblocks;
     uint8_t* sW = smem;                                             // [KBn][128 x 64] bf16
     uint8_t* sX = sW + (size_t)KBn * kCvKBBytes;                    // [stages][KBn][128 x 64] bf16
-    float4* row_stat = reinterpret_cast<float4*>(sX + (size_t)kCvStages * KBn * kCvKBBytes);   // [128] (m, s, sx, sy)
-    float* pz_s = reinterpret_cast<float*>(row_stat + kCvRows);     // [4 epilogue warps][kMaxD]
+    float4* row_stat = reinterpret_cast<float4*>(sX + (size_t)kCvStages * KBn * kCvKBBytes);   // [kCvParts column parts][128] (m, s, sx, sy)
+    float* pz_s = reinterpret_cast<float*>(row_stat + kCvParts * kCvRows); // [4 finalising warps][kMaxD]
     int* bins_s = reinterpret_cast<int*>(pz_s + 4 * kMaxD);         // [4][kMaxD]
     uint64_t* bars = reinterpret_cast<uint64_t*>(bins_s + 4 * kMaxD);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
@@ -125,11 +129,11 @@ __global__ void __launch_bounds__(kCvThreads, 1) conv_head_fwd_kernel(const __gr
         }
         for (int i = 0; i < kCvAcc; ++i) {
             mbar_init(b_afull + 8 * i, 1);
-            mbar_init(b_aempty + 8 * i, 4);                          // one elected lane per epilogue warp
+            mbar_init(b_aempty + 8 * i, kCvEpiWarps);                // one elected lane per epilogue warp
         }
         mbar_fence_init();
     }
-    if (warp == 5) tmem_alloc(smem_u32(tmem_slot), 512);
+    if (warp == kCvEpiWarps + 1) tmem_alloc(smem_u32(tmem_slot), 512);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -139,7 +143,7 @@ __global__ void __launch_bounds__(kCvThreads, 1) conv_head_fwd_kernel(const __gr
     const int row0 = grp * kCvRows;                                  // first output row of this CTA
     const int T = p.n_tiles;
 
-    if (warp == 4) {
+    if (warp == kCvEpiWarps) {
         // ------------------------------------------------------------ TMA producer
         if (lane == 0) {
             mbar_arrive_expect_tx(b_wfull, (uint32_t)KBn * kCvKBBytes);
@@ -153,7 +157,7 @@ __global__ void __launch_bounds__(kCvThreads, 1) conv_head_fwd_kernel(const __gr
             }
         }
         __syncwarp();
-    } else if (warp == 5) {
+    } else if (warp == kCvEpiWarps + 1) {
         // ------------------------------------------------------------ MMA issuer
         mbar_wait(b_wfull, 0);
         for (int t = 0; t < T; ++t) {
@@ -175,8 +179,9 @@ __global__ void __launch_bounds__(kCvThreads, 1) conv_head_fwd_kernel(const __gr
             __syncwarp();
         }
     } else {
-        // ------------------------------------------------------------ epilogue: thread = output row
-        const int row = warp * 32 + lane, grow = row0 + row;         // TMEM lane = row; warp w may only touch lanes 32w..32w+31
+        // ------------------------------------------------------------ epilogue: thread = output row, warp pair = column halves
+        const int quarter = warp & 3, part = warp >> 2;              // a warp may only touch TMEM lanes 32*(warp%4) .. +31
+        const int row = quarter * 32 + lane, grow = row0 + row;
         const bool live = grow < p.rows_total;
         const float bl = (live && p.bias) ? p.bias[grow] * kLog2e : 0.f;
         const int Wd = p.f.t.W;
@@ -187,9 +192,9 @@ __global__ void __launch_bounds__(kCvThreads, 1) conv_head_fwd_kernel(const __gr
             mbar_wait(b_afull + 8 * a, ia & 1);
             tc_fence_after();
 #pragma unroll 1
-            for (int c0 = 0; c0 < kCvPix; c0 += 32) {
+            for (int c0 = part * (kCvPix / kCvParts); c0 < (part + 1) * (kCvPix / kCvParts); c0 += 32) {
                 uint32_t r[32];
-                tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(a * kCvPix + c0), r);
+                tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(a * kCvPix + c0), r);
                 const int pix = t * kCvPix + c0;                     // 32 consecutive pixels of one image row (W >= 32)
                 const int hh = pix / Wd, w0 = pix - hh * Wd;
                 if (lrow && live) {
@@ -199,23 +204,26 @@ __global__ void __launch_bounds__(kCvThreads, 1) conv_head_fwd_kernel(const __gr
                         *reinterpret_cast<float4*>(lrow + pix + i) = make_float4(__uint_as_float(r[i]) + bb, __uint_as_float(r[i + 1]) + bb,
                                                                                  __uint_as_float(r[i + 2]) + bb, __uint_as_float(r[i + 3]) + bb);
                 }
-                float cm = __uint_as_float(r[0]);
+                float cm4[4];                                        // four independent chains instead of one of length 32
 #pragma unroll
-                for (int i = 1; i < 32; ++i) cm = fmaxf(cm, __uint_as_float(r[i]));
-                cm = fmaf(cm, kLog2e, bl);                           // chunk max in the log2 domain (bias included)
-                if (cm > m) {                                        // per-row running max: rescale four registers
+                for (int j = 0; j < 4; ++j) cm4[j] = __uint_as_float(r[j]);
+#pragma unroll
+                for (int i = 4; i < 32; ++i) cm4[i & 3] = fmaxf(cm4[i & 3], __uint_as_float(r[i]));
+                const float cm = fmaf(fmaxf(fmaxf(cm4[0], cm4[1]), fmaxf(cm4[2], cm4[3])), kLog2e, bl);   // log2 domain, bias included
+                if (cm > m) {                                        // per-row running max: rescale three registers
                     const float sc = ex2(m - cm);
                     s *= sc; sx *= sc; sy *= sc;
                     m = cm;
                 }
                 const float sh = bl - m;
-                float cs = 0.f, cx = 0.f;
+                float cs4[4] = {0.f, 0.f, 0.f, 0.f}, cx4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
                 for (int i = 0; i < 32; ++i) {
                     const float e = ex2(fmaf(__uint_as_float(r[i]), kLog2e, sh));
-                    cs += e;
-                    cx = fmaf((float)i, e, cx);
+                    cs4[i & 3] += e;
+                    cx4[i & 3] = fmaf((float)i, e, cx4[i & 3]);
                 }
+                const float cs = (cs4[0] + cs4[1]) + (cs4[2] + cs4[3]), cx = (cx4[0] + cx4[1]) + (cx4[2] + cx4[3]);
                 s += cs;
                 sx += fmaf((float)w0, cs, cx);
                 sy = fmaf((float)hh, cs, sy);
@@ -224,35 +232,44 @@ __global__ void __launch_bounds__(kCvThreads, 1) conv_head_fwd_kernel(const __gr
             __syncwarp();
             if (lane == 0) mbar_arrive(b_aempty + 8 * a);
         }
-        // ---- merge the rows of each joint and finalise (one joint per epilogue warp and round)
-        row_stat[row] = make_float4(m, s, sx, sy);
-        asm volatile("bar.sync 1, 128;" ::: "memory");               // the four epilogue warps only
+        // ---- merge the two column halves and the rows of each joint, then finalise (one joint per warp 0..3 and round)
+        row_stat[part * kCvRows + row] = make_float4(m, s, sx, sy);
+        asm volatile("bar.sync 1, %0;" ::"n"(kCvEpiWarps * 32) : "memory");   // the epilogue warps only
         const int D = p.f.t.D, jpc = kCvRows / D;                    // joints per CTA
-        for (int jl = warp; jl < jpc; jl += 4) {
-            const int k = row0 / D + jl;
-            if (k >= p.f.K) continue;
-            float* pz = pz_s + warp * kMaxD;                         // one scratch row per finalising warp
-            float M = kNegHuge;
-            for (int d = lane; d < D; d += 32) M = fmaxf(M, row_stat[jl * D + d].x);
-            M = warp_max(M);
-            float ax = 0.f, ay = 0.f, as = 0.f;
-            for (int d = lane; d < D; d += 32) {
-                const float4 q = row_stat[jl * D + d];
-                const float sc = ex2(q.x - M);
-                pz[d] = q.y * sc;
-                as = fmaf(q.y, sc, as);
-                ax = fmaf(q.z, sc, ax);
-                ay = fmaf(q.w, sc, ay);
+        if (warp < 4) {
+            for (int jl = warp; jl < jpc; jl += 4) {
+                const int k = row0 / D + jl;
+                if (k >= p.f.K) continue;
+                float* pz = pz_s + warp * kMaxD;                     // one scratch row per finalising warp
+                float M = kNegHuge;
+                for (int d = lane; d < D; d += 32)
+#pragma unroll
+                    for (int q = 0; q < kCvParts; ++q) M = fmaxf(M, row_stat[q * kCvRows + jl * D + d].x);
+                M = warp_max(M);
+                float ax = 0.f, ay = 0.f, as = 0.f;
+                for (int d = lane; d < D; d += 32) {
+                    float pd = 0.f;
+#pragma unroll
+                    for (int q = 0; q < kCvParts; ++q) {             // log-sum-exp merge of the column parts, fixed order
+                        const float4 v = row_stat[q * kCvRows + jl * D + d];
+                        const float sc = ex2(v.x - M);
+                        pd = fmaf(v.y, sc, pd);
+                        ax = fmaf(v.z, sc, ax);
+                        ay = fmaf(v.w, sc, ay);
+                    }
+                    pz[d] = pd;
+                    as += pd;
+                }
+                as = warp_sum(as); ax = warp_sum(ax); ay = warp_sum(ay);
+                __syncwarp();
+                finalise_unit(p.f, b * p.f.K + k, pz, bins_s + warp * kMaxD, M, ax / as, ay / as, lane);
+                __syncwarp();
             }
-            as = warp_sum(as); ax = warp_sum(ax); ay = warp_sum(ay);
-            __syncwarp();
-            finalise_unit(p.f, b * p.f.K + k, pz, bins_s + warp * kMaxD, M, ax / as, ay / as, lane);
-            __syncwarp();
         }
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 5) {
+    if (warp == kCvEpiWarps + 1) {
         tc_fence_after();
         tmem_dealloc(tmem_base, 512);
     }
@@ -300,7 +317,7 @@ cudaError_t launch_conv_head_fwd(const void* x_nhwc, const void* w, const float*
     p.kblocks = C / kCvKB;
     CUtensorMap map_w, map_x;
     if (!make_map(&map_w, w, p.rows_total, C) || !make_map(&map_x, x_nhwc, (long long)B * p.HW, C)) return cudaErrorNotSupported;
-    const size_t smem = 1024 + (size_t)(1 + kCvStages) * p.kblocks * kCvKBBytes + kCvRows * sizeof(float4) + 8 * kMaxD * 4 + 16 * 8 + 16;
+    const size_t smem = 1024 + (size_t)(1 + kCvStages) * p.kblocks * kCvKBBytes + kCvParts * kCvRows * sizeof(float4) + 8 * kMaxD * 4 + 16 * 8 + 16;
     cudaError_t e = cudaFuncSetAttribute(conv_head_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     conv_head_fwd_kernel<<<B * p.groups, kCvThreads, smem, st>>>(map_w, map_x, p);
