@@ -7,19 +7,24 @@
 //
 //   logits[b, k*D+d, p] = sum_c Wt[k*D+d, c] * X[b, p, c] + bias[k*D+d]        p = h*W+w, C = 256
 //
-// One CTA per (sample b, group of 128 output rows = 128/D joints):
-//   warp 16     TMA producer: the 128 x C weight slab once (bf16, K-major, SWIZZLE_128B), then the sample's
-//               activations as 128-pixel tiles (channels-last bf16, K-major) through a 2-stage ring
-//   warp 17     MMA issuer: one elected thread, tcgen05.mma.cta_group::1.kind::f16 M=128 N=128 K=16, 16 per tile,
-//               accumulators in TMEM (4 x 128 columns, so the epilogue of tile t overlaps the MMAs of t+1..t+3);
-//               tcgen05.commit releases the smem stage and publishes the accumulator
-//   warps 0..15 epilogue: thread = TMEM lane = output row (joint, d), warps w, w+4, w+8, w+12 share a lane quarter and
-//               split the tile's columns (four warps per scheduler: one's tcgen05.ld / reduction chains hide behind the
-//               others' MUFU work - with one warp per scheduler the kernel ran at 2.4x the MUFU floor); tcgen05.ld 32 columns at a time; the softmax statistics of the row (running max, sum e,
-//               sum w*e, sum h*e) stay in FOUR registers per thread - rows are depth bins, so the depth marginal pz[d]
-//               is simply the row sum; no shuffles per tile
-//   unit end    rows of a joint are merged through shared memory (log-sum-exp) and handed to the same finaliser as
-//               the streaming kernel (find_peak, top-NH, window depth, outputs, saved statistics)
+// Persistent CTAs (one per SM) walk the work items (sample b, group of 128 output rows = 128/D joints) in b-major
+// order, so the ~9 row groups of a sample run at the same time on neighbouring CTAs and share its activations in L2:
+//   warp 16      TMA producer: the item's 128 x C weight slab (bf16, K-major, SWIZZLE_128B) as soon as the previous item's
+//                MMAs have retired, then the sample's activations as 128-pixel tiles (channels-last bf16, K-major)
+//                through a 2-stage ring; barrier phases run on across items
+//   warp 17      MMA issuer: one elected thread, tcgen05.mma.cta_group::1.kind::f16 M=128 N=128 K=16, 16 per tile, with
+//                precomputed shared-memory descriptors (the issue loop is ~5 instructions per MMA); accumulators in
+//                TMEM (4 x 128 columns: the epilogue of tile t overlaps the MMAs of t+1..t+3); tcgen05.commit releases
+//                the smem stage and publishes the accumulator
+//   warps 0..15  epilogue: thread = TMEM lane = output row (joint, d); warps w, w+4, w+8, w+12 share a lane quarter and
+//                take 32 columns each; tcgen05.ld; the softmax statistics of the row (running max, sum e, sum w*e,
+//                sum h*e) stay in FOUR registers per thread - rows are depth bins, so the depth marginal pz[d] is simply
+//                the row sum; no shuffles per tile
+//   warps 18,19  finalisers: merge the column parts and the rows of a joint (log-sum-exp through double-buffered shared
+//                memory) and run the same finaliser as the streaming kernel (find_peak, top-NH, window depth, outputs,
+//                saved statistics) while the other warps are already on the next item
+// Measured on the way here (B=256, ablations): a non-persistent CTA per item spent 0.25 ms of 0.62 ms in start-up /
+// tear-down, and computing the descriptors inside the issue loop cost ~65 cycles per MMA.
 // Roofline: tensor (2*K*D*C flops per pixel = 584 GFLOP at B=256) with MUFU.EX2 of the epilogue at the same
 // order (one exp per logit); HBM traffic is the activations only (0.54 GB).
 #include <cuda.h>
@@ -30,7 +35,8 @@ namespace xsup {
 
 constexpr int kCvEpiWarps = 16;         // four per TMEM lane quarter: each takes 32 of a tile's 128 columns
 constexpr int kCvParts = kCvEpiWarps / 4;
-constexpr int kCvThreads = (kCvEpiWarps + 2) * 32;
+constexpr int kCvFinWarps = 2;
+constexpr int kCvThreads = (kCvEpiWarps + 2 + kCvFinWarps) * 32;
 constexpr int kCvRows = 128;           // UMMA M: output rows per CTA
 constexpr int kCvPix = 128;            // UMMA N: pixels per tile
 constexpr int kCvKB = 64;              // channels per swizzle-128B k-block (bf16)
@@ -46,6 +52,7 @@ struct ConvHeadParams {
     int groups;                 // CTAs per sample = ceil(K*D / 128)
     int n_tiles;                // HW / 128
     int kblocks;                // C / 64
+    int items;                  // B * groups
 };
 
 // ------------------------------------------------------------------ PTX wrappers (sm_100a)
@@ -63,14 +70,16 @@ __device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+// D[tmem] (+)= A[smem desc] * B[smem desc]; ACC = false overwrites the accumulator (first MMA of a tile)
+template <bool ACC>
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc) {
     asm volatile(
         "{\n\t"
         ".reg .pred p;\n\t"
         "setp.ne.b32 p, %4, 0;\n\t"
         "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
         "}" ::"r"(tmem_d),
-        "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        "l"(desc_a), "l"(desc_b), "r"(idesc), "n"(ACC ? 1 : 0)
         : "memory");
 }
 // arrives on the mbarrier when all previously issued tcgen05.mma of this thread have completed
@@ -103,6 +112,7 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
 constexpr uint32_t kCvIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(kCvPix >> 3) << 17) | ((uint32_t)(kCvRows >> 4) << 24);
 
 // ------------------------------------------------------------------ kernel
+template <int KBN>
 __global__ void __launch_bounds__(kCvThreads, 1) conv_head_fwd_kernel(const __grid_constant__ CUtensorMap map_w,
                                                                       const __grid_constant__ CUtensorMap map_x,
                                                                       const ConvHeadParams p) {
@@ -110,19 +120,20 @@ __global__ void __launch_bounds__(kCvThreads, 1) conv_head_fwd_kernel(const __gr
     // the dynamic shared window is only 16-byte aligned by contract: round up to the 1024 B the swizzle needs
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int KBn = p.kblocks;
-    uint8_t* sW = smem;                                             // [KBn][128 x 64] bf16
-    uint8_t* sX = sW + (size_t)KBn * kCvKBBytes;                    // [stages][KBn][128 x 64] bf16
-    float4* row_stat = reinterpret_cast<float4*>(sX + (size_t)kCvStages * KBn * kCvKBBytes);   // [kCvParts column parts][128] (m, s, sx, sy)
-    float* pz_s = reinterpret_cast<float*>(row_stat + kCvParts * kCvRows); // [4 finalising warps][kMaxD]
-    int* bins_s = reinterpret_cast<int*>(pz_s + 4 * kMaxD);         // [4][kMaxD]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(bins_s + 4 * kMaxD);
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
-    const uint32_t b_wfull = smem_u32(bars), b_xfull = b_wfull + 8, b_xempty = b_xfull + 8 * kCvStages,
-                   b_afull = b_xempty + 8 * kCvStages, b_aempty = b_afull + 8 * kCvAcc;
+    uint8_t* sW = smem;                                             // [KBN][128 x 64] bf16
+    uint8_t* sX = sW + (size_t)KBN * kCvKBBytes;                    // [stages][KBN][128 x 64] bf16
+    float4* row_stat = reinterpret_cast<float4*>(sX + (size_t)kCvStages * KBN * kCvKBBytes);   // [2 items][kCvParts][128] (m, s, sx, sy)
+    float* pz_s = reinterpret_cast<float*>(row_stat + 2 * kCvParts * kCvRows);                 // [kCvFinWarps][kMaxD]
+    int* bins_s = reinterpret_cast<int*>(pz_s + kCvFinWarps * kMaxD);                          // [kCvFinWarps][kMaxD]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(bins_s + kCvFinWarps * kMaxD);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 24);
+    const uint32_t b_wfull = smem_u32(bars), b_wempty = b_wfull + 8, b_xfull = b_wempty + 8, b_xempty = b_xfull + 8 * kCvStages,
+                   b_afull = b_xempty + 8 * kCvStages, b_aempty = b_afull + 8 * kCvAcc, b_rsfull = b_aempty + 8 * kCvAcc,
+                   b_rsfree = b_rsfull + 16;
 
     if (threadIdx.x == 0) {
         mbar_init(b_wfull, 1);
+        mbar_init(b_wempty, 1);
         for (int i = 0; i < kCvStages; ++i) {
             mbar_init(b_xfull + 8 * i, 1);
             mbar_init(b_xempty + 8 * i, 1);
@@ -131,6 +142,10 @@ __global__ void __launch_bounds__(kCvThreads, 1) conv_head_fwd_kernel(const __gr
             mbar_init(b_afull + 8 * i, 1);
             mbar_init(b_aempty + 8 * i, kCvEpiWarps);                // one elected lane per epilogue warp
         }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(b_rsfull + 8 * i, kCvEpiWarps);
+            mbar_init(b_rsfree + 8 * i, kCvFinWarps);
+        }
         mbar_fence_init();
     }
     if (warp == kCvEpiWarps + 1) tmem_alloc(smem_u32(tmem_slot), 512);
@@ -138,71 +153,93 @@ __global__ void __launch_bounds__(kCvThreads, 1) conv_head_fwd_kernel(const __gr
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-
-    const int b = blockIdx.x / p.groups, grp = blockIdx.x - b * p.groups;
-    const int row0 = grp * kCvRows;                                  // first output row of this CTA
     const int T = p.n_tiles;
 
     if (warp == kCvEpiWarps) {
         // ------------------------------------------------------------ TMA producer
         if (lane == 0) {
-            mbar_arrive_expect_tx(b_wfull, (uint32_t)KBn * kCvKBBytes);
-            for (int kb = 0; kb < KBn; ++kb) tma_load_2d(smem_u32(sW) + kb * kCvKBBytes, &map_w, kb * kCvKB, row0, b_wfull);
-            for (int t = 0; t < T; ++t) {
-                const int s = t % kCvStages, it = t / kCvStages;
-                mbar_wait(b_xempty + 8 * s, (it & 1) ^ 1);
-                mbar_arrive_expect_tx(b_xfull + 8 * s, (uint32_t)KBn * kCvKBBytes);
-                const uint32_t dst = smem_u32(sX) + (uint32_t)s * KBn * kCvKBBytes;
-                for (int kb = 0; kb < KBn; ++kb) tma_load_2d(dst + kb * kCvKBBytes, &map_x, kb * kCvKB, b * p.HW + t * kCvPix, b_xfull + 8 * s);
+            int g = 0, n = 0;                                        // tiles / items this CTA has started
+            for (int item = blockIdx.x; item < p.items; item += gridDim.x, ++n) {
+                const int b = item / p.groups, row0 = (item - b * p.groups) * kCvRows;
+                mbar_wait(b_wempty, (n & 1) ^ 1);                    // the previous item's MMAs no longer read the slab
+                mbar_arrive_expect_tx(b_wfull, (uint32_t)KBN * kCvKBBytes);
+#pragma unroll
+                for (int kb = 0; kb < KBN; ++kb) tma_load_2d(smem_u32(sW) + kb * kCvKBBytes, &map_w, kb * kCvKB, row0, b_wfull);
+                for (int t = 0; t < T; ++t, ++g) {
+                    const int s = g % kCvStages, it = g / kCvStages;
+                    mbar_wait(b_xempty + 8 * s, (it & 1) ^ 1);
+                    mbar_arrive_expect_tx(b_xfull + 8 * s, (uint32_t)KBN * kCvKBBytes);
+                    const uint32_t dst = smem_u32(sX) + (uint32_t)s * KBN * kCvKBBytes;
+#pragma unroll
+                    for (int kb = 0; kb < KBN; ++kb) tma_load_2d(dst + kb * kCvKBBytes, &map_x, kb * kCvKB, b * p.HW + t * kCvPix, b_xfull + 8 * s);
+                }
             }
         }
         __syncwarp();
     } else if (warp == kCvEpiWarps + 1) {
         // ------------------------------------------------------------ MMA issuer
-        mbar_wait(b_wfull, 0);
-        for (int t = 0; t < T; ++t) {
-            const int s = t % kCvStages, it = t / kCvStages, a = t % kCvAcc, ia = t / kCvAcc;
-            mbar_wait(b_aempty + 8 * a, (ia & 1) ^ 1);               // the epilogue has drained this accumulator
-            mbar_wait(b_xfull + 8 * s, it & 1);                      // the tile has landed
-            tc_fence_after();
-            if (lane == 0) {
-                const uint32_t xs = smem_u32(sX) + (uint32_t)s * KBn * kCvKBBytes, ws = smem_u32(sW);
-                for (int kb = 0; kb < KBn; ++kb) {
-                    const uint64_t da = umma_desc_sw128(ws + kb * kCvKBBytes), db = umma_desc_sw128(xs + kb * kCvKBBytes);
+        uint64_t da[KBN], db0[KBN];                                  // descriptors of the slab and of ring stage 0, per k-block
 #pragma unroll
-                    for (int k = 0; k < kCvKB / 16; ++k)             // +32 B per K step of 16 bf16: +2 in the address field
-                        umma_f16(tmem_base + (uint32_t)a * kCvPix, da + 2 * k, db + 2 * k, kCvIdesc, (kb | k) != 0);
-                }
-                umma_commit(b_xempty + 8 * s);                       // smem stage reusable once these MMAs have read it
-                umma_commit(b_afull + 8 * a);                        // accumulator complete
-            }
-            __syncwarp();
+        for (int kb = 0; kb < KBN; ++kb) {
+            da[kb] = umma_desc_sw128(smem_u32(sW) + kb * kCvKBBytes);
+            db0[kb] = umma_desc_sw128(smem_u32(sX) + kb * kCvKBBytes);
         }
-    } else {
-        // ------------------------------------------------------------ epilogue: thread = output row, warp pair = column halves
+        constexpr uint64_t kStageStep = (uint64_t)((KBN * kCvKBBytes) >> 4);   // start-address field units
+        int g = 0, n = 0;
+        for (int item = blockIdx.x; item < p.items; item += gridDim.x, ++n) {
+            mbar_wait(b_wfull, n & 1);
+            for (int t = 0; t < T; ++t, ++g) {
+                const int s = g % kCvStages, it = g / kCvStages, a = g % kCvAcc, ia = g / kCvAcc;
+                mbar_wait(b_aempty + 8 * a, (ia & 1) ^ 1);           // the epilogue has drained this accumulator
+                mbar_wait(b_xfull + 8 * s, it & 1);                  // the tile has landed
+                tc_fence_after();
+                if (lane == 0) {
+                    const uint32_t acc = tmem_base + (uint32_t)a * kCvPix;
+                    const uint64_t soff = (uint64_t)s * kStageStep;
+#pragma unroll
+                    for (int kb = 0; kb < KBN; ++kb) {
+                        const uint64_t a0 = da[kb], b0 = db0[kb] + soff;
+                        // +32 B per K step of 16 bf16 inside the 128-byte swizzle atom: +2 in the start-address field
+                        if (kb == 0) umma_f16<false>(acc, a0, b0, kCvIdesc); else umma_f16<true>(acc, a0, b0, kCvIdesc);
+                        umma_f16<true>(acc, a0 + 2, b0 + 2, kCvIdesc);
+                        umma_f16<true>(acc, a0 + 4, b0 + 4, kCvIdesc);
+                        umma_f16<true>(acc, a0 + 6, b0 + 6, kCvIdesc);
+                    }
+                    umma_commit(b_xempty + 8 * s);                   // smem stage reusable once these MMAs have read it
+                    umma_commit(b_afull + 8 * a);                    // accumulator complete
+                    if (t == T - 1) umma_commit(b_wempty);           // the slab may be replaced
+                }
+                __syncwarp();
+            }
+        }
+    } else if (warp < kCvEpiWarps) {
+        // ------------------------------------------------------------ epilogue: thread = output row, 32 columns per warp and tile
         const int quarter = warp & 3, part = warp >> 2;              // a warp may only touch TMEM lanes 32*(warp%4) .. +31
-        const int row = quarter * 32 + lane, grow = row0 + row;
-        const bool live = grow < p.rows_total;
-        const float bl = (live && p.bias) ? p.bias[grow] * kLog2e : 0.f;
-        const int Wd = p.f.t.W;
-        float m = kNegHuge, s = 0.f, sx = 0.f, sy = 0.f;
-        float* lrow = p.logits_out ? p.logits_out + ((size_t)b * p.rows_total + grow) * p.HW : nullptr;
-        for (int t = 0; t < T; ++t) {
-            const int a = t % kCvAcc, ia = t / kCvAcc;
-            mbar_wait(b_afull + 8 * a, ia & 1);
-            tc_fence_after();
-#pragma unroll 1
-            for (int c0 = part * (kCvPix / kCvParts); c0 < (part + 1) * (kCvPix / kCvParts); c0 += 32) {
+        const int row = quarter * 32 + lane;
+        const int Wd = p.f.t.W, c0 = part * 32;
+        int g = 0, n = 0;
+        for (int item = blockIdx.x; item < p.items; item += gridDim.x, ++n) {
+            const int b = item / p.groups, row0 = (item - b * p.groups) * kCvRows, grow = row0 + row;
+            const bool live = grow < p.rows_total;
+            const float bias = (live && p.bias) ? p.bias[grow] : 0.f, bl = bias * kLog2e;
+            float m = kNegHuge, s = 0.f, sx = 0.f, sy = 0.f;
+            float* lrow = p.logits_out ? p.logits_out + ((size_t)b * p.rows_total + grow) * p.HW : nullptr;
+            for (int t = 0; t < T; ++t, ++g) {
+                const int a = g % kCvAcc, ia = g / kCvAcc;
+                mbar_wait(b_afull + 8 * a, ia & 1);
+                tc_fence_after();
                 uint32_t r[32];
                 tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(a * kCvPix + c0), r);
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(b_aempty + 8 * a);        // values are in registers: release the accumulator early
                 const int pix = t * kCvPix + c0;                     // 32 consecutive pixels of one image row (W >= 32)
                 const int hh = pix / Wd, w0 = pix - hh * Wd;
                 if (lrow && live) {
-                    const float bb = p.bias ? p.bias[grow] : 0.f;
 #pragma unroll
                     for (int i = 0; i < 32; i += 4)
-                        *reinterpret_cast<float4*>(lrow + pix + i) = make_float4(__uint_as_float(r[i]) + bb, __uint_as_float(r[i + 1]) + bb,
-                                                                                 __uint_as_float(r[i + 2]) + bb, __uint_as_float(r[i + 3]) + bb);
+                        *reinterpret_cast<float4*>(lrow + pix + i) = make_float4(__uint_as_float(r[i]) + bias, __uint_as_float(r[i + 1]) + bias,
+                                                                                 __uint_as_float(r[i + 2]) + bias, __uint_as_float(r[i + 3]) + bias);
                 }
                 float cm4[4];                                        // four independent chains instead of one of length 32
 #pragma unroll
@@ -228,30 +265,38 @@ __global__ void __launch_bounds__(kCvThreads, 1) conv_head_fwd_kernel(const __gr
                 sx += fmaf((float)w0, cs, cx);
                 sy = fmaf((float)hh, cs, sy);
             }
-            tc_fence_before();
+            // hand the row statistics of this item to the finalisers (double-buffered: they lag by up to one item)
+            const int buf = n & 1, u = n >> 1;
+            mbar_wait(b_rsfree + 8 * buf, (u & 1) ^ 1);
+            row_stat[(buf * kCvParts + part) * kCvRows + row] = make_float4(m, s, sx, sy);
             __syncwarp();
-            if (lane == 0) mbar_arrive(b_aempty + 8 * a);
+            if (lane == 0) mbar_arrive(b_rsfull + 8 * buf);
         }
-        // ---- merge the two column halves and the rows of each joint, then finalise (one joint per warp 0..3 and round)
-        row_stat[part * kCvRows + row] = make_float4(m, s, sx, sy);
-        asm volatile("bar.sync 1, %0;" ::"n"(kCvEpiWarps * 32) : "memory");   // the epilogue warps only
-        const int D = p.f.t.D, jpc = kCvRows / D;                    // joints per CTA
-        if (warp < 4) {
-            for (int jl = warp; jl < jpc; jl += 4) {
+    } else {
+        // ------------------------------------------------------------ finalisers: one joint per warp and round
+        const int fw = warp - (kCvEpiWarps + 2);
+        const int D = p.f.t.D, jpc = kCvRows / D;                    // joints per item
+        float* pz = pz_s + fw * kMaxD;
+        int n = 0;
+        for (int item = blockIdx.x; item < p.items; item += gridDim.x, ++n) {
+            const int b = item / p.groups, row0 = (item - b * p.groups) * kCvRows;
+            const int buf = n & 1, u = n >> 1;
+            mbar_wait(b_rsfull + 8 * buf, u & 1);
+            const float4* rs = row_stat + (size_t)buf * kCvParts * kCvRows;
+            for (int jl = fw; jl < jpc; jl += kCvFinWarps) {
                 const int k = row0 / D + jl;
-                if (k >= p.f.K) continue;
-                float* pz = pz_s + warp * kMaxD;                     // one scratch row per finalising warp
+                if (k >= p.f.K) continue;                            // padding rows of the last group
                 float M = kNegHuge;
                 for (int d = lane; d < D; d += 32)
 #pragma unroll
-                    for (int q = 0; q < kCvParts; ++q) M = fmaxf(M, row_stat[q * kCvRows + jl * D + d].x);
+                    for (int q = 0; q < kCvParts; ++q) M = fmaxf(M, rs[q * kCvRows + jl * D + d].x);
                 M = warp_max(M);
                 float ax = 0.f, ay = 0.f, as = 0.f;
                 for (int d = lane; d < D; d += 32) {
                     float pd = 0.f;
 #pragma unroll
                     for (int q = 0; q < kCvParts; ++q) {             // log-sum-exp merge of the column parts, fixed order
-                        const float4 v = row_stat[q * kCvRows + jl * D + d];
+                        const float4 v = rs[q * kCvRows + jl * D + d];
                         const float sc = ex2(v.x - M);
                         pd = fmaf(v.y, sc, pd);
                         ax = fmaf(v.z, sc, ax);
@@ -262,9 +307,11 @@ __global__ void __launch_bounds__(kCvThreads, 1) conv_head_fwd_kernel(const __gr
                 }
                 as = warp_sum(as); ax = warp_sum(ax); ay = warp_sum(ay);
                 __syncwarp();
-                finalise_unit(p.f, b * p.f.K + k, pz, bins_s + warp * kMaxD, M, ax / as, ay / as, lane);
+                finalise_unit(p.f, b * p.f.K + k, pz, bins_s + fw * kMaxD, M, ax / as, ay / as, lane);
                 __syncwarp();
             }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(b_rsfree + 8 * buf);
         }
     }
     tc_fence_before();
@@ -303,8 +350,17 @@ static bool make_map(CUtensorMap* map, const void* base, long long rows, int C) 
                CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
+template <int KBN>
+static cudaError_t launch_kbn(const CUtensorMap& map_w, const CUtensorMap& map_x, const ConvHeadParams& p, int grid, size_t smem, cudaStream_t st) {
+    auto kern = conv_head_fwd_kernel<KBN>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    kern<<<grid, kCvThreads, smem, st>>>(map_w, map_x, p);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_conv_head_fwd(const void* x_nhwc, const void* w, const float* bias, float* logits_out, FwdParams f, int B, int C,
-                                 cudaStream_t st) {
+                                 int num_sms, cudaStream_t st) {
     ConvHeadParams p{};
     p.f = f;
     p.bias = bias;
@@ -315,13 +371,18 @@ cudaError_t launch_conv_head_fwd(const void* x_nhwc, const void* w, const float*
     p.groups = (p.rows_total + kCvRows - 1) / kCvRows;
     p.n_tiles = p.HW / kCvPix;
     p.kblocks = C / kCvKB;
+    p.items = B * p.groups;
     CUtensorMap map_w, map_x;
     if (!make_map(&map_w, w, p.rows_total, C) || !make_map(&map_x, x_nhwc, (long long)B * p.HW, C)) return cudaErrorNotSupported;
-    const size_t smem = 1024 + (size_t)(1 + kCvStages) * p.kblocks * kCvKBBytes + kCvParts * kCvRows * sizeof(float4) + 8 * kMaxD * 4 + 16 * 8 + 16;
-    cudaError_t e = cudaFuncSetAttribute(conv_head_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    conv_head_fwd_kernel<<<B * p.groups, kCvThreads, smem, st>>>(map_w, map_x, p);
-    return cudaGetLastError();
+    const size_t smem = 1024 + (size_t)(1 + kCvStages) * p.kblocks * kCvKBBytes + 2 * kCvParts * kCvRows * sizeof(float4) +
+                        2 * kCvFinWarps * kMaxD * 4 + 24 * 8 + 16;
+    const int grid = p.items < num_sms ? p.items : num_sms;          // persistent: one CTA per SM
+    switch (p.kblocks) {
+        case 1: return launch_kbn<1>(map_w, map_x, p, grid, smem, st);
+        case 2: return launch_kbn<2>(map_w, map_x, p, grid, smem, st);
+        case 3: return launch_kbn<3>(map_w, map_x, p, grid, smem, st);
+        default: return launch_kbn<4>(map_w, map_x, p, grid, smem, st);
+    }
 }
 
 }  // namespace xsup

@@ -114,7 +114,7 @@ cudaError_t launch_disc_min_loss_bwd(const float* logits, const int64_t* sel, co
 
 // conv-fused forward (conv_head_fwd.cu)
 cudaError_t launch_conv_head_fwd(const void* x_nhwc, const void* w, const float* bias, float* logits_out, FwdParams f, int B, int C,
-                                 cudaStream_t st);
+                                 int num_sms, cudaStream_t st);
 
 void count_launches(int n);
 
