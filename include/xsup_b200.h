@@ -281,6 +281,9 @@ int xsup_disc_min_loss_bwd(const float* logits, const int64_t* sel, const float*
  *   kps, depth_prob_map, peak_idx, stats: as xsup_integral_fwd (s->dtype is ignored: the operands are bf16, the
  *   accumulation and all statistics are fp32); logits_out: NULL, or [B, K*D, H, W] fp32 to also materialise the
  *   logits (validation).  Constraints: 128 % D == 0, (H*W) % 128 == 0, W % 32 == 0, C % 64 == 0, C <= 256. */
+/* [B, C, H*W] fp32 (NCHW-contiguous activations of a plain backbone) -> [B, H*W, C] bf16, the operand layout of
+ * xsup_conv_head_fwd, in one pass (transpose + round-to-nearest-even).  C % 64 == 0, (H*W) % 64 == 0. */
+int xsup_pack_nhwc_bf16(const float* x_nchw, void* x_nhwc_bf16, int32_t B, int32_t C, int32_t HW, void* stream);
 int xsup_conv_head_fwd(const void* x_nhwc, const void* weight, const float* bias, float* kps, float* depth_prob_map,
                        int64_t* peak_idx, float* stats, float* logits_out, const xsup_shape_t* s, int32_t C, void* stream);
 

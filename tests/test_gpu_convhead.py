@@ -55,6 +55,24 @@ def test_conv_head_matches_reference(ops, oracle, B, K, D, C, NH, NS):
     assert float((l4.cpu().double() - ref0).abs().max()) / float(ref0.abs().max()) < 1e-5
 
 
+def test_pack_kernel_equals_torch_conversion(ops):
+    """NCHW fp32 -> channels-last bf16 in one pass: bit-identical to torch's cast + permute."""
+    dev = torch.device("cuda:0")
+    cabi = importlib.import_module("x-as-supervision_b200._cabi")
+    g = torch.Generator().manual_seed(1)
+    for B, C, H, W in ((3, 256, 64, 64), (2, 64, 32, 32), (1, 128, 8, 8)):
+        x = (torch.randn(B, C, H, W, generator=g) * 3).to(dev)
+        out = torch.empty((B, C, H, W), dtype=torch.bfloat16, device=dev, memory_format=torch.channels_last)
+        cabi.check(cabi.lib.xsup_pack_nhwc_bf16(x.data_ptr(), out.data_ptr(), B, C, H * W, cabi.stream_ptr(dev)), "pack")
+        ref = x.to(dtype=torch.bfloat16, memory_format=torch.channels_last)
+        assert out.is_contiguous(memory_format=torch.channels_last) and torch.equal(out, ref)
+    # and conv_integral_head takes the fp32 NCHW tensor through it
+    x, w, bias = _case(2, 3, 64, 256, seed=5)
+    a = ops.conv_integral_head(x.to(dev), w.to(dev), bias.to(dev), 3, 3, 15)
+    b = ops.conv_integral_head(x.to(dev).to(dtype=torch.bfloat16, memory_format=torch.channels_last), w.to(dev), bias.to(dev), 3, 3, 15)
+    assert all(torch.equal(u, v) for u, v in zip(a, b))
+
+
 def test_conv_head_shape_errors(ops):
     dev = torch.device("cuda:0")
     with pytest.raises(RuntimeError, match="divide 128"):

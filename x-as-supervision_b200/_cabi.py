@@ -33,7 +33,7 @@ SYMBOLS = (
     "xsup_mask_loss_fwd", "xsup_mask_loss_bwd",
     "xsup_eval_select", "xsup_triangulate", "xsup_root_centre_fwd", "xsup_root_centre_bwd",
     "xsup_disc_min_loss_fwd", "xsup_disc_min_loss_bwd",
-    "xsup_conv_head_fwd",
+    "xsup_conv_head_fwd", "xsup_pack_nhwc_bf16",
 )
 MAX_VIEWS = 8
 MAX_LINES = 32
@@ -125,6 +125,8 @@ def _load():
     lib.xsup_mask_loss_bwd.argtypes = [vp, vp, vp, ml, vp, vp, vp, vp]
     lib.xsup_conv_head_fwd.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, C.POINTER(Shape), i32, vp]
     lib.xsup_conv_head_fwd.restype = C.c_int
+    lib.xsup_pack_nhwc_bf16.argtypes = [vp, vp, i32, i32, i32, vp]
+    lib.xsup_pack_nhwc_bf16.restype = C.c_int
     lib.xsup_eval_select.argtypes = [vp, vp, C.POINTER(Eval), vp, vp, vp, vp, vp, vp, vp, vp]
     lib.xsup_triangulate.argtypes = [C.POINTER(Tri), vp, vp]
     lib.xsup_root_centre_fwd.argtypes = [vp, vp, i32, i32, i32, vp]

@@ -491,6 +491,18 @@ int xsup_disc_min_loss_bwd(const float* logits, const int64_t* sel, const float*
 }
 
 // ------------------------------------------------------------------------------------------------ conv-fused forward
+int xsup_pack_nhwc_bf16(const float* x_nchw, void* x_nhwc_bf16, int32_t B, int32_t C, int32_t HW, void* stream) {
+    if (B < 0 || C < 64 || C % 64 || HW < 64 || HW % 64) return fail(XSUP_E_SHAPE, "xsup_pack_nhwc_bf16: need C and H*W multiples of 64");
+    if (B > 65535) return fail(XSUP_E_SHAPE, "xsup_pack_nhwc_bf16: B > 65535");
+    if (B == 0) return XSUP_OK;
+    if (!x_nchw || !x_nhwc_bf16) return fail(XSUP_E_NULL, "xsup_pack_nhwc_bf16: NULL pointer");
+    if (!aligned16(x_nchw) || !aligned16(x_nhwc_bf16)) return fail(XSUP_E_ALIGN, "xsup_pack_nhwc_bf16: tensors must be 16-byte aligned");
+    cudaError_t e = launch_pack_nhwc_bf16(x_nchw, x_nhwc_bf16, B, C, HW, (cudaStream_t)stream);
+    if (e != cudaSuccess) return cuda_fail(e, "xsup_pack_nhwc_bf16 launch");
+    count_launches(1);
+    return XSUP_OK;
+}
+
 int xsup_conv_head_fwd(const void* x_nhwc, const void* weight, const float* bias, float* kps, float* depth_prob_map, int64_t* peak_idx,
                        float* stats, float* logits_out, const xsup_shape_t* s, int32_t C, void* stream) {
     if (int rc = check_shape(s)) return rc;

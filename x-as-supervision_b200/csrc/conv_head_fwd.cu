@@ -322,6 +322,43 @@ __global__ void __launch_bounds__(kCvThreads, 1) conv_head_fwd_kernel(const __gr
     }
 }
 
+// ------------------------------------------------------------------ activation packing
+// [B, C, HW] fp32 (what a plain NCHW backbone hands over) -> [B, HW, C] bf16 (channels-last, the K-major operand the
+// tensor maps above describe): a 64 x 64 tile transpose through shared memory with the cast fused in; reads are
+// 128-bit along the pixels, writes 128-bit along the channels.  1.07 GB in + 0.54 GB out at B=256.
+__global__ void __launch_bounds__(256) pack_nhwc_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, int C, int HW) {
+    __shared__ float tile[64][65];
+    const int p0 = blockIdx.x * 64, c0 = blockIdx.y * 64, b = blockIdx.z;
+    const float* src = x + ((size_t)b * C + c0) * HW + p0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int q = threadIdx.x + 256 * i;                       // 1024 float4 = 64 channels x 16 pixel quads
+        const int c = q >> 4, pq = (q & 15) * 4;
+        const float4 v = *reinterpret_cast<const float4*>(src + (size_t)c * HW + pq);
+        tile[c][pq] = v.x; tile[c][pq + 1] = v.y; tile[c][pq + 2] = v.z; tile[c][pq + 3] = v.w;
+    }
+    __syncthreads();
+    __nv_bfloat16* dst = y + ((size_t)b * HW + p0) * C + c0;
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        const int q = threadIdx.x + 256 * i;                       // 512 chunks = 64 pixels x 8 groups of 8 channels
+        const int pp = q >> 3, cg = (q & 7) * 8;
+        uint4 o;
+        uint32_t* ow = reinterpret_cast<uint32_t*>(&o);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const __nv_bfloat162 h = __floats2bfloat162_rn(tile[cg + 2 * j][pp], tile[cg + 2 * j + 1][pp]);
+            ow[j] = *reinterpret_cast<const uint32_t*>(&h);
+        }
+        *reinterpret_cast<uint4*>(dst + (size_t)pp * C + cg) = o;
+    }
+}
+
+cudaError_t launch_pack_nhwc_bf16(const float* x, void* y, int B, int C, int HW, cudaStream_t st) {
+    pack_nhwc_bf16_kernel<<<dim3(HW / 64, C / 64, B), 256, 0, st>>>(x, static_cast<__nv_bfloat16*>(y), C, HW);
+    return cudaGetLastError();
+}
+
 // ------------------------------------------------------------------ host side
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,

@@ -365,7 +365,14 @@ def conv_integral_head(x: torch.Tensor, weight: torch.Tensor, bias: Optional[tor
     dev = x.device
     xb = x.detach()
     if xb.dtype != torch.bfloat16 or not xb.is_contiguous(memory_format=torch.channels_last):
-        xb = xb.to(dtype=torch.bfloat16, memory_format=torch.channels_last)
+        if xb.dtype == torch.float32 and xb.is_contiguous() and C % 64 == 0 and (H * W) % 64 == 0 and B > 0:
+            packed = torch.empty((B, C, H, W), dtype=torch.bfloat16, device=dev, memory_format=torch.channels_last)
+            with torch.cuda.device(dev):                  # one pass: NCHW fp32 -> channels-last bf16 (transpose + cast fused)
+                cabi.check(cabi.lib.xsup_pack_nhwc_bf16(xb.data_ptr(), packed.data_ptr(), B, C, H * W, cabi.stream_ptr(dev)),
+                           "xsup_pack_nhwc_bf16")
+            xb = packed
+        else:
+            xb = xb.to(dtype=torch.bfloat16, memory_format=torch.channels_last)
     wb = w2.to(device=dev, dtype=torch.bfloat16).contiguous()
     bf = bias.detach().to(device=dev, dtype=torch.float32).contiguous() if bias is not None else None
     shape = cabi.make_shape(B, num_kp, D, H, W, num_hypo, neighbor_size, torch.bfloat16, cabi.HEAD_MULTI)
