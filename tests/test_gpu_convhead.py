@@ -79,3 +79,48 @@ def test_conv_head_shape_errors(ops):
         ops.conv_integral_head(torch.zeros(1, 64, 48, 48, device=dev), torch.zeros(2 * 48, 64, device=dev), None, 2, 3, 15)
     with pytest.raises(RuntimeError, match="channels"):
         ops.conv_integral_head(torch.zeros(1, 96, 64, 64, device=dev), torch.zeros(2 * 64, 96, device=dev), None, 2, 3, 15)
+
+
+def test_detector_forward_fused_matches_forward(ops):
+    """KPDetector3DMulti.forward_fused on a ResPoseNet-shaped net: same outputs as the unfused forward up to the bf16
+    rounding of the conv operands (compared against forward() on a copy of the net whose last conv sees the same
+    rounded operands)."""
+    from torch import nn
+    det_mod = importlib.import_module("x-as-supervision_b200.detector")
+    dev = torch.device("cuda:0")
+    K, D, C = 17, 64, 256
+
+    class Head(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.features = nn.ModuleList([nn.Conv2d(8, C, 3, padding=1), nn.ReLU(), nn.Conv2d(C, K * D, 1, bias=True)])
+
+        def forward(self, x):
+            for layer in self.features:
+                x = layer(x)
+            return x
+
+    class Net(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.backbone = nn.Conv2d(3, 8, 3, padding=1)
+            self.head = Head()
+
+        def forward(self, x):
+            return self.head(self.backbone(x))
+
+    torch.manual_seed(0)
+    net = Net().to(dev)
+    det = det_mod.KPDetector3DMulti("resnet_multi", K, D, 3, 15, net=net).eval()
+    x = torch.randn(2, 3, D, D, device=dev)
+    kps_f, dmap_f = det.forward_fused(x)
+    with torch.no_grad():
+        y = net.backbone(x)
+        for layer in list(net.head.features)[:-1]:
+            y = layer(y)
+        last = net.head.features[-1]
+        logits = torch.nn.functional.conv2d(y.bfloat16().double(), last.weight.bfloat16().double(), last.bias.double())
+        kps_r, dmap_r, _ = ops.integral_multi_head(logits.float(), K, 3, 15)
+    assert float((kps_f - kps_r).abs().max()) < 1e-5 and float((dmap_f - dmap_r).abs().max()) < 1e-5
+    with pytest.raises(RuntimeError, match="1x1"):
+        det_mod.KPDetector3DMulti("x", K, D, 3, 15, net=nn.Identity()).forward_fused(x)

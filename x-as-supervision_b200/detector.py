@@ -67,6 +67,34 @@ class KPDetector3DMulti(nn.Module):
         kps, depth_prob_map, _ = ops.integral_multi_head(heatmap, self.num_kp, self.num_hypo, self.neighbor_size)
         return kps, depth_prob_map
 
+    @torch.no_grad()
+    def forward_fused(self, x):
+        """Inference path (eval.py:120) with the final `Conv2d(C, K*D, 1)` of `self.net.head`
+        (deconv_head.py:33-35) fused into the head tail on the tensor cores: the `[B, K*D, H, W]` logits are never
+        materialised.  Needs the reference's network layout (`net.backbone`, `net.head.features[-1]` a 1x1 conv with
+        bias); returns the same `(kps, depth_prob_map)` as `forward`, with the conv operands rounded to bf16."""
+        feats, last = _split_final_conv(self.net)
+        y = feats(x)
+        kps, depth_prob_map, _ = ops.conv_integral_head(y, last.weight, last.bias, self.num_kp, self.num_hypo, self.neighbor_size)
+        return kps, depth_prob_map
+
+
+def _split_final_conv(net):
+    """(callable producing the input of the final 1x1 conv, that conv) for a ResPoseNet-shaped `net`
+    (modules/integral_base_modules/network.py:10-19, deconv_head.py:22-35)."""
+    head = getattr(net, "head", None)
+    layers = getattr(head, "features", None)
+    if layers is None or len(layers) == 0 or not isinstance(layers[-1], nn.Conv2d) or tuple(layers[-1].kernel_size) != (1, 1):
+        raise RuntimeError("forward_fused needs net.head.features to end with a 1x1 nn.Conv2d (the reference's DeconvHead "
+                           "with conv_kernel_size=1 and with_bias_end=True)")
+
+    def feats(x):
+        x = net.backbone(x)
+        for layer in list(layers)[:-1]:
+            x = layer(x)
+        return x
+    return feats, layers[-1]
+
 
 class KPDetector3D(nn.Module):
     """modules/keypoint_detector_integral.py:6 — single hypothesis, output `[B,1,K,3]`."""
