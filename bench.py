@@ -267,8 +267,8 @@ def run_ours(args, c):
 
     graphed = None
     if args.graph:
-        if group is not None:
-            raise SystemExit("--graph needs --scope local (or one GPU): the NVLink exchange carries a per-call sequence number")
+        if group is not None and not isinstance(group, pkg.dist.PeerExchange):
+            raise SystemExit("--graph with --scope global needs the NVLink exchange (--exchange nvlink), not NCCL")
         for _ in range(3):
             step()                                          # per-kernel events of the eager path (roofline block)
         torch.cuda.synchronize()
@@ -278,7 +278,7 @@ def run_ours(args, c):
         torch.cuda.synchronize()
         record["on"] = False
         graphed = ops.GraphedReprojStep(logits, target, cams, K, NH, NS, w_mse=w[0], w_bone=w[1], w_kp=w[2], w_kp2d=w[3],
-                                        reduction="batch")
+                                        reduction="batch", group=group)
         eager_step, launches_per_step = step, None
         n_a = ops.launch_count()
         eager_step()

@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define XSUP_ABI_VERSION 4
+#define XSUP_ABI_VERSION 5
 
 enum { XSUP_F32 = 0, XSUP_BF16 = 1 };
 enum { XSUP_HEAD_MULTI = 0, XSUP_HEAD_SINGLE = 1 };
@@ -145,6 +145,9 @@ typedef struct {
     void* const* peer_bufs;
     int32_t rank, world;
     uint32_t step;
+    uint32_t* seq;   /* DEVICE counter (zero-initialised, private to this rank) or NULL.  When given, the kernel itself
+                      * takes the sequence number as ++(*seq) and `step` is ignored: the call can then be captured in
+                      * a CUDA graph and replayed (a by-value step would repeat).  All ranks must make the same calls. */
 } xsup_xchg_t;
 #define XSUP_XCHG_SLOT 64
 size_t xsup_xchg_floats(int32_t world);

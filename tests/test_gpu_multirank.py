@@ -40,8 +40,20 @@ def _worker(rank, world, port, out, transport):
                 x, target[lo:hi].to(dev), {k: v[lo:hi].to(dev) for k, v in cams.items()}, K, NH, NS, reduction="batch",
                 group=group, **W)
             (lp + ls).backward()
-        torch.save({"loss": (lp.item(), ls.item()), "sel": sel.cpu(), "grad": x.grad.cpu(), "range": (lo, hi)},
-                   os.path.join(out, "rank%d.pt" % rank))
+        res = {"loss": (lp.item(), ls.item()), "sel": sel.cpu(), "grad": x.grad.cpu(), "range": (lo, hi)}
+        if transport == "nvlink":
+            # the same step captured as ONE CUDA graph (the exchange kernel keeps its sequence number on the device)
+            # and replayed three times on every rank: every replay must reproduce the eager result bit for bit
+            step = ops.GraphedReprojStep(logits[lo:hi].to(dev), target[lo:hi].to(dev), {k: v[lo:hi].to(dev) for k, v in cams.items()},
+                                         K, NH, NS, reduction="batch", group=group, **W)
+            ok = True
+            for _ in range(3):
+                glp, gls, gsel = step()
+                torch.cuda.synchronize()
+                ok = ok and torch.equal(glp, lp.detach()) and torch.equal(gls, ls.detach()) and torch.equal(gsel, sel) \
+                    and torch.equal(step.grad, x.grad)
+            res["graph_ok"] = bool(ok)
+        torch.save(res, os.path.join(out, "rank%d.pt" % rank))
     finally:
         dist.destroy_process_group()
 
@@ -66,6 +78,7 @@ def test_two_gpus_global_scope_equals_single_gpu(synth, tmp_path, transport):
                                                    reduction="batch", **W)
     (lp + ls).backward()
     for r in res:
+        assert r.get("graph_ok", True), "CUDA-graph replay of the global-scope step differs from the eager step"
         assert torch.equal(r["sel"], sel.cpu())                                   # same slots on every rank
         assert abs(r["loss"][0] - lp.item()) < 1e-6 * abs(lp.item()) and abs(r["loss"][1] - ls.item()) < 1e-6 * abs(ls.item())
         lo, hi = r["range"]

@@ -77,7 +77,7 @@ class Tri(C.Structure):
 
 
 class Xchg(C.Structure):
-    _fields_ = [("peer_bufs", C.c_void_p), ("rank", C.c_int32), ("world", C.c_int32), ("step", C.c_uint32)]
+    _fields_ = [("peer_bufs", C.c_void_p), ("rank", C.c_int32), ("world", C.c_int32), ("step", C.c_uint32), ("seq", C.c_void_p)]
 
 
 def _load():
@@ -144,7 +144,7 @@ def _load():
 
 
 lib = _load()
-ABI_VERSION = 4
+ABI_VERSION = 5
 if lib.xsup_abi_version() != ABI_VERSION:
     raise ImportError("libxsup_b200.so ABI version %d, expected %d: rebuild with __graft_entry__.build()"
                       % (lib.xsup_abi_version(), ABI_VERSION))

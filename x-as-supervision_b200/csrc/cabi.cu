@@ -247,8 +247,8 @@ size_t xsup_xchg_floats(int32_t world) { return world > 0 ? (size_t)2 * world * 
 
 int xsup_partial_allreduce(float* partial, int32_t n, const xsup_xchg_t* x, void* stream) {
     if (!partial || !x || !x->peer_bufs) return fail(XSUP_E_NULL, "xsup_partial_allreduce: NULL pointer");
-    if (n < 1 || n > XSUP_XCHG_SLOT - 1 || x->world < 1 || x->world > 64 || x->rank < 0 || x->rank >= x->world || x->step == 0)
-        return fail(XSUP_E_SHAPE, "xsup_partial_allreduce: need 1 <= n <= %d, 1 <= world <= 64, 0 <= rank < world, step >= 1", XSUP_XCHG_SLOT - 1);
+    if (n < 1 || n > XSUP_XCHG_SLOT - 1 || x->world < 1 || x->world > 64 || x->rank < 0 || x->rank >= x->world || (x->step == 0 && !x->seq))
+        return fail(XSUP_E_SHAPE, "xsup_partial_allreduce: need 1 <= n <= %d, 1 <= world <= 64, 0 <= rank < world, step >= 1 (or a device sequence counter)", XSUP_XCHG_SLOT - 1);
     cudaError_t e = launch_partial_allreduce(partial, n, *x, (cudaStream_t)stream);
     if (e != cudaSuccess) return cuda_fail(e, "xsup_partial_allreduce launch");
     count_launches(1);

@@ -260,12 +260,17 @@ __device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
     return v;
 }
 __global__ void __launch_bounds__(64) partial_allreduce_kernel(float* __restrict__ partial, int n, void* const* __restrict__ peers,
-                                                               int rank, int world, uint32_t step) {
+                                                               int rank, int world, uint32_t step_arg, uint32_t* seq) {
     __shared__ int timed_out;
+    __shared__ uint32_t s_step;
     const int t = threadIdx.x;
-    const size_t par = step & 1u;
-    if (t == 0) timed_out = 0;
+    if (t == 0) {
+        timed_out = 0;
+        s_step = seq ? (*seq += 1u) : step_arg;          // device-side sequence number: replayable from a CUDA graph
+    }
     __syncthreads();
+    const uint32_t step = s_step;
+    const size_t par = step & 1u;
     if (t < world) {                                   // one thread per destination GPU
         float* dst = static_cast<float*>(peers[t]) + (par * world + rank) * XSUP_XCHG_SLOT;
         for (int i = 0; i < n; ++i) dst[i] = partial[i];
@@ -289,7 +294,7 @@ __global__ void __launch_bounds__(64) partial_allreduce_kernel(float* __restrict
 }
 
 cudaError_t launch_partial_allreduce(float* partial, int n, const xsup_xchg_t& x, cudaStream_t st) {
-    partial_allreduce_kernel<<<1, 64, 0, st>>>(partial, n, x.peer_bufs, x.rank, x.world, x.step);
+    partial_allreduce_kernel<<<1, 64, 0, st>>>(partial, n, x.peer_bufs, x.rank, x.world, x.step, x.seq);
     return cudaGetLastError();
 }
 

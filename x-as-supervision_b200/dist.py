@@ -47,15 +47,15 @@ class PeerExchange:
         self.peer_ptrs = torch.tensor([int(p) for p in self.handle.buffer_ptrs], dtype=torch.int64, device=self.device)
         torch.cuda.synchronize(self.device)
         dist.barrier(self.group)                       # every mailbox is zeroed before anyone publishes
-        self.step = 0
+        # the call sequence number lives on the device and is advanced by the kernel, so a captured call can be replayed
+        self.seq = torch.zeros(1, dtype=torch.int32, device=self.device)
 
     def all_reduce_(self, t: torch.Tensor) -> torch.Tensor:
         """In-place SUM over the ranks of a small contiguous fp32 CUDA tensor (<= 63 elements)."""
         from . import _cabi as cabi
         if not (t.is_cuda and t.dtype == torch.float32 and t.is_contiguous()):
             raise ValueError("PeerExchange.all_reduce_ needs a contiguous float32 CUDA tensor")
-        self.step += 1
-        x = cabi.Xchg(self.peer_ptrs.data_ptr(), self.rank, self.world, self.step)
+        x = cabi.Xchg(self.peer_ptrs.data_ptr(), self.rank, self.world, 0, self.seq.data_ptr())
         with torch.cuda.device(self.device):
             cabi.check(cabi.lib.xsup_partial_allreduce(t.data_ptr(), t.numel(), x, cabi.stream_ptr(self.device)),
                        "xsup_partial_allreduce")

@@ -307,12 +307,13 @@ class GraphedReprojStep:
         loss_pseudo, loss_sym, sel = step()               # replays; step.grad holds d(loss_pseudo + loss_sym)/d logits
 
     Static tensors: `logits`, `target`, `cams[...]` (inputs), `grad`, `kps`, `kps_world`, `loss_pseudo`, `loss_sym`,
-    `sel` (outputs).  Rank-local only (`group=None`): the NVLink exchange carries a per-call sequence number that a
-    replayed graph would repeat."""
+    `sel` (outputs).  `group` may be None (rank-local selection) or a `dist.PeerExchange` (global selection: its
+    in-kernel NVLink all-reduce keeps the call sequence number on the device, so it replays correctly; every rank
+    must then replay the same number of times).  A `torch.distributed` process group is not captured here."""
 
     def __init__(self, logits, target, cams, num_kp, num_hypo, neighbor_size, warmup: int = 3, **kw):
-        if kw.get("group") is not None:
-            raise ValueError("GraphedReprojStep is rank-local: pass group=None")
+        if kw.get("group") is not None and not isinstance(kw["group"], xdist.PeerExchange):
+            raise ValueError("GraphedReprojStep takes group=None or a dist.PeerExchange")
         cabi.require_cuda(logits, "logits")
         dev = logits.device
         self.logits = logits.detach().clone().requires_grad_(True)
