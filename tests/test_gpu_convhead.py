@@ -124,3 +124,20 @@ def test_detector_forward_fused_matches_forward(ops):
     assert float((kps_f - kps_r).abs().max()) < 1e-5 and float((dmap_f - dmap_r).abs().max()) < 1e-5
     with pytest.raises(RuntimeError, match="1x1"):
         det_mod.KPDetector3DMulti("x", K, D, 3, 15, net=nn.Identity()).forward_fused(x)
+
+
+def test_conv_head_other_shapes(ops, oracle):
+    """C = 192 (three k-blocks), non-square maps (H != W; D == W as the reference requires), one joint per CTA (D = 128)."""
+    dev = torch.device("cuda:0")
+    for B, K, D, H, C in ((2, 5, 64, 32, 192), (1, 2, 128, 64, 128), (2, 9, 32, 96, 64)):
+        g = torch.Generator().manual_seed(B + K + D)
+        x = torch.randn(B, C, H, D, generator=g)
+        w = torch.randn(K * D, C, generator=g) / C ** 0.5
+        bias = torch.randn(K * D, generator=g)
+        kps, dmap, idx, logits = ops.conv_integral_head(x.to(dev), w.to(dev), bias.to(dev), K, 3, 15, return_logits=True)
+        ref = torch.einsum("oc,bchw->bohw", w.bfloat16().double(), x.bfloat16().double()) + bias.double().view(1, -1, 1, 1)
+        assert float((logits.cpu().double() - ref).abs().max()) / float(ref.abs().max()) < 1e-5
+        okps, odmap, oidx = oracle.integral_multi(ref, K, 3, 15)
+        assert torch.equal(idx.cpu(), oidx)
+        assert float((kps.cpu().double() - okps).abs().max()) < 1e-5
+        assert float((dmap.cpu().double() - odmap).abs().max()) < 1e-5 * float(odmap.abs().max())
