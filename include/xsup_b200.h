@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define XSUP_ABI_VERSION 5
+#define XSUP_ABI_VERSION 6
 
 enum { XSUP_F32 = 0, XSUP_BF16 = 1 };
 enum { XSUP_HEAD_MULTI = 0, XSUP_HEAD_SINGLE = 1 };
@@ -289,6 +289,15 @@ int xsup_disc_min_loss_bwd(const float* logits, const int64_t* sel, const float*
 int xsup_pack_nhwc_bf16(const float* x_nchw, void* x_nhwc_bf16, int32_t B, int32_t C, int32_t HW, void* stream);
 int xsup_conv_head_fwd(const void* x_nhwc, const void* weight, const float* bias, float* kps, float* depth_prob_map,
                        int64_t* peak_idx, float* stats, float* logits_out, const xsup_shape_t* s, int32_t C, void* stream);
+
+/* Backward of the conv-fused head without the logits: (1) xsup_integral_coef turns g_kps + the saved statistics into
+ * the per-unit coefficient blocks (the first half of xsup_integral_bwd); (2) xsup_conv_head_bwd_g recomputes the
+ * logits tile by tile on the tensor cores and writes d loss / d logits as bf16 `g [B, K*D, H*W]` (a quarter of the
+ * traffic of reading fp32 logits and writing an fp32 gradient) plus `gbias_part [B, 4, K*D]` fp32 (sum over them = d
+ * loss / d bias).  d loss / d x = g^T W and d loss / d W = g X are then two plain bf16 library GEMMs on `g`. */
+int xsup_integral_coef(const float* stats, const float* g_kps, float* coef_ws, const xsup_shape_t* s, void* stream);
+int xsup_conv_head_bwd_g(const void* x_nhwc, const void* weight, const float* bias, const float* coef_ws, void* g_out,
+                         float* gbias_part, const xsup_shape_t* s, int32_t C, void* stream);
 
 #ifdef __cplusplus
 }

@@ -26,7 +26,7 @@ def test_library_exports_every_declared_symbol(cabi):
     assert declared == set(cabi.SYMBOLS)
     for name in declared:
         assert hasattr(cabi.lib, name), name
-    assert cabi.lib.xsup_abi_version() == cabi.ABI_VERSION == 5
+    assert cabi.lib.xsup_abi_version() == cabi.ABI_VERSION == 6
 
 
 def test_struct_layouts_match_header(cabi):

@@ -141,3 +141,35 @@ def test_conv_head_other_shapes(ops, oracle):
         assert torch.equal(idx.cpu(), oidx)
         assert float((kps.cpu().double() - okps).abs().max()) < 1e-5
         assert float((dmap.cpu().double() - odmap).abs().max()) < 1e-5 * float(odmap.abs().max())
+
+
+@pytest.mark.parametrize("B,K,D,C", [(2, 3, 64, 128), (3, 17, 64, 256), (2, 4, 32, 64)])
+def test_conv_head_backward_matches_autograd(ops, oracle, B, K, D, C):
+    """d x, d W, d bias of the differentiable conv-fused head against fp64 autograd of the reference op sequence
+    (1x1 conv -> integral head) on the same bf16-rounded operands.  d loss / d logits is written once in bf16, so the
+    tolerance is the bf16 one of the north star: 2^-8 relative to the largest gradient (measured ~1e-3); the
+    recomputed d loss / d logits itself is checked to that bound element-wise."""
+    dev = torch.device("cuda:0")
+    NH, NS = 3, 15 if D >= 64 else 5
+    x, w, bias = _case(B, K, D, C, seed=B * 31 + K)
+    gen = torch.Generator().manual_seed(77)
+    gk = torch.randn(B, NH, K, 3, generator=gen)
+    xd = x.to(dev).requires_grad_(True)
+    wd = w.to(dev).view(K * D, C, 1, 1).requires_grad_(True)
+    bd = bias.to(dev).requires_grad_(True)
+    kps, dmap, idx = ops.conv_integral_head_train(xd, wd, bd, K, NH, NS)
+    kps.backward(gk.to(dev))
+    # fp64 reference on the bf16-rounded operands
+    x64 = x.bfloat16().double().requires_grad_(True)
+    w64 = w.bfloat16().double().requires_grad_(True)
+    b64 = bias.double().requires_grad_(True)
+    logits = torch.einsum("oc,bchw->bohw", w64, x64) + b64.view(1, -1, 1, 1)
+    logits.retain_grad()
+    okps, _, oidx = oracle.integral_multi(logits, K, NH, NS)
+    assert torch.equal(idx.cpu(), oidx) and float((kps.detach().cpu().double() - okps.detach()).abs().max()) < 1e-5
+    okps.backward(gk.double())
+    tol = 2.0 ** -8
+    for name, ours, ref in (("dx", xd.grad, x64.grad), ("dW", wd.grad.view(K * D, C), w64.grad), ("dbias", bd.grad, b64.grad)):
+        err = float((ours.cpu().double() - ref).abs().max()) / float(ref.abs().max())
+        assert err < tol, (name, err)
+    assert xd.grad.shape == xd.shape and xd.grad.dtype == xd.dtype and wd.grad.shape == wd.shape

@@ -491,6 +491,7 @@ int xsup_disc_min_loss_bwd(const float* logits, const int64_t* sel, const float*
 }
 
 // ------------------------------------------------------------------------------------------------ conv-fused forward
+static int check_conv_shape(const xsup_shape_t* s, int C, const char* who);
 int xsup_pack_nhwc_bf16(const float* x_nchw, void* x_nhwc_bf16, int32_t B, int32_t C, int32_t HW, void* stream) {
     if (B < 0 || C < 64 || C % 64 || HW < 64 || HW % 64) return fail(XSUP_E_SHAPE, "xsup_pack_nhwc_bf16: need C and H*W multiples of 64");
     if (B > 65535) return fail(XSUP_E_SHAPE, "xsup_pack_nhwc_bf16: B > 65535");
@@ -505,11 +506,7 @@ int xsup_pack_nhwc_bf16(const float* x_nchw, void* x_nhwc_bf16, int32_t B, int32
 
 int xsup_conv_head_fwd(const void* x_nhwc, const void* weight, const float* bias, float* kps, float* depth_prob_map, int64_t* peak_idx,
                        float* stats, float* logits_out, const xsup_shape_t* s, int32_t C, void* stream) {
-    if (int rc = check_shape(s)) return rc;
-    if (128 % s->D) return fail(XSUP_E_SHAPE, "xsup_conv_head_fwd: depth_dim %d must divide 128 (output rows per CTA)", s->D);
-    if ((s->H * s->W) % 128 || s->W % 32) return fail(XSUP_E_SHAPE, "xsup_conv_head_fwd: H*W must be a multiple of 128 and W of 32");
-    if (C < 64 || C % 64 || C > 256) return fail(XSUP_E_SHAPE, "xsup_conv_head_fwd: channels %d must be 64, 128, 192 or 256", C);
-    if ((long long)s->B * s->H * s->W > 0x7fffffffLL) return fail(XSUP_E_SHAPE, "xsup_conv_head_fwd: too many pixels");
+    if (int rc = check_conv_shape(s, C, "xsup_conv_head_fwd")) return rc;
     if (s->B == 0) return XSUP_OK;
     if (!x_nhwc || !weight || !kps || !depth_prob_map || !stats) return fail(XSUP_E_NULL, "xsup_conv_head_fwd: NULL pointer");
     if (!aligned16(x_nhwc) || !aligned16(weight) || !aligned16(logits_out)) return fail(XSUP_E_ALIGN, "xsup_conv_head_fwd: x/weight/logits_out must be 16-byte aligned");
@@ -523,6 +520,49 @@ int xsup_conv_head_fwd(const void* x_nhwc, const void* weight, const float* bias
     cudaError_t e = launch_conv_head_fwd(x_nhwc, weight, bias, logits_out, f, s->B, C, sms, (cudaStream_t)stream);
     if (e == cudaErrorNotSupported) return fail(XSUP_E_DEVICE, "xsup_conv_head_fwd: cuTensorMapEncodeTiled unavailable or rejected the tensors");
     if (e != cudaSuccess) return cuda_fail(e, "xsup_conv_head_fwd launch");
+    count_launches(1);
+    return XSUP_OK;
+}
+
+static int check_conv_shape(const xsup_shape_t* s, int C, const char* who) {
+    if (int rc = check_shape(s)) return rc;
+    if (128 % s->D) return fail(XSUP_E_SHAPE, "%s: depth_dim %d must divide 128 (output rows per CTA)", who, s->D);
+    if ((s->H * s->W) % 128 || s->W % 32) return fail(XSUP_E_SHAPE, "%s: H*W must be a multiple of 128 and W of 32", who);
+    if (C < 64 || C % 64 || C > 256) return fail(XSUP_E_SHAPE, "%s: channels %d must be 64, 128, 192 or 256", who, C);
+    if ((long long)s->B * s->H * s->W > 0x7fffffffLL) return fail(XSUP_E_SHAPE, "%s: too many pixels", who);
+    return XSUP_OK;
+}
+
+int xsup_integral_coef(const float* stats, const float* g_kps, float* coef_ws, const xsup_shape_t* s, void* stream) {
+    if (int rc = check_shape(s)) return rc;
+    if (s->B == 0) return XSUP_OK;
+    if (!stats || !g_kps || !coef_ws) return fail(XSUP_E_NULL, "xsup_integral_coef: NULL pointer");
+    CoefParams c{};
+    c.stats = stats; c.g_kps = g_kps; c.coef = coef_ws;
+    c.n_units = s->B * s->K; c.K = s->K; c.D = s->D; c.H = s->H; c.W = s->W; c.NH = s->NH; c.NS = s->NS; c.head = s->head;
+    c.stats_stride = (int)stats_stride(*s); c.coef_stride = (int)coef_stride(*s);
+    c.counter = reinterpret_cast<int*>(coef_ws + (size_t)c.n_units * c.coef_stride);
+    cudaError_t e = launch_integral_coef(c, (cudaStream_t)stream);
+    if (e != cudaSuccess) return cuda_fail(e, "xsup_integral_coef launch");
+    count_launches(1);
+    return XSUP_OK;
+}
+
+int xsup_conv_head_bwd_g(const void* x_nhwc, const void* weight, const float* bias, const float* coef_ws, void* g_out, float* gbias_part,
+                         const xsup_shape_t* s, int32_t C, void* stream) {
+    if (int rc = check_conv_shape(s, C, "xsup_conv_head_bwd_g")) return rc;
+    if (s->B == 0) return XSUP_OK;
+    if (!x_nhwc || !weight || !coef_ws || !g_out) return fail(XSUP_E_NULL, "xsup_conv_head_bwd_g: NULL pointer");
+    if (!aligned16(x_nhwc) || !aligned16(weight) || !aligned16(g_out)) return fail(XSUP_E_ALIGN, "xsup_conv_head_bwd_g: x/weight/g_out must be 16-byte aligned");
+    int sms = 0;
+    if (int rc = device_info(sms)) return rc;
+    FwdParams f{};
+    f.n_units = s->B * s->K; f.K = s->K; f.NH = s->NH; f.NS = s->NS; f.head = s->head;
+    f.t.D = s->D; f.t.H = s->H; f.t.W = s->W;
+    cudaError_t e = launch_conv_head_bwd_g(x_nhwc, weight, bias, coef_ws, (int)coef_stride(*s), g_out, gbias_part, f, s->B, C, sms,
+                                           (cudaStream_t)stream);
+    if (e == cudaErrorNotSupported) return fail(XSUP_E_DEVICE, "xsup_conv_head_bwd_g: cuTensorMapEncodeTiled unavailable or rejected the tensors");
+    if (e != cudaSuccess) return cuda_fail(e, "xsup_conv_head_bwd_g launch");
     count_launches(1);
     return XSUP_OK;
 }

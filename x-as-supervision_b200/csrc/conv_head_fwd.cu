@@ -48,6 +48,11 @@ struct ConvHeadParams {
     FwdParams f;                // kps, dmap, peak_idx, stats, K, NH, NS, head, stats_stride, t.{D,H,W}
     const float* bias;          // [K*D] or nullptr
     float* logits_out;          // optional [B, K*D, H*W] fp32 (validation); nullptr in production
+    // backward mode (MODE = 1): d loss / d logits, recomputed from the same GEMM
+    const float* coef;          // [B*K][coef_stride]: lse2, a, b, base0, wc, hc, -, -, c[0..D)  (integral_coef_kernel)
+    int coef_stride;
+    __nv_bfloat16* g_out;       // [B, K*D, H*W] bf16
+    float* gbias_part;          // [B, kCvParts, K*D] fp32: per-item partial sums of g over the pixels
     int C, HW, rows_total;      // channels, pixels per sample, K*D
     int groups;                 // CTAs per sample = ceil(K*D / 128)
     int n_tiles;                // HW / 128
@@ -112,7 +117,7 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
 constexpr uint32_t kCvIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(kCvPix >> 3) << 17) | ((uint32_t)(kCvRows >> 4) << 24);
 
 // ------------------------------------------------------------------ kernel
-template <int KBN>
+template <int KBN, int MODE>            // MODE 0: forward statistics + finaliser; MODE 1: backward, emits d loss / d logits in bf16
 __global__ void __launch_bounds__(kCvThreads, 1) conv_head_fwd_kernel(const __grid_constant__ CUtensorMap map_w,
                                                                       const __grid_constant__ CUtensorMap map_x,
                                                                       const ConvHeadParams p) {
@@ -222,6 +227,44 @@ __global__ void __launch_bounds__(kCvThreads, 1) conv_head_fwd_kernel(const __gr
             const int b = item / p.groups, row0 = (item - b * p.groups) * kCvRows, grow = row0 + row;
             const bool live = grow < p.rows_total;
             const float bias = (live && p.bias) ? p.bias[grow] : 0.f, bl = bias * kLog2e;
+            if (MODE == 1) {
+                // ---- backward: g = p * (a (w - wc) + b (h - hc) + c[d] + base0), p = 2^(l log2e - lse2)  
+                const int D = p.f.t.D, k = grow / D, d = grow - k * D;
+                float nlse = 0.f, ca = 0.f, cb = 0.f, cbase = 0.f, wc = 0.f, hc = 0.f;
+                if (live) {
+                    const float* cf = p.coef + ((size_t)b * p.f.K + k) * p.coef_stride;
+                    nlse = bl - cf[0]; ca = cf[1]; cb = cf[2]; cbase = cf[3] + cf[8 + d]; wc = cf[4]; hc = cf[5];
+                }
+                __nv_bfloat16* grow_out = p.g_out + ((size_t)b * p.rows_total + grow) * p.HW;
+                float gsum = 0.f;
+                for (int t = 0; t < T; ++t, ++g) {
+                    const int a = g % kCvAcc, ia = g / kCvAcc;
+                    mbar_wait(b_afull + 8 * a, ia & 1);
+                    tc_fence_after();
+                    uint32_t r[32];
+                    tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(a * kCvPix + c0), r);
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(b_aempty + 8 * a);
+                    if (!live) continue;
+                    const int pix = t * kCvPix + c0;
+                    const int hh = pix / Wd, w0 = pix - hh * Wd;
+                    const float rowterm = fmaf(ca, (float)w0 - wc, fmaf(cb, (float)hh - hc, cbase));
+                    uint32_t o[16];
+#pragma unroll
+                    for (int i = 0; i < 32; i += 2) {
+                        const float g0 = ex2(fmaf(__uint_as_float(r[i]), kLog2e, nlse)) * fmaf(ca, (float)i, rowterm);
+                        const float g1 = ex2(fmaf(__uint_as_float(r[i + 1]), kLog2e, nlse)) * fmaf(ca, (float)(i + 1), rowterm);
+                        gsum += g0 + g1;
+                        asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(o[i >> 1]) : "f"(g1), "f"(g0));
+                    }
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+                        *reinterpret_cast<uint4*>(grow_out + pix + 8 * i) = make_uint4(o[4 * i], o[4 * i + 1], o[4 * i + 2], o[4 * i + 3]);
+                }
+                if (live && p.gbias_part) p.gbias_part[((size_t)b * kCvParts + part) * p.rows_total + grow] = gsum;
+                continue;
+            }
             float m = kNegHuge, s = 0.f, sx = 0.f, sy = 0.f;
             float* lrow = p.logits_out ? p.logits_out + ((size_t)b * p.rows_total + grow) * p.HW : nullptr;
             for (int t = 0; t < T; ++t, ++g) {
@@ -272,7 +315,7 @@ __global__ void __launch_bounds__(kCvThreads, 1) conv_head_fwd_kernel(const __gr
             __syncwarp();
             if (lane == 0) mbar_arrive(b_rsfull + 8 * buf);
         }
-    } else {
+    } else if (MODE == 0) {
         // ------------------------------------------------------------ finalisers: one joint per warp and round
         const int fw = warp - (kCvEpiWarps + 2);
         const int D = p.f.t.D, jpc = kCvRows / D;                    // joints per item
@@ -387,13 +430,34 @@ static bool make_map(CUtensorMap* map, const void* base, long long rows, int C) 
                CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-template <int KBN>
+template <int KBN, int MODE>
 static cudaError_t launch_kbn(const CUtensorMap& map_w, const CUtensorMap& map_x, const ConvHeadParams& p, int grid, size_t smem, cudaStream_t st) {
-    auto kern = conv_head_fwd_kernel<KBN>;
+    auto kern = conv_head_fwd_kernel<KBN, MODE>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     kern<<<grid, kCvThreads, smem, st>>>(map_w, map_x, p);
     return cudaGetLastError();
+}
+
+template <int MODE>
+static cudaError_t launch_conv_head(const void* x_nhwc, const void* w, ConvHeadParams p, int B, int num_sms, cudaStream_t st) {
+    p.HW = p.f.t.H * p.f.t.W;
+    p.rows_total = p.f.K * p.f.t.D;
+    p.groups = (p.rows_total + kCvRows - 1) / kCvRows;
+    p.n_tiles = p.HW / kCvPix;
+    p.kblocks = p.C / kCvKB;
+    p.items = B * p.groups;
+    CUtensorMap map_w, map_x;
+    if (!make_map(&map_w, w, p.rows_total, p.C) || !make_map(&map_x, x_nhwc, (long long)B * p.HW, p.C)) return cudaErrorNotSupported;
+    const size_t smem = 1024 + (size_t)(1 + kCvStages) * p.kblocks * kCvKBBytes + 2 * kCvParts * kCvRows * sizeof(float4) +
+                        2 * kCvFinWarps * kMaxD * 4 + 24 * 8 + 16;
+    const int grid = p.items < num_sms ? p.items : num_sms;          // persistent: one CTA per SM
+    switch (p.kblocks) {
+        case 1: return launch_kbn<1, MODE>(map_w, map_x, p, grid, smem, st);
+        case 2: return launch_kbn<2, MODE>(map_w, map_x, p, grid, smem, st);
+        case 3: return launch_kbn<3, MODE>(map_w, map_x, p, grid, smem, st);
+        default: return launch_kbn<4, MODE>(map_w, map_x, p, grid, smem, st);
+    }
 }
 
 cudaError_t launch_conv_head_fwd(const void* x_nhwc, const void* w, const float* bias, float* logits_out, FwdParams f, int B, int C,
@@ -403,23 +467,22 @@ cudaError_t launch_conv_head_fwd(const void* x_nhwc, const void* w, const float*
     p.bias = bias;
     p.logits_out = logits_out;
     p.C = C;
-    p.HW = f.t.H * f.t.W;
-    p.rows_total = f.K * f.t.D;
-    p.groups = (p.rows_total + kCvRows - 1) / kCvRows;
-    p.n_tiles = p.HW / kCvPix;
-    p.kblocks = C / kCvKB;
-    p.items = B * p.groups;
-    CUtensorMap map_w, map_x;
-    if (!make_map(&map_w, w, p.rows_total, C) || !make_map(&map_x, x_nhwc, (long long)B * p.HW, C)) return cudaErrorNotSupported;
-    const size_t smem = 1024 + (size_t)(1 + kCvStages) * p.kblocks * kCvKBBytes + 2 * kCvParts * kCvRows * sizeof(float4) +
-                        2 * kCvFinWarps * kMaxD * 4 + 24 * 8 + 16;
-    const int grid = p.items < num_sms ? p.items : num_sms;          // persistent: one CTA per SM
-    switch (p.kblocks) {
-        case 1: return launch_kbn<1>(map_w, map_x, p, grid, smem, st);
-        case 2: return launch_kbn<2>(map_w, map_x, p, grid, smem, st);
-        case 3: return launch_kbn<3>(map_w, map_x, p, grid, smem, st);
-        default: return launch_kbn<4>(map_w, map_x, p, grid, smem, st);
-    }
+    return launch_conv_head<0>(x_nhwc, w, p, B, num_sms, st);
+}
+
+// d loss / d logits of the fused head, recomputed (never read from memory): the same GEMM, then per element one exp and
+// the closed form of SURVEY App. A.2 with the coefficient blocks of integral_coef_kernel; written as bf16 [B, K*D, H*W]
+cudaError_t launch_conv_head_bwd_g(const void* x_nhwc, const void* w, const float* bias, const float* coef, int coef_stride, void* g_out,
+                                   float* gbias_part, FwdParams f, int B, int C, int num_sms, cudaStream_t st) {
+    ConvHeadParams p{};
+    p.f = f;
+    p.bias = bias;
+    p.C = C;
+    p.coef = coef;
+    p.coef_stride = coef_stride;
+    p.g_out = static_cast<__nv_bfloat16*>(g_out);
+    p.gbias_part = gbias_part;
+    return launch_conv_head<1>(x_nhwc, w, p, B, num_sms, st);
 }
 
 }  // namespace xsup

@@ -24,7 +24,8 @@ from . import dist as xdist
 
 __all__ = ["IntegralMultiHead", "IntegralSingleHead", "PatchToWorld", "IntegralReprojMinLoss", "integral_multi_head",
            "integral_single_head", "convert_patch_to_world", "convert_world_to_patch", "find_peak",
-           "integral_reproj_min_loss", "launch_count", "GraphedReprojStep", "conv_integral_head"]
+           "integral_reproj_min_loss", "launch_count", "GraphedReprojStep", "conv_integral_head", "ConvIntegralHead",
+           "conv_integral_head_train"]
 
 launch_count = cabi.launch_count
 
@@ -388,3 +389,100 @@ def conv_integral_head(x: torch.Tensor, weight: torch.Tensor, bias: Optional[tor
                                                logits.data_ptr() if return_logits else None, shape, C, cabi.stream_ptr(dev)),
                    "xsup_conv_head_fwd")
     return (kps, dmap, idx, logits) if return_logits else (kps, dmap, idx)
+
+
+def _bmm_f32(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
+    """bf16 x bf16 batched matmul with an fp32 result (library GEMM; `out_dtype` exists in recent PyTorch)."""
+    try:
+        return torch.bmm(a, b, out_dtype=torch.float32)
+    except TypeError:                                        # older signature: accumulate in fp32 anyway, round once
+        return torch.bmm(a, b).float()
+
+
+class ConvIntegralHead(torch.autograd.Function):
+    """Differentiable conv-fused head: `Conv2d(C, K*D, 1)` + integral multi-hypothesis head with NO logits tensor in
+    either direction.
+
+    forward : `xsup_conv_head_fwd` (tcgen05 GEMM, softmax statistics from the TMEM accumulators).
+    backward: `xsup_integral_coef` (g_kps + saved statistics -> per-unit coefficients), `xsup_conv_head_bwd_g` (the same
+              GEMM again, d loss / d logits formed in the epilogue and written once as bf16), then the two remaining
+              contractions as plain library GEMMs on that tensor: d x = g^T W (bf16, channels-last like x) and
+              d W = sum_b g_b x_b (fp32 accumulate), d bias from the kernel's per-item partial sums.
+    Gradients carry one bf16 rounding of d loss / d logits (relative 2^-9 per element), the same class of error as a
+    bf16 autocast backward of the reference's conv."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, num_kp, num_hypo, neighbor_size):
+        cabi.require_cuda(x, "x")
+        B, C, H, W = x.shape
+        dev = x.device
+        w2 = weight.detach().reshape(weight.shape[0], -1)
+        D = w2.shape[0] // num_kp
+        if w2.shape[1] != C or D * num_kp != w2.shape[0]:
+            raise ValueError("weight is %s, expected [num_kp*D, %d(,1,1)]" % (tuple(weight.shape), C))
+        xb = x.detach()
+        if xb.dtype != torch.bfloat16 or not xb.is_contiguous(memory_format=torch.channels_last):
+            if xb.dtype == torch.float32 and xb.is_contiguous() and C % 64 == 0 and (H * W) % 64 == 0 and B > 0:
+                packed = torch.empty((B, C, H, W), dtype=torch.bfloat16, device=dev, memory_format=torch.channels_last)
+                with torch.cuda.device(dev):
+                    cabi.check(cabi.lib.xsup_pack_nhwc_bf16(xb.data_ptr(), packed.data_ptr(), B, C, H * W, cabi.stream_ptr(dev)),
+                               "xsup_pack_nhwc_bf16")
+                xb = packed
+            else:
+                xb = xb.to(dtype=torch.bfloat16, memory_format=torch.channels_last)
+        wb = w2.to(device=dev, dtype=torch.bfloat16).contiguous()
+        bf = bias.detach().to(device=dev, dtype=torch.float32).contiguous() if bias is not None else None
+        shape = cabi.make_shape(B, num_kp, D, H, W, num_hypo, neighbor_size, torch.bfloat16, cabi.HEAD_MULTI)
+        kps = torch.empty(B, num_hypo, num_kp, 3, dtype=torch.float32, device=dev)
+        dmap = torch.empty(num_kp, D, dtype=torch.float32, device=dev)
+        idx = torch.empty(B, num_kp, num_hypo, dtype=torch.int64, device=dev)
+        stats = torch.empty(cabi.lib.xsup_stats_floats(shape), dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            cabi.check(cabi.lib.xsup_conv_head_fwd(xb.data_ptr(), wb.data_ptr(), bf.data_ptr() if bf is not None else None,
+                                                   kps.data_ptr(), dmap.data_ptr(), idx.data_ptr(), stats.data_ptr(), None, shape, C,
+                                                   cabi.stream_ptr(dev)), "xsup_conv_head_fwd")
+        ctx.save_for_backward(xb, wb, bf, stats)
+        ctx.shape, ctx.C = shape, C
+        ctx.meta = (x.dtype, weight.dtype, tuple(weight.shape), bias.dtype if bias is not None else None,
+                    x.is_contiguous(memory_format=torch.channels_last) and not x.is_contiguous())
+        ctx.mark_non_differentiable(dmap, idx)
+        return kps, dmap, idx
+
+    @staticmethod
+    def backward(ctx, g_kps, _g_dmap, _g_idx):
+        xb, wb, bf, stats = ctx.saved_tensors
+        shape, C = ctx.shape, ctx.C
+        x_dtype, w_dtype, w_shape, b_dtype, x_was_cl = ctx.meta
+        dev = xb.device
+        B, K, D, H, W = shape.B, shape.K, shape.D, shape.H, shape.W
+        KD, HW = K * D, H * W
+        g_kps = g_kps.to(torch.float32).contiguous()
+        coef = torch.empty(cabi.lib.xsup_coef_floats(shape), dtype=torch.float32, device=dev)
+        g = torch.empty(B, KD, HW, dtype=torch.bfloat16, device=dev)
+        gb = torch.empty(B, 4, KD, dtype=torch.float32, device=dev)
+        st = cabi.stream_ptr(dev)
+        with torch.cuda.device(dev):
+            cabi.check(cabi.lib.xsup_integral_coef(stats.data_ptr(), g_kps.data_ptr(), coef.data_ptr(), shape, st), "xsup_integral_coef")
+            cabi.check(cabi.lib.xsup_conv_head_bwd_g(xb.data_ptr(), wb.data_ptr(), bf.data_ptr() if bf is not None else None,
+                                                     coef.data_ptr(), g.data_ptr(), gb.data_ptr(), shape, C, st), "xsup_conv_head_bwd_g")
+        x_flat = xb.permute(0, 2, 3, 1).reshape(B, HW, C)                    # the channels-last storage viewed [B, HW, C]
+        g_x = g_w = g_b = None
+        if ctx.needs_input_grad[0]:
+            gt = g.transpose(1, 2)                                             # [B, HW, KD] view
+            if x_dtype == torch.bfloat16:
+                dx = torch.matmul(gt, wb)                                      # [B, HW, C] bf16 = channels-last d x
+            else:                                                              # fp32 input: do not round the result a second time
+                dx = _bmm_f32(gt, wb.unsqueeze(0).expand(B, KD, C)).to(x_dtype)
+            g_x = dx.view(B, H, W, C).permute(0, 3, 1, 2)                      # logical NCHW over channels-last storage
+            if not x_was_cl:
+                g_x = g_x.contiguous()
+        if ctx.needs_input_grad[1]:
+            g_w = _bmm_f32(g, x_flat).sum(0).to(w_dtype).reshape(w_shape)
+        if bf is not None and ctx.needs_input_grad[2]:
+            g_b = gb.sum(dim=(0, 1)).to(b_dtype)
+        return g_x, g_w, g_b, None, None, None
+
+
+def conv_integral_head_train(x, weight, bias, num_kp, num_hypo, neighbor_size):
+    """Differentiable form of `conv_integral_head` (see `ConvIntegralHead`): -> (kps, depth_prob_map, peak_idx)."""
+    return ConvIntegralHead.apply(x, weight, bias, num_kp, num_hypo, neighbor_size)
