@@ -83,6 +83,35 @@ def main():
         out["unfused_fp32_tf32conv"] = {"ms": round(ms_u32, 4), "conv_ms": round(ms_conv32, 4), "samples_per_s": round(B / ms_u32 * 1e3, 1)}
         out["unfused_bf16_conv_bf16_logits"] = {"ms": round(ms_u16, 4), "samples_per_s": round(B / ms_u16 * 1e3, 1)}
         out["speedup_vs_unfused_fp32"] = round(ms_u32 / ms_fused, 2)
+        # ---- training step: forward + backward to d x, d W, d bias (gradient of a random cotangent on kps)
+        gk = torch.randn(B, NH, K, 3, device=dev, generator=g)
+        xg = x.clone().requires_grad_(True)
+        xclg = xcl.clone().requires_grad_(True)
+        wg = w4.clone().requires_grad_(True)
+        bg = bias.clone().requires_grad_(True)
+
+        def fused_train(xin):
+            def run():
+                xin.grad = wg.grad = bg.grad = None
+                kps, _, _ = ops.conv_integral_head_train(xin, wg, bg, K, NH, NS)
+                kps.backward(gk)
+            return run
+
+        def unfused_train():
+            xg.grad = wg.grad = bg.grad = None
+            logits = F.conv2d(xg, wg, bg)
+            kps, _, _ = ops.integral_multi_head(logits, K, NH, NS)
+            kps.backward(gk)
+        n1 = ops.launch_count()
+        ms_ft = timeit(fused_train(xg), n=10)
+        per_step = (ops.launch_count() - n1) // 13
+        ms_ft_cl = timeit(fused_train(xclg), n=10)
+        ms_ut = timeit(unfused_train, n=5)
+        out["train_fwd_bwd"] = {"fused_from_nchw_fp32_ms": round(ms_ft, 3), "fused_from_nhwc_bf16_ms": round(ms_ft_cl, 3),
+                                "unfused_cudnn_conv_plus_streaming_head_ms": round(ms_ut, 3), "speedup": round(ms_ut / ms_ft, 2),
+                                "xsup_launches_per_step": int(per_step),
+                                "note": "fused: pack, conv_head_fwd, coef, conv_head_bwd_g (ours) + 2 cuBLAS GEMMs on the bf16 gradient; "
+                                        "unfused: cuDNN conv fwd/bwd (TF32) + integral_fwd/bwd on 4.56 GB of fp32 logits"}
     print(json.dumps(out), flush=True)
 
 
