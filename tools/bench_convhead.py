@@ -83,6 +83,18 @@ def main():
         out["unfused_fp32_tf32conv"] = {"ms": round(ms_u32, 4), "conv_ms": round(ms_conv32, 4), "samples_per_s": round(B / ms_u32 * 1e3, 1)}
         out["unfused_bf16_conv_bf16_logits"] = {"ms": round(ms_u16, 4), "samples_per_s": round(B / ms_u16 * 1e3, 1)}
         out["speedup_vs_unfused_fp32"] = round(ms_u32 / ms_fused, 2)
+        # the strongest unfused pipeline we know of: a bf16 batched GEMM straight into NCHW bf16 logits (cuBLAS), then the
+        # streaming kernel on those bf16 logits
+        x_flat_t = xcl.permute(0, 2, 3, 1).reshape(B, D * D, C).transpose(1, 2)           # [B, C, HW] view of the channels-last storage
+        wexp = wb.unsqueeze(0).expand(B, K * D, C)
+
+        def unfused_best():
+            logits = torch.baddbmm(bias.bfloat16().view(1, -1, 1), wexp, x_flat_t)           # [B, K*D, HW] bf16
+            return ops.integral_multi_head(logits.view(B, K * D, D, D), K, NH, NS)
+        ms_ub = timeit(unfused_best)
+        out["unfused_bf16_bmm_bf16_logits"] = {"ms": round(ms_ub, 4), "samples_per_s": round(B / ms_ub * 1e3, 1),
+                                                "note": "cuBLAS batched GEMM writing 2.28 GB of bf16 logits + integral_fwd_kernel<bf16> reading them"}
+        out["speedup_vs_best_unfused"] = round(ms_ub / ms_fused, 2)
         # ---- training step: forward + backward to d x, d W, d bias (gradient of a random cotangent on kps)
         gk = torch.randn(B, NH, K, 3, device=dev, generator=g)
         xg = x.clone().requires_grad_(True)
@@ -107,8 +119,20 @@ def main():
         per_step = (ops.launch_count() - n1) // 13
         ms_ft_cl = timeit(fused_train(xclg), n=10)
         ms_ut = timeit(unfused_train, n=5)
+        wbg = wb.clone().requires_grad_(True)
+        bbg = bias.bfloat16().clone().requires_grad_(True)
+
+        def unfused_best_train():
+            xclg.grad = wbg.grad = bbg.grad = None
+            xf = xclg.permute(0, 2, 3, 1).reshape(B, D * D, C).transpose(1, 2)
+            logits = torch.baddbmm(bbg.view(1, -1, 1), wbg.unsqueeze(0).expand(B, K * D, C), xf)
+            kps, _, _ = ops.integral_multi_head(logits.view(B, K * D, D, D), K, NH, NS)
+            kps.backward(gk)
+        ms_ubt = timeit(unfused_best_train, n=5)
         out["train_fwd_bwd"] = {"fused_from_nchw_fp32_ms": round(ms_ft, 3), "fused_from_nhwc_bf16_ms": round(ms_ft_cl, 3),
                                 "unfused_cudnn_conv_plus_streaming_head_ms": round(ms_ut, 3), "speedup": round(ms_ut / ms_ft, 2),
+                                "unfused_bf16_bmm_autograd_plus_streaming_head_bf16_ms": round(ms_ubt, 3),
+                                "speedup_vs_best_unfused_bf16": round(ms_ubt / ms_ft_cl, 2),
                                 "xsup_launches_per_step": int(per_step),
                                 "note": "fused: pack, conv_head_fwd, coef, conv_head_bwd_g (ours) + 2 cuBLAS GEMMs on the bf16 gradient; "
                                         "unfused: cuDNN conv fwd/bwd (TF32) + integral_fwd/bwd on 4.56 GB of fp32 logits"}
