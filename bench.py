@@ -371,8 +371,9 @@ def run_ours(args, c):
     h2d = h_logits.numel() * h_logits.element_size() + h_target.numel() * 4 + sum(v.numel() * 4 for v in h_cams.values())
     d2h = 2 * 4 + 2 * 8 + h_out["kps"].numel() * 4
 
-    e2e = {"value": round(B * world / (e2e_ms * 1e-3), 1), "unit": UNIT, "h2d_bytes_per_step": int(h2d),
-           "d2h_bytes_per_step": int(d2h), "ms_per_step": round(e2e_ms, 3), "steps": e2e_steps,
+    e2e = {"value": round(B * world / (e2e_ms * 1e-3), 1), "unit": UNIT, "h2d_bytes_per_step": int(h2d) * world,
+           "d2h_bytes_per_step": int(d2h) * world, "bytes_are": "whole job (all %d ranks)" % world, "ms_per_step": round(e2e_ms, 3),
+           "steps": e2e_steps,
            "note": "pinned host -> device copy of logits/target/cameras, fused op fwd+bwd, loss/sel/kps read back; PCIe-bound"}
     return finish(args, c, rank, world, dev, B, K, R, NH, ms, k_fwd, k_bwd, value, launches, clocks, e2e)
 
