@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define XSUP_ABI_VERSION 6
+#define XSUP_ABI_VERSION 7
 
 enum { XSUP_F32 = 0, XSUP_BF16 = 1 };
 enum { XSUP_HEAD_MULTI = 0, XSUP_HEAD_SINGLE = 1 };
@@ -298,6 +298,19 @@ int xsup_conv_head_fwd(const void* x_nhwc, const void* weight, const float* bias
 int xsup_integral_coef(const float* stats, const float* g_kps, float* coef_ws, const xsup_shape_t* s, void* stream);
 int xsup_conv_head_bwd_g(const void* x_nhwc, const void* weight, const float* bias, const float* coef_ws, void* g_out,
                          float* gbias_part, const xsup_shape_t* s, int32_t C, void* stream);
+
+/* The three pose loss terms on their own (modules/base_losses/loss_func.py:18-52), for callers that use them outside
+ * the fused per-camera op: x [B,K,C] fp32 -> loss (device scalar), and the vector-Jacobian product g_x [B,K,C].
+ *   XSUP_TERM_MSE   compute_supervision(keypoint, keypoint_gt, feature_shape, mode): gt [B,K,C]; feature_shape (HOST pointer
+ *                   to 3 floats, or NULL) rescales x as :39-45; flag 0 = mode 'mean' (divide by B*K*C), 1 = 'sum' (by B, :51)
+ *   XSUP_TERM_BONE  compute_bone_sym_loss(keypoints): needs K >= 17; mean over B*4; flag ignored
+ *   XSUP_TERM_KP    compute_kp_sym_loss(keypoints, is_3D = flag): needs K >= 15; mean over B*2*C
+ * sample_ws: B floats of scratch. */
+enum { XSUP_TERM_MSE = 0, XSUP_TERM_BONE = 1, XSUP_TERM_KP = 2 };
+int xsup_pose_term_fwd(const float* x, const float* gt, const float* feature_shape, int32_t term, int32_t flag, int32_t B,
+                       int32_t K, int32_t C, float* sample_ws, float* loss, void* stream);
+int xsup_pose_term_bwd(const float* x, const float* gt, const float* feature_shape, int32_t term, int32_t flag, int32_t B,
+                       int32_t K, int32_t C, const float* g_loss, float* g_x, void* stream);
 
 #ifdef __cplusplus
 }

@@ -26,7 +26,7 @@ def test_library_exports_every_declared_symbol(cabi):
     assert declared == set(cabi.SYMBOLS)
     for name in declared:
         assert hasattr(cabi.lib, name), name
-    assert cabi.lib.xsup_abi_version() == cabi.ABI_VERSION == 6
+    assert cabi.lib.xsup_abi_version() == cabi.ABI_VERSION == 7
 
 
 def test_struct_layouts_match_header(cabi):
@@ -152,6 +152,12 @@ def test_no_cpu_fallback(cabi):
         sk.skeleton_mask(torch.zeros(1, 18, 2), 64, [0, 1], [1, 2], 0.003)
     with pytest.raises(RuntimeError, match="no CPU path"):
         sk.compute_mask_reconstruction_loss(torch.zeros(1, 1, 8, 8), torch.zeros(1, 1, 8, 8))
+    losses = importlib.import_module("x-as-supervision_b200.losses")
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        losses.compute_supervision(torch.zeros(1, 18, 3), torch.zeros(1, 18, 3))
+    ev = importlib.import_module("x-as-supervision_b200.evalops")
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        ev.compute_disc_loss(torch.zeros(4, 3, 1), None)
 
 
 def test_cal_links_matches_the_reference_tables(cabi):

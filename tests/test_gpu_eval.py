@@ -127,3 +127,55 @@ def test_disc_loss_matches_oracle(ev, oracle, dev, shape):
             assert float((y.grad.cpu().double() - y64.grad).abs().max()) < 1e-6 * float(y64.grad.abs().max())
     with pytest.raises(ValueError, match="Invalid dimension"):
         ev.compute_disc_loss(torch.zeros(3, device=dev), None)
+
+
+def test_standalone_pose_terms_match_oracle(oracle, dev):
+    """compute_supervision (mean / sum / feature_shape), compute_bone_sym_loss, compute_kp_sym_loss (3-D, 2-D) and their
+    gradients against the fp64 oracle (= the reference's loss_func, checked in test_oracle_golden.py)."""
+    import __graft_entry__ as ge
+    ge.build()
+    pkg = importlib.import_module("x-as-supervision_b200")
+    pkg.load_native()
+    L = pkg.losses
+    g = torch.Generator().manual_seed(11)
+    B, K = 9, 18
+    world = torch.randn(B, K, 3, generator=g) * 400
+    kp = torch.rand(B, K, 3, generator=g) * 2 - 1
+    gt = torch.rand(B, K, 3, generator=g) * 2 - 1
+
+    def check(ours_fn, ref_fn, x, tol=1e-5):
+        a = x.to(dev).requires_grad_(True)
+        b = x.double().requires_grad_(True)
+        la, lb = ours_fn(a), ref_fn(b)
+        assert abs(float(la) - float(lb)) <= tol * abs(float(lb)), (float(la), float(lb))
+        la.backward()
+        lb.backward()
+        assert float((a.grad.cpu().double() - b.grad).abs().max()) <= tol * float(b.grad.abs().max())
+
+    check(lambda a: L.compute_supervision(a, gt.to(dev)), lambda b: oracle.supervision_mse(b, gt.double()), kp)
+    check(lambda a: L.compute_supervision(a, gt.to(dev), mode="sum"), lambda b: ((b - gt.double()) ** 2).sum() / B, kp)
+
+    def ref_fs(b):
+        k = b.clone()
+        k[:, :, :2] = (k[:, :, :2] + 1) / 2.0
+        k[:, :, 0] = k[:, :, 0] * (64 - 1)
+        k[:, :, 1] = k[:, :, 1] * (48 - 1)
+        k[:, :, 2] = k[:, :, 2] * (32 - 1)
+        return ((k - gt.double() * 30) ** 2).mean()
+    check(lambda a: L.compute_supervision(a, gt.to(dev) * 30, feature_shape=(64, 48, 32)), ref_fs, kp)
+    check(L.compute_bone_sym_loss, oracle.bone_sym, world)
+    check(lambda a: L.compute_kp_sym_loss(a), lambda b: oracle.kp_sym(b, True), world)
+    check(lambda a: L.compute_kp_sym_loss(a, is_3D=False), lambda b: oracle.kp_sym(b, False), kp[..., :2].contiguous())
+    with pytest.raises(RuntimeError, match="joints up to 16"):
+        L.compute_bone_sym_loss(torch.zeros(2, 10, 3, device=dev))
+    # a zero-length bone: the reference's torch.norm has a zero subgradient there (the oracle's sqrt would give NaN), so the
+    # gradient must stay finite and equal torch.norm's
+    w0 = world.clone()
+    w0[0, 16] = w0[0, 15]
+    a = w0.to(dev).requires_grad_(True)
+    L.compute_bone_sym_loss(a).backward()
+    b = w0.double().requires_grad_(True)
+    bone = torch.norm(b[:, [16, 15, 13, 12, 3, 2, 6, 5], :] - b[:, [15, 14, 12, 11, 2, 1, 5, 4], :], dim=2) * 1e-3
+    torch.nn.functional.mse_loss(bone[:, [0, 2, 4, 6]], bone[:, [1, 3, 5, 7]]).backward()
+    assert torch.isfinite(a.grad).all() and torch.isfinite(b.grad).all()
+    assert float((a.grad.cpu().double() - b.grad).abs().max()) <= 1e-5 * float(b.grad.abs().max())

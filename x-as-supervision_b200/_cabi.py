@@ -34,7 +34,9 @@ SYMBOLS = (
     "xsup_eval_select", "xsup_triangulate", "xsup_root_centre_fwd", "xsup_root_centre_bwd",
     "xsup_disc_min_loss_fwd", "xsup_disc_min_loss_bwd",
     "xsup_conv_head_fwd", "xsup_pack_nhwc_bf16", "xsup_integral_coef", "xsup_conv_head_bwd_g",
+    "xsup_pose_term_fwd", "xsup_pose_term_bwd",
 )
+TERM_MSE, TERM_BONE, TERM_KP = 0, 1, 2
 MAX_VIEWS = 8
 MAX_LINES = 32
 MASK_MSE, MASK_CLIP_MEAN, MASK_WEIGHTED = 0, 1, 2
@@ -127,6 +129,10 @@ def _load():
     lib.xsup_conv_head_fwd.restype = C.c_int
     lib.xsup_pack_nhwc_bf16.argtypes = [vp, vp, i32, i32, i32, vp]
     lib.xsup_pack_nhwc_bf16.restype = C.c_int
+    lib.xsup_pose_term_fwd.argtypes = [vp, vp, vp, i32, i32, i32, i32, i32, vp, vp, vp]
+    lib.xsup_pose_term_fwd.restype = C.c_int
+    lib.xsup_pose_term_bwd.argtypes = [vp, vp, vp, i32, i32, i32, i32, i32, vp, vp, vp]
+    lib.xsup_pose_term_bwd.restype = C.c_int
     lib.xsup_integral_coef.argtypes = [vp, vp, vp, C.POINTER(Shape), vp]
     lib.xsup_integral_coef.restype = C.c_int
     lib.xsup_conv_head_bwd_g.argtypes = [vp, vp, vp, vp, vp, vp, C.POINTER(Shape), i32, vp]
@@ -148,7 +154,7 @@ def _load():
 
 
 lib = _load()
-ABI_VERSION = 6
+ABI_VERSION = 7
 if lib.xsup_abi_version() != ABI_VERSION:
     raise ImportError("libxsup_b200.so ABI version %d, expected %d: rebuild with __graft_entry__.build()"
                       % (lib.xsup_abi_version(), ABI_VERSION))

@@ -567,4 +567,46 @@ int xsup_conv_head_bwd_g(const void* x_nhwc, const void* weight, const float* bi
     return XSUP_OK;
 }
 
+// ------------------------------------------------------------------------------------------------ stand-alone pose loss terms
+static int pose_term_params(PoseTermParams& p, double& denom, const float* x, const float* gt, const float* fs, int term, int sum_mode,
+                            int B, int K, int C, const char* who) {
+    if (term < XSUP_TERM_MSE || term > XSUP_TERM_KP) return fail(XSUP_E_SHAPE, "%s: unknown term %d", who, term);
+    if (B < 1 || K < 1 || C < 2 || C > 3) return fail(XSUP_E_SHAPE, "%s: need B >= 1, K >= 1, C in {2,3}", who);
+    if (term == XSUP_TERM_BONE && K < 17) return fail(XSUP_E_SHAPE, "%s: the bone term indexes joints up to 16 (loss_func.py:20), K is %d", who, K);
+    if (term == XSUP_TERM_KP && K < 15) return fail(XSUP_E_SHAPE, "%s: the keypoint term indexes joints up to 14 (loss_func.py:28), K is %d", who, K);
+    if (!x || (term == XSUP_TERM_MSE && !gt)) return fail(XSUP_E_NULL, "%s: NULL pointer", who);
+    p = PoseTermParams{};
+    p.x = x; p.gt = gt; p.B = B; p.K = K; p.C = C; p.term = term; p.use_fs = (term == XSUP_TERM_MSE && fs) ? 1 : 0;
+    if (p.use_fs) { p.fs[0] = fs[0]; p.fs[1] = fs[1]; p.fs[2] = fs[2]; }
+    p.is_3d = (term == XSUP_TERM_KP && sum_mode) ? 1 : 0;
+    if (term == XSUP_TERM_MSE) denom = sum_mode ? (double)B : (double)B * K * C;
+    else if (term == XSUP_TERM_BONE) denom = (double)B * 4.0;
+    else denom = (double)B * 2.0 * C;
+    return XSUP_OK;
+}
+
+int xsup_pose_term_fwd(const float* x, const float* gt, const float* feature_shape, int32_t term, int32_t sum_mode, int32_t B, int32_t K,
+                       int32_t C, float* sample_ws, float* loss, void* stream) {
+    PoseTermParams p;
+    double denom = 1.0;
+    if (int rc = pose_term_params(p, denom, x, gt, feature_shape, term, sum_mode, B, K, C, "xsup_pose_term_fwd")) return rc;
+    if (!sample_ws || !loss) return fail(XSUP_E_NULL, "xsup_pose_term_fwd: NULL pointer");
+    cudaError_t e = launch_pose_term_fwd(p, denom, sample_ws, loss, (cudaStream_t)stream);
+    if (e != cudaSuccess) return cuda_fail(e, "xsup_pose_term_fwd launch");
+    count_launches(2);
+    return XSUP_OK;
+}
+
+int xsup_pose_term_bwd(const float* x, const float* gt, const float* feature_shape, int32_t term, int32_t sum_mode, int32_t B, int32_t K,
+                       int32_t C, const float* g_loss, float* g_x, void* stream) {
+    PoseTermParams p;
+    double denom = 1.0;
+    if (int rc = pose_term_params(p, denom, x, gt, feature_shape, term, sum_mode, B, K, C, "xsup_pose_term_bwd")) return rc;
+    if (!g_loss || !g_x) return fail(XSUP_E_NULL, "xsup_pose_term_bwd: NULL pointer");
+    cudaError_t e = launch_pose_term_bwd(p, denom, g_loss, g_x, (cudaStream_t)stream);
+    if (e != cudaSuccess) return cuda_fail(e, "xsup_pose_term_bwd launch");
+    count_launches(1);
+    return XSUP_OK;
+}
+
 }  // extern "C"

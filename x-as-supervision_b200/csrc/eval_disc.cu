@@ -264,3 +264,133 @@ cudaError_t launch_disc_min_loss_bwd(const float* logits, const int64_t* sel, co
 }
 
 }  // namespace xsup
+
+// ---------------------------------------------------------------------------------------------- stand-alone pose loss terms
+// compute_supervision / compute_bone_sym_loss / compute_kp_sym_loss (modules/base_losses/loss_func.py:18-52) on their own,
+// for callers that use them outside the fused per-camera op (which evaluates the same terms per hypothesis in
+// reproj_loss_fwd_kernel).  x [B,K,C]; one thread per sample forms the sample's un-normalised sum, one CTA adds them in
+// fixed order.  The backward is the analytic VJP, one thread per sample.
+namespace xsup {
+
+__constant__ int c_pt_bone_child[8] = {16, 15, 13, 12, 3, 2, 6, 5};     // loss_func.py:20
+__constant__ int c_pt_bone_parent[8] = {15, 14, 12, 11, 2, 1, 5, 4};
+__constant__ int c_pt_mid_a[2] = {11, 1};                               // loss_func.py:28
+__constant__ int c_pt_mid_b[2] = {14, 4};
+
+__device__ __forceinline__ float pt_scaled(const PoseTermParams& p, float v, int c) {
+    // compute_supervision's feature_shape branch (loss_func.py:39-45): x,y -> (v+1)/2*(fs-1), z -> v*(fs-1)
+    if (!p.use_fs) return v;
+    return c < 2 ? (v + 1.0f) / 2.0f * (p.fs[c] - 1.0f) : v * (p.fs[2] - 1.0f);
+}
+
+__global__ void __launch_bounds__(128) pose_term_fwd_kernel(const PoseTermParams p, float* __restrict__ sample_sums) {
+    const int b = blockIdx.x * 128 + threadIdx.x;
+    if (b >= p.B) return;
+    const float* x = p.x + (size_t)b * p.K * p.C;
+    float a = 0.f;
+    if (p.term == XSUP_TERM_MSE) {
+        const float* g = p.gt + (size_t)b * p.K * p.C;
+        for (int i = 0; i < p.K * p.C; ++i) {
+            const float d = pt_scaled(p, x[i], i % p.C) - g[i];
+            a = fmaf(d, d, a);
+        }
+    } else if (p.term == XSUP_TERM_BONE) {
+        float n[8];
+        for (int i = 0; i < 8; ++i) {
+            const float* c = x + c_pt_bone_child[i] * p.C;
+            const float* q = x + c_pt_bone_parent[i] * p.C;
+            float s = 0.f;
+            for (int d = 0; d < p.C; ++d) s = fmaf(c[d] - q[d], c[d] - q[d], s);
+            n[i] = sqrtf(s) * 1e-3f;
+        }
+        for (int i = 0; i < 8; i += 2) a = fmaf(n[i] - n[i + 1], n[i] - n[i + 1], a);
+    } else {                                                           // XSUP_TERM_KP: is_3D scales by 1e-3
+        const float sc = p.is_3d ? 1e-3f : 1.0f;
+        for (int s = 0; s < 2; ++s) {
+            const int ir = s ? 0 : p.K - 1;
+            for (int d = 0; d < p.C; ++d) {
+                const float mid = (x[c_pt_mid_a[s] * p.C + d] + x[c_pt_mid_b[s] * p.C + d]) / 2.0f;
+                const float e = mid * sc - x[ir * p.C + d] * sc;
+                a = fmaf(e, e, a);
+            }
+        }
+    }
+    sample_sums[b] = a;
+}
+
+__global__ void __launch_bounds__(256) pose_term_reduce_kernel(const float* __restrict__ sample_sums, int B, double denom, float* __restrict__ loss) {
+    __shared__ double sh[256];
+    double a = 0.0;
+    for (int i = threadIdx.x; i < B; i += 256) a += (double)sample_sums[i];
+    sh[threadIdx.x] = a;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if (threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *loss = (float)(sh[0] / denom);
+}
+
+__global__ void __launch_bounds__(128) pose_term_bwd_kernel(const PoseTermParams p, const float* __restrict__ g_loss, float inv_denom,
+                                                            float* __restrict__ g_x) {
+    const int b = blockIdx.x * 128 + threadIdx.x;
+    if (b >= p.B) return;
+    const float* x = p.x + (size_t)b * p.K * p.C;
+    float* g = g_x + (size_t)b * p.K * p.C;
+    const float s0 = *g_loss * inv_denom;
+    if (p.term == XSUP_TERM_MSE) {
+        const float* t = p.gt + (size_t)b * p.K * p.C;
+        for (int i = 0; i < p.K * p.C; ++i) {
+            const int c = i % p.C;
+            const float jac = !p.use_fs ? 1.0f : (c < 2 ? 0.5f * (p.fs[c] - 1.0f) : p.fs[2] - 1.0f);
+            g[i] = s0 * 2.0f * (pt_scaled(p, x[i], c) - t[i]) * jac;
+        }
+        return;
+    }
+    for (int i = 0; i < p.K * p.C; ++i) g[i] = 0.f;
+    if (p.term == XSUP_TERM_BONE) {
+        float n[8], len[8];
+        for (int i = 0; i < 8; ++i) {
+            float s = 0.f;
+            for (int d = 0; d < p.C; ++d) {
+                const float v = x[c_pt_bone_child[i] * p.C + d] - x[c_pt_bone_parent[i] * p.C + d];
+                s = fmaf(v, v, s);
+            }
+            len[i] = sqrtf(s);
+            n[i] = len[i] * 1e-3f;
+        }
+        for (int i = 0; i < 8; ++i) {
+            const float dn = s0 * 2.0f * (n[i] - n[i ^ 1]) * 1e-3f;   // d/d n_i of (n_2p - n_2p+1)^2, times d n / d |v|
+            const float il = len[i] > 0.f ? 1.0f / len[i] : 0.f;     // torch.norm's backward is 0 at 0
+            for (int d = 0; d < p.C; ++d) {
+                const float v = x[c_pt_bone_child[i] * p.C + d] - x[c_pt_bone_parent[i] * p.C + d];
+                g[c_pt_bone_child[i] * p.C + d] += dn * v * il;
+                g[c_pt_bone_parent[i] * p.C + d] -= dn * v * il;
+            }
+        }
+    } else {
+        const float sc = p.is_3d ? 1e-3f : 1.0f;
+        for (int s = 0; s < 2; ++s) {
+            const int ia = c_pt_mid_a[s], ib = c_pt_mid_b[s], ir = s ? 0 : p.K - 1;
+            for (int d = 0; d < p.C; ++d) {
+                const float e = (x[ia * p.C + d] + x[ib * p.C + d]) / 2.0f * sc - x[ir * p.C + d] * sc;
+                const float ge = s0 * 2.0f * e * sc;
+                g[ia * p.C + d] += 0.5f * ge;
+                g[ib * p.C + d] += 0.5f * ge;
+                g[ir * p.C + d] -= ge;
+            }
+        }
+    }
+}
+
+cudaError_t launch_pose_term_fwd(const PoseTermParams& p, double denom, float* sample_sums, float* loss, cudaStream_t st) {
+    pose_term_fwd_kernel<<<(p.B + 127) / 128, 128, 0, st>>>(p, sample_sums);
+    pose_term_reduce_kernel<<<1, 256, 0, st>>>(sample_sums, p.B, denom, loss);
+    return cudaGetLastError();
+}
+cudaError_t launch_pose_term_bwd(const PoseTermParams& p, double denom, const float* g_loss, float* g_x, cudaStream_t st) {
+    pose_term_bwd_kernel<<<(p.B + 127) / 128, 128, 0, st>>>(p, g_loss, (float)(1.0 / denom), g_x);
+    return cudaGetLastError();
+}
+
+}  // namespace xsup

@@ -104,6 +104,14 @@ struct EvalParams {
     int perm[32];
 };
 typedef xsup_tri_t TriParams;
+struct PoseTermParams {
+    const float* x;
+    const float* gt;
+    int B, K, C, term, use_fs, is_3d;
+    float fs[3];
+};
+cudaError_t launch_pose_term_fwd(const PoseTermParams& p, double denom, float* sample_sums, float* loss, cudaStream_t st);
+cudaError_t launch_pose_term_bwd(const PoseTermParams& p, double denom, const float* g_loss, float* g_x, cudaStream_t st);
 cudaError_t launch_eval_select(const EvalParams& p, cudaStream_t st);
 cudaError_t launch_triangulate(const TriParams& p, float* world, cudaStream_t st);
 cudaError_t launch_root_centre_fwd(const float* world, float* out, int N, int K, int dim, cudaStream_t st);
