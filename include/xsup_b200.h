@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define XSUP_ABI_VERSION 7
+#define XSUP_ABI_VERSION 8
 
 enum { XSUP_F32 = 0, XSUP_BF16 = 1 };
 enum { XSUP_HEAD_MULTI = 0, XSUP_HEAD_SINGLE = 1 };
@@ -261,10 +261,13 @@ typedef struct {
 } xsup_tri_t;
 int xsup_triangulate(const xsup_tri_t* t, float* world, void* stream);
 
-/* modules/model.py:123-124: out [N,K,dim] = (world [N,K,3] - world[:, 0]) / 1000, first `dim` coordinates
- * (DISC_SUP_DIMENSION); `_bwd` is its vector-Jacobian product (g_world [N,K,3]). */
-int xsup_root_centre_fwd(const float* world, float* out, int32_t N, int32_t K, int32_t dim, void* stream);
-int xsup_root_centre_bwd(const float* g_out, float* g_world, int32_t N, int32_t K, int32_t dim, void* stream);
+/* modules/model.py:123-124, literally `(w - w[:, [0], :]) / 1000` then the first `dim` (DISC_SUP_DIMENSION) of every
+ * coordinate triple: world [N, M, R] -> out [N, M, R/3*dim], item 0 along the second axis subtracted.  For the stacked
+ * [B, NH, K, 3] tensor the reference passes, N = B, M = NH, R = 3K: every hypothesis relative to HYPOTHESIS 0 (what
+ * that expression means on a 4-D tensor); for [B, K, 3], N = B, M = K, R = 3: relative to the root joint.  `_bwd` is the
+ * vector-Jacobian product (g_world [N, M, R]). */
+int xsup_root_centre_fwd(const float* world, float* out, int32_t N, int32_t M, int32_t R, int32_t dim, void* stream);
+int xsup_root_centre_bwd(const float* g_out, float* g_world, int32_t N, int32_t M, int32_t R, int32_t dim, void* stream);
 
 /* One term of compute_disc_loss (modules/base_losses/loss_func.py:54-76) on logits [B,NH,C]:
  * loss = mean over (b,c) of min over h of (x - target)^2; sel [B,C] int64 = the argmin (first minimum).  NH = 1

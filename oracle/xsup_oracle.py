@@ -491,8 +491,11 @@ def triangulate(kps_by_cam, cams_by_cam, img_hw=(256, 256), is_norm=True, rect_w
 
 # --------------------------------------------------------------------------- discriminator-side glue
 def root_centre(world, dim=3):
-    """model.py:123-124: world joints relative to joint 0, in metres, first `dim` coordinates."""
-    return ((world - world[..., [0], :]) / 1000)[..., :dim]
+    """model.py:123-124, literally: `(w - w[:, [0], :]) / 1000`, then the first `dim` coordinates.  On the stacked
+    `[B, NH, K, 3]` world joints the reference passes, `[:, [0], :]` indexes the HYPOTHESIS axis: every hypothesis is
+    expressed relative to hypothesis 0 (which becomes all zeros), not relative to the root joint; on a `[B, K, 3]`
+    tensor the same expression is the usual root-joint centring."""
+    return ((world - world[:, [0]]) / 1000)[..., :dim]
 
 
 def disc_loss(pred_logits, gt_logits=None):

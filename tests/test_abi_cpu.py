@@ -26,7 +26,7 @@ def test_library_exports_every_declared_symbol(cabi):
     assert declared == set(cabi.SYMBOLS)
     for name in declared:
         assert hasattr(cabi.lib, name), name
-    assert cabi.lib.xsup_abi_version() == cabi.ABI_VERSION == 7
+    assert cabi.lib.xsup_abi_version() == cabi.ABI_VERSION == 8
 
 
 def test_struct_layouts_match_header(cabi):
@@ -88,7 +88,8 @@ def test_eval_structs_and_validation(cabi):
     assert cabi.lib.xsup_triangulate(t, p, None) == -1                                                    # one view
     t = cabi.Tri(2, 4, 18, 256, 256, 1, 2000.0)
     assert cabi.lib.xsup_triangulate(t, p, None) == -3                                                    # NULL keypoints
-    assert cabi.lib.xsup_root_centre_fwd(p, p, 4, 18, 4, None) == -1                                      # dim > 3
+    assert cabi.lib.xsup_root_centre_fwd(p, p, 4, 3, 54, 4, None) == -1                                   # dim > 3
+    assert cabi.lib.xsup_root_centre_fwd(p, p, 4, 3, 55, 3, None) == -1                                   # R not a multiple of 3
     assert cabi.lib.xsup_disc_min_loss_fwd(p, 0, 3, 1, 1.0, p, p, None) == -1                             # empty batch
 
 

@@ -93,19 +93,24 @@ def test_triangulation_matches_oracle(ev, oracle, synth, dev, V, B, K):
 
 
 @pytest.mark.parametrize("dim", [3, 2])
-def test_root_centre_and_batched_scoring(ev, oracle, dev, dim):
+@pytest.mark.parametrize("shape", [(6, 3, 18, 3), (5, 18, 3), (1, 1, 17, 3)])
+def test_root_centre_matches_the_reference_expression(ev, oracle, dev, dim, shape):
+    """model.py:123-124 on the stacked [B,NH,K,3] tensor (relative to hypothesis 0, the reference's literal behaviour) and on
+    a [B,K,3] tensor (relative to the root joint), with the VJP."""
     g = torch.Generator().manual_seed(9)
-    world = torch.randn(6, 3, 18, 3, generator=g) * 400
+    world = torch.randn(shape, generator=g) * 400
     w = world.to(dev).requires_grad_(True)
     out = ev.root_centre(w, dim)
     w64 = world.double().requires_grad_(True)
-    ref = oracle.root_centre(w64, dim)
-    assert float((out.detach().cpu().double() - ref.detach()).abs().max()) < 1e-6 * float(ref.abs().max())
+    ref = ((w64 - w64[:, [0], :]) / 1000)[..., :dim]                      # the reference's own expression
+    assert torch.equal(ref, oracle.root_centre(w64, dim))
+    assert tuple(out.shape) == tuple(ref.shape)
+    assert float((out.detach().cpu().double() - ref.detach()).abs().max()) <= 1e-6 * max(float(ref.abs().max()), 1e-30)
     G = torch.randn(out.shape, generator=g)
     out.backward(G.to(dev))
     ref.backward(G.double())
-    assert float((w.grad.cpu().double() - w64.grad).abs().max()) < 1e-6 * float(w64.grad.abs().max())
-    assert float(out.detach()[..., 0, :].abs().max()) == 0.0        # the root is exactly the origin
+    assert float((w.grad.cpu().double() - w64.grad).abs().max()) <= 1e-6 * float(w64.grad.abs().max())
+    assert float(out.detach()[:, 0].abs().max()) == 0.0               # item 0 of axis 1 is exactly the origin
 
 
 @pytest.mark.parametrize("shape", [(16, 1), (16, 3, 1), (5, 4, 2), (256, 3, 1)])

@@ -139,8 +139,8 @@ def _load():
     lib.xsup_conv_head_bwd_g.restype = C.c_int
     lib.xsup_eval_select.argtypes = [vp, vp, C.POINTER(Eval), vp, vp, vp, vp, vp, vp, vp, vp]
     lib.xsup_triangulate.argtypes = [C.POINTER(Tri), vp, vp]
-    lib.xsup_root_centre_fwd.argtypes = [vp, vp, i32, i32, i32, vp]
-    lib.xsup_root_centre_bwd.argtypes = [vp, vp, i32, i32, i32, vp]
+    lib.xsup_root_centre_fwd.argtypes = [vp, vp, i32, i32, i32, i32, vp]
+    lib.xsup_root_centre_bwd.argtypes = [vp, vp, i32, i32, i32, i32, vp]
     lib.xsup_disc_min_loss_fwd.argtypes = [vp, i32, i32, i32, f32, vp, vp, vp]
     lib.xsup_disc_min_loss_bwd.argtypes = [vp, vp, vp, i32, i32, i32, f32, vp, vp]
     for name in SYMBOLS:
@@ -154,7 +154,7 @@ def _load():
 
 
 lib = _load()
-ABI_VERSION = 7
+ABI_VERSION = 8
 if lib.xsup_abi_version() != ABI_VERSION:
     raise ImportError("libxsup_b200.so ABI version %d, expected %d: rebuild with __graft_entry__.build()"
                       % (lib.xsup_abi_version(), ABI_VERSION))

@@ -450,23 +450,23 @@ int xsup_triangulate(const xsup_tri_t* t, float* world, void* stream) {
     return XSUP_OK;
 }
 
-static int check_root(const void* a, const void* b, int N, int K, int dim, const char* who) {
-    if (N < 0 || K < 1 || dim < 1 || dim > 3) return fail(XSUP_E_SHAPE, "%s: need N >= 0, K >= 1, 1 <= dim <= 3", who);
+static int check_root(const void* a, const void* b, int N, int M, int R, int dim, const char* who) {
+    if (N < 0 || M < 1 || R < 3 || R % 3 || dim < 1 || dim > 3) return fail(XSUP_E_SHAPE, "%s: need N >= 0, M >= 1, R a positive multiple of 3, 1 <= dim <= 3", who);
     if (N > 0 && (!a || !b)) return fail(XSUP_E_NULL, "%s: NULL pointer", who);
     return XSUP_OK;
 }
-int xsup_root_centre_fwd(const float* world, float* out, int32_t N, int32_t K, int32_t dim, void* stream) {
-    if (int rc = check_root(world, out, N, K, dim, "xsup_root_centre_fwd")) return rc;
+int xsup_root_centre_fwd(const float* world, float* out, int32_t N, int32_t M, int32_t R, int32_t dim, void* stream) {
+    if (int rc = check_root(world, out, N, M, R, dim, "xsup_root_centre_fwd")) return rc;
     if (N == 0) return XSUP_OK;
-    cudaError_t e = launch_root_centre_fwd(world, out, N, K, dim, (cudaStream_t)stream);
+    cudaError_t e = launch_root_centre_fwd(world, out, N, M, R, dim, (cudaStream_t)stream);
     if (e != cudaSuccess) return cuda_fail(e, "xsup_root_centre_fwd launch");
     count_launches(1);
     return XSUP_OK;
 }
-int xsup_root_centre_bwd(const float* g_out, float* g_world, int32_t N, int32_t K, int32_t dim, void* stream) {
-    if (int rc = check_root(g_out, g_world, N, K, dim, "xsup_root_centre_bwd")) return rc;
+int xsup_root_centre_bwd(const float* g_out, float* g_world, int32_t N, int32_t M, int32_t R, int32_t dim, void* stream) {
+    if (int rc = check_root(g_out, g_world, N, M, R, dim, "xsup_root_centre_bwd")) return rc;
     if (N == 0) return XSUP_OK;
-    cudaError_t e = launch_root_centre_bwd(g_out, g_world, N, K, dim, (cudaStream_t)stream);
+    cudaError_t e = launch_root_centre_bwd(g_out, g_world, N, M, R, dim, (cudaStream_t)stream);
     if (e != cudaSuccess) return cuda_fail(e, "xsup_root_centre_bwd launch");
     count_launches(1);
     return XSUP_OK;

@@ -179,41 +179,42 @@ cudaError_t launch_triangulate(const TriParams& p, float* world, cudaStream_t st
 }
 
 // ---------------------------------------------------------------------------------------------- root-centring (model.py:123-124)
-// out[n,k,:dim] = (world[n,k,:dim] - world[n,0,:dim]) / 1000; one warp per row n, lane-strided over joints
-__global__ void __launch_bounds__(128) root_centre_fwd_kernel(const float* __restrict__ world, float* __restrict__ out, int N, int K,
-                                                              int dim) {
+// world [N, M, R] (R = 3 * joints-per-item): out[n, m, :] = (world[n, m, :] - world[n, 0, :]) / 1000, keeping the first
+// `dim` of every coordinate triple.  For the reference's stacked [B, NH, K, 3] input N = B, M = NH, R = 3K (relative to
+// HYPOTHESIS 0 - the literal meaning of `[:, [0], :]` there); for a [B, K, 3] input N = B, M = K, R = 3 (root joint).
+__global__ void __launch_bounds__(128) root_centre_fwd_kernel(const float* __restrict__ world, float* __restrict__ out, int N, int M,
+                                                              int R, int dim) {
     const int n = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (n >= N) return;
-    const float* w = world + (size_t)n * K * 3;
-    for (int e = lane; e < K * dim; e += 32) {
-        const int k = e / dim, c = e - k * dim;
-        out[(size_t)n * K * dim + e] = (w[k * 3 + c] - w[c]) / 1000.0f;
+    const float* w = world + (size_t)n * M * R;
+    const int Ro = R / 3 * dim;
+    for (int e = lane; e < M * R; e += 32) {
+        const int m = e / R, r = e - m * R, c = r % 3;
+        if (c < dim) out[((size_t)n * M + m) * Ro + (r / 3) * dim + c] = (w[e] - w[r]) / 1000.0f;
     }
 }
 __global__ void __launch_bounds__(128) root_centre_bwd_kernel(const float* __restrict__ g_out, float* __restrict__ g_world, int N,
-                                                              int K, int dim) {
+                                                              int M, int R, int dim) {
     const int n = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (n >= N) return;
-    const float* g = g_out + (size_t)n * K * dim;
-    float* gw = g_world + (size_t)n * K * 3;
-    // joint 0 receives minus the sum over all joints (its own +1/1000 cancels); fixed lane order + shuffle tree
-    float s[3] = {0.f, 0.f, 0.f};
-    for (int k = lane; k < K; k += 32)
-        for (int c = 0; c < dim; ++c) s[c] += g[k * dim + c];
-    for (int c = 0; c < 3; ++c) s[c] = warp_sum(s[c]);
-    for (int e = lane; e < K * 3; e += 32) {
-        const int k = e / 3, c = e - k * 3;
-        float v = 0.f;
-        if (c < dim) v = (g[k * dim + c] - (k == 0 ? s[c] : 0.f)) / 1000.0f;
-        gw[e] = v;
+    const int Ro = R / 3 * dim;
+    const float* g = g_out + (size_t)n * M * Ro;
+    float* gw = g_world + (size_t)n * M * R;
+    // item 0 receives minus the sum over all items (its own +1/1000 cancels); fixed order over m per lane
+    for (int r = lane; r < R; r += 32) {
+        const int c = r % 3, ro = (r / 3) * dim + c;
+        float s = 0.f;
+        if (c < dim)
+            for (int m = 0; m < M; ++m) s += g[m * Ro + ro];
+        for (int m = 0; m < M; ++m) gw[m * R + r] = c < dim ? (g[m * Ro + ro] - (m == 0 ? s : 0.f)) / 1000.0f : 0.f;
     }
 }
-cudaError_t launch_root_centre_fwd(const float* world, float* out, int N, int K, int dim, cudaStream_t st) {
-    root_centre_fwd_kernel<<<(N + 3) / 4, 128, 0, st>>>(world, out, N, K, dim);
+cudaError_t launch_root_centre_fwd(const float* world, float* out, int N, int M, int R, int dim, cudaStream_t st) {
+    root_centre_fwd_kernel<<<(N + 3) / 4, 128, 0, st>>>(world, out, N, M, R, dim);
     return cudaGetLastError();
 }
-cudaError_t launch_root_centre_bwd(const float* g_out, float* g_world, int N, int K, int dim, cudaStream_t st) {
-    root_centre_bwd_kernel<<<(N + 3) / 4, 128, 0, st>>>(g_out, g_world, N, K, dim);
+cudaError_t launch_root_centre_bwd(const float* g_out, float* g_world, int N, int M, int R, int dim, cudaStream_t st) {
+    root_centre_bwd_kernel<<<(N + 3) / 4, 128, 0, st>>>(g_out, g_world, N, M, R, dim);
     return cudaGetLastError();
 }
 

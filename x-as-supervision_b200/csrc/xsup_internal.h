@@ -114,8 +114,8 @@ cudaError_t launch_pose_term_fwd(const PoseTermParams& p, double denom, float* s
 cudaError_t launch_pose_term_bwd(const PoseTermParams& p, double denom, const float* g_loss, float* g_x, cudaStream_t st);
 cudaError_t launch_eval_select(const EvalParams& p, cudaStream_t st);
 cudaError_t launch_triangulate(const TriParams& p, float* world, cudaStream_t st);
-cudaError_t launch_root_centre_fwd(const float* world, float* out, int N, int K, int dim, cudaStream_t st);
-cudaError_t launch_root_centre_bwd(const float* g_out, float* g_world, int N, int K, int dim, cudaStream_t st);
+cudaError_t launch_root_centre_fwd(const float* world, float* out, int N, int M, int R, int dim, cudaStream_t st);
+cudaError_t launch_root_centre_bwd(const float* g_out, float* g_world, int N, int M, int R, int dim, cudaStream_t st);
 cudaError_t launch_disc_min_loss_fwd(const float* logits, int B, int NH, int C, float target, float* loss, int64_t* sel, cudaStream_t st);
 cudaError_t launch_disc_min_loss_bwd(const float* logits, const int64_t* sel, const float* g_loss, int B, int NH, int C, float target,
                                      float* g_logits, cudaStream_t st);

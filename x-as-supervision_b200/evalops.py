@@ -114,35 +114,39 @@ def triangulation(keypoints: Dict[str, torch.Tensor], params: Dict[str, torch.Te
 
 
 class RootCentre(torch.autograd.Function):
-    """world `[..., K, 3]` -> `(world - world[..., [0], :]) / 1000` sliced to `dim` coordinates (model.py:123-124)."""
+    """`(world - world[:, [0], :]) / 1000` sliced to `dim` coordinates, exactly as model.py:123-124 writes it."""
 
     @staticmethod
     def forward(ctx, world, dim):
         cabi.require_cuda(world, "world joints")
         w = world.detach().to(torch.float32).contiguous()
-        K = w.shape[-2]
-        N = w.numel() // (K * 3) if w.numel() else 0
+        if w.dim() not in (3, 4) or w.shape[-1] != 3:
+            raise ValueError("world joints must be [B, K, 3] or [B, NH, K, 3], got %s" % (tuple(world.shape),))
+        N, M = w.shape[0], w.shape[1]
+        R = w.numel() // max(N * M, 1) if w.numel() else 3 * (w.shape[2] if w.dim() == 4 else 1)
         out = torch.empty(w.shape[:-1] + (dim,), dtype=torch.float32, device=w.device)
         with torch.cuda.device(w.device):
-            cabi.check(cabi.lib.xsup_root_centre_fwd(w.data_ptr(), out.data_ptr(), N, K, dim, cabi.stream_ptr(w.device)),
+            cabi.check(cabi.lib.xsup_root_centre_fwd(w.data_ptr(), out.data_ptr(), N, M, R, dim, cabi.stream_ptr(w.device)),
                        "xsup_root_centre_fwd")
-        ctx.meta = (N, K, dim, tuple(w.shape))
+        ctx.meta = (N, M, R, dim, tuple(w.shape), world.dtype)
         return out
 
     @staticmethod
     def backward(ctx, g_out):
-        N, K, dim, shape = ctx.meta
+        N, M, R, dim, shape, in_dtype = ctx.meta
         g = g_out.to(torch.float32).contiguous()
         gw = torch.empty(shape, dtype=torch.float32, device=g.device)
         with torch.cuda.device(g.device):
-            cabi.check(cabi.lib.xsup_root_centre_bwd(g.data_ptr(), gw.data_ptr(), N, K, dim, cabi.stream_ptr(g.device)),
+            cabi.check(cabi.lib.xsup_root_centre_bwd(g.data_ptr(), gw.data_ptr(), N, M, R, dim, cabi.stream_ptr(g.device)),
                        "xsup_root_centre_bwd")
-        return gw, None
+        return gw.to(in_dtype), None
 
 
 def root_centre(world: torch.Tensor, dim: int = 3) -> torch.Tensor:
-    """`[B,NH,K,3]` (or `[B,K,3]`) world joints -> root-relative metres, ready for ONE batched discriminator call on
-    `out.flatten(0, -3)` instead of the reference's NH calls (model.py:126-129)."""
+    """model.py:123-124 kept literally: item 0 along axis 1 is subtracted.  On the stacked `[B, NH, K, 3]` world
+    joints the reference passes that axis is the HYPOTHESIS axis (hypothesis 0 becomes all zeros, the others are
+    expressed relative to it); pass a `[B, K, 3]` tensor for the usual root-joint centring.  The result
+    `out.flatten(0, 1)` feeds ONE batched discriminator call instead of the reference's NH calls (model.py:126-129)."""
     return RootCentre.apply(world, int(dim))
 
 
