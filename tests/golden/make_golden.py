@@ -293,11 +293,71 @@ def eval_case(util, lf, eu, name, B, NH, K, V, seed):
     print("wrote", name, "swapped joints", int(out["is_trans_f64"].sum()), "disc", out["disc_f64"])
 
 
+def stub_discriminator(K, dim, dtype):
+    """A seeded stand-in for the GCN discriminator (PyG is not installed here): [N, K, dim] -> [N, 1]."""
+    g = torch.Generator().manual_seed(7)
+    lin = nn.Linear(K * dim, 1)
+    with torch.no_grad():
+        lin.weight.copy_(torch.randn(1, K * dim, generator=g, dtype=torch.float32) * 0.5)   # same bits whatever the default dtype
+        lin.bias.fill_(0.25)
+    net = nn.Sequential(nn.Flatten(), lin).to(dtype)
+    net.name = "Linear"                      # Counter3DDisc reads `.name` (model.py:207)
+    return net
+
+
+def model_case(multi, model, name, B, K, R, NH, NS, seed, sym, use_dis_map, grad_stride):
+    """The reference's own Counter3DModel.forward and Counter3DDisc.forward (modules/model.py) on a two-camera batch, with
+    KPDetector3DMulti(backbone = identity) as regressor and a seeded linear discriminator; loss_values, their sum as the
+    trainer forms it (train.py:182-183) and its gradient w.r.t. every logits tensor."""
+    cfg = synth.model_cfg(sym=sym, use_dis_map=use_dis_map)
+    batch = synth.model_batch(B, K, R, seed=seed)
+    out = {"meta": np.array([B, K, R, NH, NS, seed, grad_stride, int(use_dis_map)]),
+           "sym": np.array(sym if sym is not None else [np.nan] * 3, dtype=np.float64),
+           "in_checksum": checksum(batch["cam_0_img"]), "mask_checksum": checksum(batch["cam_1_mask"])}
+    for tag, dt in (("f32", torch.float32), ("f64", torch.float64)):
+        def go():
+            x = {k: (v.to(dt).clone() if v.is_floating_point() else v.clone()) for k, v in batch.items()}
+            leaves = {}
+            for k in list(x):
+                if k.endswith("_img"):
+                    x[k].requires_grad_(True)
+                    leaves[k] = x[k]
+            det = multi.KPDetector3DMulti("resnet_multi", K, R, NH, NS)
+            disc = stub_discriminator(K, 3, dt)
+            m = model.Counter3DModel(cfg, det, None, None, physique_network=None)
+            loss_values, output = m(x, disc)
+            total = sum(v.mean() for v in loss_values.values())
+            total.backward()
+            d = model.Counter3DDisc(cfg, disc, None, None)
+            loss_disc, _ = d({k: v.detach() for k, v in x.items()}, det)
+            res = {"loss_" + k: v.mean().detach() for k, v in loss_values.items()}
+            res["loss_total"] = total.detach()
+            res["loss_disc"] = loss_disc.detach()
+            res["recon_cam_0"] = output["mask_heatmap_line_cam_0"].detach()
+            res["kp_gt_world"] = output["kp_gt_world"].detach()
+            res["pose_3d_gt_cam_1_pseudo"] = output["pose_3d_gt_cam_1_pseudo"].detach()
+            for k, v in leaves.items():
+                gf = v.grad.flatten()
+                res["grad_sub_" + k] = gf[::grad_stride].clone()
+                res["grad_norms_" + k] = torch.tensor([gf.double().abs().max().item(), gf.double().norm().item()])
+            return res
+        for k, v in run_in(dt, go).items():
+            out[k + "_" + tag] = v.numpy()
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
+    print("wrote", name, {k: float(out[k]) for k in out if k.startswith("loss_") and k.endswith("_f64")})
+
+
 def main():
     torch.manual_seed(0)
     torch.set_num_threads(8)
     multi, single, util, lf = load_reference()
     model = importlib.import_module("modules.model")
+    if "--only-model" in sys.argv or "--only-skeleton" not in sys.argv and "--only-eval" not in sys.argv:
+        # SynthS2-like (symmetry incl. kp_2d, geodesic-weighted reconstruction) and SurS1-like (no symmetry, plain clip) loss graphs
+        model_case(multi, model, "model_synths2_k18_r32", B=3, K=18, R=32, NH=3, NS=15, seed=90, sym=(0.1, 0.1, 0.5), use_dis_map=True, grad_stride=251)
+        model_case(multi, model, "model_surs1_k18_r32", B=2, K=18, R=32, NH=3, NS=15, seed=95, sym=None, use_dis_map=False, grad_stride=251)
+        if "--only-model" in sys.argv:
+            return
     if "--only-eval" in sys.argv:
         eval_case(util, lf, load_eval_utils(), "eval_k18_nh3_v4", B=6, NH=3, K=18, V=4, seed=80)
         return

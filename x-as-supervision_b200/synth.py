@@ -18,7 +18,7 @@ import torch
 
 __all__ = ["iid_logits", "blob_logits", "pseudo_joints", "cameras", "camera_dict", "CAM_FIELDS",
            "H36M_PARENTS", "LINE_SELECT", "BODY_WIDTH", "skeleton_pose2d", "silhouette_mask", "geodesic_weight",
-           "eval_predictions", "SWITCH_LIST"]
+           "eval_predictions", "SWITCH_LIST", "model_batch", "model_cfg"]
 
 # order of the per-sample camera tensors everywhere in this package
 CAM_FIELDS = ("trans_image", "pelvis", "k_mat", "trans_world", "rot_world")
@@ -212,3 +212,31 @@ def eval_predictions(B: int, NH: int, K: int, seed: int = 80, img_size: float = 
             perm[a], perm[b] = b, a
     kps[1::2] = kps[1::2][:, :, perm]
     return kps.contiguous(), jp.contiguous()
+
+
+# --------------------------------------------------------------------------------------- whole loss-graph inputs
+def model_cfg(cam_ids=(0, 1), sym=(0.1, 0.1, 0.5), w_pseudo=1.0, w_gen=0.5, w_rec=0.02, use_dis_map=True, w_disc=0.5):
+    """`model_params` of config/HM36_Multi_*.yaml reduced to what Counter3DModel / Counter3DDisc read (model.py:24-48,195-216)."""
+    loss = {"smpl_pseudo_img_loss": {"weight": w_pseudo}, "smpl_gen_loss": {"weight": w_gen},
+            "recons_loss": {"use_dis_map": use_dis_map, "weight": w_rec}, "smpl_disc_loss": {"weight": w_disc, "update_interval": 1}}
+    if sym is not None:
+        loss["symmetry_loss"] = {"weight": {"bone": sym[0], "kp": sym[1], "kp_2d": sym[2]}}
+    return {"cam_id_list": list(cam_ids), "parent_ids": list(H36M_PARENTS), "line_select_ids": list(LINE_SELECT), "body_width": 3.0,
+            "loss_config": loss, "smpl_disc_params": {"disc_sup_dim": 3}}
+
+
+def model_batch(B: int, K: int, R: int, cam_ids=(0, 1), seed: int = 90) -> Dict[str, torch.Tensor]:
+    """The dict the data loader hands to Counter3DModel.forward (dataloader.py:160-230), with the detector's backbone
+    replaced by the identity: `{cam}_img` / `{cam}_pseudo_img` ARE the `[B, K*R, R, R]` logits (so the "image" is RxR)."""
+    x = {}
+    for i, c in enumerate(cam_ids):
+        key = "cam_%d" % c
+        x[key + "_img"] = blob_logits(B, K, R, R, R, seed=seed + 10 * i)
+        x[key + "_pseudo_img"] = blob_logits(B, K, R, R, R, seed=seed + 10 * i + 1)
+        x[key + "_pseudo_joints"] = pseudo_joints(B, K, seed=seed + 10 * i + 2)
+        x[key + "_joints"] = torch.rand(B, K, 3, generator=_gen(seed + 10 * i + 3)) * (R - 1)
+        for k, v in cameras(B, seed=seed + 10 * i + 4, img=R).items():
+            x[key + "_" + k] = v
+        x[key + "_mask"] = silhouette_mask(skeleton_pose2d(B, K, seed=seed + 10 * i + 5, jitter=0.03), R)
+        x[key + "_geodesic_dis"] = geodesic_weight(x[key + "_mask"], seed=seed + 10 * i + 6)
+    return x
