@@ -345,6 +345,23 @@ class GraphedReprojStep:
         return self.loss_pseudo, self.loss_sym, self.sel
 
 
+def _nhwc_bf16(x: torch.Tensor) -> torch.Tensor:
+    """`x [B,C,H,W]` as bf16 with channels-last storage (the K-major operand of the conv-fused kernels): used in place when
+    it already is; a contiguous fp32 NCHW tensor goes through `xsup_pack_nhwc_bf16` (transpose + rounding in one pass);
+    anything else through torch's conversion."""
+    xb = x.detach()
+    if xb.dtype == torch.bfloat16 and xb.is_contiguous(memory_format=torch.channels_last):
+        return xb
+    B, C, H, W = xb.shape
+    if xb.dtype == torch.float32 and xb.is_contiguous() and C % 64 == 0 and (H * W) % 64 == 0 and B > 0:
+        packed = torch.empty((B, C, H, W), dtype=torch.bfloat16, device=xb.device, memory_format=torch.channels_last)
+        with torch.cuda.device(xb.device):
+            cabi.check(cabi.lib.xsup_pack_nhwc_bf16(xb.data_ptr(), packed.data_ptr(), B, C, H * W, cabi.stream_ptr(xb.device)),
+                       "xsup_pack_nhwc_bf16")
+        return packed
+    return xb.to(dtype=torch.bfloat16, memory_format=torch.channels_last)
+
+
 def conv_integral_head(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor], num_kp: int, num_hypo: int,
                        neighbor_size: int, return_logits: bool = False):
     """The head's final `Conv2d(C, K*D, 1)` (deconv_head.py:33-35) fused with the integral multi-hypothesis head
@@ -365,16 +382,7 @@ def conv_integral_head(x: torch.Tensor, weight: torch.Tensor, bias: Optional[tor
     if D * num_kp != w2.shape[0]:
         raise ValueError("weight rows %d are not a multiple of num_kp %d" % (w2.shape[0], num_kp))
     dev = x.device
-    xb = x.detach()
-    if xb.dtype != torch.bfloat16 or not xb.is_contiguous(memory_format=torch.channels_last):
-        if xb.dtype == torch.float32 and xb.is_contiguous() and C % 64 == 0 and (H * W) % 64 == 0 and B > 0:
-            packed = torch.empty((B, C, H, W), dtype=torch.bfloat16, device=dev, memory_format=torch.channels_last)
-            with torch.cuda.device(dev):                  # one pass: NCHW fp32 -> channels-last bf16 (transpose + cast fused)
-                cabi.check(cabi.lib.xsup_pack_nhwc_bf16(xb.data_ptr(), packed.data_ptr(), B, C, H * W, cabi.stream_ptr(dev)),
-                           "xsup_pack_nhwc_bf16")
-            xb = packed
-        else:
-            xb = xb.to(dtype=torch.bfloat16, memory_format=torch.channels_last)
+    xb = _nhwc_bf16(x)
     wb = w2.to(device=dev, dtype=torch.bfloat16).contiguous()
     bf = bias.detach().to(device=dev, dtype=torch.float32).contiguous() if bias is not None else None
     shape = cabi.make_shape(B, num_kp, D, H, W, num_hypo, neighbor_size, torch.bfloat16, cabi.HEAD_MULTI)
@@ -420,16 +428,7 @@ class ConvIntegralHead(torch.autograd.Function):
         D = w2.shape[0] // num_kp
         if w2.shape[1] != C or D * num_kp != w2.shape[0]:
             raise ValueError("weight is %s, expected [num_kp*D, %d(,1,1)]" % (tuple(weight.shape), C))
-        xb = x.detach()
-        if xb.dtype != torch.bfloat16 or not xb.is_contiguous(memory_format=torch.channels_last):
-            if xb.dtype == torch.float32 and xb.is_contiguous() and C % 64 == 0 and (H * W) % 64 == 0 and B > 0:
-                packed = torch.empty((B, C, H, W), dtype=torch.bfloat16, device=dev, memory_format=torch.channels_last)
-                with torch.cuda.device(dev):
-                    cabi.check(cabi.lib.xsup_pack_nhwc_bf16(xb.data_ptr(), packed.data_ptr(), B, C, H * W, cabi.stream_ptr(dev)),
-                               "xsup_pack_nhwc_bf16")
-                xb = packed
-            else:
-                xb = xb.to(dtype=torch.bfloat16, memory_format=torch.channels_last)
+        xb = _nhwc_bf16(x)
         wb = w2.to(device=dev, dtype=torch.bfloat16).contiguous()
         bf = bias.detach().to(device=dev, dtype=torch.float32).contiguous() if bias is not None else None
         shape = cabi.make_shape(B, num_kp, D, H, W, num_hypo, neighbor_size, torch.bfloat16, cabi.HEAD_MULTI)
