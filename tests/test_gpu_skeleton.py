@@ -107,7 +107,7 @@ def _grad_err(ours, ref64, kind):
 
 
 @pytest.mark.parametrize("kind", POSES)
-@pytest.mark.parametrize("S", [64, 256])
+@pytest.mark.parametrize("S", [64, 256, 36, 100])          # 36 and 100: ragged 16x8 edge tiles (S % 16 != 0, S % 8 != 0)
 def test_rasteriser_against_oracle(sk, oracle, synth, dev, kind, S):
     B, K = 3, 18
     parent, child = _links(sk, synth)
