@@ -481,3 +481,50 @@ def test_largest_sweep_batch_in_place(ops, synth, dev):
     assert torch.equal(grad[pick], gs)
     s = grad.view(B * K, -1).double().sum(-1).abs().max().item()
     assert s < 1e-6 * grad.abs().max().item() * R ** 3
+
+
+@pytest.mark.parametrize("R,NH,NS", [(16, 14, 1), (16, 14, 31), (32, 30, 3), (16, 1, 33)])
+def test_extreme_hypothesis_counts_and_windows(ops, oracle, synth, dev, R, NH, NS):
+    """The limits the ABI accepts: NH = D-2 (every interior bin becomes a hypothesis, mostly filler slots), a window of
+    one bin, and a window wider than the whole depth axis (the average pools then cover the zero padding only)."""
+    B, K = 2, 3
+    logits = synth.iid_logits(B, K, R, R, R, seed=R + NH + NS)
+    gw = torch.randn(B, NH, K, 3, generator=torch.Generator().manual_seed(5), dtype=torch.float64)
+    okps, odmap, oidx, ograd = _oracle_head(oracle, logits.double(), K, NH, NS, gw)
+    x = logits.to(dev).requires_grad_(True)
+    kps, dmap, idx = ops.integral_multi_head(x, K, NH, NS)
+    (kps * gw.float().to(dev)).sum().backward()
+    pz64 = oracle.marginals(oracle.softmax_volume(logits.double(), K))[2]
+    ties = _near_tie_rows(pz64, min(NH, R - 3))
+    same = idx.cpu().numpy() == oidx.numpy()
+    assert same[~ties].all()
+    assert sorted(idx[0, 0].tolist()) == sorted(set(idx[0, 0].tolist())), "a bin was selected twice"
+    if same.all():
+        assert (kps.detach().cpu().double() - okps).abs().max().item() < TOL
+        assert rel_inf(x.grad.cpu().numpy(), ograd.numpy()) < TOL
+    with pytest.raises(RuntimeError, match="num_hypo"):
+        ops.integral_multi_head(x.detach(), K, R - 1, NS)          # NH > D-2
+
+
+def test_geometry_with_general_matrices(ops, oracle, synth, dev):
+    """`rot_world` that is not orthonormal and a sheared crop affine: the reference inverts both with `torch.linalg.inv`
+    (util.py:64,93), so the kernels use the general 2x2 / 3x3 inverses, not transposes; VJP included."""
+    B, K = 5, 18
+    g = torch.Generator().manual_seed(12)
+    cams = synth.cameras(B, seed=13)
+    cams["rot_world"] = cams["rot_world"] + 0.15 * torch.randn(B, 3, 3, generator=g)
+    cams["trans_image"][:, :, :2] += 0.05 * torch.randn(B, 2, 2, generator=g)
+    kps = synth.pseudo_joints(B, K, seed=14)
+    x = kps.to(dev).requires_grad_(True)
+    params = {k: v.to(dev) for k, v in synth.camera_dict(cams, "cam_0").items()}
+    world = ops.convert_patch_to_world(x, params, "cam_0", is_norm=True)
+    x64 = kps.double().requires_grad_(True)
+    c64 = {k: v.double() for k, v in cams.items()}
+    oworld = oracle.patch_to_world(x64, c64)
+    assert rel_inf(world.detach().cpu().numpy(), oworld.detach().numpy()) < TOL
+    gw = torch.randn(B, K, 3, generator=g)
+    world.backward(gw.to(dev))
+    oworld.backward(gw.double())
+    assert rel_inf(x.grad.cpu().numpy(), x64.grad.numpy()) < TOL
+    back = ops.convert_world_to_patch(world.detach(), params, "cam_0", is_norm=True)
+    assert float((back.cpu() - kps).abs().max()) < 1e-3           # round trip through fp32 world millimetres
