@@ -184,3 +184,31 @@ def test_standalone_pose_terms_match_oracle(oracle, dev):
     torch.nn.functional.mse_loss(bone[:, [0, 2, 4, 6]], bone[:, [1, 3, 5, 7]]).backward()
     assert torch.isfinite(a.grad).all() and torch.isfinite(b.grad).all()
     assert float((a.grad.cpu().double() - b.grad).abs().max()) <= 1e-5 * float(b.grad.abs().max())
+
+
+def test_exact_ties_follow_the_reference_operators(ev, oracle, dev):
+    """Strict comparisons and first-minimum argmins, on inputs built to tie exactly: `torch.lt` in switch_points
+    (eval_utils.py:26), `argmin(dim=1)` in the best-hypothesis selection (eval.py:139), `min(dim=1)` in compute_disc_loss
+    (loss_func.py:59), `mask > 0.1` in the clip filter (loss_func.py:9)."""
+    B, NH, K = 3, 3, 18
+    jp = torch.full((B, K, 3), 127.5)                          # gt at the patch centre: normalised (0, 0, 0.5)
+    kps = torch.zeros(B, NH, K, 3)
+    kps[..., 2] = 0.5
+    kps[:, :, 1, 0] = 0.25                                      # joint 1 and its mirror joint 4 are equally far from gt: no swap
+    kps[:, :, 4, 0] = -0.25
+    kps[:, 1] = kps[:, 0]                                       # hypotheses 0 and 1 identical: argmin must return 0
+    kps[:, 2, :, 2] = 0.75
+    out = ev.eval_select(kps.to(dev), jp.to(dev), 256.0, "best")
+    k3, k2, tr, err, bi, b2, _ = oracle.eval_select(kps, jp, 256.0, "best")
+    assert not bool(out["is_trans"].any()) and not bool(tr.any())
+    assert int(out["best_idx"].max()) == 0 and torch.equal(out["best_idx"].cpu(), bi) and torch.equal(out["best_2d_idx"].cpu(), b2)
+    # discriminator term: equal logits in two slots -> the gradient goes to the first
+    x = torch.tensor([[[0.5], [0.5], [2.0]]], device=dev, requires_grad=True)
+    ev.compute_disc_loss(x, None).backward()
+    assert x.grad[0, 0, 0] != 0 and x.grad[0, 1, 0] == 0 and x.grad[0, 2, 0] == 0
+    # clip filter: a mask value of exactly 0.1 is filtered out (strict >)
+    sk = importlib.import_module("x-as-supervision_b200.skeleton")
+    m = torch.full((1, 1, 4, 4), 0.1, device=dev)
+    m[0, 0, 0, 0] = 0.5
+    loss = sk.compute_mask_reconstruction_loss(m, torch.zeros_like(m), weight=torch.ones_like(m), use_clip=True)
+    assert abs(float(loss) - 0.25 / 16) < 1e-7
