@@ -116,7 +116,10 @@ def test_incumbent_eager_timings(oracle, synth):
         total.backward()
 
     te3, to3 = _time(eager3, steps=3, warmup=1), _time(ours3, steps=10, warmup=2)
+    graphed = model.GraphedLossGraph(ours_model, xb, disc)
+    tg3 = _time(graphed, steps=20, warmup=3)
     out["loss_graph_4cam_b32"] = {"eager_ms": round(te3, 3), "ours_ms": round(to3, 3), "speedup": round(te3 / to3, 2),
+                                  "ours_cuda_graph_ms": round(tg3, 3), "speedup_cuda_graph": round(te3 / tg3, 2),
                                   "note": "Counter3DModel.forward + backward to 8 logits tensors [32, 18*64, 64, 64] (4 cameras x real/pseudo image)"}
     assert to3 < te3
     print("\n[incumbent]", json.dumps(out))

@@ -22,7 +22,7 @@ import torch
 
 from . import evalops, ops, skeleton
 
-__all__ = ["Counter3DModel", "Counter3DDisc", "cal_links"]
+__all__ = ["Counter3DModel", "Counter3DDisc", "GraphedLossGraph", "cal_links"]
 
 cal_links = skeleton.cal_links
 _CAM_FIELDS = ("trans_image", "pelvis", "k_mat", "trans_world", "rot_world")
@@ -82,12 +82,12 @@ class Counter3DModel(torch.nn.Module):
                     w_kp2d=sym_w["kp_2d"] if sym_w is not None and "kp_2d" in sym_w else None, reduction="batch", group=None)
                 loss_sym = loss_sym + ls
             kps_ori[cam_key], kps_world_ori[cam_key] = kps, world
-            output["pose_2d_pred_{}_ori".format(cam_key)] = kps.detach()[[0], 0, ...].clone()
+            output["pose_2d_pred_{}_ori".format(cam_key)] = kps.detach()[0:1, 0, ...].clone()
             output["depth_map_{}".format(cam_key)] = depth_map
             output["pose_3d_depth_{}".format(cam_key)] = world.detach()[:, 0, ...].clone()
 
         if not mono:
-            output["kp_gt_world"] = ops.convert_patch_to_world(x["cam_0_joints"], x, "cam_0", is_norm=False)[[0], ...]
+            output["kp_gt_world"] = ops.convert_patch_to_world(x["cam_0_joints"], x, "cam_0", is_norm=False)[0:1, ...]
 
         # skeleton mask of hypothesis 0 (model.py:88-96), fused with the reconstruction loss when that is configured (:181-190)
         reconstructed, loss_rec = {}, 0
@@ -134,11 +134,11 @@ class Counter3DModel(torch.nn.Module):
                     lp, _, _, kps, _, _, _ = ops.integral_reproj_min_loss(logits, gt, _cams(x, cam_key), K, NH, NS, img_hw=img_hw,
                                                                           rect_width=2000.0, w_mse=1.0, reduction="batch", group=None)
                 loss_pseudo = loss_pseudo + lp
-                output["pose_2d_pred_{}_pseudo".format(cam_key)] = kps.detach()[[0], 0, ...].clone()
+                output["pose_2d_pred_{}_pseudo".format(cam_key)] = kps.detach()[0:1, 0, ...].clone()
                 output["pose_3d_pred_{}_pseudo".format(cam_key)] = ops.convert_patch_to_world(
-                    kps.detach()[:, 0, ...], x, cam_key, is_norm=True, RECT_WIDTH=256, mono=True, patch=False)[[0], ...]
+                    kps.detach()[:, 0, ...], x, cam_key, is_norm=True, RECT_WIDTH=256, mono=True, patch=False)[0:1, ...]
                 output["pose_3d_gt_{}_pseudo".format(cam_key)] = ops.convert_patch_to_world(
-                    gt, x, cam_key, is_norm=True, RECT_WIDTH=256, mono=True, patch=False)[[0], ...]
+                    gt, x, cam_key, is_norm=True, RECT_WIDTH=256, mono=True, patch=False)[0:1, ...]
             loss_values["smpl_pseudo_img"] = loss_pseudo * cfg["smpl_pseudo_img_loss"]["weight"]
 
         if "physique_recons_loss" in cfg and self.physique_network is not None:
@@ -147,7 +147,7 @@ class Counter3DModel(torch.nn.Module):
             for cam_id in cam_id_list:
                 cam_key = "cam_{}".format(cam_id)
                 phy = self.physique_network(reconstructed[cam_key])
-                output["mask_physique_{}".format(cam_key)] = phy.detach()[[0], ...]
+                output["mask_physique_{}".format(cam_key)] = phy.detach()[0:1, ...]
                 loss_phy = loss_phy + skeleton.compute_mask_reconstruction_loss(
                     phy, x["{}_mask".format(cam_key)], weight=x["{}_geodesic_dis".format(cam_key)] if use_dis_map else None)
             loss_values["physique_recons"] = loss_phy * cfg["physique_recons_loss"]["weight"]
@@ -186,13 +186,61 @@ class Counter3DDisc(torch.nn.Module):
             pred_joints, _ = regressor(x["{}_img".format(cam_key)])
             smpl_joints = x["{}_pseudo_joints".format(cam_key)]
             smpl_joints_world = ops.convert_patch_to_world(smpl_joints, x, cam_key, is_norm=True, RECT_WIDTH=256, mono=True, patch=False)
-            output["pose_smpl_2d_{}".format(cam_key)] = smpl_joints[[0], ...]
-            output["pose_smpl_3d_{}".format(cam_key)] = smpl_joints_world[[0], ...].clone()
+            output["pose_smpl_2d_{}".format(cam_key)] = smpl_joints[0:1, ...]
+            output["pose_smpl_3d_{}".format(cam_key)] = smpl_joints_world[0:1, ...].clone()
             B, NH = pred_joints.shape[:2]
             pred_logits = self.smpl_discriminator(pred_joints.detach()[..., :dim].flatten(0, 1).contiguous()).reshape(B, NH, -1)
             smpl_logits = self.smpl_discriminator(smpl_joints[..., :dim])
-            output["smpl_logits_{}".format(cam_key)] = smpl_logits[[0], ...]
-            output["pred_logits_{}".format(cam_key)] = pred_logits[[0], 0, ...]
+            output["smpl_logits_{}".format(cam_key)] = smpl_logits[0:1, ...]
+            output["pred_logits_{}".format(cam_key)] = pred_logits[0:1, 0, ...]
             loss_disc = loss_disc + evalops.compute_disc_loss(pred_logits, smpl_logits)
         loss_disc = loss_disc * self.loss_config["smpl_disc_loss"]["weight"]
         return loss_disc, output
+
+
+class GraphedLossGraph:
+    """`Counter3DModel.forward` + backward of `sum(v.mean() for v in loss_values.values())` (train.py:182-184) captured once
+    into a CUDA graph.  At the reference's batch size (32 per GPU, 4 cameras) the loss graph is a few dozen short launches
+    and the step is bound by the host issuing them; replaying it as one graph removes that.
+
+        g = GraphedLossGraph(model, x, smpl_discriminator)       # x: the data-loader dict (tensors are cloned into static buffers)
+        g.x['cam_0_img'].detach().copy_(new_logits) ...          # refresh the static inputs in place
+        loss_values = g()                                        # replay; g.grads[key] = d total / d x[key] for the '*_img' tensors
+
+    Every tensor of `x` whose key ends in '_img' is treated as a differentiable input (it is what the backbone produces in
+    the real pipeline); parameters of `smpl_discriminator` do not receive gradients here (the reference detaches its input
+    in this pass, model.py:128)."""
+
+    def __init__(self, model: "Counter3DModel", x, smpl_discriminator, warmup: int = 3):
+        dev = next(v.device for v in x.values() if torch.is_tensor(v))
+        self.x = {k: (v.detach().clone() if torch.is_tensor(v) else v) for k, v in x.items()}
+        self.leaves = [k for k, v in self.x.items() if torch.is_tensor(v) and k.endswith("_img") and v.is_floating_point()]
+        for k in self.leaves:
+            self.x[k].requires_grad_(True)
+
+        def run():
+            for k in self.leaves:
+                self.x[k].grad = None
+            loss_values, output = model(self.x, smpl_discriminator)
+            total = sum(v.mean() for v in loss_values.values())
+            total.backward()
+            return loss_values, output, total
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            for _ in range(max(1, warmup)):
+                run()
+        torch.cuda.current_stream(dev).wait_stream(side)
+        for k in self.leaves:
+            self.x[k].grad = None
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            loss_values, output, total = run()
+        self.loss_values = {k: v.detach() for k, v in loss_values.items()}
+        self.output = output
+        self.total = total.detach()
+        self.grads = {k: self.x[k].grad for k in self.leaves}
+
+    def __call__(self):
+        self.graph.replay()
+        return self.loss_values
