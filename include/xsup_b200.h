@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define XSUP_ABI_VERSION 8
+#define XSUP_ABI_VERSION 9
 
 enum { XSUP_F32 = 0, XSUP_BF16 = 1 };
 enum { XSUP_HEAD_MULTI = 0, XSUP_HEAD_SINGLE = 1 };
@@ -132,7 +132,7 @@ int xsup_reproj_loss_fwd(const float* kps, const float* target, const xsup_cam_t
                          float* sample_terms, float* partial, const xsup_loss_cfg_t* cfg, void* stream);
 
 /* The one exchange step of the path when the batch is sharded over GPUs and the winner is chosen on the
- * GLOBAL batch: all-reduce(SUM) of `partial[n]` (n <= 48 floats) done by ONE kernel over NVLink peer memory.
+ * GLOBAL batch: all-reduce(SUM) of `partial[n]` (n <= XSUP_XCHG_SLOT-1 floats: [XSUP_LOSS_TERMS, NH] for every NH the head accepts) done by ONE kernel over NVLink peer memory.
  * Every rank owns a zero-initialised mailbox of xsup_xchg_floats(world) floats that all peers have mapped
  * (e.g. torch symmetric memory); `peer_bufs` is a DEVICE array of the `world` mailbox addresses as seen from
  * this process (own included).  The kernel stores its partial sums into slot [step&1][rank] of every mailbox
@@ -149,7 +149,7 @@ typedef struct {
                       * takes the sequence number as ++(*seq) and `step` is ignored: the call can then be captured in
                       * a CUDA graph and replayed (a by-value step would repeat).  All ranks must make the same calls. */
 } xsup_xchg_t;
-#define XSUP_XCHG_SLOT 64
+#define XSUP_XCHG_SLOT 1024   /* floats per (parity, source rank) slot: n data floats + the flag in the last word */
 size_t xsup_xchg_floats(int32_t world);
 int xsup_partial_allreduce(float* partial, int32_t n, const xsup_xchg_t* x, void* stream);
 

@@ -26,14 +26,14 @@ def test_library_exports_every_declared_symbol(cabi):
     assert declared == set(cabi.SYMBOLS)
     for name in declared:
         assert hasattr(cabi.lib, name), name
-    assert cabi.lib.xsup_abi_version() == cabi.ABI_VERSION == 8
+    assert cabi.lib.xsup_abi_version() == cabi.ABI_VERSION == 9
 
 
 def test_struct_layouts_match_header(cabi):
     assert C.sizeof(cabi.Shape) == 9 * 4
     assert C.sizeof(cabi.Cam) == 5 * C.sizeof(C.c_void_p)
     assert C.sizeof(cabi.LossCfg) == 13 * 4
-    assert C.sizeof(cabi.Xchg) == 32 and cabi.lib.xsup_xchg_floats(8) == 2 * 8 * 64
+    assert C.sizeof(cabi.Xchg) == 32 and cabi.lib.xsup_xchg_floats(8) == 2 * 8 * 1024
 
 
 def test_skeleton_structs_and_validation(cabi):

@@ -13,7 +13,7 @@ from conftest import ROOT
 
 pytestmark = pytest.mark.gpu
 
-B, K, R, NH, NS = 8, 18, 32, 3, 15
+B, K, R, NS = 8, 18, 32, 15
 W = dict(w_mse=1.0, w_bone=0.1, w_kp=0.1, w_kp2d=0.0)
 
 
@@ -21,7 +21,7 @@ def _inputs(synth):
     return (synth.blob_logits(B, K, R, R, R, seed=101), synth.pseudo_joints(B, K, seed=102), synth.cameras(B, seed=103))
 
 
-def _worker(rank, world, port, out, transport):
+def _worker(rank, world, port, out, transport, NH):
     sys.path.insert(0, ROOT)
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
@@ -59,14 +59,15 @@ def _worker(rank, world, port, out, transport):
 
 
 @pytest.mark.timeout(300)
-@pytest.mark.parametrize("transport", ["nvlink", "nccl"])
-def test_two_gpus_global_scope_equals_single_gpu(synth, tmp_path, transport):
+@pytest.mark.parametrize("transport,NH", [("nvlink", 3), ("nccl", 3), ("nvlink", 16), ("nvlink", 30)])
+def test_two_gpus_global_scope_equals_single_gpu(synth, tmp_path, transport, NH):
+    """NH = 16 and D-2 = 30: the exchanged [4, NH] partial sums no longer fit one 64-float line (mailbox slots hold 1023)."""
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
     import __graft_entry__ as ge
     ge.build()
-    world, port = 2, 29500 + (os.getpid() * 2 + (transport == "nccl")) % 2000
-    mp.spawn(_worker, args=(world, port, str(tmp_path), transport), nprocs=world, join=True)
+    world, port = 2, 29500 + (os.getpid() * 4 + (transport == "nccl") + NH) % 2000
+    mp.spawn(_worker, args=(world, port, str(tmp_path), transport, NH), nprocs=world, join=True)
     res = [torch.load(os.path.join(str(tmp_path), "rank%d.pt" % r), weights_only=False) for r in range(world)]
 
     pkg = importlib.import_module("x-as-supervision_b200")

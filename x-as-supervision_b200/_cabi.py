@@ -154,7 +154,7 @@ def _load():
 
 
 lib = _load()
-ABI_VERSION = 8
+ABI_VERSION = 9
 if lib.xsup_abi_version() != ABI_VERSION:
     raise ImportError("libxsup_b200.so ABI version %d, expected %d: rebuild with __graft_entry__.build()"
                       % (lib.xsup_abi_version(), ABI_VERSION))

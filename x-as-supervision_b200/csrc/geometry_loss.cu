@@ -271,11 +271,14 @@ __global__ void __launch_bounds__(64) partial_allreduce_kernel(float* __restrict
     __syncthreads();
     const uint32_t step = s_step;
     const size_t par = step & 1u;
-    if (t < world) {                                   // one thread per destination GPU
-        float* dst = static_cast<float*>(peers[t]) + (par * world + rank) * XSUP_XCHG_SLOT;
-        for (int i = 0; i < n; ++i) dst[i] = partial[i];
-        st_release_sys(reinterpret_cast<uint32_t*>(dst + XSUP_XCHG_SLOT - 1), step);
+    for (int d = 0; d < world; ++d) {                  // publish: coalesced P2P stores into slot [par][rank] of every mailbox
+        float* dst = static_cast<float*>(peers[d]) + (par * world + rank) * XSUP_XCHG_SLOT;
+        for (int i = t; i < n; i += 64) dst[i] = partial[i];
     }
+    __threadfence_system();
+    __syncthreads();
+    if (t < world)                                     // one thread per destination GPU raises that mailbox's flag
+        st_release_sys(reinterpret_cast<uint32_t*>(static_cast<float*>(peers[t]) + (par * world + rank) * XSUP_XCHG_SLOT + XSUP_XCHG_SLOT - 1), step);
     float* mine = static_cast<float*>(peers[rank]) + par * world * XSUP_XCHG_SLOT;
     if (t < world) {                                   // one thread per source GPU
         const uint32_t* flag = reinterpret_cast<const uint32_t*>(mine + (size_t)t * XSUP_XCHG_SLOT + XSUP_XCHG_SLOT - 1);
@@ -286,10 +289,10 @@ __global__ void __launch_bounds__(64) partial_allreduce_kernel(float* __restrict
         }
     }
     __syncthreads();
-    if (t < n) {
+    for (int i = t; i < n; i += 64) {                  // fixed rank order: bit-identical sums on every rank
         float a = 0.f;
-        for (int r = 0; r < world; ++r) a += *reinterpret_cast<volatile float*>(mine + (size_t)r * XSUP_XCHG_SLOT + t);
-        partial[t] = timed_out ? __int_as_float(0x7fc00000) : a;
+        for (int r = 0; r < world; ++r) a += *reinterpret_cast<volatile float*>(mine + (size_t)r * XSUP_XCHG_SLOT + i);
+        partial[i] = timed_out ? __int_as_float(0x7fc00000) : a;
     }
 }
 

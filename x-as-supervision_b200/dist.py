@@ -52,7 +52,7 @@ class PeerExchange:
         self.seq = torch.zeros(1, dtype=torch.int32, device=self.device)
 
     def all_reduce_(self, t: torch.Tensor) -> torch.Tensor:
-        """In-place SUM over the ranks of a small contiguous fp32 CUDA tensor (<= 63 elements)."""
+        """In-place SUM over the ranks of a small contiguous fp32 CUDA tensor (<= XSUP_XCHG_SLOT-1 = 1023 elements)."""
         from . import _cabi as cabi
         if not (t.is_cuda and t.dtype == torch.float32 and t.is_contiguous()):
             raise ValueError("PeerExchange.all_reduce_ needs a contiguous float32 CUDA tensor")
