@@ -41,6 +41,31 @@ __device__ __forceinline__ int take_best_peak(float (&cv)[kMaxD / 32], int lane)
     return bd;
 }
 
+// All NH entries of topk at once: the position of every candidate in the order (value desc, bin asc) is the number of
+// bins that precede it, counted against all D bins with one shuffle per bin.  ~D*(2 + 3*ceil(D/32)) issue slots whatever NH
+// is, against ~250 per hypothesis for the serial selection above; same total order, so the same bins.
+// NJ = ceil(D/32) is a template parameter: predicated-off compares of unused register slots still take issue slots, and
+// this warp shares its scheduler with four streaming warps.
+template <int NJ>
+__device__ __forceinline__ void rank_peaks(const float (&cv)[kMaxD / 32], int NH, int lane, int* bins) {
+    int rank[NJ];
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) rank[j] = 0;
+#pragma unroll
+    for (int jj = 0; jj < NJ; ++jj) {
+#pragma unroll 8
+        for (int l = 0; l < 32; ++l) {
+            const float ov = __shfl_sync(0xffffffffu, cv[jj], l);
+            const int od = l + 32 * jj;
+#pragma unroll
+            for (int j = 0; j < NJ; ++j) rank[j] += (ov > cv[j] || (ov == cv[j] && od < lane + 32 * j)) ? 1 : 0;
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < NJ; ++j)
+        if (cv[j] >= 0.0f && rank[j] < NH) bins[rank[j]] = lane + 32 * j;      // bins >= D carry -1 and are never chosen
+}
+
 // ----------------------------------------------------------------------------------------------
 // Unit epilogue, executed by one full warp.  On entry pz[0..D) in shared memory holds the raw
 // (un-normalised) depth marginal relative to the log2-domain reference `M`; xbar, ybar are the
@@ -89,12 +114,22 @@ __device__ inline void finalise_unit(const FwdParams& p, int unit, float* pz, in
 
     // find_peak (…_multi.py:24-34): non-strict interior local maxima, value-descending top-NH.
     // Candidates with value 0 (non-peaks) fill the remaining slots by ascending bin.
-    // Phase 1 (serial in h, the selection is a dependency chain): the NH peak bins into shared memory.
+    // Phase 1: the NH peak bins into shared memory — serially (arg-max, mark, repeat: a dependency chain of ~250 issue
+    // slots per hypothesis) or, when that would cost more than twice the all-at-once ranking, by rank.  At 32^3 with
+    // NH = 16 the serial chain (~4 000 cycles) was as long as streaming the 128 KB unit.
     float cv[kMaxD / 32];
     peak_candidates(pz, D, lane, cv);
-    for (int h = 0; h < NH; ++h) {
-        const int bd = take_best_peak(cv, lane);
-        if (lane == 0) bins[h] = bd;
+    const int nj = (D + 31) >> 5;
+    if (125 * NH > D * (2 + 3 * nj)) {
+        if (nj == 1) rank_peaks<1>(cv, NH, lane, bins);
+        else if (nj == 2) rank_peaks<2>(cv, NH, lane, bins);
+        else if (nj <= 4) rank_peaks<4>(cv, NH, lane, bins);
+        else rank_peaks<kMaxD / 32>(cv, NH, lane, bins);
+    } else {
+        for (int h = 0; h < NH; ++h) {
+            const int bd = take_best_peak(cv, lane);
+            if (lane == 0) bins[h] = bd;
+        }
     }
     __syncwarp();
     // Phase 2 (one lane per hypothesis, no shuffles): windowed depth expectation (…_multi.py:57-62): zero-padded,
