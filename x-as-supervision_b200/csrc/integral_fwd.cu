@@ -6,13 +6,13 @@
 // over the volume and materialises the probabilities; this kernel reads every logit from HBM
 // exactly once and writes O(D) floats per (b,k) unit.
 //
-// Structure (one persistent CTA per SM, 18 warps):
+// Structure (one persistent CTA per SM, 19 warps):
 //   warp 16      producer : 1-D bulk async copies (TMA, UBLKCP) global -> smem ring, mbarrier tx-count
 //   warps 0..15  consumers: 4 warps per ring stage, one 512*U-byte "task" each; LDS.128 into
 //                registers, early release of the slot, warp-uniform running max (CREDUX.MAX.F32),
 //                one MUFU.EX2 per element, per-lane column accumulators (x), row-weighted sum (y),
 //                per-task depth-slice sum (pz)
-//   warp 17      finaliser: log-sum-exp combine of the per-task/per-warp partials, peaks, top-NH,
+//   warps 17,18  finalisers (even / odd units): log-sum-exp combine of the per-task/per-warp partials, peaks, top-NH,
 //                window depth, outputs + saved-for-backward stats; overlaps the next unit's stream
 #include "xsup_internal.h"
 #include "xsup_finalise.cuh"
@@ -36,9 +36,9 @@ __global__ void __launch_bounds__(kFwdThreads, 1) integral_fwd_kernel(const FwdP
     uint8_t* ring = smem;
     float2* pz_table = reinterpret_cast<float2*>(smem + (size_t)nst * t.stage_bytes);   // [2][TU] (m, sum)
     float4* unit_part = reinterpret_cast<float4*>(pz_table + 2 * TU);                   // [2][kConsumerWarps][2]
-    float* pz_final = reinterpret_cast<float*>(unit_part + 4 * kConsumerWarps);         // [kMaxD]
-    int* peak_bins = reinterpret_cast<int*>(pz_final + kMaxD);                          // [kMaxD]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(peak_bins + kMaxD);
+    float* pz_final = reinterpret_cast<float*>(unit_part + 4 * kConsumerWarps);         // [2][kMaxD]
+    int* peak_bins = reinterpret_cast<int*>(pz_final + 2 * kMaxD);                      // [2][kMaxD]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(peak_bins + 2 * kMaxD);
     volatile int2* hdr = reinterpret_cast<volatile int2*>(bars + 2 * kMaxStages + 4);   // [nst] (unit, stage in unit)
     const uint32_t full0 = smem_u32(bars), empty0 = full0 + 8u * nst;
     const uint32_t pfull0 = empty0 + 8u * nst, pempty0 = pfull0 + 16u;
@@ -92,10 +92,14 @@ __global__ void __launch_bounds__(kFwdThreads, 1) integral_fwd_kernel(const FwdP
                 mbar_arrive(full0 + 8u * slot);
             }
         }
-    } else if (warp == kConsumerWarps + 1) {
-        // ------------------------------------------------------------------ finaliser
-        for (int it = 0;; ++it) {
-            const int buf = it & 1;
+    } else if (warp > kConsumerWarps) {
+        // ------------------------------------------------------------------ finalisers
+        // two warps, one per partial buffer: the first takes this CTA's even units, the second the odd ones, so a
+        // unit's epilogue may last two unit-streaming times before it stalls the ring (64 KB bf16 units stream in 1.4 us)
+        const int buf = warp - kConsumerWarps - 1;
+        float* pz_mine = pz_final + buf * kMaxD;
+        int* bins_mine = peak_bins + buf * kMaxD;
+        for (int it = buf;; it += 2) {
             mbar_wait(pfull0 + 8u * buf, (it >> 1) & 1);
             float4 up = make_float4(kNegHuge, 0.f, 0.f, 0.f), uq = make_float4(0.f, 0.f, 0.f, 0.f);
             if (lane < kConsumerWarps) {
@@ -116,11 +120,11 @@ __global__ void __launch_bounds__(kFwdThreads, 1) integral_fwd_kernel(const FwdP
                     const float2 e = tab[d * t.parts + q];
                     a = fmaf(e.y, ex2(e.x - M), a);
                 }
-                pz_final[d] = a;
+                pz_mine[d] = a;
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(pempty0 + 8u * buf);      // partial buffers may be refilled
-            finalise_unit(p, unit, pz_final, peak_bins, M, xbar, ybar, lane);
+            finalise_unit(p, unit, pz_mine, bins_mine, M, xbar, ybar, lane);
             __syncwarp();
         }
     } else {
@@ -226,13 +230,15 @@ __global__ void __launch_bounds__(kFwdThreads, 1) integral_fwd_kernel(const FwdP
                 fresh = true;
             }
         }
-        // end of stream: pass the sentinel on to the finaliser
-        const int buf = it & 1;
-        if (it >= 2) mbar_wait(pempty0 + 8u * buf, ((it >> 1) - 1) & 1);
-        if (lane == 0) {
-            unit_part[(buf * kConsumerWarps + warp) * 2] = make_float4(kNegHuge, 0.f, 0.f, 0.f);
-            unit_part[(buf * kConsumerWarps + warp) * 2 + 1] = make_float4(0.f, 0.f, __int_as_float(-1), 0.f);
-            mbar_arrive(pfull0 + 8u * buf);
+        // end of stream: pass the sentinel on to both finalisers (the next use of either buffer)
+        for (int e = 0; e < 2; ++e) {
+            const int ie = it + e, buf = ie & 1;
+            if (ie >= 2) mbar_wait(pempty0 + 8u * buf, ((ie >> 1) - 1) & 1);
+            if (lane == 0) {
+                unit_part[(buf * kConsumerWarps + warp) * 2] = make_float4(kNegHuge, 0.f, 0.f, 0.f);
+                unit_part[(buf * kConsumerWarps + warp) * 2 + 1] = make_float4(0.f, 0.f, __int_as_float(-1), 0.f);
+                mbar_arrive(pfull0 + 8u * buf);
+            }
         }
     }
 }
@@ -339,7 +345,7 @@ cudaError_t launch_integral_fwd(FwdParams p, bool fast, int dtype, int num_sms, 
         return cudaGetLastError();
     }
     const size_t fixed = (size_t)2 * p.t.tasks_per_unit * sizeof(float2) + 4 * kConsumerWarps * sizeof(float4) +
-                         2 * kMaxD * sizeof(float) + (size_t)(2 * kMaxStages + 4) * 8 + (size_t)kMaxStages * sizeof(int2);
+                         4 * kMaxD * sizeof(float) + (size_t)(2 * kMaxStages + 4) * 8 + (size_t)kMaxStages * sizeof(int2);
     int nst = (int)((kSmemBudget - fixed) / p.t.stage_bytes);
     nst = nst > kMaxStages ? kMaxStages : nst;
     // A slot must always be consumed by the same warp group (slot = s % nst, group = s % kGroups): a waiter

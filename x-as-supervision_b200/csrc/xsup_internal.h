@@ -4,7 +4,7 @@
 
 namespace xsup {
 
-constexpr int kFwdThreads = (kConsumerWarps + 2) * 32;   // 16 consumers + producer + finaliser
+constexpr int kFwdThreads = (kConsumerWarps + 3) * 32;   // 16 consumers + producer + 2 finalisers (even / odd units)
 constexpr int kBwdThreads = (kConsumerWarps + 1) * 32;   // 16 consumers + producer
 constexpr size_t kSmemBudget = 227 * 1024;               // per-CTA opt-in maximum on sm_100
 constexpr int kMaxStages = 16;
