@@ -1,0 +1,133 @@
+"""Randomised pin of the CPU oracle against the reference itself, imported live from /root/reference.
+
+The committed goldens (tests/golden/*.npz) fix a handful of seeds and shapes; this file draws many more and compares,
+in fp64, every stage of the path with what the UNMODIFIED reference modules compute on the same tensors.  It only runs
+where the reference checkout exists (the build container); on the GPU box it skips — nothing there reads the reference.
+CPU only, a few seconds."""
+import importlib.util
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import ROOT, rel_inf
+
+REF = os.environ.get("XSUP_REFERENCE", "/root/reference")
+pytestmark = pytest.mark.skipif(not os.path.isdir(os.path.join(REF, "modules")), reason="reference checkout not present")
+
+
+@pytest.fixture(scope="module")
+def ref():
+    spec = importlib.util.spec_from_file_location("xsup_make_golden", os.path.join(ROOT, "tests", "golden", "make_golden.py"))
+    mg = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mg)
+    multi, single, util, lf = mg.load_reference()
+    return dict(mg=mg, multi=multi, single=single, util=util, lf=lf)
+
+
+def _shapes(n, seed):
+    rng = np.random.RandomState(seed)
+    out = []
+    for i in range(n):
+        R = int(rng.choice([8, 12, 16, 24]))
+        NH = int(rng.choice([1, 2, 3, 5]))
+        NS = int(rng.choice([1, 3, 7, 15]))
+        out.append((int(rng.randint(1, 4)), int(rng.choice([3, 17, 18])), R, min(NH, R - 2), NS, 1000 + 17 * i + seed))
+    return out
+
+
+def _num_peaks(logits, B, K, R):
+    p = torch.softmax(logits.double().view(B, K, -1), 2).view(B, K, R, R, R)
+    pz = p.sum(dim=(3, 4))
+    mid = pz[..., 1:-1]
+    return ((mid >= pz[..., :-2]) & (mid >= pz[..., 2:])).sum(-1)
+
+
+@pytest.mark.parametrize("B,K,R,NH,NS,seed", _shapes(10, 1))
+@pytest.mark.parametrize("gen", ["iid_logits", "blob_logits"])
+def test_head_forward_and_backward(ref, oracle, synth, gen, B, K, R, NH, NS, seed):
+    """…_multi.py:66-88 and its autograd, against oracle.integral_multi and the closed-form backward (App. A.2)."""
+    logits = getattr(synth, gen)(B, K, R, R, R, seed=seed).double()
+    gw = torch.randn(B, NH, K, 3, generator=torch.Generator().manual_seed(seed), dtype=torch.float64)
+
+    def go():
+        det = ref["multi"].KPDetector3DMulti("resnet_multi", K, R, NH, NS)
+        x = logits.clone().requires_grad_(True)
+        kps, dmap = det(x)
+        with torch.no_grad():
+            p = torch.softmax(x.detach().view(B, K, -1), 2).view(B, K, R, R, R)
+            idx = det.find_peak(p.sum(dim=3).sum(dim=3))
+        (kps * gw).sum().backward()
+        return kps.detach(), dmap.detach(), idx, x.grad
+    r_kps, r_dmap, r_idx, r_grad = ref["mg"].run_in(torch.float64, go)
+
+    kps, dmap, idx = oracle.integral_multi(logits, K, NH, NS)
+    defined = (torch.arange(NH)[None, None, :] < _num_peaks(logits, B, K, R)[..., None])      # [B,K,NH]
+    assert torch.equal(idx[defined], r_idx[defined])                                           # bit-exact where defined
+    assert rel_inf(dmap.numpy(), r_dmap.numpy()) < 1e-12
+    m = defined.permute(0, 2, 1)[..., None].expand_as(kps)
+    assert (kps - r_kps)[m].abs().max().item() < 1e-12
+    assert (kps[..., :2] - r_kps[..., :2]).abs().max().item() < 1e-12
+    if bool(defined.all()):
+        closed = oracle.integral_multi_backward(logits, gw, K, NH, NS)
+        assert rel_inf(closed.numpy(), r_grad.numpy()) < 1e-10
+
+
+@pytest.mark.parametrize("B,K,seed,mpi", [(1, 17, 5, False), (4, 18, 6, True), (7, 3, 7, False), (2, 25, 8, True)])
+def test_geometry_both_directions(ref, oracle, synth, B, K, seed, mpi):
+    """util.py:61-168: patch -> world, its inverse, the mono branch."""
+    util = ref["util"]
+    cams = {k: v.double() for k, v in synth.cameras(B, seed=seed, mpi=mpi).items()}
+    params = synth.camera_dict(cams, "cam_0")
+    kps = synth.pseudo_joints(B, K, seed=seed + 1).double()
+    r_world = util.convert_patch_to_world(kps, params, "cam_0", is_norm=True)
+    r_back = util.convert_world_to_patch(r_world, params, "cam_0", is_norm=True)
+    world = oracle.patch_to_world(kps, cams)
+    assert rel_inf(world.numpy(), r_world.numpy()) < 1e-12
+    assert rel_inf(oracle.world_to_patch(r_world, cams).numpy(), r_back.numpy()) < 1e-10
+    r_raw = util.convert_patch_to_world(kps, params, "cam_0", is_norm=False)
+    assert rel_inf(oracle.patch_to_world(kps, cams, is_norm=False).numpy(), r_raw.numpy()) < 1e-12
+
+
+@pytest.mark.parametrize("B,K,R,NH,NS,seed", [(2, 17, 32, 3, 15, 31), (3, 18, 32, 2, 7, 32), (1, 17, 24, 3, 3, 33), (4, 18, 12, 1, 15, 34)])
+@pytest.mark.parametrize("weights", [(3.0, None, None, None), (1.0, 0.1, 0.1, 0.0), (1.0, 0.1, 0.1, 0.5)])
+def test_fused_loss_and_gradient(ref, oracle, synth, B, K, R, NH, NS, seed, weights):
+    """model.py:71-79,105-114,158-162 driven with the reference's own functions, against oracle.fused_forward + autograd."""
+    multi, util, lf = ref["multi"], ref["util"], ref["lf"]
+    w_mse, w_bone, w_kp, w_kp2d = weights
+    logits = synth.iid_logits(B, K, R, R, R, seed=seed).double()
+    if int(_num_peaks(logits, B, K, R).min()) < NH:
+        pytest.skip("a row has fewer than NH depth peaks: the reference's loss rides on topk's order among tied zeros")
+    target = synth.pseudo_joints(B, K, seed=seed + 2).double()
+    cams = {k: v.double() for k, v in synth.cameras(B, seed=seed + 3).items()}
+    params = synth.camera_dict(cams, "cam_0")
+    use_sym = any(w is not None for w in (w_bone, w_kp, w_kp2d))
+
+    def go():
+        det = multi.KPDetector3DMulti("resnet_multi", K, R, NH, NS)
+        x = logits.clone().requires_grad_(True)
+        kps, _ = det(x)
+        world = torch.stack([util.convert_patch_to_world(kps[:, i], params, "cam_0", is_norm=True) for i in range(NH)], dim=1)
+        lp = torch.min(torch.stack([lf.compute_supervision(kps[:, i], target) for i in range(NH)])) * w_mse
+        ls = torch.zeros((), dtype=torch.float64)
+        if use_sym:
+            sym = []
+            for i in range(NH):
+                t = lf.compute_bone_sym_loss(world[:, i]) * (w_bone or 0.0) + lf.compute_kp_sym_loss(world[:, i]) * (w_kp or 0.0)
+                if w_kp2d is not None:
+                    t = t + lf.compute_kp_sym_loss(kps[:, i, :, :2], is_3D=False) * 1e2 * w_kp2d
+                sym.append(t)
+            ls = torch.min(torch.stack(sym))
+        (lp + ls).backward()
+        return lp.detach(), ls.detach(), x.grad
+    r_lp, r_ls, r_grad = ref["mg"].run_in(torch.float64, go)
+
+    x = logits.clone().requires_grad_(True)
+    out = oracle.fused_forward(x, K, NH, NS, target, cams, w_mse=w_mse, w_bone=w_bone, w_kp=w_kp, w_kp2d=w_kp2d, reduction="batch")
+    lp, ls = out[0], out[1]
+    (lp + ls).backward()
+    assert abs(lp.item() - r_lp.item()) <= 1e-12 * max(abs(r_lp.item()), 1e-30)
+    assert abs(ls.item() - r_ls.item()) <= 1e-12 * max(abs(r_ls.item()), 1e-30)
+    assert rel_inf(x.grad.numpy(), r_grad.numpy()) < 1e-10
