@@ -131,3 +131,83 @@ def test_fused_loss_and_gradient(ref, oracle, synth, B, K, R, NH, NS, seed, weig
     assert abs(lp.item() - r_lp.item()) <= 1e-12 * max(abs(r_lp.item()), 1e-30)
     assert abs(ls.item() - r_ls.item()) <= 1e-12 * max(abs(r_ls.item()), 1e-30)
     assert rel_inf(x.grad.numpy(), r_grad.numpy()) < 1e-10
+
+
+# --------------------------------------------------------------------------------------------- widening rows
+@pytest.mark.parametrize("B,K,S,seed,extension", [(1, 18, 40, 51, True), (2, 18, 64, 52, False), (3, 18, 36, 53, True), (2, 18, 100, 54, True)])
+def test_skeleton_rasteriser_and_mask_loss(ref, oracle, synth, B, K, S, seed, extension):
+    """util.py:21-59 -> model.py:94 -> loss_func.py:4-16 in its four (weight, use_clip) variants, values and keypoint gradients."""
+    util, lf = ref["util"], ref["lf"]
+    model = importlib.import_module("modules.model")
+    parent, child = model.cal_links(list(synth.H36M_PARENTS), line_select_ids=list(synth.LINE_SELECT), use_root=False, extension=extension)
+    assert (list(parent), list(child)) == tuple(map(list, oracle.skeleton_links(synth.H36M_PARENTS, synth.LINE_SELECT, extension=extension)))
+    pose = synth.skeleton_pose2d(B, K, seed=seed).double()
+    gt = synth.silhouette_mask(synth.skeleton_pose2d(B, K, seed=seed + 1, jitter=0.03), S).double()
+    wmap = synth.geodesic_weight(gt.float(), seed=seed + 2).double()
+    G = torch.randn(B, 1, S, S, generator=torch.Generator().manual_seed(seed), dtype=torch.float64)
+
+    def run(draw, loss_fn, take_max):
+        kp = pose.clone().requires_grad_(True)
+        heat = draw(kp)
+        recon = take_max(kp, heat)
+        res = {"heat": heat.detach(), "recon": recon.detach()}
+        res["g_recon"], = torch.autograd.grad((recon * G).sum(), kp, retain_graph=True)
+        for vname, use_w, clip in (("mse", False, False), ("clip", False, True), ("w", True, False), ("wclip", True, True)):
+            loss = loss_fn(recon, gt, weight=wmap if use_w else None, use_clip=clip)
+            res["shape_" + vname] = tuple(loss.shape)
+            res["loss_" + vname] = loss.mean().detach()
+            res["g_" + vname], = torch.autograd.grad(loss.mean(), kp, retain_graph=True)
+        return res
+    r = ref["mg"].run_in(torch.float64, lambda: run(lambda kp: util.draw_lines(kp, S, parent, child, synth.BODY_WIDTH),
+                                                    lf.compute_mask_reconstruction_loss,
+                                                    lambda kp, heat: torch.max(heat.clone(), dim=1, keepdim=True)[0]))
+    o = run(lambda kp: oracle.draw_lines(kp, S, parent, child, synth.BODY_WIDTH), oracle.mask_recon_loss,
+            lambda kp, heat: oracle.skeleton_mask(kp, S, parent, child, synth.BODY_WIDTH))
+    for k in r:
+        if k.startswith("shape_"):
+            assert o[k] == r[k], k
+            continue
+        # weight=None + use_clip rides through an fp32 mask in the reference even in its fp64 run (loss_func.py:9-10)
+        tol = 2e-5 if k.endswith("_clip") else 1e-10
+        assert rel_inf(o[k].numpy(), r[k].numpy()) < tol, k
+
+
+@pytest.mark.parametrize("B,NH,K,V,seed", [(3, 3, 18, 4, 61), (5, 2, 17, 2, 62), (2, 5, 18, 3, 63)])
+def test_eval_selection_triangulation_and_disc_loss(ref, oracle, synth, B, NH, K, V, seed):
+    """eval.py:122-148 with eval_utils.switch_points / per_act_mse, util.triangulation, loss_func.compute_disc_loss."""
+    util, lf = ref["util"], ref["lf"]
+    eu = ref["mg"].load_eval_utils()
+    kps, jp = (t.double() for t in synth.eval_predictions(B, NH, K, seed=seed))
+    kp_gt = jp.clone()
+    kp_gt[..., :2] = kp_gt[..., :2] / (256.0 - 1) * 2 - 1
+    kp_gt[..., 2] = kp_gt[..., 2] / (256.0 - 1)
+    kd, k2 = kps.clone(), kps.clone()[..., :2]
+    tr = None
+    for h in range(NH):
+        k2[:, h, ...], _ = eu.switch_points(k2[:, h, ...], kp_gt[..., :2])
+        kd[:, h, ...], tr = eu.switch_points(kd[:, h, ...], kp_gt, switch_all=False)
+    best_idx = (kd - kp_gt[:, None, ...]).pow(2).sum(dim=-1).argmin(dim=1)
+    kbest = torch.gather(kd, 1, best_idx[:, None, :, None].expand(-1, -1, -1, 3)).squeeze(1)
+    best_2d_idx = (k2 - kp_gt[:, None, ..., :2]).pow(2).sum(dim=-1).argmin(dim=1)
+    k2best = torch.gather(k2, 1, best_2d_idx[:, None, :, None].expand(-1, -1, -1, 2)).squeeze(1)
+    o3, o2, otr, oerr, obi, ob2, _ = oracle.eval_select(kps, jp, 256.0, "best")
+    assert torch.equal(obi, best_idx) and torch.equal(ob2, best_2d_idx) and torch.equal(otr, tr)
+    assert torch.equal(o3, kbest) and torch.equal(o2, k2best)
+    assert rel_inf(oerr.numpy(), eu.per_act_mse(k2best, kp_gt[..., :2]).numpy()) < 1e-12
+
+    gen = torch.Generator().manual_seed(400 + seed)
+    world = torch.randn(B, K, 3, generator=gen, dtype=torch.float64) * 300
+    cams = [{k: v.double() for k, v in synth.cameras(B, seed=seed + 10 + i).items()} for i in range(V)]
+    params, kd3 = {}, {}
+    for i, c in enumerate(cams):
+        params.update(synth.camera_dict(c, "cam_%d" % i))
+        kd3["cam_%d" % i] = util.convert_world_to_patch(world, params, "cam_%d" % i, is_norm=True) \
+            + 0.002 * torch.randn(B, K, 3, generator=gen, dtype=torch.float64)
+    r_tri = ref["mg"].run_in(torch.float64, lambda: util.triangulation(kd3, params, list(range(V))))
+    tri = oracle.triangulate([kd3["cam_%d" % i] for i in range(V)], cams)
+    assert (tri - r_tri.double()).abs().max().item() < 1e-3        # mm; the reference stores through a float32 buffer (util.py:226)
+
+    p2, g2 = torch.randn(B, 1, generator=gen, dtype=torch.float64), torch.randn(B, 1, generator=gen, dtype=torch.float64)
+    p3, g3 = torch.randn(B, NH, 1, generator=gen, dtype=torch.float64), torch.randn(B, NH, 1, generator=gen, dtype=torch.float64)
+    for a, b in ((p2, None), (p3, None), (p2, g2), (p3, g3), (p3, g2)):
+        assert abs(float(oracle.disc_loss(a, b)) - float(lf.compute_disc_loss(a, b))) < 1e-12
