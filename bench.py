@@ -89,17 +89,19 @@ def cpu_step_fn(c, B, threads):
     return step
 
 
-def time_cpu(c, steps, warmup, B=CPU_SAMPLE_B):
+def time_cpu(c, steps, warmup, B=CPU_SAMPLE_B, min_seconds=0.0, max_steps=400):
+    """Median step time of the CPU port over `steps` steps, continued until `min_seconds` of timed work (bounded by
+    `max_steps`).  Returns (samples/s, threads, median seconds per step, steps timed)."""
     threads = os.cpu_count() or 1
     step = cpu_step_fn(c, B, threads)
     for _ in range(warmup):
         step()
     ts = []
-    for _ in range(steps):
+    while len(ts) < steps or (sum(ts) < min_seconds and len(ts) < max_steps):
         t0 = time.perf_counter()
         step()
         ts.append(time.perf_counter() - t0)
-    return B / statistics.median(ts), threads, statistics.median(ts)
+    return B / statistics.median(ts), threads, statistics.median(ts), len(ts)
 
 
 def run_reference(args, c):
@@ -108,7 +110,7 @@ def run_reference(args, c):
         return 0
     steps = max(1, min(args.steps, 10))
     warmup = max(1, min(args.warmup, 2))
-    v, threads, t = time_cpu(c, steps, warmup)
+    v, threads, t, _ = time_cpu(c, steps, warmup)
     sample = "B=%d of the workload per step (%s, K=%d, %d^3, NH=%d), torch CPU fp32 port of the reference ops, %d steps" % (
         CPU_SAMPLE_B, c["dtype"], c["K"], c["R"], c["NH"], steps)
     line = {"impl": "reference", "metric": METRIC, "value": round(v, 2), "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
@@ -426,10 +428,10 @@ def finish(args, c, rank, world, dev, B, K, R, NH, ms, k_fwd, k_bwd, value, laun
         if getattr(args, "graph_info", None):
             line["cuda_graph_replay"] = args.graph_info
         if world == 1 and not args.no_cpu:
-            v, threads, t = time_cpu(c, 3, 1)
+            v, threads, t, n_cpu = time_cpu(c, 3, 1, min_seconds=10.0)
             line["cpu_baseline"] = {"value": round(v, 2), "unit": UNIT, "cores": threads, "kind": "port",
                                     "sample": "B=%d (BASELINE configs[0]) of the same workload, torch CPU fp32 port of the reference ops, "
-                                              "median of 3 after 1 warm-up, %.2f s per step" % (CPU_SAMPLE_B, t)}
+                                              "median of %d steps (10 s of CPU work) after 1 warm-up, %.2f s per step" % (CPU_SAMPLE_B, n_cpu, t)}
         else:
             line["cpu_baseline"] = None
         print(json.dumps(line), flush=True)
