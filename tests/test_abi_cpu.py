@@ -36,6 +36,20 @@ def test_struct_layouts_match_header(cabi):
     assert C.sizeof(cabi.Xchg) == 32 and cabi.lib.xsup_xchg_floats(8) == 2 * 8 * 1024
 
 
+def test_exchange_slot_holds_the_partial_sums_of_every_accepted_shape():
+    """The mailbox slot (data + flag word) is sized from the ABI's own limits: [XSUP_LOSS_TERMS, NH] with NH <= D-2 <= kMaxD-2.
+    (ABI v8 held 63 floats and global scope failed at NH = 16.)"""
+    import re
+    from conftest import ROOT
+    import os
+    hdr = open(os.path.join(ROOT, "include", "xsup_b200.h")).read()
+    common = open(os.path.join(ROOT, "x-as-supervision_b200", "csrc", "xsup_common.cuh")).read()
+    slot = int(re.search(r"#define\s+XSUP_XCHG_SLOT\s+(\d+)", hdr).group(1))
+    terms = int(re.search(r"#define\s+XSUP_LOSS_TERMS\s+(\d+)", hdr).group(1))
+    max_d = int(re.search(r"constexpr int kMaxD = (\d+);", common).group(1))
+    assert slot - 1 >= terms * (max_d - 2)
+
+
 def test_skeleton_structs_and_validation(cabi):
     assert C.sizeof(cabi.Skel) == (7 + 2 * cabi.MAX_LINES) * 4
     assert C.sizeof(cabi.MaskLoss) == 16
