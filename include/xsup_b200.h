@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define XSUP_ABI_VERSION 9
+#define XSUP_ABI_VERSION 10
 
 enum { XSUP_F32 = 0, XSUP_BF16 = 1 };
 enum { XSUP_HEAD_MULTI = 0, XSUP_HEAD_SINGLE = 1 };
@@ -121,6 +121,35 @@ int xsup_patch_to_world_bwd(const float* kps, const float* g_world, const xsup_c
 int xsup_world_to_patch_fwd(const float* world, const xsup_cam_t* cam, float* kps, int32_t B, int32_t J,
                             int32_t img_h, int32_t img_w, float rect_width, int32_t flags, void* stream);
 
+/* The same geometry stage by stage, with the reference's free parameters (modules/util.py:61-125): every one of
+ * convert_patch_to_image (:61-82), convert_image_to_world (:85-95), convert_image_to_patch (:98-113),
+ * convert_world_to_image (:116-125) and the two composites (:128-152, :155-168) is one call, selected by `flags`:
+ *   XSUP_GEOM_PATCH_STAGE   the patch <-> image stage (crop affine `trans_image`, px <-> mm depth via `depth_scale`, `pelvis`)
+ *   XSUP_GEOM_CAMERA_STAGE  the image <-> world stage (pinhole fx, fy, cx, cy; extrinsics rot_world / trans_world)
+ *   XSUP_GEOM_NORM          is_norm (patch coordinates in [-1,1] / [0,1])        XSUP_GEOM_MONO  util.py:145-150
+ * fx, fy, cx, cy: element b at [b*intr_stride] (1 for the reference's [B,1] tensors; for a k_mat [B,3,3] pass
+ * k_mat+0, k_mat+4, k_mat+2, k_mat+5 with stride 9).  Tensors of a stage that is not selected may be NULL.
+ * `xsup_geom_patch_to_world` runs patch -> image -> world (the selected stages), `xsup_geom_world_to_patch` runs
+ * world -> image -> patch; `in`, `out` are [B,J,3].  The `_vjp` forms take the forward input again plus g_out = d loss / d out
+ * and write g_in = d loss / d in. */
+enum { XSUP_GEOM_NORM = 1, XSUP_GEOM_MONO = 2, XSUP_GEOM_PATCH_STAGE = 4, XSUP_GEOM_CAMERA_STAGE = 8 };
+typedef struct {
+    int32_t B, J;
+    int32_t img_d, img_h, img_w;   /* image_depth, image_height, image_width (util.py:61) */
+    float depth_scale;             /* mm per depth pixel: RECT_WIDTH / image width in the composites (util.py:138) */
+    int32_t flags;
+    int32_t intr_stride;
+    const float* trans_image;      /* [B,2,3] */
+    const float* pelvis;           /* [B,3]   */
+    const float* fx; const float* fy; const float* cx; const float* cy;
+    const float* trans_world;      /* [B,3]   */
+    const float* rot_world;        /* [B,3,3] */
+} xsup_geom_t;
+int xsup_geom_patch_to_world(const float* in, float* out, const xsup_geom_t* g, void* stream);
+int xsup_geom_patch_to_world_vjp(const float* in, const float* g_out, float* g_in, const xsup_geom_t* g, void* stream);
+int xsup_geom_world_to_patch(const float* in, float* out, const xsup_geom_t* g, void* stream);
+int xsup_geom_world_to_patch_vjp(const float* in, const float* g_out, float* g_in, const xsup_geom_t* g, void* stream);
+
 /* Replaces the per-hypothesis Python loops of modules/model.py:71-79,105-114,158-162 and the loss
  * primitives modules/base_losses/loss_func.py:18-52 for one camera.
  *   kps      [B,NH,K,3]  from xsup_integral_fwd        target [B,K,3] pseudo joints
@@ -148,6 +177,9 @@ typedef struct {
     uint32_t* seq;   /* DEVICE counter (zero-initialised, private to this rank) or NULL.  When given, the kernel itself
                       * takes the sequence number as ++(*seq) and `step` is ignored: the call can then be captured in
                       * a CUDA graph and replayed (a by-value step would repeat).  All ranks must make the same calls. */
+    uint32_t* err;   /* DEVICE word (zero-initialised) or NULL: set to 1, and never cleared, when a wait for a peer timed
+                      * out.  The sums of that call are NaN and the mailboxes are out of step from then on: the host
+                      * must check the word (it costs a read-back, so not on every step) and rebuild the exchange. */
 } xsup_xchg_t;
 #define XSUP_XCHG_SLOT 1024   /* floats per (parity, source rank) slot: n data floats + the flag in the last word */
 size_t xsup_xchg_floats(int32_t world);
@@ -163,6 +195,33 @@ int xsup_reproj_select(const float* kps, const float* target, const float* sampl
  * receive gradient (torch.min semantics; exact ties resolve to the lowest slot).              */
 int xsup_reproj_loss_bwd(const float* kps, const float* target, const xsup_cam_t* cam, const int64_t* sel,
                          const float* g_loss, float* g_kps, const xsup_loss_cfg_t* cfg, void* stream);
+
+/* The three calls above (and the exchange between them) as ONE launch: per-(sample, hypothesis) world lift + loss
+ * terms, then the last CTA to finish forms the fixed-order batch sums, all-reduces them over NVLink peer memory when
+ * `xchg` is given (reduction 'batch'; for 'sample' / 'joint' it is the reported loss that is summed over ranks) and
+ * selects the slots.  Bit-identical to xsup_reproj_loss_fwd -> [xsup_partial_allreduce] -> xsup_reproj_select.
+ *   xchg    NULL (rank-local selection, what the reference does under DDP) or the mailbox description
+ *   ticket  one zero-initialised DEVICE word; the kernel leaves it zero again.  xsup_integral_fwd zeroes the
+ *           XSUP_SCHED_WORDS ints that follow the statistics (stats + B*K*xsup_stats_stride): word 0 is its own
+ *           work-claim counter, word 1 is free for this ticket. */
+#define XSUP_SCHED_WORDS 16
+int xsup_reproj_fused_fwd(const float* kps, const float* target, const xsup_cam_t* cam, float* world, float* sample_terms,
+                          float* partial, float* loss, int64_t* sel, const xsup_loss_cfg_t* cfg, const xsup_xchg_t* xchg,
+                          uint32_t* ticket, void* stream);
+
+/* Backward of the fused per-camera op up to the coefficient blocks of the streaming head backward, as ONE launch:
+ * xsup_reproj_loss_bwd, the sum with upstream gradients on kps / kps_world, and xsup_integral_coef, without writing
+ * d loss / d kps to HBM.  Follow it with xsup_integral_bwd_apply.
+ *   g_lp, g_ls   DEVICE scalars d L / d loss_pseudo, d L / d loss_sym (NULL = 0)
+ *   g_kps_in     [B,NH,K,3] upstream gradient on kps (e.g. from the skeleton rasteriser, model.py:91) or NULL
+ *   g_world      [B,NH,K,3] upstream gradient on kps_world (e.g. the generator loss with use_aug, model.py:138) or NULL
+ *   stats        from xsup_integral_fwd;  coef_ws [xsup_coef_floats] out;  g_kps_out [B,NH,K,3] out or NULL */
+int xsup_reproj_fused_bwd(const float* kps, const float* target, const xsup_cam_t* cam, const int64_t* sel, const float* g_lp,
+                          const float* g_ls, const float* g_kps_in, const float* g_world, const float* stats, float* coef_ws,
+                          float* g_kps_out, const xsup_loss_cfg_t* cfg, const xsup_shape_t* s, void* stream);
+/* The streaming half of xsup_integral_bwd: coefficient blocks (from xsup_reproj_fused_bwd or xsup_integral_coef) ->
+ * g_logits in one read + one write of the volume. */
+int xsup_integral_bwd_apply(const void* logits, const float* coef_ws, void* g_logits, const xsup_shape_t* s, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Skeleton rasteriser + mask-reconstruction loss.
@@ -241,7 +300,7 @@ int xsup_mask_loss_bwd(const float* mask, const float* gt, const float* weight, 
  *   gt_norm [B,K,3].  is_trans, err2d, best_idx, best_2d_idx, gt_norm may be NULL.  K <= 32. */
 typedef struct {
     int32_t B, NH, K;
-    float img_size;            /* Eval.img_size (eval.py:72), 256 */
+    float img_size;            /* Eval.img_size (eval.py:72), 256; 0 = `joints_px` is already normalised (switch_points on its own, eval_utils.py:7) */
     int32_t best;              /* 1: mode 'best', 0: 'confident' */
     int32_t perm[32];
 } xsup_eval_t;
@@ -314,6 +373,10 @@ int xsup_pose_term_fwd(const float* x, const float* gt, const float* feature_sha
                        int32_t K, int32_t C, float* sample_ws, float* loss, void* stream);
 int xsup_pose_term_bwd(const float* x, const float* gt, const float* feature_shape, int32_t term, int32_t flag, int32_t B,
                        int32_t K, int32_t C, const float* g_loss, float* g_x, void* stream);
+/* compute_supervision(..., mode='none') (loss_func.py:46-47, nn.MSELoss(reduction='none')): out [B,K,C] = (x' - gt)^2 with
+ * x' the optionally feature_shape-rescaled x.  g_out == NULL: forward; else out = g_out * d out / d x (the VJP). */
+int xsup_pose_sqerr(const float* x, const float* gt, const float* feature_shape, int32_t B, int32_t K, int32_t C,
+                    const float* g_out, float* out, void* stream);
 
 #ifdef __cplusplus
 }

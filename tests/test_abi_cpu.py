@@ -26,14 +26,74 @@ def test_library_exports_every_declared_symbol(cabi):
     assert declared == set(cabi.SYMBOLS)
     for name in declared:
         assert hasattr(cabi.lib, name), name
-    assert cabi.lib.xsup_abi_version() == cabi.ABI_VERSION == 9
+    assert cabi.lib.xsup_abi_version() == cabi.ABI_VERSION == 10
+    assert int(re.search(r"#define\s+XSUP_ABI_VERSION\s+(\d+)", header).group(1)) == cabi.ABI_VERSION
+
+
+def test_python_constants_match_the_header_defines(cabi):
+    """A stale Python copy of a protocol constant under-allocates silently (XCHG_SLOT once said 64 against 1024)."""
+    header = open(os.path.join(ROOT, "include", "xsup_b200.h")).read()
+
+    def define(name):
+        return int(re.search(r"#define\s+%s\s+(\d+)" % name, header).group(1))
+    assert cabi.XCHG_SLOT == define("XSUP_XCHG_SLOT")
+    assert cabi.LOSS_TERMS == define("XSUP_LOSS_TERMS")
+    assert cabi.MAX_LINES == define("XSUP_MAX_LINES")
+    assert cabi.MAX_VIEWS == define("XSUP_MAX_VIEWS")
+    assert cabi.MASK_SUMS == define("XSUP_MASK_SUMS")
+    assert cabi.SCHED_WORDS == define("XSUP_SCHED_WORDS")
+    assert cabi.lib.xsup_xchg_floats(3) == 2 * 3 * cabi.XCHG_SLOT
+    enum = re.search(r"enum \{ XSUP_GEOM_NORM = (\d+), XSUP_GEOM_MONO = (\d+), XSUP_GEOM_PATCH_STAGE = (\d+), XSUP_GEOM_CAMERA_STAGE = (\d+) \}", header)
+    assert tuple(int(v) for v in enum.groups()) == (cabi.GEOM_NORM, cabi.GEOM_MONO, cabi.GEOM_PATCH_STAGE, cabi.GEOM_CAMERA_STAGE)
+    assert (cabi.FLAG_NORM, cabi.FLAG_MONO, cabi.FLAG_PATCH) == (cabi.GEOM_NORM, cabi.GEOM_MONO, cabi.GEOM_PATCH_STAGE)
 
 
 def test_struct_layouts_match_header(cabi):
     assert C.sizeof(cabi.Shape) == 9 * 4
     assert C.sizeof(cabi.Cam) == 5 * C.sizeof(C.c_void_p)
     assert C.sizeof(cabi.LossCfg) == 13 * 4
-    assert C.sizeof(cabi.Xchg) == 32 and cabi.lib.xsup_xchg_floats(8) == 2 * 8 * 1024
+    assert C.sizeof(cabi.Xchg) == 40 and cabi.lib.xsup_xchg_floats(8) == 2 * 8 * 1024
+    assert C.sizeof(cabi.Geom) == 8 * 4 + 8 * C.sizeof(C.c_void_p)
+
+
+def test_geometry_stage_validation(cabi):
+    buf = (C.c_float * 64)()
+    p = C.addressof(buf)
+    g = cabi.Geom(2, 4, 256, 256, 256, 7.8125, cabi.GEOM_NORM | cabi.GEOM_PATCH_STAGE, 1)
+    assert cabi.lib.xsup_geom_patch_to_world(p, p, g, None) == -3               # patch stage without trans_image / pelvis
+    g.trans_image, g.pelvis = p, p
+    g.depth_scale = 0.0
+    assert cabi.lib.xsup_geom_world_to_patch(p, p, g, None) == -1               # depth_scale must be positive
+    g = cabi.Geom(2, 4, 2, 2, 2, 1.0, cabi.GEOM_CAMERA_STAGE, 1)
+    assert cabi.lib.xsup_geom_world_to_patch(p, p, g, None) == -3               # camera stage without intrinsics
+    g = cabi.Geom(2, 4, 2, 2, 2, 1.0, 64, 1)
+    assert cabi.lib.xsup_geom_patch_to_world(p, p, g, None) == -1               # unknown flag bit
+    g = cabi.Geom(0, 4, 2, 2, 2, 1.0, 0, 1)
+    assert cabi.lib.xsup_geom_patch_to_world(None, None, g, None) == 0          # empty batch: no-op
+    g = cabi.Geom(2, 4, 2, 2, 2, 1.0, 0, 1)
+    assert cabi.lib.xsup_geom_patch_to_world_vjp(p, None, p, g, None) == -3     # VJP without the upstream gradient
+
+
+def test_fused_loss_validation(cabi):
+    buf = (C.c_float * 64)()
+    p = C.addressof(buf)
+    cam = cabi.Cam(p, p, p, p, p)
+    cfg = cabi.LossCfg(4, 18, 3, 256, 256, 2000.0, 1.0, 0, 0, 0, 0, 0, 4)
+    assert cabi.lib.xsup_reproj_fused_fwd(p, p, cam, p, p, p, p, p, cfg, None, None, None) == -3        # no ticket word
+    x = cabi.Xchg(None, 0, 2, 0, p, p)
+    assert cabi.lib.xsup_reproj_fused_fwd(p, p, cam, p, p, p, p, p, cfg, x, p, None) == -3           # exchange without mailboxes
+    x = cabi.Xchg(p, 2, 2, 0, p, p)
+    assert cabi.lib.xsup_reproj_fused_fwd(p, p, cam, p, p, p, p, p, cfg, x, p, None) == -1           # rank outside [0, world)
+    s = cabi.make_shape(4, 17, 64, 64, 64, 3, 15, torch.float32)
+    assert cabi.lib.xsup_reproj_fused_bwd(p, p, cam, p, None, None, None, None, p, p, None, cfg, s, None) == -1   # K disagrees
+    s = cabi.make_shape(4, 18, 64, 64, 64, 3, 15, torch.float32, cabi.HEAD_SINGLE)
+    s.NH = 1
+    assert cabi.lib.xsup_reproj_fused_bwd(p, p, cam, p, None, None, None, None, p, p, None, cfg, s, None) == -1   # single head
+    s = cabi.make_shape(4, 18, 64, 64, 64, 3, 15, torch.float32)
+    assert cabi.lib.xsup_integral_bwd_apply(None, p, p, s, None) == -3
+    assert cabi.lib.xsup_pose_sqerr(p, None, None, 2, 18, 3, None, p, None) == -3                       # no ground truth
+    cfg_e = cabi.Eval(4, 3, 18, 0.5, 1)
+    assert cabi.lib.xsup_eval_select(p, p, cfg_e, p, p, None, None, None, None, None, None) == -1       # img_size in (0, 1]
 
 
 def test_exchange_slot_holds_the_partial_sums_of_every_accepted_shape():

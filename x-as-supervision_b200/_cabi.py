@@ -35,13 +35,18 @@ SYMBOLS = (
     "xsup_disc_min_loss_fwd", "xsup_disc_min_loss_bwd",
     "xsup_conv_head_fwd", "xsup_pack_nhwc_bf16", "xsup_integral_coef", "xsup_conv_head_bwd_g",
     "xsup_pose_term_fwd", "xsup_pose_term_bwd",
+    # ABI v10
+    "xsup_geom_patch_to_world", "xsup_geom_patch_to_world_vjp", "xsup_geom_world_to_patch", "xsup_geom_world_to_patch_vjp",
+    "xsup_reproj_fused_fwd", "xsup_reproj_fused_bwd", "xsup_integral_bwd_apply", "xsup_pose_sqerr",
 )
+GEOM_NORM, GEOM_MONO, GEOM_PATCH_STAGE, GEOM_CAMERA_STAGE = 1, 2, 4, 8
+SCHED_WORDS = 16
 TERM_MSE, TERM_BONE, TERM_KP = 0, 1, 2
 MAX_VIEWS = 8
 MAX_LINES = 32
 MASK_MSE, MASK_CLIP_MEAN, MASK_WEIGHTED = 0, 1, 2
 MASK_SUMS = 4
-XCHG_SLOT = 64
+XCHG_SLOT = 1024      # floats per (parity, source rank) mailbox slot: XSUP_XCHG_SLOT
 
 
 class Shape(C.Structure):
@@ -79,7 +84,15 @@ class Tri(C.Structure):
 
 
 class Xchg(C.Structure):
-    _fields_ = [("peer_bufs", C.c_void_p), ("rank", C.c_int32), ("world", C.c_int32), ("step", C.c_uint32), ("seq", C.c_void_p)]
+    _fields_ = [("peer_bufs", C.c_void_p), ("rank", C.c_int32), ("world", C.c_int32), ("step", C.c_uint32), ("seq", C.c_void_p),
+                ("err", C.c_void_p)]
+
+
+class Geom(C.Structure):
+    _fields_ = [("B", C.c_int32), ("J", C.c_int32), ("img_d", C.c_int32), ("img_h", C.c_int32), ("img_w", C.c_int32),
+                ("depth_scale", C.c_float), ("flags", C.c_int32), ("intr_stride", C.c_int32),
+                ("trans_image", C.c_void_p), ("pelvis", C.c_void_p), ("fx", C.c_void_p), ("fy", C.c_void_p), ("cx", C.c_void_p),
+                ("cy", C.c_void_p), ("trans_world", C.c_void_p), ("rot_world", C.c_void_p)]
 
 
 def _load():
@@ -137,6 +150,20 @@ def _load():
     lib.xsup_integral_coef.restype = C.c_int
     lib.xsup_conv_head_bwd_g.argtypes = [vp, vp, vp, vp, vp, vp, C.POINTER(Shape), i32, vp]
     lib.xsup_conv_head_bwd_g.restype = C.c_int
+    gp = C.POINTER(Geom)
+    lib.xsup_geom_patch_to_world.argtypes = [vp, vp, gp, vp]
+    lib.xsup_geom_patch_to_world_vjp.argtypes = [vp, vp, vp, gp, vp]
+    lib.xsup_geom_world_to_patch.argtypes = [vp, vp, gp, vp]
+    lib.xsup_geom_world_to_patch_vjp.argtypes = [vp, vp, vp, gp, vp]
+    lib.xsup_reproj_fused_fwd.argtypes = [vp, vp, C.POINTER(Cam), vp, vp, vp, vp, vp, C.POINTER(LossCfg), C.POINTER(Xchg), vp, vp]
+    lib.xsup_reproj_fused_bwd.argtypes = [vp, vp, C.POINTER(Cam), vp, vp, vp, vp, vp, vp, vp, vp, C.POINTER(LossCfg),
+                                          C.POINTER(Shape), vp]
+    lib.xsup_integral_bwd_apply.argtypes = [vp, vp, vp, C.POINTER(Shape), vp]
+    lib.xsup_pose_sqerr.argtypes = [vp, vp, vp, i32, i32, i32, vp, vp, vp]
+    for name in ("xsup_geom_patch_to_world", "xsup_geom_patch_to_world_vjp", "xsup_geom_world_to_patch",
+                 "xsup_geom_world_to_patch_vjp", "xsup_reproj_fused_fwd", "xsup_reproj_fused_bwd", "xsup_integral_bwd_apply",
+                 "xsup_pose_sqerr"):
+        getattr(lib, name).restype = C.c_int
     lib.xsup_eval_select.argtypes = [vp, vp, C.POINTER(Eval), vp, vp, vp, vp, vp, vp, vp, vp]
     lib.xsup_triangulate.argtypes = [C.POINTER(Tri), vp, vp]
     lib.xsup_root_centre_fwd.argtypes = [vp, vp, i32, i32, i32, i32, vp]
@@ -154,7 +181,7 @@ def _load():
 
 
 lib = _load()
-ABI_VERSION = 9
+ABI_VERSION = 10
 if lib.xsup_abi_version() != ABI_VERSION:
     raise ImportError("libxsup_b200.so ABI version %d, expected %d: rebuild with __graft_entry__.build()"
                       % (lib.xsup_abi_version(), ABI_VERSION))

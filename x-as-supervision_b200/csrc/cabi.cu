@@ -125,7 +125,8 @@ int xsup_integral_fwd(const void* logits, float* kps, float* depth_prob_map, int
     p.counter = reinterpret_cast<int*>(stats + (size_t)p.n_units * p.stats_stride);
     const bool fast = make_tiling(*s, p.t);
     cudaError_t e = cudaSuccess;
-    if (fast) e = cudaMemsetAsync(p.counter, 0, sizeof(int), (cudaStream_t)stream);
+    // all XSUP_SCHED_WORDS: word 0 is the work-claim counter, word 1 the ticket of xsup_reproj_fused_fwd
+    e = cudaMemsetAsync(p.counter, 0, kSchedWords * sizeof(int), (cudaStream_t)stream);
     if (e != cudaSuccess) return cuda_fail(e, "xsup_integral_fwd counter reset");
     e = launch_integral_fwd(p, fast, s->dtype, sms, (cudaStream_t)stream);
     if (e != cudaSuccess) return cuda_fail(e, "xsup_integral_fwd launch");
@@ -159,6 +160,25 @@ int xsup_integral_bwd(const void* logits, const float* stats, const float* g_kps
     return XSUP_OK;
 }
 
+int xsup_integral_bwd_apply(const void* logits, const float* coef_ws, void* g_logits, const xsup_shape_t* s, void* stream) {
+    if (int rc = check_shape(s)) return rc;
+    if (s->B == 0) return XSUP_OK;
+    if (!logits || !g_logits || !coef_ws) return fail(XSUP_E_NULL, "xsup_integral_bwd_apply: NULL pointer");
+    if (!aligned16(logits) || !aligned16(g_logits) || !aligned16(coef_ws))
+        return fail(XSUP_E_ALIGN, "xsup_integral_bwd_apply: logits/g_logits/coef_ws must be 16-byte aligned");
+    int sms = 0;
+    if (int rc = device_info(sms)) return rc;
+    BwdParams p{};
+    p.logits = logits; p.coef = coef_ws; p.g_logits = g_logits;
+    p.n_units = s->B * s->K; p.coef_stride = (int)coef_stride(*s);
+    p.counter = reinterpret_cast<int*>(const_cast<float*>(coef_ws) + (size_t)p.n_units * p.coef_stride);   // zeroed by the coefficient kernel
+    const bool fast = make_tiling(*s, p.t);
+    cudaError_t e = launch_integral_bwd(p, fast, s->dtype, sms, (cudaStream_t)stream);
+    if (e != cudaSuccess) return cuda_fail(e, "xsup_integral_bwd_apply launch");
+    count_launches(1);
+    return XSUP_OK;
+}
+
 int xsup_find_peak(const float* pz, int64_t* idx, int32_t rows, int32_t D, int32_t NH, void* stream) {
     if (!pz || !idx) return fail(XSUP_E_NULL, "xsup_find_peak: NULL pointer");
     if (rows < 0 || D < 3 || D > kMaxD || NH < 1 || NH > D - 2) return fail(XSUP_E_SHAPE, "xsup_find_peak: need 3 <= D <= %d and 1 <= NH <= D-2", kMaxD);
@@ -176,48 +196,80 @@ static int check_cam(const xsup_cam_t* cam, const char* who) {
     return XSUP_OK;
 }
 
-static int geom_params(GeomParams& g, const xsup_cam_t* cam, int B, int J, int img_h, int img_w, float rect_width, int flags,
-                       const char* who) {
+// ---- geometry: one validated description, four entry points + the three round-1 wrappers
+static int check_geom(const xsup_geom_t* g, const char* who) {
+    if (!g) return fail(XSUP_E_NULL, "%s: geometry description is NULL", who);
+    if (g->B < 0 || g->J <= 0) return fail(XSUP_E_SHAPE, "%s: bad sizes (B=%d J=%d)", who, g->B, g->J);
+    if (g->flags & ~(XSUP_GEOM_NORM | XSUP_GEOM_MONO | XSUP_GEOM_PATCH_STAGE | XSUP_GEOM_CAMERA_STAGE)) return fail(XSUP_E_SHAPE, "%s: unknown flag bits 0x%x", who, g->flags);
+    if (g->flags & XSUP_GEOM_PATCH_STAGE) {
+        if (!g->trans_image || !g->pelvis) return fail(XSUP_E_NULL, "%s: the patch stage needs trans_image and pelvis", who);
+        if (!(g->depth_scale > 0.0f)) return fail(XSUP_E_SHAPE, "%s: depth_scale must be positive", who);
+        if ((g->flags & XSUP_GEOM_NORM) && (g->img_d <= 1 || g->img_h <= 1 || g->img_w <= 1)) return fail(XSUP_E_SHAPE, "%s: image extents must exceed 1", who);
+    }
+    if ((g->flags & XSUP_GEOM_CAMERA_STAGE) && !(g->flags & XSUP_GEOM_MONO)) {
+        if (!g->fx || !g->fy || !g->cx || !g->cy || !g->trans_world || !g->rot_world) return fail(XSUP_E_NULL, "%s: the camera stage needs fx, fy, cx, cy, trans_world, rot_world", who);
+        if (g->intr_stride < 1) return fail(XSUP_E_SHAPE, "%s: intr_stride must be >= 1", who);
+    }
+    return XSUP_OK;
+}
+
+static int run_geom(int dir, const float* in, const float* g_out, float* out, bool vjp, const xsup_geom_t* g, void* stream, const char* who) {
+    if (int rc = check_geom(g, who)) return rc;
+    if (g->B == 0) return XSUP_OK;
+    if (!in || !out || (vjp && !g_out)) return fail(XSUP_E_NULL, "%s: NULL pointer", who);
+    cudaError_t e = launch_geom(dir, in, vjp ? g_out : nullptr, out, *g, (cudaStream_t)stream);
+    if (e != cudaSuccess) return cuda_fail(e, who);
+    count_launches(1);
+    return XSUP_OK;
+}
+
+int xsup_geom_patch_to_world(const float* in, float* out, const xsup_geom_t* g, void* stream) {
+    return run_geom(0, in, nullptr, out, false, g, stream, "xsup_geom_patch_to_world");
+}
+int xsup_geom_patch_to_world_vjp(const float* in, const float* g_out, float* g_in, const xsup_geom_t* g, void* stream) {
+    return run_geom(0, in, g_out, g_in, true, g, stream, "xsup_geom_patch_to_world_vjp");
+}
+int xsup_geom_world_to_patch(const float* in, float* out, const xsup_geom_t* g, void* stream) {
+    return run_geom(1, in, nullptr, out, false, g, stream, "xsup_geom_world_to_patch");
+}
+int xsup_geom_world_to_patch_vjp(const float* in, const float* g_out, float* g_in, const xsup_geom_t* g, void* stream) {
+    return run_geom(1, in, g_out, g_in, true, g, stream, "xsup_geom_world_to_patch_vjp");
+}
+
+// the composites with the data loader's tensors (k_mat instead of fx..cy; depth extent = image width, util.py:137-138)
+static int geom_from_cam(xsup_geom_t& g, const xsup_cam_t* cam, int B, int J, int img_h, int img_w, float rect_width, int flags, const char* who) {
     if (int rc = check_cam(cam, who)) return rc;
     if (B < 0 || J <= 0 || img_h <= 1 || img_w <= 1) return fail(XSUP_E_SHAPE, "%s: bad sizes", who);
-    g.cam = *cam; g.B = B; g.J = J; g.img_h = img_h; g.img_w = img_w; g.flags = flags; g.rect_width = rect_width;
+    g = xsup_geom_t{};
+    g.B = B; g.J = J; g.img_d = img_w; g.img_h = img_h; g.img_w = img_w;
+    g.depth_scale = 1.0f / (float)img_w * rect_width;
+    g.flags = (flags & (XSUP_GEOM_NORM | XSUP_GEOM_MONO | XSUP_GEOM_PATCH_STAGE)) | XSUP_GEOM_CAMERA_STAGE;
+    g.intr_stride = 9;
+    g.trans_image = cam->trans_image; g.pelvis = cam->pelvis;
+    g.fx = cam->k_mat; g.fy = cam->k_mat + 4; g.cx = cam->k_mat + 2; g.cy = cam->k_mat + 5;
+    g.trans_world = cam->trans_world; g.rot_world = cam->rot_world;
     return XSUP_OK;
 }
 
 int xsup_patch_to_world_fwd(const float* kps, const xsup_cam_t* cam, float* world, int32_t B, int32_t J, int32_t img_h,
                             int32_t img_w, float rect_width, int32_t flags, void* stream) {
-    GeomParams g{};
-    if (int rc = geom_params(g, cam, B, J, img_h, img_w, rect_width, flags, "xsup_patch_to_world_fwd")) return rc;
-    if (!kps || !world) return fail(XSUP_E_NULL, "xsup_patch_to_world_fwd: NULL pointer");
-    if (B == 0) return XSUP_OK;
-    cudaError_t e = launch_patch_to_world_fwd(kps, world, g, (cudaStream_t)stream);
-    if (e != cudaSuccess) return cuda_fail(e, "xsup_patch_to_world_fwd launch");
-    count_launches(1);
-    return XSUP_OK;
+    xsup_geom_t g;
+    if (int rc = geom_from_cam(g, cam, B, J, img_h, img_w, rect_width, flags, "xsup_patch_to_world_fwd")) return rc;
+    return run_geom(0, kps, nullptr, world, false, &g, stream, "xsup_patch_to_world_fwd");
 }
 
 int xsup_patch_to_world_bwd(const float* kps, const float* g_world, const xsup_cam_t* cam, float* g_kps, int32_t B, int32_t J,
                             int32_t img_h, int32_t img_w, float rect_width, int32_t flags, void* stream) {
-    GeomParams g{};
-    if (int rc = geom_params(g, cam, B, J, img_h, img_w, rect_width, flags, "xsup_patch_to_world_bwd")) return rc;
-    if (!kps || !g_world || !g_kps) return fail(XSUP_E_NULL, "xsup_patch_to_world_bwd: NULL pointer");
-    if (B == 0) return XSUP_OK;
-    cudaError_t e = launch_patch_to_world_bwd(kps, g_world, g_kps, g, (cudaStream_t)stream);
-    if (e != cudaSuccess) return cuda_fail(e, "xsup_patch_to_world_bwd launch");
-    count_launches(1);
-    return XSUP_OK;
+    xsup_geom_t g;
+    if (int rc = geom_from_cam(g, cam, B, J, img_h, img_w, rect_width, flags, "xsup_patch_to_world_bwd")) return rc;
+    return run_geom(0, kps, g_world, g_kps, true, &g, stream, "xsup_patch_to_world_bwd");
 }
 
 int xsup_world_to_patch_fwd(const float* world, const xsup_cam_t* cam, float* kps, int32_t B, int32_t J, int32_t img_h,
                             int32_t img_w, float rect_width, int32_t flags, void* stream) {
-    GeomParams g{};
-    if (int rc = geom_params(g, cam, B, J, img_h, img_w, rect_width, flags, "xsup_world_to_patch_fwd")) return rc;
-    if (!kps || !world) return fail(XSUP_E_NULL, "xsup_world_to_patch_fwd: NULL pointer");
-    if (B == 0) return XSUP_OK;
-    cudaError_t e = launch_world_to_patch_fwd(world, kps, g, (cudaStream_t)stream);
-    if (e != cudaSuccess) return cuda_fail(e, "xsup_world_to_patch_fwd launch");
-    count_launches(1);
-    return XSUP_OK;
+    xsup_geom_t g;
+    if (int rc = geom_from_cam(g, cam, B, J, img_h, img_w, rect_width, flags | XSUP_GEOM_PATCH_STAGE, "xsup_world_to_patch_fwd")) return rc;
+    return run_geom(1, world, nullptr, kps, false, &g, stream, "xsup_world_to_patch_fwd");
 }
 
 static int check_cfg(const xsup_loss_cfg_t* c, const char* who) {
@@ -243,12 +295,12 @@ int xsup_reproj_loss_fwd(const float* kps, const float* target, const xsup_cam_t
     return XSUP_OK;
 }
 
+static int check_xchg(const xsup_xchg_t* x, int n, const char* who);
 size_t xsup_xchg_floats(int32_t world) { return world > 0 ? (size_t)2 * world * XSUP_XCHG_SLOT : 0; }
 
 int xsup_partial_allreduce(float* partial, int32_t n, const xsup_xchg_t* x, void* stream) {
-    if (!partial || !x || !x->peer_bufs) return fail(XSUP_E_NULL, "xsup_partial_allreduce: NULL pointer");
-    if (n < 1 || n > XSUP_XCHG_SLOT - 1 || x->world < 1 || x->world > 64 || x->rank < 0 || x->rank >= x->world || (x->step == 0 && !x->seq))
-        return fail(XSUP_E_SHAPE, "xsup_partial_allreduce: need 1 <= n <= %d, 1 <= world <= 64, 0 <= rank < world, step >= 1 (or a device sequence counter)", XSUP_XCHG_SLOT - 1);
+    if (!partial || !x) return fail(XSUP_E_NULL, "xsup_partial_allreduce: NULL pointer");
+    if (int rc = check_xchg(x, n, "xsup_partial_allreduce")) return rc;
     cudaError_t e = launch_partial_allreduce(partial, n, *x, (cudaStream_t)stream);
     if (e != cudaSuccess) return cuda_fail(e, "xsup_partial_allreduce launch");
     count_launches(1);
@@ -273,6 +325,52 @@ int xsup_reproj_loss_bwd(const float* kps, const float* target, const xsup_cam_t
     if (cfg->B == 0) return XSUP_OK;
     cudaError_t e = launch_reproj_loss_bwd(kps, target, *cam, sel, g_loss, g_kps, *cfg, (cudaStream_t)stream);
     if (e != cudaSuccess) return cuda_fail(e, "xsup_reproj_loss_bwd launch");
+    count_launches(1);
+    return XSUP_OK;
+}
+
+static int check_xchg(const xsup_xchg_t* x, int n, const char* who) {
+    if (!x->peer_bufs) return fail(XSUP_E_NULL, "%s: peer_bufs is NULL", who);
+    if (n < 1 || n > XSUP_XCHG_SLOT - 1 || x->world < 1 || x->world > 64 || x->rank < 0 || x->rank >= x->world || (x->step == 0 && !x->seq))
+        return fail(XSUP_E_SHAPE, "%s: need 1 <= n <= %d, 1 <= world <= 64, 0 <= rank < world, step >= 1 (or a device sequence counter)", who, XSUP_XCHG_SLOT - 1);
+    return XSUP_OK;
+}
+
+int xsup_reproj_fused_fwd(const float* kps, const float* target, const xsup_cam_t* cam, float* world, float* sample_terms,
+                          float* partial, float* loss, int64_t* sel, const xsup_loss_cfg_t* cfg, const xsup_xchg_t* xchg,
+                          uint32_t* ticket, void* stream) {
+    if (int rc = check_cfg(cfg, "xsup_reproj_fused_fwd")) return rc;
+    if (int rc = check_cam(cam, "xsup_reproj_fused_fwd")) return rc;
+    if (!kps || !target || !world || !sample_terms || !partial || !loss || !sel || !ticket) return fail(XSUP_E_NULL, "xsup_reproj_fused_fwd: NULL pointer");
+    if (cfg->B == 0) return fail(XSUP_E_SHAPE, "xsup_reproj_fused_fwd: empty batch");
+    xsup_xchg_t x{};
+    if (xchg) {
+        if (int rc = check_xchg(xchg, XSUP_LOSS_TERMS * cfg->NH, "xsup_reproj_fused_fwd")) return rc;
+        x = *xchg;
+    }
+    cudaError_t e = launch_reproj_fused_fwd(kps, target, *cam, world, sample_terms, partial, loss, sel, *cfg, x, ticket, (cudaStream_t)stream);
+    if (e != cudaSuccess) return cuda_fail(e, "xsup_reproj_fused_fwd launch");
+    count_launches(1);
+    return XSUP_OK;
+}
+
+int xsup_reproj_fused_bwd(const float* kps, const float* target, const xsup_cam_t* cam, const int64_t* sel, const float* g_lp,
+                          const float* g_ls, const float* g_kps_in, const float* g_world, const float* stats, float* coef_ws,
+                          float* g_kps_out, const xsup_loss_cfg_t* cfg, const xsup_shape_t* s, void* stream) {
+    if (int rc = check_cfg(cfg, "xsup_reproj_fused_bwd")) return rc;
+    if (int rc = check_cam(cam, "xsup_reproj_fused_bwd")) return rc;
+    if (int rc = check_shape(s)) return rc;
+    if (s->head != XSUP_HEAD_MULTI || s->B != cfg->B || s->K != cfg->K || s->NH != cfg->NH)
+        return fail(XSUP_E_SHAPE, "xsup_reproj_fused_bwd: shape and loss cfg disagree (B, K, NH) or the head is not the multi-hypothesis one");
+    if (!kps || !target || !sel || !stats || !coef_ws) return fail(XSUP_E_NULL, "xsup_reproj_fused_bwd: NULL pointer");
+    if (cfg->B == 0) return XSUP_OK;
+    CoefParams c{};
+    c.stats = stats; c.g_kps = nullptr; c.coef = coef_ws;
+    c.n_units = s->B * s->K; c.K = s->K; c.D = s->D; c.H = s->H; c.W = s->W; c.NH = s->NH; c.NS = s->NS; c.head = s->head;
+    c.stats_stride = (int)stats_stride(*s); c.coef_stride = (int)coef_stride(*s);
+    c.counter = reinterpret_cast<int*>(coef_ws + (size_t)c.n_units * c.coef_stride);
+    cudaError_t e = launch_reproj_fused_bwd(kps, target, *cam, sel, g_lp, g_ls, g_kps_in, g_world, g_kps_out, *cfg, c, (cudaStream_t)stream);
+    if (e != cudaSuccess) return cuda_fail(e, "xsup_reproj_fused_bwd launch");
     count_launches(1);
     return XSUP_OK;
 }
@@ -419,7 +517,7 @@ int xsup_eval_select(const float* kps, const float* joints_px, const xsup_eval_t
                      float* err2d, int64_t* best_idx, int64_t* best_2d_idx, float* gt_norm, void* stream) {
     if (!cfg) return fail(XSUP_E_NULL, "xsup_eval_select: cfg is NULL");
     if (cfg->B < 0 || cfg->NH < 1 || cfg->K < 1 || cfg->K > 32) return fail(XSUP_E_SHAPE, "xsup_eval_select: need B >= 0, NH >= 1, 1 <= K <= 32 (one joint per lane)");
-    if (!(cfg->img_size > 1.0f)) return fail(XSUP_E_SHAPE, "xsup_eval_select: img_size must exceed 1");
+    if (!(cfg->img_size > 1.0f) && cfg->img_size != 0.0f) return fail(XSUP_E_SHAPE, "xsup_eval_select: img_size must exceed 1 (or be 0: ground truth already normalised)");
     for (int k = 0; k < cfg->K; ++k)
         if (cfg->perm[k] < 0 || cfg->perm[k] >= cfg->K) return fail(XSUP_E_SHAPE, "xsup_eval_select: perm[%d] = %d outside [0,%d)", k, cfg->perm[k], cfg->K);
     if (cfg->B == 0) return XSUP_OK;
@@ -605,6 +703,19 @@ int xsup_pose_term_bwd(const float* x, const float* gt, const float* feature_sha
     if (!g_loss || !g_x) return fail(XSUP_E_NULL, "xsup_pose_term_bwd: NULL pointer");
     cudaError_t e = launch_pose_term_bwd(p, denom, g_loss, g_x, (cudaStream_t)stream);
     if (e != cudaSuccess) return cuda_fail(e, "xsup_pose_term_bwd launch");
+    count_launches(1);
+    return XSUP_OK;
+}
+
+int xsup_pose_sqerr(const float* x, const float* gt, const float* feature_shape, int32_t B, int32_t K, int32_t C, const float* g_out,
+                    float* out, void* stream) {
+    PoseTermParams p;
+    double denom = 1.0;
+    if (B == 0) return XSUP_OK;
+    if (int rc = pose_term_params(p, denom, x, gt, feature_shape, XSUP_TERM_MSE, 0, B, K, C, "xsup_pose_sqerr")) return rc;
+    if (!out) return fail(XSUP_E_NULL, "xsup_pose_sqerr: NULL pointer");
+    cudaError_t e = launch_pose_sqerr(p, g_out, out, (cudaStream_t)stream);
+    if (e != cudaSuccess) return cuda_fail(e, "xsup_pose_sqerr launch");
     count_launches(1);
     return XSUP_OK;
 }

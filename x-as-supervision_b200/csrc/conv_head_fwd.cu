@@ -450,7 +450,8 @@ static bool make_map(CUtensorMap* map, const void* base, long long rows, int C) 
 template <int KBN, int MODE>
 static cudaError_t launch_kbn(const CUtensorMap& map_w, const CUtensorMap& map_x, const ConvHeadParams& p, int grid, size_t smem, cudaStream_t st) {
     auto kern = conv_head_fwd_kernel<KBN, MODE>;
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    static unsigned long long attr_done = 0;             // per instantiation; one bit per device
+    cudaError_t e = ensure_max_smem(kern, attr_done);
     if (e != cudaSuccess) return e;
     kern<<<grid, kCvThreads, smem, st>>>(map_w, map_x, p);
     return cudaGetLastError();

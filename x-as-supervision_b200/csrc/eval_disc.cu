@@ -26,9 +26,13 @@ __global__ void __launch_bounds__(128) eval_select_kernel(const EvalParams p) {
     float gx = 0.f, gy = 0.f, gz = 0.f;
     if (on) {
         const float* g = p.joints_px + ((size_t)b * K + k) * 3;
-        gx = fmaf(2.0f, __fdiv_rn(g[0], s1), -1.0f);               // eval.py:126-127
-        gy = fmaf(2.0f, __fdiv_rn(g[1], s1), -1.0f);
-        gz = __fdiv_rn(g[2], s1);
+        if (p.img_size > 0.0f) {
+            gx = fmaf(2.0f, __fdiv_rn(g[0], s1), -1.0f);           // eval.py:126-127
+            gy = fmaf(2.0f, __fdiv_rn(g[1], s1), -1.0f);
+            gz = __fdiv_rn(g[2], s1);
+        } else {                                                   // img_size == 0: the ground truth is already normalised
+            gx = g[0]; gy = g[1]; gz = g[2];
+        }
         if (p.gt_norm) {
             float* o = p.gt_norm + ((size_t)b * K + k) * 3;
             o[0] = gx; o[1] = gy; o[2] = gz;
@@ -391,6 +395,23 @@ cudaError_t launch_pose_term_fwd(const PoseTermParams& p, double denom, float* s
 }
 cudaError_t launch_pose_term_bwd(const PoseTermParams& p, double denom, const float* g_loss, float* g_x, cudaStream_t st) {
     pose_term_bwd_kernel<<<(p.B + 127) / 128, 128, 0, st>>>(p, g_loss, (float)(1.0 / denom), g_x);
+    return cudaGetLastError();
+}
+
+// compute_supervision(mode='none') (loss_func.py:46-47, nn.MSELoss(reduction='none')): the element-wise squared error
+// tensor [B,K,C], and its VJP.
+__global__ void __launch_bounds__(256) pose_sqerr_kernel(const PoseTermParams p, const float* __restrict__ g_out, float* __restrict__ out) {
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    if (i >= p.B * p.K * p.C) return;
+    const int c = i % p.C;
+    const float d = pt_scaled(p, p.x[i], c) - p.gt[i];
+    if (!g_out) { out[i] = d * d; return; }
+    const float jac = !p.use_fs ? 1.0f : (c < 2 ? 0.5f * (p.fs[c] - 1.0f) : p.fs[2] - 1.0f);
+    out[i] = g_out[i] * 2.0f * d * jac;
+}
+cudaError_t launch_pose_sqerr(const PoseTermParams& p, const float* g_out, float* out, cudaStream_t st) {
+    const int n = p.B * p.K * p.C;
+    pose_sqerr_kernel<<<(n + 255) / 256, 256, 0, st>>>(p, g_out, out);
     return cudaGetLastError();
 }
 

@@ -110,74 +110,151 @@ __device__ __forceinline__ void patch_to_world_vjp(const Cam& m, const Img& im, 
 }
 
 // ---------------------------------------------------------------------------------------------- standalone geometry
-__global__ void patch_to_world_fwd_kernel(const float* __restrict__ kps, float* __restrict__ world, const GeomParams g) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= g.B * g.J) return;
-    const Cam m = load_cam(g.cam, i / g.J);
-    const Img im = make_img(g.img_h, g.img_w, g.rect_width);
-    float w[3], u, v, Z;
-    patch_to_world(m, im, g.flags, kps[3 * i], kps[3 * i + 1], kps[3 * i + 2], w, u, v, Z);
-    world[3 * i] = w[0]; world[3 * i + 1] = w[1]; world[3 * i + 2] = w[2];
-}
-
-__global__ void patch_to_world_bwd_kernel(const float* __restrict__ kps, const float* __restrict__ g_world,
-                                          float* __restrict__ g_kps, const GeomParams g) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= g.B * g.J) return;
-    const Cam m = load_cam(g.cam, i / g.J);
-    const Img im = make_img(g.img_h, g.img_w, g.rect_width);
-    float w[3], u, v, Z;
-    patch_to_world(m, im, g.flags, kps[3 * i], kps[3 * i + 1], kps[3 * i + 2], w, u, v, Z);
-    const float gw[3] = {g_world[3 * i], g_world[3 * i + 1], g_world[3 * i + 2]};
-    float o[3];
-    patch_to_world_vjp(m, im, g.flags, u, v, Z, gw, o);
-    g_kps[3 * i] = o[0]; g_kps[3 * i + 1] = o[1]; g_kps[3 * i + 2] = o[2];
-}
-
-__global__ void world_to_patch_fwd_kernel(const float* __restrict__ world, float* __restrict__ kps, const GeomParams g) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= g.B * g.J) return;
-    const Cam m = load_cam(g.cam, i / g.J);
-    const Img im = make_img(g.img_h, g.img_w, g.rect_width);
-    const float wx = world[3 * i], wy = world[3 * i + 1], wz = world[3 * i + 2];
-    const float X = m.r[0] * wx + m.r[1] * wy + m.r[2] * wz + m.tw[0];      // util.py:120
-    const float Y = m.r[3] * wx + m.r[4] * wy + m.r[5] * wz + m.tw[1];
-    const float Z = m.r[6] * wx + m.r[7] * wy + m.r[8] * wz + m.tw[2];
-    const float u = X / Z * m.fx + m.cx, v = Y / Z * m.fy + m.cy;          // util.py:122-123
-    float z = (Z - m.pz) / im.ds;                                          // util.py:102-103
-    float x = m.a00 * u + m.a01 * v + m.t0, y = m.a10 * u + m.a11 * v + m.t1;
-    if (g.flags & F_NORM) {                                                // util.py:108-111
-        x = x / im.wm1 * 2.0f - 1.0f;
-        y = y / im.hm1 * 2.0f - 1.0f;
-        z = z / im.dm1;
+// The four stage functions of util.py:61-125 and their two composites (:128-168) are one pair of kernels driven by
+// stage flags: XSUP_GEOM_PATCH_STAGE = patch<->image (crop affine, px<->mm depth), XSUP_GEOM_CAMERA_STAGE =
+// image<->world (pinhole, extrinsics).  Tensors a stage does not need may be NULL.
+__device__ __forceinline__ Cam load_cam_g(const xsup_geom_t& g, int b) {
+    Cam m;
+    m.a00 = m.a11 = m.ai00 = m.ai11 = 1.f; m.a01 = m.a10 = m.ai01 = m.ai10 = 0.f; m.t0 = m.t1 = 0.f; m.pz = 0.f;
+    m.fx = m.fy = 1.f; m.cx = m.cy = 0.f;
+#pragma unroll
+    for (int i = 0; i < 9; ++i) m.r[i] = m.ri[i] = (i % 4 == 0) ? 1.f : 0.f;
+    m.tw[0] = m.tw[1] = m.tw[2] = 0.f;
+    if (g.flags & XSUP_GEOM_PATCH_STAGE) {
+        const float* A = g.trans_image + (size_t)b * 6;
+        m.a00 = A[0]; m.a01 = A[1]; m.t0 = A[2]; m.a10 = A[3]; m.a11 = A[4]; m.t1 = A[5];
+        const float idet = 1.0f / (m.a00 * m.a11 - m.a01 * m.a10);
+        m.ai00 = m.a11 * idet; m.ai01 = -m.a01 * idet; m.ai10 = -m.a10 * idet; m.ai11 = m.a00 * idet;
+        m.pz = g.pelvis[(size_t)b * 3 + 2];
     }
-    kps[3 * i] = x; kps[3 * i + 1] = y; kps[3 * i + 2] = z;
+    if ((g.flags & XSUP_GEOM_CAMERA_STAGE) && !(g.flags & XSUP_GEOM_MONO)) {
+        const size_t is = (size_t)b * g.intr_stride;
+        m.fx = g.fx[is]; m.fy = g.fy[is]; m.cx = g.cx[is]; m.cy = g.cy[is];
+        const float* R = g.rot_world + (size_t)b * 9;
+#pragma unroll
+        for (int i = 0; i < 9; ++i) m.r[i] = R[i];
+        const float c00 = R[4] * R[8] - R[5] * R[7], c01 = R[5] * R[6] - R[3] * R[8], c02 = R[3] * R[7] - R[4] * R[6];
+        const float rdet = 1.0f / (R[0] * c00 + R[1] * c01 + R[2] * c02);
+        m.ri[0] = c00 * rdet; m.ri[1] = (R[2] * R[7] - R[1] * R[8]) * rdet; m.ri[2] = (R[1] * R[5] - R[2] * R[4]) * rdet;
+        m.ri[3] = c01 * rdet; m.ri[4] = (R[0] * R[8] - R[2] * R[6]) * rdet; m.ri[5] = (R[2] * R[3] - R[0] * R[5]) * rdet;
+        m.ri[6] = c02 * rdet; m.ri[7] = (R[1] * R[6] - R[0] * R[7]) * rdet; m.ri[8] = (R[0] * R[4] - R[1] * R[3]) * rdet;
+        const float* T = g.trans_world + (size_t)b * 3;
+        m.tw[0] = T[0]; m.tw[1] = T[1]; m.tw[2] = T[2];
+    }
+    return m;
+}
+__device__ __forceinline__ Img make_img_g(const xsup_geom_t& g) {
+    return Img{(float)(g.img_w - 1), (float)(g.img_h - 1), (float)(g.img_d - 1), g.depth_scale};
+}
+__device__ __forceinline__ int internal_flags(const xsup_geom_t& g) {
+    return ((g.flags & XSUP_GEOM_NORM) ? F_NORM : 0) | ((g.flags & XSUP_GEOM_MONO) ? F_MONO : 0) |
+           ((g.flags & XSUP_GEOM_PATCH_STAGE) ? F_PATCH : 0);
 }
 
-cudaError_t launch_patch_to_world_fwd(const float* kps, float* world, const GeomParams& g, cudaStream_t st) {
-    const int n = g.B * g.J;
-    patch_to_world_fwd_kernel<<<(n + 127) / 128, 128, 0, st>>>(kps, world, g);
-    return cudaGetLastError();
+// world/image -> image/patch (util.py:116-125 then :98-113) and the intermediates its VJP needs
+__device__ __forceinline__ void world_to_patch(const Cam& m, const Img& im, int gflags, float wx, float wy, float wz, float (&o)[3],
+                                               float& X, float& Y, float& Z) {
+    float u = wx, v = wy, zc = wz;
+    X = wx; Y = wy; Z = wz;
+    if (gflags & XSUP_GEOM_CAMERA_STAGE) {
+        X = m.r[0] * wx + m.r[1] * wy + m.r[2] * wz + m.tw[0];               // util.py:120
+        Y = m.r[3] * wx + m.r[4] * wy + m.r[5] * wz + m.tw[1];
+        Z = m.r[6] * wx + m.r[7] * wy + m.r[8] * wz + m.tw[2];
+        u = X / Z * m.fx + m.cx;                                             // util.py:122-123
+        v = Y / Z * m.fy + m.cy;
+        zc = Z;
+    }
+    if (gflags & XSUP_GEOM_PATCH_STAGE) {
+        float z = (zc - m.pz) / im.ds;                                       // util.py:102-103
+        float x = m.a00 * u + m.a01 * v + m.t0, y = m.a10 * u + m.a11 * v + m.t1;
+        if (gflags & XSUP_GEOM_NORM) {                                       // util.py:108-111
+            x = x / im.wm1 * 2.0f - 1.0f;
+            y = y / im.hm1 * 2.0f - 1.0f;
+            z = z / im.dm1;
+        }
+        o[0] = x; o[1] = y; o[2] = z;
+    } else {
+        o[0] = u; o[1] = v; o[2] = zc;
+    }
 }
-cudaError_t launch_patch_to_world_bwd(const float* kps, const float* g_world, float* g_kps, const GeomParams& g,
-                                           cudaStream_t st) {
-    const int n = g.B * g.J;
-    patch_to_world_bwd_kernel<<<(n + 127) / 128, 128, 0, st>>>(kps, g_world, g_kps, g);
-    return cudaGetLastError();
+__device__ __forceinline__ void world_to_patch_vjp(const Cam& m, const Img& im, int gflags, float X, float Y, float Z,
+                                                   const float (&go)[3], float (&gi)[3]) {
+    float gu = go[0], gv = go[1], gz = go[2];
+    if (gflags & XSUP_GEOM_PATCH_STAGE) {
+        float gx = go[0], gy = go[1], gzz = go[2];
+        if (gflags & XSUP_GEOM_NORM) { gx = gx / im.wm1 * 2.0f; gy = gy / im.hm1 * 2.0f; gzz = gzz / im.dm1; }
+        gu = m.a00 * gx + m.a10 * gy;
+        gv = m.a01 * gx + m.a11 * gy;
+        gz = gzz / im.ds;
+    }
+    if (gflags & XSUP_GEOM_CAMERA_STAGE) {
+        const float iz = 1.0f / Z;
+        const float gX = gu * m.fx * iz, gY = gv * m.fy * iz;
+        const float gZ = gz - (gX * X + gY * Y) * iz;
+        gi[0] = m.r[0] * gX + m.r[3] * gY + m.r[6] * gZ;
+        gi[1] = m.r[1] * gX + m.r[4] * gY + m.r[7] * gZ;
+        gi[2] = m.r[2] * gX + m.r[5] * gY + m.r[8] * gZ;
+    } else {
+        gi[0] = gu; gi[1] = gv; gi[2] = gz;
+    }
 }
-cudaError_t launch_world_to_patch_fwd(const float* world, float* kps, const GeomParams& g, cudaStream_t st) {
+
+// dir 0: patch -> world direction (convert_patch_to_image / convert_image_to_world / convert_patch_to_world)
+// dir 1: world -> patch direction (convert_world_to_image / convert_image_to_patch / convert_world_to_patch)
+// g_out == nullptr: forward (out = f(in)); else out = VJP of g_out at `in`.
+template <int DIR>
+__global__ void __launch_bounds__(128) geom_kernel(const float* __restrict__ in, const float* __restrict__ g_out, float* __restrict__ out,
+                                                   const xsup_geom_t g) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= g.B * g.J) return;
+    const Cam m = load_cam_g(g, i / g.J);
+    const Img im = make_img_g(g);
+    const float a = in[3 * i], b = in[3 * i + 1], c = in[3 * i + 2];
+    float o[3];
+    if (DIR == 0) {
+        const int fl = internal_flags(g);
+        float w[3], u, v, Z;
+        if (g.flags & XSUP_GEOM_CAMERA_STAGE) {
+            patch_to_world(m, im, fl, a, b, c, w, u, v, Z);
+            if (g_out) {
+                const float gw[3] = {g_out[3 * i], g_out[3 * i + 1], g_out[3 * i + 2]};
+                patch_to_world_vjp(m, im, fl, u, v, Z, gw, o);
+            } else { o[0] = w[0]; o[1] = w[1]; o[2] = w[2]; }
+        } else {                                                  // convert_patch_to_image alone: the affine part only
+            patch_to_world(m, im, fl | F_MONO, a, b, c, w, u, v, Z);   // (u, v, Z) are the image-space point
+            if (g_out) {
+                float gx = m.ai00 * g_out[3 * i] + m.ai10 * g_out[3 * i + 1], gy = m.ai01 * g_out[3 * i] + m.ai11 * g_out[3 * i + 1],
+                      gz = g_out[3 * i + 2] * im.ds;
+                if (g.flags & XSUP_GEOM_NORM) { gx *= im.wm1 * 0.5f; gy *= im.hm1 * 0.5f; gz *= im.dm1; }
+                if (!(g.flags & XSUP_GEOM_PATCH_STAGE)) { gx = g_out[3 * i]; gy = g_out[3 * i + 1]; gz = g_out[3 * i + 2]; }
+                o[0] = gx; o[1] = gy; o[2] = gz;
+            } else { o[0] = u; o[1] = v; o[2] = Z; }
+        }
+    } else {
+        float X, Y, Z;
+        world_to_patch(m, im, g.flags, a, b, c, o, X, Y, Z);
+        if (g_out) {
+            const float go[3] = {g_out[3 * i], g_out[3 * i + 1], g_out[3 * i + 2]};
+            float gi[3];
+            world_to_patch_vjp(m, im, g.flags, X, Y, Z, go, gi);
+            o[0] = gi[0]; o[1] = gi[1]; o[2] = gi[2];
+        }
+    }
+    out[3 * i] = o[0]; out[3 * i + 1] = o[1]; out[3 * i + 2] = o[2];
+}
+
+cudaError_t launch_geom(int dir, const float* in, const float* g_out, float* out, const xsup_geom_t& g, cudaStream_t st) {
     const int n = g.B * g.J;
-    world_to_patch_fwd_kernel<<<(n + 127) / 128, 128, 0, st>>>(world, kps, g);
+    if (dir == 0) geom_kernel<0><<<(n + 127) / 128, 128, 0, st>>>(in, g_out, out, g);
+    else geom_kernel<1><<<(n + 127) / 128, 128, 0, st>>>(in, g_out, out, g);
     return cudaGetLastError();
 }
 
 // ---------------------------------------------------------------------------------------------- loss forward
 // one warp per (sample, hypothesis); lane = joint (K <= 32)
-__global__ void __launch_bounds__(128) reproj_loss_fwd_kernel(const float* __restrict__ kps, const float* __restrict__ target,
-                                                              const xsup_cam_t cam, float* __restrict__ world,
-                                                              float* __restrict__ sample_terms, const xsup_loss_cfg_t c) {
-    const int wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-    if (wid >= c.B * c.NH) return;
+__device__ __forceinline__ void loss_fwd_warp(const float* __restrict__ kps, const float* __restrict__ target, const xsup_cam_t& cam,
+                                              float* __restrict__ world, float* __restrict__ sample_terms, const xsup_loss_cfg_t& c,
+                                              int wid, int lane) {
     const int b = wid / c.NH, h = wid - b * c.NH, K = c.K;
     const Cam m = load_cam(cam, b);
     const Img im = make_img(c.img_h, c.img_w, c.rect_width);
@@ -228,14 +305,26 @@ __global__ void __launch_bounds__(128) reproj_loss_fwd_kernel(const float* __res
     }
 }
 
-// partial[term,h] = sum_b sample_terms[b,term,h]; one warp per (term,h), fixed order
+__global__ void __launch_bounds__(128) reproj_loss_fwd_kernel(const float* __restrict__ kps, const float* __restrict__ target,
+                                                              const xsup_cam_t cam, float* __restrict__ world,
+                                                              float* __restrict__ sample_terms, const xsup_loss_cfg_t c) {
+    const int wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (wid >= c.B * c.NH) return;
+    loss_fwd_warp(kps, target, cam, world, sample_terms, c, wid, lane);
+}
+
+// partial[col] = sum_b sample_terms[b,col], col = (term,h); one warp per column, fixed order (lane-strided, then the
+// xor tree), so the sums - and with them the selected slot - are bit-reproducible.  L2 loads: in the fused kernel the
+// terms were written by other CTAs of the same grid.
+__device__ __forceinline__ float partial_col(const float* sample_terms, int B, int stride, int col, int lane) {
+    float a = 0.f;
+    for (int b = lane; b < B; b += 32) a += __ldcg(sample_terms + (size_t)b * stride + col);
+    return warp_sum(a);
+}
 __global__ void __launch_bounds__(32) reproj_partial_kernel(const float* __restrict__ sample_terms, float* __restrict__ partial,
                                                             int B, int NH) {
-    const int col = blockIdx.x, lane = threadIdx.x, stride = XSUP_LOSS_TERMS * NH;
-    float a = 0.f;
-    for (int b = lane; b < B; b += 32) a += sample_terms[(size_t)b * stride + col];
-    a = warp_sum(a);
-    if (lane == 0) partial[col] = a;
+    const float a = partial_col(sample_terms, B, XSUP_LOSS_TERMS * NH, blockIdx.x, threadIdx.x);
+    if (threadIdx.x == 0) partial[blockIdx.x] = a;
 }
 
 cudaError_t launch_reproj_loss_fwd(const float* kps, const float* target, const xsup_cam_t& cam, float* world,
@@ -259,11 +348,14 @@ __device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
     asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
-__global__ void __launch_bounds__(64) partial_allreduce_kernel(float* __restrict__ partial, int n, void* const* __restrict__ peers,
-                                                               int rank, int world, uint32_t step_arg, uint32_t* seq) {
+// Block-level body (any blockDim >= world, all threads of the block call it; ends with every thread seeing buf[]).
+// A peer that never arrives (~10 s) turns the sums into NaN and raises the sticky word *err, which the host checks
+// (dist.PeerExchange.check): after a timeout the mailboxes are out of step and the exchange must be rebuilt.
+__device__ void xchg_allreduce_block(float* buf, int n, void* const* __restrict__ peers, int rank, int world, uint32_t step_arg,
+                                     uint32_t* seq, uint32_t* err) {
     __shared__ int timed_out;
     __shared__ uint32_t s_step;
-    const int t = threadIdx.x;
+    const int t = threadIdx.x, nt = blockDim.x;
     if (t == 0) {
         timed_out = 0;
         s_step = seq ? (*seq += 1u) : step_arg;          // device-side sequence number: replayable from a CUDA graph
@@ -273,7 +365,7 @@ __global__ void __launch_bounds__(64) partial_allreduce_kernel(float* __restrict
     const size_t par = step & 1u;
     for (int d = 0; d < world; ++d) {                  // publish: coalesced P2P stores into slot [par][rank] of every mailbox
         float* dst = static_cast<float*>(peers[d]) + (par * world + rank) * XSUP_XCHG_SLOT;
-        for (int i = t; i < n; i += 64) dst[i] = partial[i];
+        for (int i = t; i < n; i += nt) dst[i] = buf[i];
     }
     __threadfence_system();
     __syncthreads();
@@ -289,15 +381,21 @@ __global__ void __launch_bounds__(64) partial_allreduce_kernel(float* __restrict
         }
     }
     __syncthreads();
-    for (int i = t; i < n; i += 64) {                  // fixed rank order: bit-identical sums on every rank
+    for (int i = t; i < n; i += nt) {                  // fixed rank order: bit-identical sums on every rank
         float a = 0.f;
         for (int r = 0; r < world; ++r) a += *reinterpret_cast<volatile float*>(mine + (size_t)r * XSUP_XCHG_SLOT + i);
-        partial[i] = timed_out ? __int_as_float(0x7fc00000) : a;
+        buf[i] = timed_out ? __int_as_float(0x7fc00000) : a;
     }
+    if (t == 0 && timed_out && err) *err = 1u;
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(64) partial_allreduce_kernel(float* partial, int n, const xsup_xchg_t x) {
+    xchg_allreduce_block(partial, n, x.peer_bufs, x.rank, x.world, x.step, x.seq, x.err);
 }
 
 cudaError_t launch_partial_allreduce(float* partial, int n, const xsup_xchg_t& x, cudaStream_t st) {
-    partial_allreduce_kernel<<<1, 64, 0, st>>>(partial, n, x.peer_bufs, x.rank, x.world, x.step, x.seq);
+    partial_allreduce_kernel<<<1, 64, 0, st>>>(partial, n, x);
     return cudaGetLastError();
 }
 
@@ -317,9 +415,10 @@ __device__ float block_sum_256(float v, float* scratch) {
     return r;
 }
 
-__global__ void __launch_bounds__(256) reproj_select_kernel(const float* __restrict__ kps, const float* __restrict__ target,
-                                                            const float* __restrict__ sample_terms, const float* __restrict__ partial,
-                                                            float* __restrict__ loss, int64_t* __restrict__ sel, const xsup_loss_cfg_t c) {
+// 256 threads.  `sample_terms` / `partial` may have been written earlier in the same kernel (fused forward): no
+// __restrict__ / read-only path on them.
+__device__ void select_block(const float* __restrict__ kps, const float* __restrict__ target, const float* sample_terms,
+                             const float* partial, float* loss, int64_t* __restrict__ sel, const xsup_loss_cfg_t& c) {
     __shared__ float scratch[8];
     const int NH = c.NH, K = c.K, B = c.B;
     const float n = (float)c.batch_total;
@@ -390,6 +489,53 @@ __global__ void __launch_bounds__(256) reproj_select_kernel(const float* __restr
     if (threadIdx.x == 0) { loss[0] = c.w_mse * acc / (n * (float)K * 3.0f); loss[1] = 0.f; }
 }
 
+__global__ void __launch_bounds__(256) reproj_select_kernel(const float* __restrict__ kps, const float* __restrict__ target,
+                                                            const float* sample_terms, const float* partial, float* loss,
+                                                            int64_t* __restrict__ sel, const xsup_loss_cfg_t c) {
+    select_block(kps, target, sample_terms, partial, loss, sel, c);
+}
+
+// ---------------------------------------------------------------------------------------------- fused forward
+// loss terms per (sample, hypothesis) -> last CTA done: fixed-order batch sums -> [NVLink exchange] -> selection.
+// One launch instead of loss_fwd + partial + exchange + select; the exchange rides inside the compute kernel.
+__global__ void __launch_bounds__(256) reproj_fused_fwd_kernel(const float* __restrict__ kps, const float* __restrict__ target,
+                                                               const xsup_cam_t cam, float* __restrict__ world, float* sample_terms,
+                                                               float* partial, float* loss, int64_t* __restrict__ sel,
+                                                               const xsup_loss_cfg_t c, const xsup_xchg_t x, unsigned int* ticket) {
+    __shared__ int s_last;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int wid = blockIdx.x * 8 + warp;
+    if (wid < c.B * c.NH) loss_fwd_warp(kps, target, cam, world, sample_terms, c, wid, lane);
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    const int cols = XSUP_LOSS_TERMS * c.NH;
+    for (int col = warp; col < cols; col += 8) {
+        const float a = partial_col(sample_terms, c.B, cols, col, lane);
+        if (lane == 0) partial[col] = a;
+    }
+    __syncthreads();
+    const bool xch = x.peer_bufs != nullptr && x.world > 1;
+    if (xch && c.reduction == XSUP_REDUCE_BATCH) xchg_allreduce_block(partial, cols, x.peer_bufs, x.rank, x.world, x.step, x.seq, x.err);
+    select_block(kps, target, sample_terms, partial, loss, sel, c);
+    if (xch && c.reduction != XSUP_REDUCE_BATCH) {       // reporting only: the gradient needs just batch_total
+        __syncthreads();
+        xchg_allreduce_block(loss, 2, x.peer_bufs, x.rank, x.world, x.step, x.seq, x.err);
+    }
+    if (threadIdx.x == 0) *ticket = 0u;                  // re-armed for the next call on the same buffers
+}
+
+cudaError_t launch_reproj_fused_fwd(const float* kps, const float* target, const xsup_cam_t& cam, float* world, float* sample_terms,
+                                    float* partial, float* loss, int64_t* sel, const xsup_loss_cfg_t& c, const xsup_xchg_t& x,
+                                    unsigned int* ticket, cudaStream_t st) {
+    const int warps = c.B * c.NH;
+    reproj_fused_fwd_kernel<<<(warps + 7) / 8, 256, 0, st>>>(kps, target, cam, world, sample_terms, partial, loss, sel, c, x, ticket);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_reproj_select(const float* kps, const float* target, const float* sample_terms, const float* partial,
                                  float* loss, int64_t* sel, const xsup_loss_cfg_t& c, cudaStream_t st) {
     reproj_select_kernel<<<1, 256, 0, st>>>(kps, target, sample_terms, partial, loss, sel, c);
@@ -397,24 +543,23 @@ cudaError_t launch_reproj_select(const float* kps, const float* target, const fl
 }
 
 // ---------------------------------------------------------------------------------------------- loss backward
-__global__ void __launch_bounds__(128) reproj_loss_bwd_kernel(const float* __restrict__ kps, const float* __restrict__ target,
-                                                              const xsup_cam_t cam, const int64_t* __restrict__ sel,
-                                                              const float* __restrict__ g_loss, float* __restrict__ g_kps,
-                                                              const xsup_loss_cfg_t c) {
-    const int wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-    if (wid >= c.B * c.NH) return;
-    const int b = wid / c.NH, h = wid - b * c.NH, K = c.K;
+// d (gl0 * pseudo + gl1 * symmetry) / d kps[b,h,lane,:] (+ the vector-Jacobian product of an upstream gradient on
+// kps_world, + an upstream gradient on kps itself) for one (sample, hypothesis); lane = joint.  Warp-uniform control flow.
+__device__ __forceinline__ void loss_bwd_warp(const float* __restrict__ kps, const float* __restrict__ target, const xsup_cam_t& cam,
+                                              const int64_t* __restrict__ sel, float gl0, float gl1,
+                                              const float* __restrict__ g_kps_in, const float* __restrict__ g_world,
+                                              const xsup_loss_cfg_t& c, int b, int h, int lane, float (&g)[3]) {
+    const int K = c.K;
     const float n = (float)c.batch_total;
-    const float gl0 = g_loss[0], gl1 = g_loss[1];
     bool on_sym = false;
     if (c.use_sym) {
         if (c.reduction == XSUP_REDUCE_BATCH) on_sym = (sel[1] == h);
         else if (c.reduction == XSUP_REDUCE_SAMPLE) on_sym = (sel[c.B + b] == h);
     }
-    float x = 0.f, y = 0.f, z = 0.f, g[3] = {0.f, 0.f, 0.f};
-    size_t o = 0;
+    float x = 0.f, y = 0.f, z = 0.f;
+    g[0] = g[1] = g[2] = 0.f;
+    const size_t o = (((size_t)b * c.NH + h) * K + (lane < K ? lane : 0)) * 3;
     if (lane < K) {
-        o = (((size_t)b * c.NH + h) * K + lane) * 3;
         x = kps[o]; y = kps[o + 1]; z = kps[o + 2];
         bool on_mse;
         if (c.reduction == XSUP_REDUCE_BATCH) on_mse = (sel[0] == h);
@@ -425,13 +570,16 @@ __global__ void __launch_bounds__(128) reproj_loss_bwd_kernel(const float* __res
             const float s = gl0 * c.w_mse * 2.0f / (n * (float)K * 3.0f);
             g[0] = s * (x - tg[0]); g[1] = s * (y - tg[1]); g[2] = s * (z - tg[2]);
         }
+        if (g_kps_in) { g[0] += g_kps_in[o]; g[1] += g_kps_in[o + 1]; g[2] += g_kps_in[o + 2]; }
     }
-    if (on_sym) {                                                            // warp-uniform
-        const Cam m = load_cam(cam, b);
-        const Img im = make_img(c.img_h, c.img_w, c.rect_width);
-        float w[3] = {0.f, 0.f, 0.f}, u = 0.f, v = 0.f, Z = 1.f;
-        if (lane < K) patch_to_world(m, im, F_NORM | F_PATCH, x, y, z, w, u, v, Z);
-        float gw[3] = {0.f, 0.f, 0.f};
+    if (!on_sym && !g_world) return;                                         // warp-uniform
+    const Cam m = load_cam(cam, b);
+    const Img im = make_img(c.img_h, c.img_w, c.rect_width);
+    float w[3] = {0.f, 0.f, 0.f}, u = 0.f, v = 0.f, Z = 1.f;
+    if (lane < K) patch_to_world(m, im, F_NORM | F_PATCH, x, y, z, w, u, v, Z);
+    float gw[3] = {0.f, 0.f, 0.f};
+    if (g_world && lane < K) { gw[0] = g_world[o]; gw[1] = g_world[o + 1]; gw[2] = g_world[o + 2]; }
+    if (on_sym) {
         // ---- bones
         const int ci = c_bone_child[lane & 7], pi = c_bone_parent[lane & 7];
         const float vx = __shfl_sync(0xffffffffu, w[0], ci) - __shfl_sync(0xffffffffu, w[0], pi);
@@ -474,13 +622,106 @@ __global__ void __launch_bounds__(128) reproj_loss_bwd_kernel(const float* __res
                 g[0] -= s2 * q0; g[1] -= s2 * q1;
             }
         }
-        if (lane < K) {
-            float gk[3];
-            patch_to_world_vjp(m, im, F_NORM | F_PATCH, u, v, Z, gw, gk);
-            g[0] += gk[0]; g[1] += gk[1]; g[2] += gk[2];
+    }
+    if (lane < K) {
+        float gk[3];
+        patch_to_world_vjp(m, im, F_NORM | F_PATCH, u, v, Z, gw, gk);
+        g[0] += gk[0]; g[1] += gk[1]; g[2] += gk[2];
+    }
+}
+
+__global__ void __launch_bounds__(128) reproj_loss_bwd_kernel(const float* __restrict__ kps, const float* __restrict__ target,
+                                                              const xsup_cam_t cam, const int64_t* __restrict__ sel,
+                                                              const float* __restrict__ g_loss, float* __restrict__ g_kps,
+                                                              const xsup_loss_cfg_t c) {
+    const int wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (wid >= c.B * c.NH) return;
+    const int b = wid / c.NH, h = wid - b * c.NH;
+    float g[3];
+    loss_bwd_warp(kps, target, cam, sel, g_loss[0], g_loss[1], nullptr, nullptr, c, b, h, lane, g);
+    if (lane < c.K) {
+        const size_t o = (((size_t)b * c.NH + h) * c.K + lane) * 3;
+        g_kps[o] = g[0]; g_kps[o + 1] = g[1]; g_kps[o + 2] = g[2];
+    }
+}
+
+// ---------------------------------------------------------------------------------------------- fused backward
+// One CTA per sample: (1) the loss VJP of every hypothesis of the sample (warp per hypothesis, lane = joint), summed
+// with the upstream gradients on kps / kps_world, kept in shared memory; (2) the coefficient blocks of the sample's K
+// units for the streaming head backward (what integral_coef_kernel derives from grad_kps in global memory).  Replaces
+// loss_bwd + the ATen zeros/stack/add glue + integral_coef: the gradient w.r.t. kps never round-trips HBM.
+__global__ void __launch_bounds__(256) reproj_fused_bwd_kernel(const float* __restrict__ kps, const float* __restrict__ target,
+                                                               const xsup_cam_t cam, const int64_t* __restrict__ sel,
+                                                               const float* __restrict__ g_lp, const float* __restrict__ g_ls,
+                                                               const float* __restrict__ g_kps_in, const float* __restrict__ g_world,
+                                                               float* __restrict__ g_kps_out, const xsup_loss_cfg_t c, const CoefParams p) {
+    extern __shared__ float sm[];
+    const int NH = c.NH, K = c.K;
+    float* gz = sm;                       // [NH][32]
+    float* gxp = sm + (size_t)NH * 32;    // [8][32] per-warp partial sums over this warp's hypotheses
+    float* gyp = gxp + 8 * 32;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, b = blockIdx.x;
+    if (b == 0 && threadIdx.x == 0) *p.counter = 0;                          // work-claim counter of the streaming kernel that follows
+    const float gl0 = g_lp ? *g_lp : 0.f, gl1 = g_ls ? *g_ls : 0.f;
+    float ax = 0.f, ay = 0.f;
+    for (int h = warp; h < NH; h += 8) {
+        float g[3];
+        loss_bwd_warp(kps, target, cam, sel, gl0, gl1, g_kps_in, g_world, c, b, h, lane, g);
+        gz[h * 32 + lane] = g[2];
+        ax += g[0];
+        ay += g[1];
+        if (g_kps_out && lane < K) {
+            const size_t o = (((size_t)b * NH + h) * K + lane) * 3;
+            g_kps_out[o] = g[0]; g_kps_out[o + 1] = g[1]; g_kps_out[o + 2] = g[2];
         }
     }
-    if (lane < K) { g_kps[o] = g[0]; g_kps[o + 1] = g[1]; g_kps[o + 2] = g[2]; }
+    gxp[warp * 32 + lane] = ax;
+    gyp[warp * 32 + lane] = ay;
+    __syncthreads();
+    const int D = p.D;
+    const float zs = 2.0f / (float)D;
+    const int half = p.NS >> 1;
+    for (int k = warp; k < K; k += 8) {
+        const int unit = b * K + k;
+        const float* st = p.stats + (size_t)unit * p.stats_stride;
+        float* cf = p.coef + (size_t)unit * p.coef_stride;
+        float gx = 0.f, gy = 0.f;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) { gx += gxp[w * 32 + k]; gy += gyp[w * 32 + k]; }
+        const float a = gx * (2.0f / (float)p.H);            // x was normalised by H (…_multi.py:78)
+        const float bb = gy * (2.0f / (float)p.W);           // y by W (…:79)
+        float dot = 0.f;
+        for (int d = lane; d < D; d += 32) {
+            float cd = 0.f;
+            for (int h = 0; h < NH; ++h) {
+                const float* sh = st + 4 + D + 3 * h;
+                const int idx = (int)sh[0];
+                if (d >= idx - half && d <= idx + half) cd += gz[h * 32 + k] * zs * ((float)d - sh[2]) / sh[1];
+            }
+            cf[8 + d] = cd;
+            dot = fmaf(cd, st[4 + d], dot);
+        }
+        dot = warp_sum(dot);
+        if (lane == 0) {
+            const float wc = rintf(st[1]), hc = rintf(st[2]);
+            cf[0] = st[0];
+            cf[1] = a;
+            cf[2] = bb;
+            cf[3] = -fmaf(a, st[1] - wc, fmaf(bb, st[2] - hc, dot));
+            cf[4] = wc;
+            cf[5] = hc;
+            cf[6] = 0.f;
+            cf[7] = 0.f;
+        }
+    }
+}
+
+cudaError_t launch_reproj_fused_bwd(const float* kps, const float* target, const xsup_cam_t& cam, const int64_t* sel, const float* g_lp,
+                                    const float* g_ls, const float* g_kps_in, const float* g_world, float* g_kps_out,
+                                    const xsup_loss_cfg_t& c, const CoefParams& p, cudaStream_t st) {
+    const size_t smem = ((size_t)c.NH * 32 + 2 * 8 * 32) * sizeof(float);       // <= 34 KB (NH <= 254)
+    reproj_fused_bwd_kernel<<<c.B, 256, smem, st>>>(kps, target, cam, sel, g_lp, g_ls, g_kps_in, g_world, g_kps_out, c, p);
+    return cudaGetLastError();
 }
 
 cudaError_t launch_reproj_loss_bwd(const float* kps, const float* target, const xsup_cam_t& cam, const int64_t* sel,

@@ -224,7 +224,8 @@ __global__ void __launch_bounds__(256) integral_bwd_generic_kernel(const BwdPara
 template <typename T, int U>
 static cudaError_t launch_fast(const BwdParams& p, int grid, size_t smem, cudaStream_t st) {
     auto kern = integral_bwd_kernel<T, U>;
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    static unsigned long long attr_done = 0;             // per instantiation; one bit per device
+    cudaError_t e = ensure_max_smem(kern, attr_done);
     if (e != cudaSuccess) return e;
     kern<<<grid, kBwdThreads, smem, st>>>(p);
     return cudaGetLastError();

@@ -322,7 +322,8 @@ cudaError_t launch_find_peak(const float* pz, int64_t* idx, int rows, int D, int
 template <typename T, int U>
 static cudaError_t launch_fast(const FwdParams& p, int grid, size_t smem, cudaStream_t st) {
     auto kern = integral_fwd_kernel<T, U>;
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    static unsigned long long attr_done = 0;             // per instantiation; one bit per device
+    cudaError_t e = ensure_max_smem(kern, attr_done);
     if (e != cudaSuccess) return e;
     kern<<<grid, kFwdThreads, smem, st>>>(p);
     return cudaGetLastError();

@@ -8,7 +8,7 @@ constexpr int kFwdThreads = (kConsumerWarps + 3) * 32;   // 16 consumers + produ
 constexpr int kBwdThreads = (kConsumerWarps + 1) * 32;   // 16 consumers + producer
 constexpr size_t kSmemBudget = 227 * 1024;               // per-CTA opt-in maximum on sm_100
 constexpr int kMaxStages = 16;
-constexpr int kSchedWords = 16;                          // ints reserved after stats / coef for the work-claim counter
+constexpr int kSchedWords = XSUP_SCHED_WORDS;                         // ints reserved after stats / coef for the work-claim counter
 
 struct FwdParams {
     const void* logits;
@@ -46,14 +46,7 @@ cudaError_t launch_find_peak(const float* pz, int64_t* idx, int rows, int D, int
 cudaError_t launch_integral_coef(const CoefParams& p, cudaStream_t st);
 cudaError_t launch_integral_bwd(BwdParams p, bool fast, int dtype, int num_sms, cudaStream_t st);
 
-struct GeomParams {
-    xsup_cam_t cam;
-    int B, J, img_h, img_w, flags;
-    float rect_width;
-};
-cudaError_t launch_patch_to_world_fwd(const float* kps, float* world, const GeomParams& g, cudaStream_t st);
-cudaError_t launch_patch_to_world_bwd(const float* kps, const float* g_world, float* g_kps, const GeomParams& g, cudaStream_t st);
-cudaError_t launch_world_to_patch_fwd(const float* world, float* kps, const GeomParams& g, cudaStream_t st);
+cudaError_t launch_geom(int dir, const float* in, const float* g_out, float* out, const xsup_geom_t& g, cudaStream_t st);
 
 cudaError_t launch_reproj_loss_fwd(const float* kps, const float* target, const xsup_cam_t& cam, float* world,
                                    float* sample_terms, float* partial, const xsup_loss_cfg_t& c, cudaStream_t st);
@@ -62,6 +55,12 @@ cudaError_t launch_reproj_select(const float* kps, const float* target, const fl
                                  float* loss, int64_t* sel, const xsup_loss_cfg_t& c, cudaStream_t st);
 cudaError_t launch_reproj_loss_bwd(const float* kps, const float* target, const xsup_cam_t& cam, const int64_t* sel,
                                    const float* g_loss, float* g_kps, const xsup_loss_cfg_t& c, cudaStream_t st);
+cudaError_t launch_reproj_fused_fwd(const float* kps, const float* target, const xsup_cam_t& cam, float* world, float* sample_terms,
+                                    float* partial, float* loss, int64_t* sel, const xsup_loss_cfg_t& c, const xsup_xchg_t& x,
+                                    unsigned int* ticket, cudaStream_t st);
+cudaError_t launch_reproj_fused_bwd(const float* kps, const float* target, const xsup_cam_t& cam, const int64_t* sel, const float* g_lp,
+                                    const float* g_ls, const float* g_kps_in, const float* g_world, float* g_kps_out,
+                                    const xsup_loss_cfg_t& c, const CoefParams& p, cudaStream_t st);
 
 // skeleton rasteriser + mask loss (skeleton_mask.cu)
 struct SkelParams {
@@ -112,6 +111,7 @@ struct PoseTermParams {
 };
 cudaError_t launch_pose_term_fwd(const PoseTermParams& p, double denom, float* sample_sums, float* loss, cudaStream_t st);
 cudaError_t launch_pose_term_bwd(const PoseTermParams& p, double denom, const float* g_loss, float* g_x, cudaStream_t st);
+cudaError_t launch_pose_sqerr(const PoseTermParams& p, const float* g_out, float* out, cudaStream_t st);
 cudaError_t launch_eval_select(const EvalParams& p, cudaStream_t st);
 cudaError_t launch_triangulate(const TriParams& p, float* world, cudaStream_t st);
 cudaError_t launch_root_centre_fwd(const float* world, float* out, int N, int M, int R, int dim, cudaStream_t st);
@@ -129,5 +129,18 @@ cudaError_t launch_conv_head_bwd_g(const void* x_nhwc, const void* w, const floa
 cudaError_t launch_pack_nhwc_bf16(const float* x, void* y, int B, int C, int HW, cudaStream_t st);
 
 void count_launches(int n);
+
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) once per (kernel instantiation, device), not on every launch
+template <typename Kern>
+inline cudaError_t ensure_max_smem(Kern kern, unsigned long long& done_mask) {
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    const unsigned long long bit = 1ull << (dev & 63);
+    if (__atomic_load_n(&done_mask, __ATOMIC_ACQUIRE) & bit) return cudaSuccess;
+    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget);
+    if (e == cudaSuccess) __atomic_fetch_or(&done_mask, bit, __ATOMIC_RELEASE);
+    return e;
+}
 
 }  // namespace xsup

@@ -24,7 +24,7 @@ from typing import Optional, Tuple
 import torch
 import torch.distributed as dist
 
-__all__ = ["shard_range", "global_batch", "global_batch_exact", "reduce_partials", "select_slots", "PeerExchange"]
+__all__ = ["shard_range", "is_active", "global_batch", "global_batch_exact", "reduce_partials", "select_slots", "PeerExchange"]
 
 
 class PeerExchange:
@@ -49,14 +49,30 @@ class PeerExchange:
         torch.cuda.synchronize(self.device)
         dist.barrier(self.group)                       # every mailbox is zeroed before anyone publishes
         # the call sequence number lives on the device and is advanced by the kernel, so a captured call can be replayed
-        self.seq = torch.zeros(1, dtype=torch.int32, device=self.device)
+        # word 0: sequence number; word 1: sticky error flag the kernel raises when a wait for a peer timed out
+        self._words = torch.zeros(2, dtype=torch.int32, device=self.device)
+        self.seq = self._words[0:1]
+        self.err = self._words[1:2]
+
+    def descriptor(self):
+        """The `xsup_xchg_t` of this mailbox (sequence number and error word live on the device)."""
+        from . import _cabi as cabi
+        return cabi.Xchg(self.peer_ptrs.data_ptr(), self.rank, self.world, 0, self.seq.data_ptr(), self.err.data_ptr())
+
+    def check(self) -> None:
+        """Raise if any exchange since construction timed out waiting for a peer (~10 s).  Reads one word back from the
+        device (synchronises the stream), so call it at a step boundary you already synchronise on, not per kernel.
+        After a timeout the ranks' sequence numbers are out of step: build a new PeerExchange."""
+        if int(self.err.item()) != 0:
+            raise RuntimeError("xsup_b200 PeerExchange: a peer did not arrive within the timeout; the sums of that step are NaN "
+                               "and the mailboxes are out of step - rebuild the PeerExchange on all ranks")
 
     def all_reduce_(self, t: torch.Tensor) -> torch.Tensor:
         """In-place SUM over the ranks of a small contiguous fp32 CUDA tensor (<= XSUP_XCHG_SLOT-1 = 1023 elements)."""
         from . import _cabi as cabi
         if not (t.is_cuda and t.dtype == torch.float32 and t.is_contiguous()):
             raise ValueError("PeerExchange.all_reduce_ needs a contiguous float32 CUDA tensor")
-        x = cabi.Xchg(self.peer_ptrs.data_ptr(), self.rank, self.world, 0, self.seq.data_ptr())
+        x = self.descriptor()
         with torch.cuda.device(self.device):
             cabi.check(cabi.lib.xsup_partial_allreduce(t.data_ptr(), t.numel(), x, cabi.stream_ptr(self.device)),
                        "xsup_partial_allreduce")
@@ -68,6 +84,11 @@ def shard_range(n: int, rank: int, world: int) -> Tuple[int, int]:
     base, rem = divmod(n, world)
     start = rank * base + min(rank, rem)
     return start, start + base + (1 if rank < rem else 0)
+
+
+def is_active(group) -> bool:
+    """True when `group` spans more than one rank (a PeerExchange or an initialised torch.distributed group)."""
+    return _active(group)
 
 
 def _active(group) -> bool:

@@ -63,16 +63,15 @@ def eval_select(kps: torch.Tensor, joints_px: torch.Tensor, img_size: float = 25
 
 def switch_points(points, gt, switch_all=False, switch_list=SWITCH_LIST):
     """eval_utils.py:7 for the per-joint mode the eval loop uses (`switch_all=False`): the fused kernel run on one
-    hypothesis with an already-normalised ground truth.  Returns (points with swaps undone, is_trans [B,K,1])."""
+    hypothesis with an already-normalised ground truth (`img_size=0`), so the swap decisions are bit-exact.  Returns (points with swaps undone, is_trans [B,K,1])."""
     if switch_all:
         raise NotImplementedError("switch_all=True is not on the eval path (eval.py:135-136 pass False)")
     C = points.shape[-1]
     p3 = points if C == 3 else torch.cat((points, points.new_zeros(points.shape[:-1] + (3 - C,))), dim=-1)
     g3 = gt if gt.shape[-1] == 3 else torch.cat((gt, gt.new_zeros(gt.shape[:-1] + (3 - gt.shape[-1],))), dim=-1)
-    # feed the kernel a pixel-space gt that normalises back to `gt`: with img_size = 2 the map is x -> 2x - 1, z -> z
-    px = g3.clone().to(torch.float32)
-    px[..., :2] = (px[..., :2] + 1) / 2
-    out = eval_select(p3.unsqueeze(1), px, img_size=2.0, mode="confident", switch_list=switch_list)
+    # img_size = 0 tells the kernel the ground truth is already normalised: its bits reach the strict `es < e` swap
+    # decision untouched, as in the reference
+    out = eval_select(p3.unsqueeze(1), g3.to(torch.float32), img_size=0.0, mode="confident", switch_list=switch_list)
     return out["kp3d"][..., :C], out["is_trans"]
 
 

@@ -12,7 +12,7 @@ import torch
 
 from . import _cabi as cabi
 
-__all__ = ["compute_supervision", "compute_bone_sym_loss", "compute_kp_sym_loss", "PoseTerm"]
+__all__ = ["compute_supervision", "compute_bone_sym_loss", "compute_kp_sym_loss", "PoseTerm", "PoseSqErr"]
 
 
 class PoseTerm(torch.autograd.Function):
@@ -52,10 +52,49 @@ class PoseTerm(torch.autograd.Function):
         return gx.to(in_dtype), None, None, None, None
 
 
+class PoseSqErr(torch.autograd.Function):
+    """Element-wise squared error `[B,K,C]` (nn.MSELoss(reduction='none'), loss_func.py:46-47) and its VJP."""
+
+    @staticmethod
+    def forward(ctx, x, gt, feature_shape):
+        cabi.require_cuda(x, "keypoints")
+        xf = x.detach().to(torch.float32).contiguous()
+        if xf.dim() != 3:
+            raise ValueError("keypoints must be [B, K, C], got %s" % (tuple(x.shape),))
+        B, K, Cc = xf.shape
+        dev = xf.device
+        g = gt.detach().to(device=dev, dtype=torch.float32).expand_as(xf).contiguous()
+        fs = (C.c_float * 3)(*[float(v) for v in (list(feature_shape) + [1.0, 1.0, 1.0])[:3]]) if feature_shape is not None else None
+        out = torch.empty_like(xf)
+        with torch.cuda.device(dev):
+            cabi.check(cabi.lib.xsup_pose_sqerr(xf.data_ptr(), g.data_ptr(), fs, B, K, Cc, None, out.data_ptr(), cabi.stream_ptr(dev)),
+                       "xsup_pose_sqerr")
+        ctx.save_for_backward(xf, g)
+        ctx.meta = (feature_shape, x.dtype)
+        return out
+
+    @staticmethod
+    def backward(ctx, g_out):
+        xf, g = ctx.saved_tensors
+        feature_shape, in_dtype = ctx.meta
+        B, K, Cc = xf.shape
+        dev = xf.device
+        fs = (C.c_float * 3)(*[float(v) for v in (list(feature_shape) + [1.0, 1.0, 1.0])[:3]]) if feature_shape is not None else None
+        go = g_out.to(torch.float32).contiguous()
+        gx = torch.empty_like(xf)
+        with torch.cuda.device(dev):
+            cabi.check(cabi.lib.xsup_pose_sqerr(xf.data_ptr(), g.data_ptr(), fs, B, K, Cc, go.data_ptr(), gx.data_ptr(),
+                                                cabi.stream_ptr(dev)), "xsup_pose_sqerr (vjp)")
+        return gx.to(in_dtype), None, None
+
+
 def compute_supervision(keypoint, keypoint_gt, feature_shape=None, mode="mean"):
-    """Same signature as loss_func.py:38.  `mode` 'mean' or 'sum' (the reference's 'none' is not used anywhere)."""
+    """Same signature as loss_func.py:38.  `mode` is nn.MSELoss's reduction: 'mean', 'sum' (then divided by the batch
+    size, :50-51) or 'none' (the element-wise `[B,K,C]` tensor)."""
+    if mode == "none":
+        return PoseSqErr.apply(keypoint, keypoint_gt, feature_shape)
     if mode not in ("mean", "sum"):
-        raise ValueError("mode must be 'mean' or 'sum', got %r" % (mode,))
+        raise ValueError("mode must be 'mean', 'sum' or 'none', got %r" % (mode,))
     return PoseTerm.apply(keypoint, keypoint_gt, cabi.TERM_MSE, int(mode == "sum"), feature_shape)
 
 

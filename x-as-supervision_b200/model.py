@@ -32,6 +32,25 @@ def _cams(x, cam_key):
     return {k: x["{}_{}".format(cam_key, k)] for k in _CAM_FIELDS}
 
 
+def _batch_dependent(module: torch.nn.Module) -> bool:
+    """True when a forward pass of `module` depends on which samples share the batch or draws random numbers: batch
+    normalisation (gcn.py:58-75 with cfg['use_bn']) or dropout, in training mode."""
+    stateful = (torch.nn.modules.batchnorm._BatchNorm, torch.nn.modules.dropout._DropoutNd)
+    return any(isinstance(m, stateful) and m.training for m in module.modules())
+
+
+def score_hypotheses(discriminator: torch.nn.Module, joints: torch.Tensor) -> torch.Tensor:
+    """Discriminator logits of all hypotheses, `[B,NH,K,dim] -> [B,NH,C]` (model.py:126-129, 251-254).
+
+    A stateless discriminator scores the NH hypotheses in ONE call on `[B*NH,K,dim]`.  With batch normalisation or
+    dropout active the batched call would pool the batch statistics over hypotheses (and update the running statistics
+    once instead of NH times), so the hypotheses go through one by one exactly as the reference loops."""
+    B, NH = joints.shape[:2]
+    if _batch_dependent(discriminator):
+        return torch.stack([discriminator(joints[:, i].contiguous()) for i in range(NH)], dim=1)
+    return discriminator(joints.flatten(0, 1).contiguous()).reshape(B, NH, -1)
+
+
 class Counter3DModel(torch.nn.Module):
     def __init__(self, cfg, regressor, smpl_layer, h36m_regressor, physique_network=None):
         super().__init__()
@@ -113,8 +132,7 @@ class Counter3DModel(torch.nn.Module):
                 cam_key = "cam_{}".format(cam_id)
                 # (w - w[:, [0], :]) / 1000 exactly as model.py:124 writes it, then ONE discriminator call for all hypotheses
                 joints = evalops.root_centre(kps_world_ori[cam_key], self.DISC_SUP_DIMENSION).detach()
-                B, NH = joints.shape[:2]
-                pred_logits = smpl_discriminator(joints.flatten(0, 1)).reshape(B, NH, -1)
+                pred_logits = score_hypotheses(smpl_discriminator, joints)
                 loss_gen = loss_gen + evalops.compute_disc_loss(pred_logits, None)
             loss_values["smpl_gen"] = loss_gen * cfg["smpl_gen_loss"]["weight"]
 
@@ -188,8 +206,7 @@ class Counter3DDisc(torch.nn.Module):
             smpl_joints_world = ops.convert_patch_to_world(smpl_joints, x, cam_key, is_norm=True, RECT_WIDTH=256, mono=True, patch=False)
             output["pose_smpl_2d_{}".format(cam_key)] = smpl_joints[0:1, ...]
             output["pose_smpl_3d_{}".format(cam_key)] = smpl_joints_world[0:1, ...].clone()
-            B, NH = pred_joints.shape[:2]
-            pred_logits = self.smpl_discriminator(pred_joints.detach()[..., :dim].flatten(0, 1).contiguous()).reshape(B, NH, -1)
+            pred_logits = score_hypotheses(self.smpl_discriminator, pred_joints.detach()[..., :dim])
             smpl_logits = self.smpl_discriminator(smpl_joints[..., :dim])
             output["smpl_logits_{}".format(cam_key)] = smpl_logits[0:1, ...]
             output["pred_logits_{}".format(cam_key)] = pred_logits[0:1, 0, ...]

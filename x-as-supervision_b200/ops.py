@@ -6,7 +6,8 @@ discriminator and trainer can call these unchanged:
 * `IntegralMultiHead`      replaces modules/keypoint_detector_integral_multi.py:69-88
 * `IntegralSingleHead`     replaces modules/keypoint_detector_integral.py:45-65
 * `PatchToWorld` / `convert_patch_to_world` / `convert_world_to_patch`
-                           replace modules/util.py:128-152 / :155-168
+                           replace modules/util.py:128-152 / :155-168; `convert_patch_to_image`, `convert_image_to_world`,
+                           `convert_image_to_patch`, `convert_world_to_image` replace :61-125 (all differentiable)
 * `IntegralReprojMinLoss`  replaces, for one camera, modules/model.py:64,71-79,105-114,158-162
                            (head + per-hypothesis world lift + loss terms + torch.min over slots)
 
@@ -23,11 +24,43 @@ from . import _cabi as cabi
 from . import dist as xdist
 
 __all__ = ["IntegralMultiHead", "IntegralSingleHead", "PatchToWorld", "IntegralReprojMinLoss", "integral_multi_head",
-           "integral_single_head", "convert_patch_to_world", "convert_world_to_patch", "find_peak",
-           "integral_reproj_min_loss", "launch_count", "GraphedReprojStep", "conv_integral_head", "ConvIntegralHead",
+           "integral_single_head", "convert_patch_to_world", "convert_world_to_patch", "convert_patch_to_image",
+           "convert_image_to_world", "convert_image_to_patch", "convert_world_to_image", "find_peak",
+           "integral_reproj_min_loss", "launch_count", "set_event_sink", "GraphedReprojStep", "conv_integral_head", "ConvIntegralHead",
            "conv_integral_head_train"]
 
 launch_count = cabi.launch_count
+_nvtx = torch.cuda.nvtx          # ranges around K1 / K2 (+ exchange) / K3: visible in nsys / ncu --nvtx, free otherwise
+_event_sink = None               # bench.py: dict name -> [(start, stop) CUDA events] recorded on the launching stream
+
+
+def set_event_sink(sink) -> None:
+    """Measurement hook: with a dict, every kernel range below also records a CUDA-event pair on the current stream
+    into `sink[range name]`; `None` switches it off.  Not for use under CUDA-graph capture."""
+    global _event_sink
+    _event_sink = sink
+
+
+class _range:
+    """NVTX range (and, when a sink is set, a CUDA-event pair) around the launches of one kernel group."""
+    __slots__ = ("name", "ev")
+
+    def __init__(self, name):
+        self.name = name
+        self.ev = None
+
+    def __enter__(self):
+        _nvtx.range_push(self.name)
+        if _event_sink is not None:
+            self.ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+            self.ev[0].record()
+
+    def __exit__(self, *exc):
+        if self.ev is not None:
+            self.ev[1].record()
+            _event_sink.setdefault(self.name, []).append(self.ev)
+        _nvtx.range_pop()
+        return False
 
 
 def _volume_dims(logits: torch.Tensor, num_kp: int) -> Tuple[int, int, int, int, int]:
@@ -51,7 +84,7 @@ def _head_forward(logits, num_kp, num_hypo, neighbor_size, head):
         torch.empty(num_kp, D, dtype=torch.float32, device=dev)
     idx = torch.empty(B, num_kp, num_hypo, dtype=torch.int64, device=dev)
     stats = torch.empty(cabi.lib.xsup_stats_floats(shape), dtype=torch.float32, device=dev)
-    with torch.cuda.device(dev):
+    with torch.cuda.device(dev), _range("xsup.K1.integral_fwd"):
         cabi.check(cabi.lib.xsup_integral_fwd(logits.data_ptr(), kps.data_ptr(), dmap.data_ptr(),
                                               idx.data_ptr() if head == cabi.HEAD_MULTI else None,
                                               stats.data_ptr(), shape, cabi.stream_ptr(dev)), "xsup_integral_fwd")
@@ -63,7 +96,7 @@ def _head_backward(logits, stats, shape, g_kps, inplace=False):
     g_kps = g_kps.to(torch.float32).contiguous()
     g_logits = logits if inplace else torch.empty_like(logits)
     coef = torch.empty(cabi.lib.xsup_coef_floats(shape), dtype=torch.float32, device=dev)
-    with torch.cuda.device(dev):
+    with torch.cuda.device(dev), _range("xsup.K3.integral_bwd"):
         cabi.check(cabi.lib.xsup_integral_bwd(logits.data_ptr(), stats.data_ptr(), g_kps.data_ptr(), g_logits.data_ptr(),
                                               coef.data_ptr(), shape, cabi.stream_ptr(dev)), "xsup_integral_bwd")
     return g_logits
@@ -136,37 +169,76 @@ def _flags(is_norm, mono, patch):
     return (cabi.FLAG_NORM if is_norm else 0) | (cabi.FLAG_MONO if mono else 0) | (cabi.FLAG_PATCH if patch else 0)
 
 
-class PatchToWorld(torch.autograd.Function):
-    """kps `[B,J,3]` + per-sample camera tensors -> world `[B,J,3]` (util.py:128-152), differentiable in kps."""
+def _f32c(t, dev, shape=None, name="tensor"):
+    t = t.detach().to(device=dev, dtype=torch.float32)
+    if shape is not None:
+        if t.numel() != int(torch.Size(shape).numel()):
+            raise ValueError("%s has %d elements, expected shape %s" % (name, t.numel(), tuple(shape)))
+        t = t.reshape(shape)
+    return t.contiguous()
+
+
+class _GeomStage(torch.autograd.Function):
+    """One call of `xsup_geom_patch_to_world` (direction 0) / `xsup_geom_world_to_patch` (direction 1) with the stages
+    `flags` select; differentiable in the points (the camera tensors are data-loader constants, as in the reference).
+
+    `intr` is a `[B,3,3]` k_mat (stride 9) or a tuple (fx, fy, cx, cy) of `[B]`-sized tensors (stride 1), or None."""
 
     @staticmethod
-    def forward(ctx, kps, trans_image, pelvis, k_mat, trans_world, rot_world, img_h, img_w, rect_width, flags):
-        cabi.require_cuda(kps, "keypoints")
-        kps = kps.to(torch.float32).contiguous()
-        B, J, _ = kps.shape
-        keep, cam = _cam_args(dict(trans_image=trans_image, pelvis=pelvis, k_mat=k_mat, trans_world=trans_world,
-                                   rot_world=rot_world), B)
-        world = torch.empty_like(kps)
-        with torch.cuda.device(kps.device):
-            cabi.check(cabi.lib.xsup_patch_to_world_fwd(kps.data_ptr(), cam, world.data_ptr(), B, J, img_h, img_w,
-                                                        float(rect_width), flags, cabi.stream_ptr(kps.device)),
-                       "xsup_patch_to_world_fwd")
-        ctx.save_for_backward(kps, *keep)
-        ctx.meta = (B, J, img_h, img_w, float(rect_width), flags)
-        return world
+    def forward(ctx, pts, direction, flags, img_dhw, depth_scale, trans_image, pelvis, intr, trans_world, rot_world):
+        cabi.require_cuda(pts, "keypoints")
+        if pts.dim() != 3 or pts.shape[-1] != 3:
+            raise ValueError("keypoints must be [B, J, 3], got %s" % (tuple(pts.shape),))
+        dev = pts.device
+        x = pts.detach().to(torch.float32).contiguous()
+        B, J, _ = x.shape
+        keep = []
+        g = cabi.Geom(B, J, int(img_dhw[0]), int(img_dhw[1]), int(img_dhw[2]), float(depth_scale), int(flags), 1)
+        if flags & cabi.GEOM_PATCH_STAGE:
+            ti, pv = _f32c(trans_image, dev, (B, 2, 3), "trans"), _f32c(pelvis, dev, (B, 3), "pelvis")
+            keep += [ti, pv]
+            g.trans_image, g.pelvis = ti.data_ptr(), pv.data_ptr()
+        if (flags & cabi.GEOM_CAMERA_STAGE) and not (flags & cabi.GEOM_MONO):
+            if isinstance(intr, (tuple, list)):
+                fx, fy, cx, cy = (_f32c(t, dev, (B,), "intrinsic") for t in intr)
+                keep += [fx, fy, cx, cy]
+                g.fx, g.fy, g.cx, g.cy, g.intr_stride = fx.data_ptr(), fy.data_ptr(), cx.data_ptr(), cy.data_ptr(), 1
+            else:
+                km = _f32c(intr, dev, (B, 3, 3), "k_mat")
+                keep.append(km)
+                base = km.data_ptr()
+                g.fx, g.fy, g.cx, g.cy, g.intr_stride = base, base + 16, base + 8, base + 20, 9
+            tw, rw = _f32c(trans_world, dev, (B, 3), "trans_world"), _f32c(rot_world, dev, (B, 3, 3), "rot_world")
+            keep += [tw, rw]
+            g.trans_world, g.rot_world = tw.data_ptr(), rw.data_ptr()
+        out = torch.empty_like(x)
+        fn = cabi.lib.xsup_geom_world_to_patch if direction else cabi.lib.xsup_geom_patch_to_world
+        with torch.cuda.device(dev):
+            cabi.check(fn(x.data_ptr(), out.data_ptr(), g, cabi.stream_ptr(dev)), "xsup_geom")
+        ctx.save_for_backward(x, *keep)
+        ctx.geom, ctx.direction, ctx.in_dtype = g, direction, pts.dtype
+        return out.to(pts.dtype) if pts.dtype != torch.float32 else out
 
     @staticmethod
-    def backward(ctx, g_world):
-        kps, *keep = ctx.saved_tensors
-        B, J, img_h, img_w, rect_width, flags = ctx.meta
-        cam = cabi.make_cam(*keep, B)
-        g_world = g_world.to(torch.float32).contiguous()
-        g_kps = torch.empty_like(kps)
-        with torch.cuda.device(kps.device):
-            cabi.check(cabi.lib.xsup_patch_to_world_bwd(kps.data_ptr(), g_world.data_ptr(), cam, g_kps.data_ptr(), B, J,
-                                                        img_h, img_w, rect_width, flags, cabi.stream_ptr(kps.device)),
-                       "xsup_patch_to_world_bwd")
-        return (g_kps,) + (None,) * 9
+    def backward(ctx, g_out):
+        x, *_keep = ctx.saved_tensors                       # `_keep` holds the tensors ctx.geom points into
+        dev = x.device
+        go = g_out.to(torch.float32).contiguous()
+        gi = torch.empty_like(x)
+        fn = cabi.lib.xsup_geom_world_to_patch_vjp if ctx.direction else cabi.lib.xsup_geom_patch_to_world_vjp
+        with torch.cuda.device(dev):
+            cabi.check(fn(x.data_ptr(), go.data_ptr(), gi.data_ptr(), ctx.geom, cabi.stream_ptr(dev)), "xsup_geom_vjp")
+        return (gi.to(ctx.in_dtype),) + (None,) * 9
+
+
+class PatchToWorld:
+    """kps `[B,J,3]` + per-sample camera tensors -> world `[B,J,3]` (util.py:128-152), differentiable in kps:
+    `_GeomStage` with both stages selected and the data loader's tensors (`k_mat`, depth extent = image width)."""
+
+    @staticmethod
+    def apply(kps, trans_image, pelvis, k_mat, trans_world, rot_world, img_h, img_w, rect_width, flags):
+        return _GeomStage.apply(kps, 0, (flags & 7) | cabi.GEOM_CAMERA_STAGE, (img_w, img_h, img_w), float(rect_width) / img_w,
+                                trans_image, pelvis, k_mat, trans_world, rot_world)
 
 
 def _unpack_params(params: Dict[str, torch.Tensor], mode: str):
@@ -183,19 +255,34 @@ def convert_patch_to_world(keypoints, params, mode, is_norm=True, RECT_WIDTH=200
 
 
 def convert_world_to_patch(keypoints, params, mode, is_norm=True, RECT_WIDTH=2000):
-    """modules/util.py:155-168 (forward perspective projection).  Not differentiable here: the
-    reference never back-propagates through it (only `project_smpl_to_patch_kps` reaches it)."""
+    """modules/util.py:155-168 (forward perspective projection, the inverse of `convert_patch_to_world`);
+    differentiable in the keypoints."""
     cams, img_h, img_w = _unpack_params(params, mode)
-    cabi.require_cuda(keypoints, "keypoints")
-    world = keypoints.detach().to(torch.float32).contiguous()
-    B, J, _ = world.shape
-    _, cam = _keep = _cam_args(cams, B)
-    out = torch.empty_like(world)
-    with torch.cuda.device(world.device):
-        cabi.check(cabi.lib.xsup_world_to_patch_fwd(world.data_ptr(), cam, out.data_ptr(), B, J, img_h, img_w,
-                                                    float(RECT_WIDTH), _flags(is_norm, False, True),
-                                                    cabi.stream_ptr(world.device)), "xsup_world_to_patch_fwd")
-    return out
+    flags = (cabi.GEOM_NORM if is_norm else 0) | cabi.GEOM_PATCH_STAGE | cabi.GEOM_CAMERA_STAGE
+    return _GeomStage.apply(keypoints, 1, flags, (img_w, img_h, img_w), float(RECT_WIDTH) / img_w, cams["trans_image"],
+                            cams["pelvis"], cams["k_mat"], cams["trans_world"], cams["rot_world"])
+
+
+def convert_patch_to_image(kps, trans, image_depth, image_height, image_width, depth_scale, pelvis, is_norm=True):
+    """modules/util.py:61-82, same signature: inverse crop affine, depth px -> mm + pelvis depth."""
+    flags = (cabi.GEOM_NORM if is_norm else 0) | cabi.GEOM_PATCH_STAGE
+    return _GeomStage.apply(kps, 0, flags, (image_depth, image_height, image_width), depth_scale, trans, pelvis, None, None, None)
+
+
+def convert_image_to_world(kps, fx, fy, u, v, trans, rot):
+    """modules/util.py:85-95, same signature: pinhole back-projection, inverse extrinsics (general 3x3 inverse)."""
+    return _GeomStage.apply(kps, 0, cabi.GEOM_CAMERA_STAGE, (2, 2, 2), 1.0, None, None, (fx, fy, u, v), trans, rot)
+
+
+def convert_image_to_patch(kps, trans, image_depth, image_height, image_width, depth_scale, pelvis, is_norm=True):
+    """modules/util.py:98-113, same signature: mm -> depth px about the pelvis, crop affine, optional normalisation."""
+    flags = (cabi.GEOM_NORM if is_norm else 0) | cabi.GEOM_PATCH_STAGE
+    return _GeomStage.apply(kps, 1, flags, (image_depth, image_height, image_width), depth_scale, trans, pelvis, None, None, None)
+
+
+def convert_world_to_image(kps, fx, fy, u, v, trans, rot):
+    """modules/util.py:116-125, same signature: extrinsics then perspective division."""
+    return _GeomStage.apply(kps, 1, cabi.GEOM_CAMERA_STAGE, (2, 2, 2), 1.0, None, None, (fx, fy, u, v), trans, rot)
 
 
 # --------------------------------------------------------------------------------------- fused head + loss
@@ -242,15 +329,25 @@ class IntegralReprojMinLoss(torch.autograd.Function):
         sel_shape = {"batch": (2,), "sample": (2, B), "joint": (B, K)}[reduction]
         sel = torch.empty(sel_shape, dtype=torch.int64, device=dev)
         st = cabi.stream_ptr(dev)
-        with torch.cuda.device(dev):
-            cabi.check(cabi.lib.xsup_reproj_loss_fwd(kps.data_ptr(), target.data_ptr(), cam, world.data_ptr(),
-                                                     sample_terms.data_ptr(), partial.data_ptr(), cfg, st), "xsup_reproj_loss_fwd")
-            if reduction == "batch":
-                xdist.reduce_partials(partial, group)            # the one exchange step of the path
-            cabi.check(cabi.lib.xsup_reproj_select(kps.data_ptr(), target.data_ptr(), sample_terms.data_ptr(),
-                                                   partial.data_ptr(), loss.data_ptr(), sel.data_ptr(), cfg, st), "xsup_reproj_select")
-            if reduction != "batch":
-                xdist.reduce_partials(loss, group)               # reporting only: the gradient needs just n_total
+        nccl_group = xdist.is_active(group) and not isinstance(group, xdist.PeerExchange)
+        with torch.cuda.device(dev), _range("xsup.K2.loss_select_fwd"):
+            if not nccl_group:
+                # ONE launch: world lift + loss terms, last CTA done -> fixed-order batch sums -> NVLink exchange -> slots
+                xchg = group.descriptor() if xdist.is_active(group) else None
+                ticket = stats.data_ptr() + 4 * (B * K * int(cabi.lib.xsup_stats_stride(shape)) + 1)
+                cabi.check(cabi.lib.xsup_reproj_fused_fwd(kps.data_ptr(), target.data_ptr(), cam, world.data_ptr(),
+                                                          sample_terms.data_ptr(), partial.data_ptr(), loss.data_ptr(),
+                                                          sel.data_ptr(), cfg, xchg, ticket, st), "xsup_reproj_fused_fwd")
+            else:
+                # a torch.distributed process group (NCCL): the all-reduce is a library call between two of our launches
+                cabi.check(cabi.lib.xsup_reproj_loss_fwd(kps.data_ptr(), target.data_ptr(), cam, world.data_ptr(),
+                                                         sample_terms.data_ptr(), partial.data_ptr(), cfg, st), "xsup_reproj_loss_fwd")
+                if reduction == "batch":
+                    xdist.reduce_partials(partial, group)        # the one exchange step of the path
+                cabi.check(cabi.lib.xsup_reproj_select(kps.data_ptr(), target.data_ptr(), sample_terms.data_ptr(),
+                                                       partial.data_ptr(), loss.data_ptr(), sel.data_ptr(), cfg, st), "xsup_reproj_select")
+                if reduction != "batch":
+                    xdist.reduce_partials(loss, group)           # reporting only: the gradient needs just n_total
         ctx.save_for_backward(logits, stats, kps, target, sel, *keep)
         ctx.shape, ctx.cfg = shape, cfg
         ctx.mark_non_differentiable(sel, dmap, idx)
@@ -261,28 +358,32 @@ class IntegralReprojMinLoss(torch.autograd.Function):
         logits, stats, kps, target, sel, *keep = ctx.saved_tensors
         shape, cfg = ctx.shape, ctx.cfg
         dev = logits.device
-        cam = cabi.make_cam(*keep, shape.B)
         if g_lp is None and g_ls is None and g_kps_out is None and g_world is None:
             return (None,) * 18
-        zero = torch.zeros((), dtype=torch.float32, device=dev)
-        g_loss = torch.stack([(g_lp if g_lp is not None else zero).to(torch.float32),
-                              (g_ls if g_ls is not None else zero).to(torch.float32)]).contiguous()
-        g_kps = torch.empty_like(kps)
+        cam = cabi.make_cam(*keep, shape.B)
+
+        def ptr(t):                                   # fp32 contiguous device tensor or NULL; no kernels for fp32 inputs
+            if t is None:
+                return None, None
+            t = t.to(torch.float32).contiguous()
+            return t, t.data_ptr()
+        g_lp, p_lp = ptr(g_lp)
+        g_ls, p_ls = ptr(g_ls)
+        g_kps_out, p_gk = ptr(g_kps_out)              # downstream use of kps (draw_lines, model.py:91)
+        g_world, p_gw = ptr(g_world)                  # downstream use of kps_world (generator loss with use_aug, model.py:138)
+        coef = torch.empty(cabi.lib.xsup_coef_floats(shape), dtype=torch.float32, device=dev)
+        g_logits = torch.empty_like(logits)
+        st = cabi.stream_ptr(dev)
         with torch.cuda.device(dev):
-            cabi.check(cabi.lib.xsup_reproj_loss_bwd(kps.data_ptr(), target.data_ptr(), cam, sel.data_ptr(), g_loss.data_ptr(),
-                                                     g_kps.data_ptr(), cfg, cabi.stream_ptr(dev)), "xsup_reproj_loss_bwd")
-            if g_world is not None:
-                # downstream use of kps_world (e.g. the generator loss with use_aug, model.py:138)
-                gw = g_world.to(torch.float32).contiguous().view(shape.B, -1, 3)
-                extra = torch.empty_like(gw)
-                cabi.check(cabi.lib.xsup_patch_to_world_bwd(kps.data_ptr(), gw.data_ptr(), cam, extra.data_ptr(), shape.B,
-                                                            shape.NH * shape.K, cfg.img_h, cfg.img_w, cfg.rect_width,
-                                                            cabi.FLAG_NORM | cabi.FLAG_PATCH, cabi.stream_ptr(dev)),
-                           "xsup_patch_to_world_bwd")
-                g_kps += extra.view_as(g_kps)
-        if g_kps_out is not None:
-            g_kps += g_kps_out                                   # downstream use of kps (draw_lines, model.py:91)
-        return (_head_backward(logits, stats, shape, g_kps),) + (None,) * 17
+            with _range("xsup.K2.loss_bwd_coef"):
+                # ONE launch: loss VJP of every hypothesis + upstream gradients -> coefficient blocks; d loss / d kps stays on chip
+                cabi.check(cabi.lib.xsup_reproj_fused_bwd(kps.data_ptr(), target.data_ptr(), cam, sel.data_ptr(), p_lp, p_ls, p_gk,
+                                                          p_gw, stats.data_ptr(), coef.data_ptr(), None, cfg, shape, st),
+                           "xsup_reproj_fused_bwd")
+            with _range("xsup.K3.integral_bwd"):
+                cabi.check(cabi.lib.xsup_integral_bwd_apply(logits.data_ptr(), coef.data_ptr(), g_logits.data_ptr(), shape, st),
+                           "xsup_integral_bwd_apply")
+        return (g_logits,) + (None,) * 17
 
 
 def integral_reproj_min_loss(logits, target, cams: Dict[str, torch.Tensor], num_kp, num_hypo, neighbor_size,
