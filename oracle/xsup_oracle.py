@@ -240,6 +240,25 @@ def supervision_mse(pred, gt):
     return ((pred - gt) ** 2).mean()
 
 
+def supervision(keypoint, keypoint_gt, feature_shape=None, mode="mean"):
+    """compute_supervision with all its arguments (loss_func.py:38-52): optional rescale of the prediction to a feature
+    grid (:39-45), then nn.MSELoss(reduction=mode) with mode in mean / sum (divided by the batch size, :50-51) / none."""
+    k = keypoint
+    if feature_shape is not None:
+        cols = [(k[..., 0] + 1) / 2.0 * (feature_shape[0] - 1), (k[..., 1] + 1) / 2.0 * (feature_shape[1] - 1)]
+        if k.shape[-1] == 3:
+            cols.append(k[..., 2] * (feature_shape[2] - 1))
+        k = torch.stack(cols, dim=-1)
+    e = (k - keypoint_gt) ** 2
+    if mode == "none":
+        return e
+    if mode == "sum":
+        return e.sum() / k.shape[0]
+    if mode == "mean":
+        return e.mean()
+    raise ValueError("unknown mode %r" % (mode,))
+
+
 def bone_sym(world):
     """compute_bone_sym_loss (loss_func.py:18-25) on `[B,K,3]` world mm."""
     v = world[:, list(BONE_CHILD), :] - world[:, list(BONE_PARENT), :]

@@ -91,6 +91,53 @@ def test_geometry_both_directions(ref, oracle, synth, B, K, seed, mpi):
     assert rel_inf(oracle.patch_to_world(kps, cams, is_norm=False).numpy(), r_raw.numpy()) < 1e-12
 
 
+@pytest.mark.parametrize("mode", ["mean", "sum", "none"])
+@pytest.mark.parametrize("fs,C", [(None, 3), ((64, 48, 32), 3), ((64, 48), 2)])
+def test_compute_supervision_all_modes(ref, oracle, synth, mode, fs, C):
+    """loss_func.py:38-52 with feature_shape and every nn.MSELoss reduction, values and gradients."""
+    kp, gt = synth.pseudo_joints(4, 18, seed=41).double()[..., :C], synth.pseudo_joints(4, 18, seed=42).double()[..., :C]
+    a, b = kp.clone().requires_grad_(True), kp.clone().requires_grad_(True)
+    ra, ob = ref["lf"].compute_supervision(a, gt, feature_shape=fs, mode=mode), oracle.supervision(b, gt, feature_shape=fs, mode=mode)
+    assert ra.shape == ob.shape
+    gw = torch.randn(ra.shape, generator=torch.Generator().manual_seed(43), dtype=torch.float64)
+    (ra * gw).sum().backward()
+    (ob * gw).sum().backward()
+    assert rel_inf(ob.detach().numpy(), ra.detach().numpy()) < 1e-12
+    assert rel_inf(b.grad.numpy(), a.grad.numpy()) < 1e-12
+
+
+@pytest.mark.parametrize("B,K,seed,mpi,is_norm", [(3, 18, 15, False, True), (2, 17, 16, True, False), (5, 4, 17, False, False)])
+def test_geometry_stage_by_stage_with_gradients(ref, oracle, synth, B, K, seed, mpi, is_norm):
+    """util.py:61-125 one stage at a time, with the free parameters the composites fix (image_depth != width, any
+    depth_scale, general matrices), values and autograd VJPs: the pin of the oracle functions that the stage-wise GPU API
+    (`ops.convert_patch_to_image` ... `ops.convert_world_to_image`) is tested against."""
+    util = ref["util"]
+    g = torch.Generator().manual_seed(seed)
+    cams = {k: v.double() for k, v in synth.cameras(B, seed=seed, mpi=mpi).items()}
+    cams["rot_world"] = cams["rot_world"] + 0.1 * torch.randn(B, 3, 3, generator=g, dtype=torch.float64)
+    cams["trans_image"][:, :, :2] += 0.05 * torch.randn(B, 2, 2, generator=g, dtype=torch.float64)
+    fx, fy, cx, cy = oracle._intrinsics(cams["k_mat"])
+    img_d, img_h, img_w, ds = 200, 240, 256, 6.5
+    kps = synth.pseudo_joints(B, K, seed=seed + 1).double()
+    if not is_norm:
+        kps = (kps + 1) * 100
+    gw = torch.randn(B, K, 3, generator=g, dtype=torch.float64)
+
+    def pair(rfn, ofn, x0, *args):
+        a, b = x0.clone().requires_grad_(True), x0.clone().requires_grad_(True)
+        ra, ob = rfn(a, *args), ofn(b, *args)
+        (ra * gw).sum().backward()
+        (ob * gw).sum().backward()
+        assert rel_inf(ob.detach().numpy(), ra.detach().numpy()) < 1e-12, rfn.__name__
+        assert rel_inf(b.grad.numpy(), a.grad.numpy()) < 1e-12, rfn.__name__
+        return ra.detach()
+    img = pair(util.convert_patch_to_image, oracle.patch_to_image, kps, cams["trans_image"], img_d, img_h, img_w, ds, cams["pelvis"], is_norm)
+    world = pair(util.convert_image_to_world, oracle.image_to_world, img, fx, fy, cx, cy, cams["trans_world"], cams["rot_world"])
+    img2 = pair(util.convert_world_to_image, oracle.world_to_image, world, fx, fy, cx, cy, cams["trans_world"], cams["rot_world"])
+    back = pair(util.convert_image_to_patch, oracle.image_to_patch, img2, cams["trans_image"], img_d, img_h, img_w, ds, cams["pelvis"], is_norm)
+    assert rel_inf(back.numpy(), kps.numpy()) < 1e-9            # the four stages compose to the identity
+
+
 @pytest.mark.parametrize("B,K,R,NH,NS,seed", [(2, 17, 32, 3, 15, 31), (3, 18, 32, 2, 7, 32), (1, 17, 24, 3, 3, 33), (4, 18, 12, 1, 15, 34)])
 @pytest.mark.parametrize("weights", [(3.0, None, None, None), (1.0, 0.1, 0.1, 0.0), (1.0, 0.1, 0.1, 0.5)])
 def test_fused_loss_and_gradient(ref, oracle, synth, B, K, R, NH, NS, seed, weights):
