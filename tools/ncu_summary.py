@@ -11,10 +11,10 @@ def launches(src, dst, cmd):
         for r in rows[1:]:
             name = r[ik].split('(')[0].replace('void ', '')[:60]
             f.write("%s,%s,%s,%s,%s\n" % (r[0], name, r[ig].replace(',', ' '), r[ib].replace(',', ' '), r[iv]))
-            agg.setdefault(name, []).append(float(r[iv].replace(',', '')))
+            agg.setdefault(name + " grid" + r[ig].replace(',', 'x').replace(' ', ''), []).append(float(r[iv].replace(',', '')))
         ours = {k: v for k, v in agg.items() if k.startswith('xsup::')}
         tot = sum(sum(v) for v in ours.values())
-        f.write("# --- xsup kernels only (the timed step): name, launches, mean_us, share\n")
+        f.write("# --- xsup kernels only, per (kernel, grid): the parity gate's small launches come first and are listed apart; name, launches, mean_us, share\n")
         for k, v in sorted(ours.items(), key=lambda kv: -sum(kv[1])):
             f.write("# %s,%d,%.1f,%.4f\n" % (k, len(v), sum(v) / len(v) / 1e3, sum(v) / tot))
             print("%-50s n=%3d mean=%9.1f us share=%5.1f%%" % (k, len(v), sum(v) / len(v) / 1e3, 100 * sum(v) / tot))
@@ -47,8 +47,8 @@ def full(rep, dst, cmd):
         for k in KEYS:
             if k in h:
                 print("  %-80s %s %s" % (k, r[h.index(k)], rows[1][h.index(k)]))
-        out[n] = int((float(r[h.index('dram__bytes_read.sum')].replace(',', '')) * {'Gbyte': 1e9, 'Mbyte': 1e6}[rows[1][h.index('dram__bytes_read.sum')]]
-                      + float(r[h.index('dram__bytes_write.sum')].replace(',', '')) * {'Gbyte': 1e9, 'Mbyte': 1e6, 'Kbyte': 1e3}[rows[1][h.index('dram__bytes_write.sum')]]))
+        scale = {'Gbyte': 1e9, 'Mbyte': 1e6, 'Kbyte': 1e3, 'byte': 1.0}
+        out[n] = int(sum(float(r[h.index(m)].replace(',', '')) * scale[rows[1][h.index(m)]] for m in ('dram__bytes_read.sum', 'dram__bytes_write.sum')))
     return out
 
 if __name__ == '__main__':
