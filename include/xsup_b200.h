@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define XSUP_ABI_VERSION 10
+#define XSUP_ABI_VERSION 11
 
 enum { XSUP_F32 = 0, XSUP_BF16 = 1 };
 enum { XSUP_HEAD_MULTI = 0, XSUP_HEAD_SINGLE = 1 };
@@ -352,12 +352,22 @@ int xsup_pack_nhwc_bf16(const float* x_nchw, void* x_nhwc_bf16, int32_t B, int32
 int xsup_conv_head_fwd(const void* x_nhwc, const void* weight, const float* bias, float* kps, float* depth_prob_map,
                        int64_t* peak_idx, float* stats, float* logits_out, const xsup_shape_t* s, int32_t C, void* stream);
 
-/* Backward of the conv-fused head without the logits: (1) xsup_integral_coef turns g_kps + the saved statistics into
- * the per-unit coefficient blocks (the first half of xsup_integral_bwd); (2) xsup_conv_head_bwd_g recomputes the
- * logits tile by tile on the tensor cores and writes d loss / d logits as bf16 `g [B, K*D, H*W]` (a quarter of the
- * traffic of reading fp32 logits and writing an fp32 gradient) plus `gbias_part [B, 4, K*D]` fp32 (sum over them = d
- * loss / d bias).  d loss / d x = g^T W and d loss / d W = g X are then two plain bf16 library GEMMs on `g`. */
+/* Backward of the conv-fused head, logits-free and on the tensor cores (csrc/conv_head_bwd.cu):
+ *   (1) xsup_integral_coef turns g_kps + the saved statistics into the per-unit coefficient blocks (the first half of
+ *       xsup_integral_bwd);
+ *   (2) xsup_conv_head_bwd recomputes the logit tiles with tcgen05.mma, forms d loss / d logits in the epilogue, keeps it in
+ *       shared memory as a bf16 MMA operand and contracts it at once:
+ *         dx     [B, H, W, C]  channels-last, bf16 (dx_f32 == 0) or fp32 (dx_f32 == 1)   = G^T W     (NULL: skipped)
+ *         dw     [K*D, C]      fp32                                                     = sum_b G X (NULL: skipped, with dbias)
+ *         dbias  [K*D]         fp32 or NULL                                             = sum_{b,p} G
+ *       dw / dbias are zeroed by the call and accumulated with fp32 atomics (the summation order over samples is not fixed).
+ *       rowcoef_ws: xsup_conv_bwd_ws_floats(s) floats of scratch.  Same shape constraints as xsup_conv_head_fwd.
+ *   xsup_conv_head_bwd_g (validation / diagnostics) writes d loss / d logits itself as bf16 `g [B, K*D, H*W]` plus
+ *   `gbias_part [B, 4, K*D]` fp32 (sum over the first two axes = d loss / d bias). */
 int xsup_integral_coef(const float* stats, const float* g_kps, float* coef_ws, const xsup_shape_t* s, void* stream);
+size_t xsup_conv_bwd_ws_floats(const xsup_shape_t* s);
+int xsup_conv_head_bwd(const void* x_nhwc, const void* weight, const float* bias, const float* coef_ws, float* rowcoef_ws, void* dx,
+                       int32_t dx_f32, float* dw, float* dbias, const xsup_shape_t* s, int32_t C, void* stream);
 int xsup_conv_head_bwd_g(const void* x_nhwc, const void* weight, const float* bias, const float* coef_ws, void* g_out,
                          float* gbias_part, const xsup_shape_t* s, int32_t C, void* stream);
 

@@ -26,7 +26,7 @@ def test_library_exports_every_declared_symbol(cabi):
     assert declared == set(cabi.SYMBOLS)
     for name in declared:
         assert hasattr(cabi.lib, name), name
-    assert cabi.lib.xsup_abi_version() == cabi.ABI_VERSION == 10
+    assert cabi.lib.xsup_abi_version() == cabi.ABI_VERSION == 11
     assert int(re.search(r"#define\s+XSUP_ABI_VERSION\s+(\d+)", header).group(1)) == cabi.ABI_VERSION
 
 

@@ -53,7 +53,34 @@ def bwd_g():
                                              shape, C, st), "bwd_g")
 
 
+rowcoef = torch.empty(cabi.lib.xsup_conv_bwd_ws_floats(shape), device=dev)
+dx = torch.empty(B, HW, C, dtype=torch.bfloat16, device=dev)
+dw = torch.empty(KD, C, device=dev)
+db = torch.empty(KD, device=dev)
+
+
+def bwd(dx_, dw_, db_):
+    cabi.check(cabi.lib.xsup_conv_head_bwd(xcl.data_ptr(), wb.data_ptr(), bias.data_ptr(), coef.data_ptr(), rowcoef.data_ptr(),
+                                           dx_.data_ptr() if dx_ is not None else None, 0, dw_.data_ptr() if dw_ is not None else None,
+                                           db_.data_ptr() if db_ is not None else None, shape, C, st), "bwd")
+
+
 out = {"fwd_ms": timeit(fwd), "coef_ms": timeit(coef_), "bwd_g_ms": timeit(bwd_g)}
+out["bwd_tc_dw_ms"] = timeit(lambda: bwd(None, dw, db))      # rowcoef + memsets + weight-stationary launch
+out["bwd_tc_dx_ms"] = timeit(lambda: bwd(dx, None, None))    # rowcoef + activation-stationary launch
+out["bwd_tc_both_ms"] = timeit(lambda: bwd(dx, dw, db))
+xg = xcl.detach().clone().requires_grad_(True)
+wg = wb.float().view(KD, C, 1, 1).requires_grad_(True)
+bg = bias.clone().requires_grad_(True)
+
+
+def train_step():
+    xg.grad = wg.grad = bg.grad = None
+    k, _, _ = ops.conv_integral_head_train(xg, wg, bg, K, NH, NS)
+    k.backward(gk)
+
+
+out["train_step_autograd_ms"] = timeit(train_step)
 out["dx_bmm_bf16_ms"] = timeit(lambda: torch.matmul(g.transpose(1, 2), wb))
 out["dx_bmm_f32out_ms"] = timeit(lambda: torch.bmm(g.transpose(1, 2), wb.unsqueeze(0).expand(B, KD, C), out_dtype=torch.float32))
 out["dw_bmm_f32_partials_ms"] = timeit(lambda: torch.bmm(g, x_flat, out_dtype=torch.float32))
@@ -63,4 +90,5 @@ out["dbias_sum_ms"] = timeit(lambda: gb.sum(dim=(0, 1)))
 out["pack_ms"] = timeit(lambda: cabi.check(cabi.lib.xsup_pack_nhwc_bf16(x.data_ptr(), xcl.data_ptr(), B, C, HW, st), "pack"))
 flops = 2.0 * KD * C * B * HW
 out["tflops"] = {k: round(flops / (out[k] * 1e-3) / 1e12, 1) for k in ("fwd_ms", "bwd_g_ms", "dx_bmm_bf16_ms", "dw_bmm_f32_partials_ms")}
+out["tflops"].update({k: round(2 * flops / (out[k] * 1e-3) / 1e12, 1) for k in ("bwd_tc_dw_ms", "bwd_tc_dx_ms")})   # two GEMMs per launch
 print(json.dumps(out))

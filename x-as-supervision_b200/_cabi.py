@@ -38,6 +38,8 @@ SYMBOLS = (
     # ABI v10
     "xsup_geom_patch_to_world", "xsup_geom_patch_to_world_vjp", "xsup_geom_world_to_patch", "xsup_geom_world_to_patch_vjp",
     "xsup_reproj_fused_fwd", "xsup_reproj_fused_bwd", "xsup_integral_bwd_apply", "xsup_pose_sqerr",
+    # ABI v11
+    "xsup_conv_bwd_ws_floats", "xsup_conv_head_bwd",
 )
 GEOM_NORM, GEOM_MONO, GEOM_PATCH_STAGE, GEOM_CAMERA_STAGE = 1, 2, 4, 8
 SCHED_WORDS = 16
@@ -150,6 +152,10 @@ def _load():
     lib.xsup_integral_coef.restype = C.c_int
     lib.xsup_conv_head_bwd_g.argtypes = [vp, vp, vp, vp, vp, vp, C.POINTER(Shape), i32, vp]
     lib.xsup_conv_head_bwd_g.restype = C.c_int
+    lib.xsup_conv_bwd_ws_floats.restype = C.c_size_t
+    lib.xsup_conv_bwd_ws_floats.argtypes = [C.POINTER(Shape)]
+    lib.xsup_conv_head_bwd.argtypes = [vp, vp, vp, vp, vp, vp, i32, vp, vp, C.POINTER(Shape), i32, vp]
+    lib.xsup_conv_head_bwd.restype = C.c_int
     gp = C.POINTER(Geom)
     lib.xsup_geom_patch_to_world.argtypes = [vp, vp, gp, vp]
     lib.xsup_geom_patch_to_world_vjp.argtypes = [vp, vp, vp, gp, vp]
@@ -181,7 +187,7 @@ def _load():
 
 
 lib = _load()
-ABI_VERSION = 10
+ABI_VERSION = 11
 if lib.xsup_abi_version() != ABI_VERSION:
     raise ImportError("libxsup_b200.so ABI version %d, expected %d: rebuild with __graft_entry__.build()"
                       % (lib.xsup_abi_version(), ABI_VERSION))

@@ -646,6 +646,33 @@ int xsup_integral_coef(const float* stats, const float* g_kps, float* coef_ws, c
     return XSUP_OK;
 }
 
+size_t xsup_conv_bwd_ws_floats(const xsup_shape_t* s) { return s ? (size_t)s->B * conv_bwd_rows_pad(s->K, s->D) * 4 : 0; }
+
+int xsup_conv_head_bwd(const void* x_nhwc, const void* weight, const float* bias, const float* coef_ws, float* rowcoef_ws, void* dx,
+                       int32_t dx_f32, float* dw, float* dbias, const xsup_shape_t* s, int32_t C, void* stream) {
+    if (int rc = check_conv_shape(s, C, "xsup_conv_head_bwd")) return rc;
+    if (s->B == 0) {
+        if (dw) {
+            cudaError_t e = cudaMemsetAsync(dw, 0, (size_t)s->K * s->D * C * sizeof(float), (cudaStream_t)stream);
+            if (e == cudaSuccess && dbias) e = cudaMemsetAsync(dbias, 0, (size_t)s->K * s->D * sizeof(float), (cudaStream_t)stream);
+            if (e != cudaSuccess) return cuda_fail(e, "xsup_conv_head_bwd memset");
+        }
+        return XSUP_OK;
+    }
+    if (!x_nhwc || !weight || !coef_ws || !rowcoef_ws) return fail(XSUP_E_NULL, "xsup_conv_head_bwd: NULL pointer");
+    if (dbias && !dw) return fail(XSUP_E_NULL, "xsup_conv_head_bwd: dbias is produced by the dw launch, pass dw as well");
+    if (!aligned16(x_nhwc) || !aligned16(weight) || !aligned16(rowcoef_ws) || !aligned16(dx) || !aligned16(dw))
+        return fail(XSUP_E_ALIGN, "xsup_conv_head_bwd: x/weight/rowcoef_ws/dx/dw must be 16-byte aligned");
+    int sms = 0;
+    if (int rc = device_info(sms)) return rc;
+    cudaError_t e = launch_conv_head_bwd(x_nhwc, weight, bias, coef_ws, (int)coef_stride(*s), rowcoef_ws, dx, dx_f32 ? 1 : 0, dw, dbias, s->B,
+                                         s->K, s->D, s->H, s->W, C, sms, (cudaStream_t)stream);
+    if (e == cudaErrorNotSupported) return fail(XSUP_E_DEVICE, "xsup_conv_head_bwd: cuTensorMapEncodeTiled unavailable or rejected the tensors");
+    if (e != cudaSuccess) return cuda_fail(e, "xsup_conv_head_bwd launch");
+    count_launches(1 + (dw ? 1 : 0) + (dx ? 1 : 0));
+    return XSUP_OK;
+}
+
 int xsup_conv_head_bwd_g(const void* x_nhwc, const void* weight, const float* bias, const float* coef_ws, void* g_out, float* gbias_part,
                          const xsup_shape_t* s, int32_t C, void* stream) {
     if (int rc = check_conv_shape(s, C, "xsup_conv_head_bwd_g")) return rc;

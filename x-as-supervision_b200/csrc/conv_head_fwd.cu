@@ -27,9 +27,8 @@
 // tear-down, and computing the descriptors inside the issue loop cost ~65 cycles per MMA.
 // Roofline: tensor (2*K*D*C flops per pixel = 584 GFLOP at B=256) with MUFU.EX2 of the epilogue at the same
 // order (one exp per logit); HBM traffic is the activations only (0.54 GB).
-#include <cuda.h>
-
 #include "xsup_finalise.cuh"
+#include "xsup_umma.cuh"
 
 namespace xsup {
 
@@ -39,7 +38,6 @@ constexpr int kCvFinWarps = 2;
 constexpr int kCvThreads = (kCvEpiWarps + 2 + kCvFinWarps) * 32;
 constexpr int kCvRows = 128;           // UMMA M: output rows per CTA
 constexpr int kCvPix = 128;            // UMMA N: pixels per tile
-constexpr int kCvKB = 64;              // channels per swizzle-128B k-block (bf16)
 constexpr int kCvStages = 2;
 constexpr int kCvAcc = 4;              // TMEM accumulator buffers (4 x 128 columns = all 512)
 constexpr int kCvKBBytes = kCvRows * kCvKB * 2;   // 16 KB: one [128 x 64] bf16 k-block (same for W and X tiles)
@@ -60,61 +58,7 @@ struct ConvHeadParams {
     int items;                  // B * groups
 };
 
-// ------------------------------------------------------------------ PTX wrappers (sm_100a)
-__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar) {
-    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(dst),
-                 "l"(map), "r"(c0), "r"(c1), "r"(bar)
-                 : "memory");
-}
-__device__ __forceinline__ void tmem_alloc(uint32_t smem_dst, uint32_t cols) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst), "r"(cols) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-// D[tmem] (+)= A[smem desc] * B[smem desc]; ACC = false overwrites the accumulator (first MMA of a tile)
-template <bool ACC>
-__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc) {
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
-        "}" ::"r"(tmem_d),
-        "l"(desc_a), "l"(desc_b), "r"(idesc), "n"(ACC ? 1 : 0)
-        : "memory");
-}
-// arrives on the mbarrier when all previously issued tcgen05.mma of this thread have completed
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
-          "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
-          "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
-          "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-        : "r"(taddr)
-        : "memory");
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-}
-// K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start address >> 4 in [0,14),
-// stride byte offset (8 rows x 128 B = 1024 B) >> 4 in [32,46), descriptor version 1 in [46,48), layout type 2 in [61,64).
-// The leading byte offset is unused for swizzled K-major operands.  Stepping K by 16 bf16 (32 B) inside the 128-byte
-// swizzle atom adds 2 to the start-address field; the hardware applies the XOR pattern on the absolute address, which
-// is why every k-block sits on a 1024-byte boundary.
-__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
-    return (uint64_t)((smem_addr & 0x3ffffu) >> 4) | ((uint64_t)(1024u >> 4) << 32) | (1ull << 46) | (2ull << 61);
-}
-// instruction descriptor (cute::UMMA::InstrDescriptor): D = f32 (bit 4), A = B = bf16 (bits 7, 10), both K-major,
-// N >> 3 in [17,23), M >> 4 in [24,29)
-constexpr uint32_t kCvIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(kCvPix >> 3) << 17) | ((uint32_t)(kCvRows >> 4) << 24);
+constexpr uint32_t kCvIdesc = umma_idesc_bf16(kCvRows, kCvPix);
 
 // ------------------------------------------------------------------ kernel
 template <int KBN, int MODE>            // MODE 0: forward statistics + finaliser; MODE 1: backward, emits d loss / d logits in bf16
@@ -420,33 +364,6 @@ cudaError_t launch_pack_nhwc_bf16(const float* x, void* y, int B, int C, int HW,
 }
 
 // ------------------------------------------------------------------ host side
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-static EncodeTiledFn encode_tiled() {
-    static EncodeTiledFn fn = nullptr;
-    if (!fn) {
-        void* ptr = nullptr;
-        cudaDriverEntryPointQueryResult q;
-        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
-            fn = reinterpret_cast<EncodeTiledFn>(ptr);
-    }
-    return fn;
-}
-
-// [rows, C] bf16 row-major (C contiguous) -> boxes of [128 rows x 64 channels], 128-byte swizzle, zero fill out of bounds
-static bool make_map(CUtensorMap* map, const void* base, long long rows, int C) {
-    EncodeTiledFn enc = encode_tiled();
-    if (!enc) return false;
-    const cuuint64_t dims[2] = {(cuuint64_t)C, (cuuint64_t)rows};
-    const cuuint64_t strides[1] = {(cuuint64_t)C * 2};
-    const cuuint32_t box[2] = {(cuuint32_t)kCvKB, (cuuint32_t)kCvRows};
-    const cuuint32_t estr[2] = {1, 1};
-    return enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-               CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
-}
-
 template <int KBN, int MODE>
 static cudaError_t launch_kbn(const CUtensorMap& map_w, const CUtensorMap& map_x, const ConvHeadParams& p, int grid, size_t smem, cudaStream_t st) {
     auto kern = conv_head_fwd_kernel<KBN, MODE>;

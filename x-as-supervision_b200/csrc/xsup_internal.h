@@ -127,6 +127,11 @@ cudaError_t launch_conv_head_fwd(const void* x_nhwc, const void* w, const float*
 cudaError_t launch_conv_head_bwd_g(const void* x_nhwc, const void* w, const float* bias, const float* coef, int coef_stride, void* g_out,
                                    float* gbias_part, FwdParams f, int B, int C, int num_sms, cudaStream_t st);
 cudaError_t launch_pack_nhwc_bf16(const float* x, void* y, int B, int C, int HW, cudaStream_t st);
+// conv-fused backward (conv_head_bwd.cu)
+int conv_bwd_rows_pad(int K, int D);
+cudaError_t launch_conv_head_bwd(const void* x_nhwc, const void* w, const float* bias, const float* coef, int coef_stride, float* rowcoef_ws,
+                                 void* dx, int dx_f32, float* dw, float* dbias, int B, int K, int D, int H, int W, int C, int num_sms,
+                                 cudaStream_t st);
 
 void count_launches(int n);
 

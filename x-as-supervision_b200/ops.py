@@ -500,25 +500,17 @@ def conv_integral_head(x: torch.Tensor, weight: torch.Tensor, bias: Optional[tor
     return (kps, dmap, idx, logits) if return_logits else (kps, dmap, idx)
 
 
-def _bmm_f32(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
-    """bf16 x bf16 batched matmul with an fp32 result (library GEMM; `out_dtype` exists in recent PyTorch)."""
-    try:
-        return torch.bmm(a, b, out_dtype=torch.float32)
-    except TypeError:                                        # older signature: accumulate in fp32 anyway, round once
-        return torch.bmm(a, b).float()
-
-
 class ConvIntegralHead(torch.autograd.Function):
-    """Differentiable conv-fused head: `Conv2d(C, K*D, 1)` + integral multi-hypothesis head with NO logits tensor in
-    either direction.
+    """Differentiable conv-fused head: `Conv2d(C, K*D, 1)` + integral multi-hypothesis head with NO logits tensor and NO
+    d loss / d logits tensor in either direction.
 
     forward : `xsup_conv_head_fwd` (tcgen05 GEMM, softmax statistics from the TMEM accumulators).
-    backward: `xsup_integral_coef` (g_kps + saved statistics -> per-unit coefficients), `xsup_conv_head_bwd_g` (the same
-              GEMM again, d loss / d logits formed in the epilogue and written once as bf16), then the two remaining
-              contractions as plain library GEMMs on that tensor: d x = g^T W (bf16, channels-last like x) and
-              d W = sum_b g_b x_b (fp32 accumulate), d bias from the kernel's per-item partial sums.
+    backward: `xsup_integral_coef` (g_kps + saved statistics -> per-unit coefficients), then `xsup_conv_head_bwd`: two
+              tensor-core launches that each recompute the logit tiles, form d loss / d logits in the epilogue as a bf16
+              shared-memory MMA operand and contract it on the spot - weight-stationary for d W (+ d bias), activation-
+              stationary for d x.  No library GEMM, no intermediate in HBM.
     Gradients carry one bf16 rounding of d loss / d logits (relative 2^-9 per element), the same class of error as a
-    bf16 autocast backward of the reference's conv."""
+    bf16 autocast backward of the reference's conv; d W / d bias are accumulated with fp32 atomics over the samples."""
 
     @staticmethod
     def forward(ctx, x, weight, bias, num_kp, num_hypo, neighbor_size):
@@ -558,28 +550,30 @@ class ConvIntegralHead(torch.autograd.Function):
         KD, HW = K * D, H * W
         g_kps = g_kps.to(torch.float32).contiguous()
         coef = torch.empty(cabi.lib.xsup_coef_floats(shape), dtype=torch.float32, device=dev)
-        g = torch.empty(B, KD, HW, dtype=torch.bfloat16, device=dev)
-        gb = torch.empty(B, 4, KD, dtype=torch.float32, device=dev)
+        rowcoef = torch.empty(cabi.lib.xsup_conv_bwd_ws_floats(shape), dtype=torch.float32, device=dev)
+        need_x, need_w = ctx.needs_input_grad[0], ctx.needs_input_grad[1] or (bf is not None and ctx.needs_input_grad[2])
+        dx_f32 = x_dtype != torch.bfloat16                                     # fp32 input: do not round the result a second time
+        # channels-last storage [B, H, W, C], returned as the logical NCHW view of it
+        dx = torch.empty((B, C, H, W), dtype=torch.float32 if dx_f32 else torch.bfloat16, device=dev,
+                         memory_format=torch.channels_last) if need_x else None
+        dw = torch.empty(KD, C, dtype=torch.float32, device=dev) if need_w else None
+        db = torch.empty(KD, dtype=torch.float32, device=dev) if (need_w and bf is not None) else None
         st = cabi.stream_ptr(dev)
         with torch.cuda.device(dev):
             cabi.check(cabi.lib.xsup_integral_coef(stats.data_ptr(), g_kps.data_ptr(), coef.data_ptr(), shape, st), "xsup_integral_coef")
-            cabi.check(cabi.lib.xsup_conv_head_bwd_g(xb.data_ptr(), wb.data_ptr(), bf.data_ptr() if bf is not None else None,
-                                                     coef.data_ptr(), g.data_ptr(), gb.data_ptr(), shape, C, st), "xsup_conv_head_bwd_g")
-        x_flat = xb.permute(0, 2, 3, 1).reshape(B, HW, C)                    # the channels-last storage viewed [B, HW, C]
+            cabi.check(cabi.lib.xsup_conv_head_bwd(xb.data_ptr(), wb.data_ptr(), bf.data_ptr() if bf is not None else None, coef.data_ptr(),
+                                                   rowcoef.data_ptr(), dx.data_ptr() if need_x else None, 1 if dx_f32 else 0,
+                                                   dw.data_ptr() if need_w else None, db.data_ptr() if db is not None else None,
+                                                   shape, C, st), "xsup_conv_head_bwd")
         g_x = g_w = g_b = None
-        if ctx.needs_input_grad[0]:
-            gt = g.transpose(1, 2)                                             # [B, HW, KD] view
-            if x_dtype == torch.bfloat16:
-                dx = torch.matmul(gt, wb)                                      # [B, HW, C] bf16 = channels-last d x
-            else:                                                              # fp32 input: do not round the result a second time
-                dx = _bmm_f32(gt, wb.unsqueeze(0).expand(B, KD, C)).to(x_dtype)
-            g_x = dx.view(B, H, W, C).permute(0, 3, 1, 2)                      # logical NCHW over channels-last storage
+        if need_x:
+            g_x = dx.to(x_dtype)
             if not x_was_cl:
                 g_x = g_x.contiguous()
         if ctx.needs_input_grad[1]:
-            g_w = _bmm_f32(g, x_flat).sum(0).to(w_dtype).reshape(w_shape)
+            g_w = dw.to(w_dtype).reshape(w_shape)
         if bf is not None and ctx.needs_input_grad[2]:
-            g_b = gb.sum(dim=(0, 1)).to(b_dtype)
+            g_b = db.to(b_dtype)
         return g_x, g_w, g_b, None, None, None
 
 
