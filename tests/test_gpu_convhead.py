@@ -173,3 +173,38 @@ def test_conv_head_backward_matches_autograd(ops, oracle, B, K, D, C):
         err = float((ours.cpu().double() - ref).abs().max()) / float(ref.abs().max())
         assert err < tol, (name, err)
     assert xd.grad.shape == xd.shape and xd.grad.dtype == xd.dtype and wd.grad.shape == wd.shape
+
+
+@pytest.mark.parametrize("B,K,D,H,C,use_bias", [(2, 5, 64, 32, 192, True), (1, 2, 128, 64, 128, False), (5, 9, 32, 96, 64, True)])
+def test_conv_head_backward_bf16_channels_last(ops, oracle, B, K, D, H, C, use_bias):
+    """The tensor-core backward (xsup_conv_head_bwd) from bf16 channels-last activations - d x comes back bf16, channels-last,
+    written by the TMA from the staged TMEM accumulator - on non-square maps, three k-blocks, one joint per 128 rows and
+    without a bias; weight rows that do not fill the last 128-row tile (K*D = 320, 288).  Reference: fp64 autograd of
+    conv -> integral head on the same bf16-rounded operands; tolerance 2^-8 of the largest gradient (one bf16 rounding of
+    d loss / d logits, one of d x)."""
+    dev = torch.device("cuda:0")
+    NH, NS = 3, 5
+    g = torch.Generator().manual_seed(B * 7 + K)
+    x = torch.randn(B, C, H, D, generator=g)
+    w = torch.randn(K * D, C, generator=g) / C ** 0.5
+    bias = torch.randn(K * D, generator=g) if use_bias else None
+    gk = torch.randn(B, NH, K, 3, generator=g)
+    xd = x.to(dev).to(dtype=torch.bfloat16, memory_format=torch.channels_last).requires_grad_(True)
+    wd = w.to(dev).requires_grad_(True)
+    bd = bias.to(dev).requires_grad_(True) if use_bias else None
+    kps, dmap, idx = ops.conv_integral_head_train(xd, wd, bd, K, NH, NS)
+    kps.backward(gk.to(dev))
+    x64 = x.bfloat16().double().requires_grad_(True)
+    w64 = w.bfloat16().double().requires_grad_(True)
+    b64 = bias.double().requires_grad_(True) if use_bias else None
+    logits = torch.einsum("oc,bchw->bohw", w64, x64)
+    if use_bias:
+        logits = logits + b64.view(1, -1, 1, 1)
+    okps, _, oidx = oracle.integral_multi(logits, K, NH, NS)
+    assert torch.equal(idx.cpu(), oidx)
+    okps.backward(gk.double())
+    assert xd.grad.dtype == torch.bfloat16 and xd.grad.is_contiguous(memory_format=torch.channels_last)
+    checks = [("dx", xd.grad.float(), x64.grad), ("dW", wd.grad, w64.grad)] + ([("dbias", bd.grad, b64.grad)] if use_bias else [])
+    for name, ours, ref in checks:
+        err = float((ours.cpu().double() - ref).abs().max()) / float(ref.abs().max())
+        assert err < 2.0 ** -8, (name, err)

@@ -49,6 +49,6 @@ if os.environ.get("TRACE"):
     tr = trace.cpu().view(16, 16)
     base = int(tr[0, 0])
     names = ["mma:iter", "aempty", "xfull", "S-issued", "gfull", "MMA2-issued", "prod:xempty", "-", "epi:afull", "ld-done", "math-done", "gbuf-free",
-             "g-published"]
+             "g-published", "item:last tile done", "item:dfull", "item:drained"]
     for gi in range(16):
-        print("tile %2d: " % (gi + 8) + "  ".join("%s=%d" % (names[j], int(tr[gi, j]) - base) for j in range(13) if names[j] != "-"))
+        print("tile %2d: " % (gi + 8) + "  ".join("%s=%d" % (names[j], int(tr[gi, j]) - base) for j in range(16) if names[j] != "-"))

@@ -10,32 +10,34 @@
 // in the epilogue (one MUFU.EX2 + 3 FP ops per element from the row coefficients), rounds it to bf16 into SHARED memory in the
 // swizzled operand layout and feeds it straight back into a second tcgen05.mma chain whose accumulator stays in TMEM:
 //
-//   MODE_DW (W-stationary): item = (sample b, 128 weight rows).  The 128 x C weight slab stays in shared memory, the sample's
-//            activations stream through as 64-pixel tiles:   S[128 rows x 64 pix] = Wt_slab * X_tile^T ;  G = f(S) ;
-//            D2[128 rows x C] += G[128 x 64] * X_tile[64 x C].  D2 is flushed once per item with fp32 RED.ADD into d Wt.
-//   MODE_DX (X-stationary): item = (sample b, 128 pixels).  The 128 x C activation tile stays, the weights stream through as
-//            64-row tiles:   S[128 pix x 64 rows] = X_tile * Wt_tile^T ;  G^T = f(S) ;  D2[128 pix x C] += G^T[128 x 64] * Wt_tile[64 x C].
-//            D2 is the finished d X tile (all K*D rows were summed in TMEM) and is written once, bf16 or fp32, channels-last.
+//   MODE_DW (W-stationary): item = (sample b, 128 weight rows).  The 128 x C weight slab is the stationary operand, the sample's
+//            activations stream through as 128-pixel tiles:   S[128 rows x 128 pix] = Wt_slab * X_tile^T ;  G = f(S) ;
+//            D2[128 rows x C] += G[128 x 128] * X_tile[128 x C].  D2 is flushed once per item with fp32 RED.ADD into d Wt.
+//   MODE_DX (X-stationary): item = (sample b, 128 pixels).  The 128 x C activation tile is the stationary operand, the weights
+//            stream through as 128-row tiles:   S[128 pix x 128 rows] = X_tile * Wt_tile^T ;  G^T = f(S) ;
+//            D2[128 pix x C] += G^T[128 x 128] * Wt_tile[128 x C].  D2 is the finished d X tile (all K*D rows were summed in
+//            TMEM) and is written once, bf16 or fp32, channels-last.
 //
-// Both modes are ONE kernel: "stationary" operand [128 x C] (A of the first GEMM, K-major), "streamed" tiles [64 x C] (B of
-// the first GEMM, K-major; B of the second GEMM read MN-major from the very same bytes), G [128 x 64] bf16 = A of the second
-// GEMM, which never leaves the tensor memory: the epilogue writes it with tcgen05.st next to the accumulators and the
-// second GEMM reads its A operand from TMEM (the way attention kernels feed P into P*V).  Warp roles (18 warps, one
-// persistent CTA per SM):
-//   warp 16      TMA producer: stationary operand per item; streamed tiles through a 4-stage ring (+ in MODE_DX the 64 row
-//                coefficients of the tile, one 1 KB bulk copy on the same barrier)
-//   warp 17      first-GEMM issuer (ONE thread; descriptors precomputed, counters instead of divisions): per item 4*C/64
-//                tcgen05.cp (stationary operand -> TMEM), per tile S = 4*C/64 MMAs M=128 N=64 K=16, A from TMEM
-//   warp 18      second-GEMM issuer (one thread): 4 MMAs M=128 N=C K=16 per tile, A = G from TMEM, as soon as the epilogue has
-//                published the tile's G.  Two issuers because the tensor-pipe queue is shallow - an issuing thread is held
-//                while its MMAs execute, and with a single issuer every barrier wait idled the pipe (measured: 2070 -> 1700
-//                cycles per tile); tcgen05.commit releases ring stage (and with it the G buffer) / accumulator
-//   warps 0..15  epilogue: tcgen05.ld (thread = TMEM lane, 16 columns per warp), G, tcgen05.st (8 packed columns), mbarrier
-//                arrive; at the end of an item they drain D2
-// TMEM: columns [0,128) = the stationary operand (copied from its shared-memory landing buffer with tcgen05.cp once per item,
-// so the first GEMM reads only its B operand from shared memory and the landing buffer is free to prefetch the next item),
-// [128,256) = 2 x S[128 x 64] fp32 - the epilogue writes G[128 x 64] bf16 (32 columns) over the head of the accumulator it
-// has just read, and the buffer returns to the first GEMM when the second GEMM that read G has retired -, [256, 256+C) = D2.
+// Both modes are ONE kernel.  Every operand tile is [128 x C] bf16 and travels through ONE 3-stage TMA ring (64 KB per stage
+// at C = 256): per item first the stationary tile, then the streamed ones.
+//   * the stationary tile is copied from its ring stage into TENSOR memory (tcgen05.cp, 8 columns per 16 channels) and the
+//     stage is released at once: the first GEMM reads A from TMEM and only B from shared memory;
+//   * a streamed tile is B of the first GEMM (K-major) and, from the very same bytes, B of the second GEMM (MN-major);
+//   * G [128 x 128] bf16 goes through one 32 KB shared-memory buffer in the swizzled K-major operand layout (A of the second GEMM).
+// Why these shapes (measured on the way here, tools/convhead_bwd_probe.py + the clock64 trace hook below): a tcgen05.mma
+// with N = 64 occupies the pipe as long as one with N = 128 (64 cycles at M = 128), so 64-row streamed tiles ran the first
+// GEMM at half rate (1500-1600 cycles per 64 rows whatever else was tuned); the tensor-pipe queue is shallow, an issuing
+// thread is held while its MMAs execute, so each GEMM chain has its own issuing thread; descriptor arithmetic and integer
+// divisions in the issue loop idled the pipe for ~1000 cycles per tile.
+// Warp roles (19 warps, one persistent CTA per SM):
+//   warp 16      TMA producer (ring entries in order: stationary, tile 0 .. T-1, next stationary, ...)
+//   warp 17      first-GEMM issuer (one thread): per item 4*C/64 tcgen05.cp + release of that stage; per tile 4*C/64 MMAs
+//                M=128 N=128 K=16 (A from TMEM) into the single S accumulator as soon as the epilogue has read the previous one
+//   warp 18      second-GEMM issuer (one thread): per tile 8 MMAs M=128 N=C K=16 (A = G from shared memory) once the epilogue
+//                has published G; its tcgen05.commit releases the ring stage and the G buffer
+//   warps 0..15  epilogue: tcgen05.ld (thread = TMEM lane, 32 columns per warp), G = f(S) with packed fp32x2 arithmetic,
+//                st.shared (XOR-swizzled 16-byte chunks), fence.proxy.async, mbarrier arrive; at the end of an item they drain D2
+// TMEM: columns [0,128) = stationary operand, [128,256) = S[128 x 128] fp32, [256, 256+C) = D2.
 // Flops: 2 GEMMs of 2*K*D*C*H*W per sample and launch (1.17 TFLOP per launch at B=256, K=17, D=64, C=256).
 #include <stdlib.h>
 
@@ -45,17 +47,14 @@
 namespace xsup {
 
 constexpr int kBwEpiWarps = 16;
-constexpr int kBwParts = kBwEpiWarps / 4;                  // warps sharing a TMEM lane quarter: 16 of a tile's 64 columns each
-constexpr int kBwThreads = (kBwEpiWarps + 3) * 32;             // + TMA producer, first-GEMM issuer, second-GEMM issuer
-constexpr int kBwM = 128;                                  // stationary rows = UMMA M
-constexpr int kBwN = 64;                                   // streamed rows per tile = N of the first GEMM, K of the second
-constexpr int kBwStages = 4;
-constexpr int kBwSAcc = 2;
-constexpr int kBwStatKB = kBwM * kCvKB * 2;                // 16 KB: one [128 x 64] bf16 k-block of the stationary operand
-constexpr int kBwStrKB = kBwN * kCvKB * 2;                 //  8 KB: one [64 x 64] bf16 k-block of a streamed tile
-constexpr int kBwTabBytes = kBwN * 16;                     //  1 KB: row coefficients of a streamed weight tile (MODE_DX)
+constexpr int kBwParts = kBwEpiWarps / 4;                  // warps sharing a TMEM lane quarter: 32 of a tile's 128 columns each
+constexpr int kBwThreads = (kBwEpiWarps + 3) * 32;         // + TMA producer, first-GEMM issuer, second-GEMM issuer
+constexpr int kBwM = 128;                                  // rows of every operand tile = UMMA M, N of the first GEMM, K of the second
+constexpr int kBwStages = 3;
+constexpr int kBwKB = kBwM * kCvKB * 2;                    // 16 KB: one [128 x 64] bf16 k-block
+constexpr int kBwGBytes = kBwM * kBwM * 2;                 // 32 KB: the G tile, two k-blocks
 constexpr int kBwACol = 0;                                 // TMEM columns [0,128): the stationary operand, bf16, 8 columns per 16 channels
-constexpr int kBwSCol = 128;                               // two S accumulators [128 x 64] fp32; G (bf16, 32 columns) overwrites the head of its own S
+constexpr int kBwSCol = 128;                               // S accumulator [128 x 128] fp32
 constexpr int kBwD2Col = 256;                              // first TMEM column of D2
 enum { MODE_DW = 0, MODE_DX = 1 };
 
@@ -117,49 +116,37 @@ __device__ __forceinline__ void umma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, ui
 __device__ __forceinline__ void tmem_cp_128x256b(uint32_t taddr, uint64_t desc) {
     asm volatile("tcgen05.cp.cta_group::1.128x256b [%0], %1;" ::"r"(taddr), "l"(desc) : "memory");
 }
-__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&r)[8]) {
-    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]),
-                 "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
-                 : "memory");
-    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ float4 lds_f4(uint32_t addr) {
-    float4 v;
-    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
-    return v;
-}
-
 #define TRACE(slot, gi) do { if (p.trace && blockIdx.x == 0 && (gi) >= 8 && (gi) < 24) p.trace[((gi) - 8) * 16 + (slot)] = clock64(); } while (0)
 // ------------------------------------------------------------------ kernel
 template <int KBN, int MODE>
 __global__ void __launch_bounds__(kBwThreads, 1) conv_head_bwd_kernel(const __grid_constant__ CUtensorMap map_stat,
                                                                       const __grid_constant__ CUtensorMap map_str,
+                                                                      const __grid_constant__ CUtensorMap map_out,
                                                                       const ConvBwdParams p) {
     constexpr int C = KBN * kCvKB;
-    constexpr uint32_t kStatBytes = KBN * kBwStatKB, kStageBytes = KBN * kBwStrKB;
-    constexpr uint32_t kIdescS = umma_idesc_bf16(kBwM, kBwN);
+    constexpr uint32_t kStageBytes = KBN * kBwKB;
+    constexpr uint32_t kIdescS = umma_idesc_bf16(kBwM, kBwM);
     constexpr uint32_t kIdesc2 = umma_idesc_bf16(kBwM, C, false, true);       // B read MN-major
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    uint8_t* sStat = smem;                                          // [KBN][128 x 64] bf16
-    uint8_t* sStr = sStat + kStatBytes;                             // [stages][KBN][64 x 64] bf16
-    uint8_t* sTab = sStr + kBwStages * kStageBytes;                 // [stages][64] float4
-    uint64_t* bars = reinterpret_cast<uint64_t*>(sTab + kBwStages * kBwTabBytes);
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 24);
-    // x_empty[s] completes when the second GEMM of the tile in stage s has retired: it frees the stage AND that tile's G buffer
-    const uint32_t b_sfull = smem_u32(bars), b_sempty = b_sfull + 8, b_xfull = b_sempty + 8, b_xempty = b_xfull + 8 * kBwStages,
-                   b_afull = b_xempty + 8 * kBwStages, b_gfull = b_afull + 8 * kBwSAcc, b_dfull = b_gfull + 16, b_dempty = b_dfull + 8;
+    uint8_t* sRing = smem;                                          // [stages][KBN][128 x 64] bf16
+    uint8_t* sG = sRing + kBwStages * kStageBytes;                  // [2][128 x 64] bf16
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sG + kBwGBytes);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
+    // ring: full[s] (TMA bytes landed) / empty[s] (the stationary copy, or the second GEMM of the tile, has retired)
+    const uint32_t b_full = smem_u32(bars), b_empty = b_full + 8 * kBwStages, b_afull = b_empty + 8 * kBwStages, b_aempty = b_afull + 8,
+                   b_gfull = b_aempty + 8, b_gempty = b_gfull + 8, b_dfull = b_gempty + 8, b_dempty = b_dfull + 8;
 
     if (threadIdx.x == 0) {
-        mbar_init(b_sfull, 1);
-        mbar_init(b_sempty, 1);
         for (int i = 0; i < kBwStages; ++i) {
-            mbar_init(b_xfull + 8 * i, 1);
-            mbar_init(b_xempty + 8 * i, 1);
+            mbar_init(b_full + 8 * i, 1);
+            mbar_init(b_empty + 8 * i, 1);
         }
-        for (int i = 0; i < kBwSAcc; ++i) mbar_init(b_afull + 8 * i, 1);
-        for (int i = 0; i < 2; ++i) mbar_init(b_gfull + 8 * i, kBwEpiWarps);
+        mbar_init(b_afull, 1);
+        mbar_init(b_aempty, kBwEpiWarps);
+        mbar_init(b_gfull, kBwEpiWarps);
+        mbar_init(b_gempty, 1);
         mbar_init(b_dfull, 1);
         mbar_init(b_dempty, kBwEpiWarps);
         mbar_fence_init();
@@ -177,134 +164,129 @@ __global__ void __launch_bounds__(kBwThreads, 1) conv_head_bwd_kernel(const __gr
         // ------------------------------------------------------------ TMA producer
         if (lane == 0) {
             int s = 0;
-            uint32_t xph = 1, sph = 1;                               // "empty" barriers: the first pass over the ring does not wait
-            const uint32_t str0 = smem_u32(sStr), stat0 = smem_u32(sStat), tab0 = smem_u32(sTab);
+            uint32_t eph = 1;                                        // "empty" barriers: the first pass over the ring does not wait
+            const uint32_t ring0 = smem_u32(sRing);
             for (int n = 0; n < n_items; ++n) {
                 const int item = blockIdx.x + n * gridDim.x;
                 const int b = item / p.per_b, j = item - b * p.per_b;
                 // stationary: weight rows [128 j, +128) (MODE_DW) or pixels [b*HW + 128 j, +128) (MODE_DX)
                 const int stat_row = MODE == MODE_DW ? j * kBwM : b * p.HW + j * kBwM;
                 const int str_row0 = MODE == MODE_DW ? b * p.HW : 0;
-                const float* tab_src = p.rowcoef + (size_t)b * p.rows_pad * 4;
-                mbar_wait(b_sempty, sph);                            // the previous item's first-GEMM MMAs have retired
-                sph ^= 1;
-                mbar_arrive_expect_tx(b_sfull, kStatBytes);
+                for (int t = -1; t < T; ++t) {
+                    mbar_wait(b_empty + 8 * s, eph);
+                    mbar_arrive_expect_tx(b_full + 8 * s, kStageBytes);
+                    const uint32_t dst = ring0 + (uint32_t)s * kStageBytes;
+                    if (t < 0) {
 #pragma unroll
-                for (int kb = 0; kb < KBN; ++kb) tma_load_2d(stat0 + kb * kBwStatKB, &map_stat, kb * kCvKB, stat_row, b_sfull);
-                for (int t = 0; t < T; ++t) {
-                    mbar_wait(b_xempty + 8 * s, xph);                // the second GEMM of the tile that used this stage has retired
-                    TRACE(6, n * T + t);
-                    mbar_arrive_expect_tx(b_xfull + 8 * s, kStageBytes + (MODE == MODE_DX ? (uint32_t)kBwTabBytes : 0u));
-                    const uint32_t dst = str0 + (uint32_t)s * kStageBytes;
+                        for (int kb = 0; kb < KBN; ++kb) tma_load_2d(dst + kb * kBwKB, &map_stat, kb * kCvKB, stat_row, b_full + 8 * s);
+                    } else {
 #pragma unroll
-                    for (int kb = 0; kb < KBN; ++kb) tma_load_2d(dst + kb * kBwStrKB, &map_str, kb * kCvKB, str_row0 + t * kBwN, b_xfull + 8 * s);
-                    if (MODE == MODE_DX) bulk_g2s(tab0 + (uint32_t)s * kBwTabBytes, tab_src + (size_t)t * kBwN * 4, kBwTabBytes, b_xfull + 8 * s);
-                    if (++s == kBwStages) { s = 0; xph ^= 1; }
+                        for (int kb = 0; kb < KBN; ++kb) tma_load_2d(dst + kb * kBwKB, &map_str, kb * kCvKB, str_row0 + t * kBwM, b_full + 8 * s);
+                    }
+                    if (++s == kBwStages) { s = 0; eph ^= 1; }
                 }
             }
         }
         __syncwarp();
     } else if (warp == kBwEpiWarps + 1) {
         // ------------------------------------------------------------ first-GEMM issuer: one thread, nothing but waits and issues
-        // (the tensor-pipe queue is shallow: an issuing thread is held while its MMAs execute, so the two GEMM chains are issued
-        //  by two threads - while one sits in its barrier waits the other one's MMAs keep the pipe busy)
         if (lane == 0) {
-            const int total = n_items * T;
-            // descriptors: high words are constant, low words = (address >> 4); K steps / stages / k-blocks add constants
+            // descriptors: high word constant, low word = (address >> 4); K steps / stages / k-blocks add constants
             const uint64_t hiK = ((uint64_t)(1024u >> 4) << 32) | (1ull << 46) | (2ull << 61);
-            uint32_t stat_lo[KBN];
-#pragma unroll
-            for (int kb = 0; kb < KBN; ++kb) stat_lo[kb] = ((smem_u32(sStat) + kb * kBwStatKB) & 0x3ffffu) >> 4;
-            const uint32_t str_lo0 = (smem_u32(sStr) & 0x3ffffu) >> 4;
-            constexpr uint32_t kStageStep = kStageBytes >> 4, kKbStep = kBwStrKB >> 4;
-            int t1 = 0, s1 = 0, a1 = 0;
-            uint32_t xph1 = 0, sph1 = 0;
-            // accumulator a1 held S and G of tile g-2: free once that tile's second GEMM has retired = x_empty of stage (g-2) & 3
-            int s_prev2 = kBwStages - 2;
-            uint32_t eph_prev2 = 1;
-            for (int g = 0; g < total; ++g) {
-                // ---- S = stationary * streamed^T, K = C
-                TRACE(0, g);
-                if (t1 == 0) {
-                    // new item: stationary operand from its landing buffer into TMEM (in order behind the previous item's MMAs);
-                    // the landing buffer is then free for the producer to prefetch the next item
-                    mbar_wait(b_sfull, sph1);
-                    sph1 ^= 1;
-                    tc_fence_after();
+            const uint32_t ring_lo0 = (smem_u32(sRing) & 0x3ffffu) >> 4;
+            constexpr uint32_t kStageStep = kStageBytes >> 4, kKbStep = kBwKB >> 4;
+            int s = 0, g = 0;
+            uint32_t fph = 0, aeph = 1;
+            for (int n = 0; n < n_items; ++n) {
+                // new item: stationary operand from its ring stage into TMEM (in order behind the previous item's MMAs), stage released
+                mbar_wait(b_full + 8 * s, fph);
+                tc_fence_after();
+                {
+                    const uint32_t lo = ring_lo0 + (uint32_t)s * kStageStep;
 #pragma unroll
                     for (int kb = 0; kb < KBN; ++kb)
 #pragma unroll
                         for (int q = 0; q < 4; ++q)
-                            tmem_cp_128x256b(tmem_base + (uint32_t)(kBwACol + (kb * 4 + q) * 8), hiK | (uint64_t)(stat_lo[kb] + 2 * q));
-                    umma_commit(b_sempty);
+                            tmem_cp_128x256b(tmem_base + (uint32_t)(kBwACol + (kb * 4 + q) * 8), hiK | (uint64_t)(lo + kb * kKbStep + 2 * q));
+                    umma_commit(b_empty + 8 * s);
+                    if (++s == kBwStages) { s = 0; fph ^= 1; }
                 }
-                mbar_wait(b_xempty + 8 * s_prev2, eph_prev2);
-                TRACE(1, g);
-                mbar_wait(b_xfull + 8 * s1, xph1);
-                TRACE(2, g);
-                tc_fence_after();
-                const uint32_t acc = tmem_base + (uint32_t)(kBwSCol + a1 * kBwN);
-                const uint32_t b_lo = str_lo0 + (uint32_t)s1 * kStageStep;
+                for (int t = 0; t < T; ++t, ++g) {
+                    TRACE(0, g);
+                    mbar_wait(b_aempty, aeph);                       // the epilogue has read the previous S
+                    aeph ^= 1;
+                    TRACE(1, g);
+                    mbar_wait(b_full + 8 * s, fph);
+                    TRACE(2, g);
+                    tc_fence_after();
+                    const uint32_t acc = tmem_base + (uint32_t)kBwSCol;
+                    const uint32_t lo = ring_lo0 + (uint32_t)s * kStageStep;
 #pragma unroll
-                for (int kb = 0; kb < KBN; ++kb) {
+                    for (int kb = 0; kb < KBN; ++kb) {
 #pragma unroll
-                    for (int q = 0; q < 4; ++q)
-                        umma_f16_ts(acc, tmem_base + (uint32_t)(kBwACol + (kb * 4 + q) * 8), hiK | (uint64_t)(b_lo + kb * kKbStep + 2 * q), kIdescS,
-                                    (kb | q) ? 1u : 0u);
+                        for (int q = 0; q < 4; ++q)
+                            umma_f16_ts(acc, tmem_base + (uint32_t)(kBwACol + (kb * 4 + q) * 8), hiK | (uint64_t)(lo + kb * kKbStep + 2 * q), kIdescS,
+                                        (kb | q) ? 1u : 0u);
+                    }
+                    umma_commit(b_afull);
+                    TRACE(3, g);
+                    if (++s == kBwStages) { s = 0; fph ^= 1; }
                 }
-                umma_commit(b_afull + 8 * a1);
-                TRACE(3, g);
-                if (++t1 == T) t1 = 0;
-                if (++s1 == kBwStages) { s1 = 0; xph1 ^= 1; }
-                a1 ^= 1;
-                if (++s_prev2 == kBwStages) { s_prev2 = 0; eph_prev2 ^= 1; }
             }
         }
         __syncwarp();
     } else if (warp == kBwEpiWarps + 2) {
-        // ------------------------------------------------------------ second-GEMM issuer: D2 += G (TMEM) * streamed (MN-major), K = 64 rows
+        // ------------------------------------------------------------ second-GEMM issuer: D2 += G (smem, K-major) * streamed (MN-major), K = 128 rows
         if (lane == 0) {
-            const int total = n_items * T;
             const uint64_t hiK = ((uint64_t)(1024u >> 4) << 32) | (1ull << 46) | (2ull << 61);
-            const uint32_t mn_lo0 = ((smem_u32(sStr) & 0x3ffffu) >> 4) | ((uint32_t)(kBwStrKB >> 4) << 16);   // + leading byte offset = next 64 channels
+            const uint32_t mn_lo0 = ((smem_u32(sRing) & 0x3ffffu) >> 4) | ((uint32_t)(kBwKB >> 4) << 16);   // + leading byte offset = next 64 channels
+            const uint32_t g_lo = (smem_u32(sG) & 0x3ffffu) >> 4;
             constexpr uint32_t kStageStep = kStageBytes >> 4;
-            int t2 = 0, s2 = 0, n2 = 0;
-            uint32_t gb2 = 0, gph2 = 0, dph2 = 0;
-            for (int h = 0; h < total; ++h) {
-                if (t2 == 0 && n2 >= 1) { mbar_wait(b_dempty, dph2); dph2 ^= 1; }   // the epilogue has drained the previous item's D2
-                mbar_wait(b_gfull + 8 * gb2, gph2);
-                TRACE(4, h);
-                tc_fence_after();
-                const uint32_t d2 = tmem_base + (uint32_t)kBwD2Col;
-                const uint32_t ga = tmem_base + (uint32_t)kBwSCol + gb2 * (uint32_t)kBwN;
-                const uint64_t db = hiK | (uint64_t)(mn_lo0 + (uint32_t)s2 * kStageStep);
+            int s = 0, h = 0;
+            uint32_t gph = 0, dph = 0;
+            for (int n = 0; n < n_items; ++n) {
+                if (++s == kBwStages) s = 0;                                      // the item's stationary entry is not ours
+                if (n >= 1) { mbar_wait(b_dempty, dph); dph ^= 1; }               // the epilogue has drained the previous item's D2
+                for (int t = 0; t < T; ++t, ++h) {
+                    mbar_wait(b_gfull, gph);
+                    gph ^= 1;
+                    TRACE(4, h);
+                    tc_fence_after();
+                    const uint32_t d2 = tmem_base + (uint32_t)kBwD2Col;
+                    const uint64_t db = hiK | (uint64_t)(mn_lo0 + (uint32_t)s * kStageStep);
 #pragma unroll
-                for (int q = 0; q < 4; ++q) umma_f16_ts(d2, ga + 8u * q, db + (uint64_t)(128 * q), kIdesc2, (t2 | q) ? 1u : 0u);
-                umma_commit(b_xempty + 8 * s2);
-                TRACE(5, h);
-                if (++t2 == T) { t2 = 0; ++n2; umma_commit(b_dfull); }
-                if (++s2 == kBwStages) s2 = 0;
-                if (gb2) gph2 ^= 1;
-                gb2 ^= 1;
+                    for (int q = 0; q < 8; ++q)
+                        umma_f16_rt(d2, hiK | (uint64_t)(g_lo + (q >> 2) * (kBwKB >> 4) + 2 * (q & 3)), db + (uint64_t)(128 * q), kIdesc2, (t | q) ? 1u : 0u);
+                    umma_commit(b_empty + 8 * s);
+                    umma_commit(b_gempty);
+                    TRACE(5, h);
+                    if (++s == kBwStages) s = 0;
+                }
+                umma_commit(b_dfull);
             }
         }
         __syncwarp();
     } else if (warp < kBwEpiWarps) {
-        // ------------------------------------------------------------ epilogue: thread = TMEM lane, 16 columns per warp and tile
+        // ------------------------------------------------------------ epilogue: thread = TMEM lane, 32 columns per warp and tile
         const int quarter = warp & 3, part = warp >> 2;
         const int row = quarter * 32 + lane;
         const uint32_t lane_addr = tmem_base + ((uint32_t)(quarter * 32) << 16);
-        const uint32_t tab0 = smem_u32(sTab) + (uint32_t)part * 256u;
+        // G tile: row = 128 bytes per k-block; this warp's 32 K-elements = chunks (part & 1) * 4 .. + 3 of k-block part >> 1
+        const uint32_t g_row = smem_u32(sG) + (uint32_t)(part >> 1) * kBwKB + (uint32_t)row * 128u;
+        const uint32_t sw = (uint32_t)(row & 7), ch0 = (uint32_t)(part & 1) * 4u;
         const int Wd = p.W;
-        int a = 0, s = 0;
-        uint32_t aph = 0, xph = 0;
+        uint32_t aph = 0, geph = 1, dph = 0;
         int gtile = 0;
-        uint32_t dph = 0;
         for (int n = 0; n < n_items; ++n) {
             const int item = blockIdx.x + n * gridDim.x;
             const int b = item / p.per_b, j = item - b * p.per_b;
-            float4 rc = make_float4(0.f, 0.f, 0.f, 0.f);            // (nlse, a, b, e) of this thread's row (MODE_DW)
-            f32x2 fw2 = pk2(0.f, 0.f), fh2 = fw2, gsum2 = fw2;
+            // MODE_DW: (nlse, a, b, e) of this thread's logit row, fixed for the item.  MODE_DX: thread = pixel, columns = logit rows:
+            // lane l fetches the coefficients of column l of the NEXT tile while this one is processed (one tile ahead), and the
+            // columns' (nlse, e) reach all lanes by shuffle; (a, b) belong to the joint, which is the same for a warp's 32 columns.
+            float4 rc = make_float4(0.f, 0.f, 0.f, 0.f);
+            f32x2 gsum2 = pk2(0.f, 0.f);
+            float fw = 0.f, fh = 0.f;
+            const float* tabg = nullptr;
             if (MODE == MODE_DW) {
                 const int r = j * kBwM + row;
                 const float* q = p.rowcoef + ((size_t)b * p.rows_pad + (r & ~1)) * 4 + (r & 1);
@@ -312,27 +294,39 @@ __global__ void __launch_bounds__(kBwThreads, 1) conv_head_bwd_kernel(const __gr
             } else {
                 const int pix = j * kBwM + row;
                 const int hh = pix / Wd;
-                fh2 = pk2((float)hh, (float)hh);
-                fw2 = pk2((float)(pix - hh * Wd), (float)(pix - hh * Wd));
+                fh = (float)hh;
+                fw = (float)(pix - hh * Wd);
+                const int r = part * 32 + lane;                       // this lane's column of tile 0
+                tabg = p.rowcoef + ((size_t)b * p.rows_pad + (r & ~1)) * 4 + (r & 1);
+                rc = make_float4(tabg[0], tabg[2], tabg[4], tabg[6]);
             }
             const f32x2 l2e2 = pk2(kLog2e, kLog2e);
             for (int t = 0; t < T; ++t) {
-                mbar_wait(b_afull + 8 * a, aph);
+                float4 rc_next = rc;
+                if (MODE == MODE_DX && t + 1 < T) {
+                    const float* q = tabg + (size_t)(t + 1) * kBwM * 4;
+                    rc_next = make_float4(__ldg(q), __ldg(q + 2), __ldg(q + 4), __ldg(q + 6));
+                }
+                mbar_wait(b_afull, aph);
+                aph ^= 1;
                 if (threadIdx.x == 0) TRACE(8, gtile);
                 tc_fence_after();
-                uint32_t r[16];
-                tmem_ld16(lane_addr + (uint32_t)(kBwSCol + a * kBwN + part * 16), r);
+                uint32_t r[32];
+                tmem_ld32(lane_addr + (uint32_t)(kBwSCol + part * 32), r);
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(b_aempty);                // values are in registers: the next S may overwrite the accumulator
                 if (threadIdx.x == 0) TRACE(9, gtile);
-                uint32_t o[8];
+                uint32_t o[16];
                 if (MODE == MODE_DW) {
-                    // columns = 16 consecutive pixels of one image row (W % 16 == 0); packed fp32x2 arithmetic, two columns per op
-                    const int pix = t * kBwN + part * 16;
+                    // columns = 32 consecutive pixels of one image row (W % 32 == 0); packed fp32x2 arithmetic, two columns per op
+                    const int pix = t * kBwM + part * 32;
                     const int hh = pix / Wd;
                     const float rowterm = fmaf(rc.y, (float)(pix - hh * Wd), fmaf(rc.z, (float)hh, rc.w));
                     f32x2 lin = pk2(rowterm, rowterm + rc.y);
                     const f32x2 step = pk2(2.f * rc.y, 2.f * rc.y), nl2 = pk2(rc.x, rc.x);
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) {
+                    for (int i = 0; i < 16; ++i) {
                         const f32x2 v = fmul2(ex2_2(ffma2(pk2u(r[2 * i], r[2 * i + 1]), l2e2, nl2)), lin);
                         gsum2 = fadd2(gsum2, v);
                         lin = fadd2(lin, step);
@@ -341,84 +335,105 @@ __global__ void __launch_bounds__(kBwThreads, 1) conv_head_bwd_kernel(const __gr
                         asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(o[i]) : "f"(v1), "f"(v0));
                     }
                 } else {
-                    // columns = 16 consecutive logit rows of the streamed weight tile: coefficients from the stage's table
-                    mbar_wait(b_xfull + 8 * s, xph);                  // (complete already: the MMAs read this stage) acquires the table
-                    const uint32_t tab = tab0 + (uint32_t)s * kBwTabBytes;
+                    const float linw = fmaf(rc.y, fw, rc.z * fh);    // a_k w + b_k h of this pixel (one joint per 32 columns: 32 | D)
+                    const f32x2 lin2 = pk2(linw, linw);
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        const float4 q0 = lds_f4(tab + 32u * i), q1 = lds_f4(tab + 32u * i + 16u);   // {nlse, nlse', a, a'}, {b, b', e, e'}
-                        const f32x2 lin = ffma2(pk2(q0.z, q0.w), fw2, ffma2(pk2(q1.x, q1.y), fh2, pk2(q1.z, q1.w)));
-                        const f32x2 v = fmul2(ex2_2(ffma2(pk2u(r[2 * i], r[2 * i + 1]), l2e2, pk2(q0.x, q0.y))), lin);
+                    for (int i = 0; i < 16; ++i) {
+                        const f32x2 nl2 = pk2(__shfl_sync(0xffffffffu, rc.x, 2 * i), __shfl_sync(0xffffffffu, rc.x, 2 * i + 1));
+                        const f32x2 e2 = pk2(__shfl_sync(0xffffffffu, rc.w, 2 * i), __shfl_sync(0xffffffffu, rc.w, 2 * i + 1));
+                        const f32x2 v = fmul2(ex2_2(ffma2(pk2u(r[2 * i], r[2 * i + 1]), l2e2, nl2)), fadd2(e2, lin2));
                         float v0, v1;
                         upk2(v, v0, v1);
                         asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(o[i]) : "f"(v1), "f"(v0));
                     }
+                    rc = rc_next;
                 }
-                // publish this warp's [32 lanes x 16 K-elements] of the G tile: 8 packed columns over the head of the accumulator,
-                // once the four warps of this lane quarter have all read their columns of it
+                // publish this warp's [32 lanes x 32 K-elements] of the G tile: 16-byte chunk c of a row sits at (c ^ (row & 7))
                 if (threadIdx.x == 0) TRACE(10, gtile);
-                asm volatile("bar.sync %0, 128;" ::"r"(1 + quarter) : "memory");
+                mbar_wait(b_gempty, geph);                            // the second GEMM of the previous tile has read G
+                geph ^= 1;
                 if (threadIdx.x == 0) TRACE(11, gtile);
-                tmem_st8(lane_addr + (uint32_t)(kBwSCol + a * kBwN + part * 8), o);
-                tc_fence_before();
+#pragma unroll
+                for (int c = 0; c < 4; ++c)
+                    asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(g_row + (((ch0 + c) ^ sw) << 4)), "r"(o[4 * c]), "r"(o[4 * c + 1]),
+                                 "r"(o[4 * c + 2]), "r"(o[4 * c + 3]) : "memory");
+                fence_proxy_async_smem();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(b_gfull + 8 * a);
+                if (lane == 0) mbar_arrive(b_gfull);
                 if (threadIdx.x == 0) TRACE(12, gtile);
                 ++gtile;
-                if (++a == kBwSAcc) { a = 0; aph ^= 1; }
-                if (++s == kBwStages) { s = 0; xph ^= 1; }
             }
             // ---- end of the item: drain D2 (this warp: its lane quarter, C/4 columns)
+            if (threadIdx.x == 0) TRACE(13, 8 + n);
             mbar_wait(b_dfull, dph);
             dph ^= 1;
+            if (threadIdx.x == 0) TRACE(14, 8 + n);
             tc_fence_after();
+            // D2 [128 x C] fp32 leaves through the (now idle) G buffer: R rows per pass are laid out as [R x 128-byte] blocks with
+            // the 128-byte swizzle and handed to the TMA (tensor store for d x, fp32 reduce-add for d W), so that every row is
+            // written as whole 128-byte lines.  (Storing straight from the TMEM lanes - one row per thread - cost ~7000 cycles per
+            // item: 32 different lines per store instruction.)
             constexpr int CW = C / kBwParts;                           // columns per warp: 16, 32, 48 or 64
+            const bool f32o = MODE == MODE_DW || p.dx_f32;
+            const int passes = f32o ? 4 : 2, R = kBwM / passes;        // 32 KB staging: 32 fp32 rows or 64 bf16 rows of C = 256
+            const int out_row0 = MODE == MODE_DW ? j * kBwM : b * p.HW + j * kBwM;
+            const uint32_t stg = smem_u32(sG);
+            for (int ps = 0; ps < passes; ++ps) {
+                const bool active = f32o ? (quarter == ps) : ((quarter >> 1) == ps);
+                if (active) {
+                    const uint32_t rloc = f32o ? (uint32_t)lane : (uint32_t)((quarter & 1) * 32 + lane);
+                    const uint32_t rbase = stg + rloc * 128u, rsw = rloc & 7u;
+#pragma unroll
+                    for (int q = 0; q < CW / 16; ++q) {
+                        uint32_t r[16];
+                        tmem_ld16(lane_addr + (uint32_t)(kBwD2Col + part * CW + q * 16), r);
+                        const uint32_t col = (uint32_t)(part * CW + q * 16);
+                        if (f32o) {
+                            const uint32_t off = col * 4u, blk = off >> 7, c0 = (off & 127u) >> 4;
+#pragma unroll
+                            for (int c = 0; c < 4; ++c)
+                                asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(rbase + blk * (uint32_t)(R * 128) + (((c0 + c) ^ rsw) << 4)),
+                                             "r"(r[4 * c]), "r"(r[4 * c + 1]), "r"(r[4 * c + 2]), "r"(r[4 * c + 3]) : "memory");
+                        } else {
+                            uint32_t ob[8];
+#pragma unroll
+                            for (int i = 0; i < 16; i += 2)
+                                asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(ob[i >> 1]) : "f"(__uint_as_float(r[i + 1])), "f"(__uint_as_float(r[i])));
+                            const uint32_t off = col * 2u, blk = off >> 7, c0 = (off & 127u) >> 4;
+#pragma unroll
+                            for (int c = 0; c < 2; ++c)
+                                asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(rbase + blk * (uint32_t)(R * 128) + (((c0 + c) ^ rsw) << 4)),
+                                             "r"(ob[4 * c]), "r"(ob[4 * c + 1]), "r"(ob[4 * c + 2]), "r"(ob[4 * c + 3]) : "memory");
+                        }
+                    }
+                    fence_proxy_async_smem();
+                }
+                asm volatile("bar.sync 1, %0;" ::"n"(kBwEpiWarps * 32) : "memory");
+                if (threadIdx.x == 0) {
+                    const int nblk = f32o ? C / 32 : C / 64, bcols = f32o ? 32 : 64;
+                    for (int blk = 0; blk < nblk; ++blk) {
+                        if (MODE == MODE_DW) tma_reduce_add_2d(&map_out, stg + (uint32_t)(blk * R * 128), blk * bcols, out_row0 + ps * R);
+                        else tma_store_2d(&map_out, stg + (uint32_t)(blk * R * 128), blk * bcols, out_row0 + ps * R);
+                    }
+                    bulk_commit();
+                    bulk_wait_read0();                                 // the staging buffer may be overwritten
+                }
+                asm volatile("bar.sync 1, %0;" ::"n"(kBwEpiWarps * 32) : "memory");
+            }
             if (MODE == MODE_DW) {
                 const int grow_i = j * kBwM + row;
-                float* dst = p.dw + (size_t)grow_i * C + part * CW;
-#pragma unroll
-                for (int q = 0; q < CW / 16; ++q) {
-                    uint32_t r[16];
-                    tmem_ld16(lane_addr + (uint32_t)(kBwD2Col + part * CW + q * 16), r);
-                    if (grow_i < p.rows_total) {
-#pragma unroll
-                        for (int i = 0; i < 16; i += 4)
-                            red_add_v4(dst + q * 16 + i, __uint_as_float(r[i]), __uint_as_float(r[i + 1]), __uint_as_float(r[i + 2]),
-                                       __uint_as_float(r[i + 3]));
-                    }
-                }
                 if (p.dbias && grow_i < p.rows_total) {
                     float g0, g1;
                     upk2(gsum2, g0, g1);
                     atomicAdd(p.dbias + grow_i, g0 + g1);
                 }
-            } else {
-                const size_t pix = (size_t)b * p.HW + (size_t)j * kBwM + row;
-#pragma unroll
-                for (int q = 0; q < CW / 16; ++q) {
-                    uint32_t r[16];
-                    tmem_ld16(lane_addr + (uint32_t)(kBwD2Col + part * CW + q * 16), r);
-                    if (p.dx_f32) {
-                        float4* dst = reinterpret_cast<float4*>(static_cast<float*>(p.dx) + pix * C + part * CW + q * 16);
-#pragma unroll
-                        for (int i = 0; i < 4; ++i)
-                            dst[i] = make_float4(__uint_as_float(r[4 * i]), __uint_as_float(r[4 * i + 1]), __uint_as_float(r[4 * i + 2]),
-                                                 __uint_as_float(r[4 * i + 3]));
-                    } else {
-                        uint32_t o[8];
-#pragma unroll
-                        for (int i = 0; i < 16; i += 2)
-                            asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(o[i >> 1]) : "f"(__uint_as_float(r[i + 1])), "f"(__uint_as_float(r[i])));
-                        uint4* dst = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.dx) + pix * C + part * CW + q * 16);
-                        dst[0] = make_uint4(o[0], o[1], o[2], o[3]);
-                        dst[1] = make_uint4(o[4], o[5], o[6], o[7]);
-                    }
-                }
             }
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(b_dempty);
+            if (threadIdx.x == 0) TRACE(15, 8 + n);
         }
+        if (threadIdx.x == 0) bulk_wait0();                            // all tensor stores / reductions of this CTA have been performed
     }
     tc_fence_before();
     __syncthreads();
@@ -430,24 +445,26 @@ __global__ void __launch_bounds__(kBwThreads, 1) conv_head_bwd_kernel(const __gr
 
 // ------------------------------------------------------------------ host side
 template <int KBN, int MODE>
-static cudaError_t launch_bwd_kbn(const CUtensorMap& map_stat, const CUtensorMap& map_str, const ConvBwdParams& p, int grid, cudaStream_t st) {
+static cudaError_t launch_bwd_kbn(const CUtensorMap& map_stat, const CUtensorMap& map_str, const CUtensorMap& map_out, const ConvBwdParams& p, int grid,
+                                  cudaStream_t st) {
     auto kern = conv_head_bwd_kernel<KBN, MODE>;
     static unsigned long long attr_done = 0;             // per instantiation; one bit per device
     cudaError_t e = ensure_max_smem(kern, attr_done);
     if (e != cudaSuccess) return e;
-    const size_t smem = 1024 + (size_t)KBN * kBwStatKB + (size_t)kBwStages * KBN * kBwStrKB + kBwStages * kBwTabBytes + 32 * 8;
-    kern<<<grid, kBwThreads, smem, st>>>(map_stat, map_str, p);
+    const size_t smem = 1024 + (size_t)kBwStages * KBN * kBwKB + kBwGBytes + 24 * 8;
+    kern<<<grid, kBwThreads, smem, st>>>(map_stat, map_str, map_out, p);
     return cudaGetLastError();
 }
 
 template <int MODE>
-static cudaError_t launch_bwd_mode(const CUtensorMap& map_stat, const CUtensorMap& map_str, const ConvBwdParams& p, int num_sms, cudaStream_t st) {
+static cudaError_t launch_bwd_mode(const CUtensorMap& map_stat, const CUtensorMap& map_str, const CUtensorMap& map_out, const ConvBwdParams& p, int num_sms,
+                                   cudaStream_t st) {
     const int grid = p.items < num_sms ? p.items : num_sms;
     switch (p.C / kCvKB) {
-        case 1: return launch_bwd_kbn<1, MODE>(map_stat, map_str, p, grid, st);
-        case 2: return launch_bwd_kbn<2, MODE>(map_stat, map_str, p, grid, st);
-        case 3: return launch_bwd_kbn<3, MODE>(map_stat, map_str, p, grid, st);
-        default: return launch_bwd_kbn<4, MODE>(map_stat, map_str, p, grid, st);
+        case 1: return launch_bwd_kbn<1, MODE>(map_stat, map_str, map_out, p, grid, st);
+        case 2: return launch_bwd_kbn<2, MODE>(map_stat, map_str, map_out, p, grid, st);
+        case 3: return launch_bwd_kbn<3, MODE>(map_stat, map_str, map_out, p, grid, st);
+        default: return launch_bwd_kbn<4, MODE>(map_stat, map_str, map_out, p, grid, st);
     }
 }
 
@@ -466,10 +483,8 @@ cudaError_t launch_conv_head_bwd(const void* x_nhwc, const void* w, const float*
     conv_rowcoef_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(coef, coef_stride, bias, rowcoef_ws, B, K, D, p.rows_pad);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
-    CUtensorMap map_w128, map_w64, map_x128, map_x64;
-    if (!make_map(&map_w128, w, p.rows_total, C, kBwM) || !make_map(&map_w64, w, p.rows_total, C, kBwN) ||
-        !make_map(&map_x128, x_nhwc, (long long)B * p.HW, C, kBwM) || !make_map(&map_x64, x_nhwc, (long long)B * p.HW, C, kBwN))
-        return cudaErrorNotSupported;
+    CUtensorMap map_w, map_x, map_o;
+    if (!make_map(&map_w, w, p.rows_total, C, kBwM) || !make_map(&map_x, x_nhwc, (long long)B * p.HW, C, kBwM)) return cudaErrorNotSupported;
     if (dw) {
         e = cudaMemsetAsync(dw, 0, (size_t)p.rows_total * C * sizeof(float), st);
         if (e != cudaSuccess) return e;
@@ -480,18 +495,20 @@ cudaError_t launch_conv_head_bwd(const void* x_nhwc, const void* w, const float*
         ConvBwdParams q = p;
         q.dw = dw; q.dbias = dbias;
         q.per_b = p.rows_pad / kBwM;
-        q.T = p.HW / kBwN;
+        q.T = p.HW / kBwM;
         q.items = B * q.per_b;
-        e = launch_bwd_mode<MODE_DW>(map_w128, map_x64, q, num_sms, st);
+        if (!make_map_out(&map_o, dw, p.rows_total, C, true, 32)) return cudaErrorNotSupported;
+        e = launch_bwd_mode<MODE_DW>(map_w, map_x, map_o, q, num_sms, st);
         if (e != cudaSuccess) return e;
     }
     if (dx) {
         ConvBwdParams q = p;
         q.dx = dx; q.dx_f32 = dx_f32;
         q.per_b = p.HW / kBwM;
-        q.T = (p.rows_total + kBwN - 1) / kBwN;
+        q.T = p.rows_pad / kBwM;
         q.items = B * q.per_b;
-        e = launch_bwd_mode<MODE_DX>(map_x128, map_w64, q, num_sms, st);
+        if (!make_map_out(&map_o, dx, (long long)B * p.HW, C, dx_f32 != 0, dx_f32 ? 32 : 64)) return cudaErrorNotSupported;
+        e = launch_bwd_mode<MODE_DX>(map_x, map_w, map_o, q, num_sms, st);
         if (e != cudaSuccess) return e;
     }
     return cudaSuccess;
