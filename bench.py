@@ -242,6 +242,7 @@ def setup(args):
             ge.build()
         if x.world > 1:
             dist.barrier()
+    x.numa = bind_to_gpu_numa(x)
     x.pkg = importlib.import_module("x-as-supervision_b200")
     x.ops, x.synth = x.pkg.load_native(), x.pkg.synth
     x.group, x.exchange = None, "none"
@@ -256,6 +257,36 @@ def setup(args):
             x.group = dist.group.WORLD
             x.exchange = "nccl all_reduce between two launches"
     return x
+
+
+def bind_to_gpu_numa(x):
+    """Pin this rank to the CPUs local to its GPU (sysfs `local_cpulist` of the PCI device) BEFORE any pinned host buffer is
+    allocated: pinned pages are placed by first touch, so the end-to-end copies then read NUMA-local memory.  Returns what it
+    did for the bench line; a single-node box (or a container without sysfs) is reported as such and left alone."""
+    info = {"bound": False}
+    try:
+        pr = x.torch.cuda.get_device_properties(x.dev)
+        bdf = "%04x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+        base = "/sys/bus/pci/devices/" + bdf
+        node = int(open(base + "/numa_node").read().strip())
+        cpus_txt = open(base + "/local_cpulist").read().strip()
+        info.update({"pci": bdf, "numa_node": node, "local_cpulist": cpus_txt})
+        cpus = set()
+        for part in cpus_txt.split(","):
+            if "-" in part:
+                a, b = part.split("-")
+                cpus.update(range(int(a), int(b) + 1))
+            elif part:
+                cpus.add(int(part))
+        allowed = os.sched_getaffinity(0)
+        nodes = [d for d in os.listdir("/sys/devices/system/node") if d.startswith("node") and d[4:].isdigit()]
+        info["numa_nodes"] = len(nodes)
+        if cpus and (cpus & allowed) and len(nodes) > 1 and (cpus & allowed) != allowed:
+            os.sched_setaffinity(0, cpus & allowed)
+            info["bound"] = True
+    except Exception as e:                                   # no sysfs / no permission: measure unbound
+        info["note"] = str(e)[:80]
+    return info
 
 
 def sync_all(x):
@@ -435,6 +466,79 @@ def run_config(x, args, name, steps):
     return out
 
 
+def run_conv_fused(x, args, c, steps):
+    """The same per-camera op with the head's final 1x1 conv (deconv_head.py:33-35) pulled in: ops.conv_integral_reproj_min_loss on
+    bf16 channels-last activations [B, 256, 64, 64] - the logits never exist, so the host->device traffic of the end-to-end
+    step is the activations (0.54 GB at B=256) instead of the logits (4.56 GB).  Device-resident timing, then the end-to-end variant with pinned host
+    activations.  Tensor-core roofline: 3 GEMMs of 2*K*D*C*H*W flops per sample are the algorithm (conv fwd, d x, d W); the
+    launches execute 5 (the backward recomputes the logit tiles in both of its launches)."""
+    torch = x.torch
+    B, K, R, NH, NS, C = c["B"], c["K"], c["R"], c["NH"], c["NS"], 256
+    out = {"workload": "final Conv2d(%d, %d, 1) + integral head + multi-hyp reprojection loss, batch %d/GPU, activations bf16 channels-last" % (C, K * R, B),
+           "batch_per_gpu": B, "channels": C, "steps": steps}
+    try:
+        gen = torch.Generator(device=x.dev).manual_seed(4321 + x.rank)
+        feat = torch.randn(B, C, R, R, device=x.dev, generator=gen).to(dtype=torch.bfloat16, memory_format=torch.channels_last).requires_grad_(True)
+        weight = (torch.randn(K * R, C, device=x.dev, generator=gen) / C ** 0.5).requires_grad_(True)
+        bias = torch.randn(K * R, device=x.dev, generator=gen).requires_grad_(True)
+        target = x.synth.pseudo_joints(B, K, seed=2 + x.rank).to(x.dev)
+        cams = {k: v.to(x.dev) for k, v in x.synth.cameras(B, seed=3 + x.rank, mpi=c["mpi"]).items()}
+        w = c["w"]
+        group = x.group if isinstance(x.group, x.pkg.dist.PeerExchange) else None
+
+        def step():
+            feat.grad = weight.grad = bias.grad = None
+            lp, ls, sel, kps, *_ = x.ops.conv_integral_reproj_min_loss(feat, weight, bias, target, cams, K, NH, NS, w_mse=w[0], w_bone=w[1],
+                                                                       w_kp=w[2], w_kp2d=w[3], reduction="batch", group=group)
+            (lp + ls).backward()
+            return lp, ls, sel, kps
+        n0 = x.ops.launch_count()
+        step()
+        out["launches_per_step"] = int(x.ops.launch_count() - n0)
+        ms = time_steps(x, step, steps, 3)
+        gemm = 2.0 * K * R * C * R * R * B
+        try:
+            peak_tf = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["bf16_tflops_sustained"])
+            peak_src = "MEASURED_PEAKS.json bf16_tflops_sustained (kernels timed inside a step)"
+        except Exception:
+            peak_tf, peak_src = 1400.0, "fallback"
+        out["device"] = {"value": round(B * x.world / (ms * 1e-3), 1), "unit": UNIT, "ms_per_step": round(ms, 4),
+                         "roofline": {"bound": "tensor", "achieved": round(3 * gemm / (ms * 1e-3) / 1e12, 1), "executed": round(5 * gemm / (ms * 1e-3) / 1e12, 1),
+                                      "peak": peak_tf, "unit": "TFLOP/s", "frac": round(3 * gemm / (ms * 1e-3) / 1e12 / peak_tf, 4),
+                                      "peak_source": peak_src,
+                                      "note": "achieved = algorithmic flops (3 GEMMs) / step time; executed counts the 2 recomputed logit GEMMs of the backward too"}}
+        # end to end: pinned host activations / target / cameras -> device, step, loss / slots / coordinates back
+        h_feat = torch.empty(feat.shape, dtype=torch.bfloat16, pin_memory=True, memory_format=torch.channels_last)
+        h_feat.copy_(feat.detach())
+        h_target = target.cpu().pin_memory()
+        h_cams = {k: v.cpu().pin_memory() for k, v in cams.items()}
+        h_out = {"loss": torch.empty(2, pin_memory=True), "sel": torch.empty(2, dtype=torch.int64, pin_memory=True),
+                 "kps": torch.empty(B, NH, K, 3, pin_memory=True)}
+
+        def e2e_step():
+            with torch.no_grad():
+                feat.copy_(h_feat, non_blocking=True)
+                target.copy_(h_target, non_blocking=True)
+                for k in cams:
+                    cams[k].copy_(h_cams[k], non_blocking=True)
+            lp, ls, sel, kps = step()
+            h_out["loss"].copy_(torch.stack((lp.detach(), ls.detach())), non_blocking=True)
+            h_out["sel"].copy_(sel, non_blocking=True)
+            h_out["kps"].copy_(kps.detach(), non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+        e_ms = time_steps(x, e2e_step, steps, 2)
+        h2d = h_feat.numel() * 2 + h_target.numel() * 4 + sum(v.numel() * 4 for v in h_cams.values())
+        out["e2e"] = {"value": round(B * x.world / (e_ms * 1e-3), 1), "unit": UNIT, "ms_per_step": round(e_ms, 3),
+                      "h2d_bytes_per_step": int(h2d) * x.world, "d2h_bytes_per_step": int(2 * 4 + 2 * 8 + h_out["kps"].numel() * 4) * x.world,
+                      "note": "activations (not logits) cross PCIe: 8.5x fewer bytes per sample than the logit-fed step; gradients d x / d W / d bias stay on the device"}
+    except torch.cuda.OutOfMemoryError as e:
+        out["error"] = "out of memory: %s" % (str(e)[:120],)
+    except RuntimeError as e:
+        out["error"] = str(e)[:200]
+    torch.cuda.empty_cache()
+    return out
+
+
 def run_ours(args, c):
     x = setup(args)
     torch, ops = x.torch, x.ops
@@ -595,7 +699,9 @@ def run_ours(args, c):
                             "share_of_e2e_step": round(h2d_ms / e2e_ms, 4),
                             "note": "the logits copy alone, all ranks copying at once (max over ranks): the PCIe / host-memory ceiling "
                                     "of this box at this N; the kernels add the rest"},
-               "note": "pinned host -> device copy of logits/target/cameras, fused op fwd+bwd, loss/sel/kps read back; PCIe-bound"}
+               "host_binding": x.numa,
+               "note": "pinned host -> device copy of logits/target/cameras, fused op fwd+bwd, loss/sel/kps read back; PCIe / host-memory "
+                       "bound (compare h2d_only): each rank is bound to its GPU's NUMA node before the pinned buffers are allocated"}
         del h_logits, d_logits, h_out, d_target, d_cams
     del logits, target, cams, step, graphed, eager_step
     torch.cuda.empty_cache()
@@ -603,6 +709,7 @@ def run_ours(args, c):
     # ---- 3c. the other BASELINE configs at this N
     if not args.no_configs and args.config == "c2":
         line_extra["configs"] = {name: run_config(x, args, name, max(5, min(args.steps, 20))) for name in ("c3", "c4")}
+        line_extra["conv_fused"] = run_conv_fused(x, args, c, max(5, min(args.steps, 20)))
 
     if x.rank == 0:
         peak, peak_src = measured_peak()

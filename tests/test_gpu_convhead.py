@@ -208,3 +208,37 @@ def test_conv_head_backward_bf16_channels_last(ops, oracle, B, K, D, H, C, use_b
     for name, ours, ref in checks:
         err = float((ours.cpu().double() - ref).abs().max()) / float(ref.abs().max())
         assert err < 2.0 ** -8, (name, err)
+
+
+@pytest.mark.parametrize("reduction,sym", [("batch", True), ("sample", False), ("joint", False)])
+def test_conv_fused_reproj_min_loss(ops, oracle, synth, reduction, sym):
+    """The whole per-camera op with the head's final conv pulled in (ConvIntegralReprojMinLoss): losses, selected slots,
+    coordinates and d x / d W / d bias against the fp64 oracle run on logits formed from the same bf16-rounded operands."""
+    dev = torch.device("cuda:0")
+    B, K, D, C, NH, NS = 4, 17, 64, 128, 3, 15
+    x, w, bias = _case(B, K, D, C, seed=91)
+    target = synth.pseudo_joints(B, K, seed=92)
+    cams = synth.cameras(B, seed=93)
+    weights = dict(w_mse=1.0, w_bone=0.1, w_kp=0.1, w_kp2d=0.0) if sym else dict(w_mse=3.0)
+    xd = x.to(dev).requires_grad_(True)
+    wd = w.to(dev).requires_grad_(True)
+    bd = bias.to(dev).requires_grad_(True)
+    dcams = {k: v.to(dev) for k, v in cams.items()}
+    n0 = ops.launch_count()
+    lp, ls, sel, kps, world, dmap, idx = ops.conv_integral_reproj_min_loss(xd, wd, bd, target.to(dev), dcams, K, NH, NS, reduction=reduction, **weights)
+    (lp + ls).backward()
+    torch.cuda.synchronize()
+    assert ops.launch_count() - n0 <= 7          # pack, conv fwd, loss fwd, loss bwd + coef, row coefficients, d W, d x
+    x64 = x.bfloat16().double().requires_grad_(True)
+    w64 = w.bfloat16().double().requires_grad_(True)
+    b64 = bias.double().requires_grad_(True)
+    logits = torch.einsum("oc,bchw->bohw", w64, x64) + b64.view(1, -1, 1, 1)
+    c64 = {k: v.double() for k, v in cams.items()}
+    olp, ols, osel, okps, oworld, odmap, oidx = oracle.fused_forward(logits, K, NH, NS, target.double(), c64, reduction=reduction, **weights)
+    (olp + ols).backward()
+    assert torch.equal(idx.cpu(), oidx) and torch.equal(sel.cpu(), osel)
+    assert float((kps.detach().cpu().double() - okps.detach()).abs().max()) < 1e-5
+    assert abs(float(lp + ls) - float(olp + ols)) <= 1e-5 * abs(float(olp + ols))
+    for name, ours, ref in (("dx", xd.grad, x64.grad), ("dW", wd.grad, w64.grad), ("dbias", bd.grad, b64.grad)):
+        err = float((ours.cpu().double() - ref).abs().max()) / float(ref.abs().max())
+        assert err < 2.0 ** -8, (name, err)

@@ -615,7 +615,10 @@ int xsup_conv_head_fwd(const void* x_nhwc, const void* weight, const float* bias
     f.n_units = s->B * s->K; f.K = s->K; f.NH = s->NH; f.NS = s->NS; f.head = s->head;
     f.stats_stride = (int)stats_stride(*s);
     f.t.D = s->D; f.t.H = s->H; f.t.W = s->W;
-    cudaError_t e = launch_conv_head_fwd(x_nhwc, weight, bias, logits_out, f, s->B, C, sms, (cudaStream_t)stream);
+    // the scheduling words after the statistics (word 1 = ticket of xsup_reproj_fused_fwd) start at zero, as after xsup_integral_fwd
+    cudaError_t e = cudaMemsetAsync(stats + (size_t)s->B * s->K * f.stats_stride, 0, kSchedWords * sizeof(int), (cudaStream_t)stream);
+    if (e != cudaSuccess) return cuda_fail(e, "xsup_conv_head_fwd scheduling-word reset");
+    e = launch_conv_head_fwd(x_nhwc, weight, bias, logits_out, f, s->B, C, sms, (cudaStream_t)stream);
     if (e == cudaErrorNotSupported) return fail(XSUP_E_DEVICE, "xsup_conv_head_fwd: cuTensorMapEncodeTiled unavailable or rejected the tensors");
     if (e != cudaSuccess) return cuda_fail(e, "xsup_conv_head_fwd launch");
     count_launches(1);

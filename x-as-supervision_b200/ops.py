@@ -27,7 +27,7 @@ __all__ = ["IntegralMultiHead", "IntegralSingleHead", "PatchToWorld", "IntegralR
            "integral_single_head", "convert_patch_to_world", "convert_world_to_patch", "convert_patch_to_image",
            "convert_image_to_world", "convert_image_to_patch", "convert_world_to_image", "find_peak",
            "integral_reproj_min_loss", "launch_count", "set_event_sink", "GraphedReprojStep", "conv_integral_head", "ConvIntegralHead",
-           "conv_integral_head_train"]
+           "conv_integral_head_train", "ConvIntegralReprojMinLoss", "conv_integral_reproj_min_loss"]
 
 launch_count = cabi.launch_count
 _nvtx = torch.cuda.nvtx          # ranges around K1 / K2 (+ exchange) / K3: visible in nsys / ncu --nvtx, free otherwise
@@ -580,3 +580,131 @@ class ConvIntegralHead(torch.autograd.Function):
 def conv_integral_head_train(x, weight, bias, num_kp, num_hypo, neighbor_size):
     """Differentiable form of `conv_integral_head` (see `ConvIntegralHead`): -> (kps, depth_prob_map, peak_idx)."""
     return ConvIntegralHead.apply(x, weight, bias, num_kp, num_hypo, neighbor_size)
+
+
+class ConvIntegralReprojMinLoss(torch.autograd.Function):
+    """`Conv2d(C, K*D, 1)` -> integral multi-hypothesis head -> per-hypothesis world lift + loss terms + min over slots, forward
+    and backward, with neither the logits nor d loss / d logits ever in HBM: `IntegralReprojMinLoss` with the head's final
+    layer (deconv_head.py:33-35) pulled in.  Four launches forward+backward apart from the two tiny set-up kernels:
+    `xsup_conv_head_fwd` (tcgen05), `xsup_reproj_fused_fwd`, `xsup_reproj_fused_bwd` (-> coefficient blocks),
+    `xsup_conv_head_bwd` (tcgen05: d W + d bias launch, d x launch).
+
+    Inputs as `ConvIntegralHead` (x `[B,C,H,W]`, weight `[K*D,C(,1,1)]`, bias) followed by the loss arguments of
+    `IntegralReprojMinLoss`; outputs (loss_pseudo, loss_sym, sel_idx, kps, kps_world, depth_prob_map, peak_idx).
+    Gradients flow to x, weight and bias from both losses and from anything downstream of `kps` / `kps_world`."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, target, trans_image, pelvis, k_mat, trans_world, rot_world, num_kp, num_hypo, neighbor_size,
+                img_hw, rect_width, w_mse, w_bone, w_kp, w_kp2d, reduction, group):
+        cabi.require_cuda(x, "x")
+        ctx.set_materialize_grads(False)
+        B, C, H, W = x.shape
+        dev = x.device
+        if B == 0:
+            raise ValueError("ConvIntegralReprojMinLoss needs a non-empty batch")
+        w2 = weight.detach().reshape(weight.shape[0], -1)
+        D = w2.shape[0] // num_kp
+        if w2.shape[1] != C or D * num_kp != w2.shape[0]:
+            raise ValueError("weight is %s, expected [num_kp*D, %d(,1,1)]" % (tuple(weight.shape), C))
+        K, NH = num_kp, num_hypo
+        xb = _nhwc_bf16(x)
+        wb = w2.to(device=dev, dtype=torch.bfloat16).contiguous()
+        bf = bias.detach().to(device=dev, dtype=torch.float32).contiguous() if bias is not None else None
+        shape = cabi.make_shape(B, K, D, H, W, NH, neighbor_size, torch.bfloat16, cabi.HEAD_MULTI)
+        kps = torch.empty(B, NH, K, 3, dtype=torch.float32, device=dev)
+        dmap = torch.empty(K, D, dtype=torch.float32, device=dev)
+        idx = torch.empty(B, K, NH, dtype=torch.int64, device=dev)
+        stats = torch.empty(cabi.lib.xsup_stats_floats(shape), dtype=torch.float32, device=dev)
+        target = target.to(device=dev, dtype=torch.float32).contiguous()
+        if tuple(target.shape) != (B, K, 3):
+            raise ValueError("target must be [B,K,3] = %s, got %s" % ((B, K, 3), tuple(target.shape)))
+        keep, cam = _cam_args(dict(trans_image=trans_image, pelvis=pelvis, k_mat=k_mat, trans_world=trans_world,
+                                   rot_world=rot_world), B)
+        if xdist.is_active(group) and not isinstance(group, xdist.PeerExchange):
+            raise ValueError("ConvIntegralReprojMinLoss takes group=None or a dist.PeerExchange (the in-kernel exchange)")
+        use_sym = any(w is not None for w in (w_bone, w_kp, w_kp2d))
+        cfg = cabi.LossCfg(B, K, NH, int(img_hw[0]), int(img_hw[1]), float(rect_width), float(w_mse),
+                           float(w_bone or 0.0), float(w_kp or 0.0), float(w_kp2d or 0.0), int(use_sym),
+                           cabi.REDUCE[reduction], xdist.global_batch(B, group))
+        world = torch.empty_like(kps)
+        sample_terms = torch.empty(B, cabi.LOSS_TERMS, NH, dtype=torch.float32, device=dev)
+        partial = torch.empty(cabi.LOSS_TERMS, NH, dtype=torch.float32, device=dev)
+        loss = torch.empty(2, dtype=torch.float32, device=dev)
+        sel = torch.empty({"batch": (2,), "sample": (2, B), "joint": (B, K)}[reduction], dtype=torch.int64, device=dev)
+        st = cabi.stream_ptr(dev)
+        with torch.cuda.device(dev):
+            with _range("xsup.K7.conv_head_fwd"):
+                cabi.check(cabi.lib.xsup_conv_head_fwd(xb.data_ptr(), wb.data_ptr(), bf.data_ptr() if bf is not None else None,
+                                                       kps.data_ptr(), dmap.data_ptr(), idx.data_ptr(), stats.data_ptr(), None, shape, C, st),
+                           "xsup_conv_head_fwd")
+            with _range("xsup.K2.loss_select_fwd"):
+                xchg = group.descriptor() if xdist.is_active(group) else None
+                ticket = stats.data_ptr() + 4 * (B * K * int(cabi.lib.xsup_stats_stride(shape)) + 1)
+                cabi.check(cabi.lib.xsup_reproj_fused_fwd(kps.data_ptr(), target.data_ptr(), cam, world.data_ptr(), sample_terms.data_ptr(),
+                                                          partial.data_ptr(), loss.data_ptr(), sel.data_ptr(), cfg, xchg, ticket, st),
+                           "xsup_reproj_fused_fwd")
+        ctx.save_for_backward(xb, wb, bf, stats, kps, target, sel, *keep)
+        ctx.shape, ctx.cfg, ctx.C = shape, cfg, C
+        ctx.meta = (x.dtype, weight.dtype, tuple(weight.shape), bias.dtype if bias is not None else None,
+                    x.is_contiguous(memory_format=torch.channels_last) and not x.is_contiguous())
+        ctx.mark_non_differentiable(sel, dmap, idx)
+        return loss[0], loss[1], sel, kps, world, dmap, idx
+
+    @staticmethod
+    def backward(ctx, g_lp, g_ls, _g_sel, g_kps_out, g_world, _g_dmap, _g_idx):
+        xb, wb, bf, stats, kps, target, sel, *keep = ctx.saved_tensors
+        shape, cfg, C = ctx.shape, ctx.cfg, ctx.C
+        x_dtype, w_dtype, w_shape, b_dtype, x_was_cl = ctx.meta
+        if g_lp is None and g_ls is None and g_kps_out is None and g_world is None:
+            return (None,) * 20
+        dev = xb.device
+        B, K, D, H, W = shape.B, shape.K, shape.D, shape.H, shape.W
+        cam = cabi.make_cam(*keep, B)
+
+        def ptr(t):
+            if t is None:
+                return None, None
+            t = t.to(torch.float32).contiguous()
+            return t, t.data_ptr()
+        g_lp, p_lp = ptr(g_lp)
+        g_ls, p_ls = ptr(g_ls)
+        g_kps_out, p_gk = ptr(g_kps_out)
+        g_world, p_gw = ptr(g_world)
+        coef = torch.empty(cabi.lib.xsup_coef_floats(shape), dtype=torch.float32, device=dev)
+        rowcoef = torch.empty(cabi.lib.xsup_conv_bwd_ws_floats(shape), dtype=torch.float32, device=dev)
+        need_x, need_w = ctx.needs_input_grad[0], ctx.needs_input_grad[1] or (bf is not None and ctx.needs_input_grad[2])
+        dx_f32 = x_dtype != torch.bfloat16
+        dx = torch.empty((B, C, H, W), dtype=torch.float32 if dx_f32 else torch.bfloat16, device=dev,
+                         memory_format=torch.channels_last) if need_x else None
+        dw = torch.empty(K * D, C, dtype=torch.float32, device=dev) if need_w else None
+        db = torch.empty(K * D, dtype=torch.float32, device=dev) if (need_w and bf is not None) else None
+        st = cabi.stream_ptr(dev)
+        with torch.cuda.device(dev):
+            with _range("xsup.K2.loss_bwd_coef"):
+                cabi.check(cabi.lib.xsup_reproj_fused_bwd(kps.data_ptr(), target.data_ptr(), cam, sel.data_ptr(), p_lp, p_ls, p_gk, p_gw,
+                                                          stats.data_ptr(), coef.data_ptr(), None, cfg, shape, st), "xsup_reproj_fused_bwd")
+            with _range("xsup.K8.conv_head_bwd"):
+                cabi.check(cabi.lib.xsup_conv_head_bwd(xb.data_ptr(), wb.data_ptr(), bf.data_ptr() if bf is not None else None, coef.data_ptr(),
+                                                       rowcoef.data_ptr(), dx.data_ptr() if need_x else None, 1 if dx_f32 else 0,
+                                                       dw.data_ptr() if need_w else None, db.data_ptr() if db is not None else None,
+                                                       shape, C, st), "xsup_conv_head_bwd")
+        g_x = g_w = g_b = None
+        if need_x:
+            g_x = dx.to(x_dtype)
+            if not x_was_cl:
+                g_x = g_x.contiguous()
+        if ctx.needs_input_grad[1]:
+            g_w = dw.to(w_dtype).reshape(w_shape)
+        if bf is not None and ctx.needs_input_grad[2]:
+            g_b = db.to(b_dtype)
+        return (g_x, g_w, g_b) + (None,) * 17
+
+
+def conv_integral_reproj_min_loss(x, weight, bias, target, cams: Dict[str, torch.Tensor], num_kp, num_hypo, neighbor_size,
+                                  img_hw: Sequence[int] = (256, 256), rect_width: float = 2000.0, w_mse: float = 1.0,
+                                  w_bone: Optional[float] = None, w_kp: Optional[float] = None, w_kp2d: Optional[float] = None,
+                                  reduction: str = "batch", group=None):
+    """Functional form of `ConvIntegralReprojMinLoss` (camera tensors as a dict, like `integral_reproj_min_loss`)."""
+    return ConvIntegralReprojMinLoss.apply(x, weight, bias, target, cams["trans_image"], cams["pelvis"], cams["k_mat"],
+                                           cams["trans_world"], cams["rot_world"], num_kp, num_hypo, neighbor_size, tuple(img_hw),
+                                           rect_width, w_mse, w_bone, w_kp, w_kp2d, reduction, group)
