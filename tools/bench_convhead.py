@@ -134,8 +134,30 @@ def main():
                                 "unfused_bf16_bmm_autograd_plus_streaming_head_bf16_ms": round(ms_ubt, 3),
                                 "speedup_vs_best_unfused_bf16": round(ms_ubt / ms_ft_cl, 2),
                                 "xsup_launches_per_step": int(per_step),
-                                "note": "fused: pack, conv_head_fwd, coef, conv_head_bwd_g (ours) + 2 cuBLAS GEMMs on the bf16 gradient; "
+                                "note": "fused: pack, conv_head_fwd, coef, conv_rowcoef, conv_head_bwd dW + dX launches (all ours, tcgen05); "
                                         "unfused: cuDNN conv fwd/bwd (TF32) + integral_fwd/bwd on 4.56 GB of fp32 logits"}
+        # ---- operand precision: the reference's conv is fp32 (TF32 on this GPU unless disabled); ours rounds x and W to bf16.
+        # Coordinates (normalised to [-1, 1]; one heat-map bin = 2/64 = 0.031) against a true-fp32 conv, for two logit scales.
+        prec = {}
+        Bp = min(B, 16)
+        for name, scale in (("logit_std_1", 1.0), ("logit_std_4", 4.0)):
+            ws = (w * scale).contiguous()
+            old = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+            torch.backends.cudnn.allow_tf32 = torch.backends.cuda.matmul.allow_tf32 = False
+            ref, _, ridx = ops.integral_multi_head(F.conv2d(x[:Bp], ws.view(K * D, C, 1, 1), bias), K, NH, NS)
+            torch.backends.cudnn.allow_tf32 = torch.backends.cuda.matmul.allow_tf32 = True
+            tf, _, tidx = ops.integral_multi_head(F.conv2d(x[:Bp], ws.view(K * D, C, 1, 1), bias), K, NH, NS)
+            torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
+            ours, _, oidx = ops.conv_integral_head(x[:Bp], ws, bias, K, NH, NS)
+            same_t, same_o = (tidx == ridx).all(dim=-1), (oidx == ridx).all(dim=-1)       # [B,K]: all NH peak bins agree
+
+            def err(a, mask):
+                d = (a - ref).abs()[..., :2]                                            # x, y: defined whatever the peaks do
+                dz = (a - ref).abs()[..., 2][mask.unsqueeze(1).expand(-1, NH, -1)]        # z where the same peaks were picked
+                return {"xy_max": float(d.max()), "xy_mean": float(d.mean()), "z_max_same_peaks": float(dz.max()) if dz.numel() else None,
+                        "units_with_same_peaks": float(mask.float().mean())}
+            prec[name] = {"tf32_conv_vs_fp32": err(tf, same_t), "bf16_fused_vs_fp32": err(ours, same_o)}
+        out["operand_precision"] = prec
     print(json.dumps(out), flush=True)
 
 
