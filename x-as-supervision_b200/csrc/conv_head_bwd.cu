@@ -100,22 +100,6 @@ __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float 
     asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
 
-// D[tmem] (+)= A[tmem] * B[smem desc]: the A operand (bf16, K-major, 2 elements per 32-bit column) comes from tensor memory
-__device__ __forceinline__ void umma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, uint32_t acc) {
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t"
-        "}" ::"r"(tmem_d),
-        "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(acc)
-        : "memory");
-}
-// shared memory -> tensor memory, 128 lanes x 256 bits: one [128 rows x 16 bf16] K-slab of a K-major operand (same descriptor
-// as the MMA would use for it); executes in issue order with the MMAs of the issuing thread
-__device__ __forceinline__ void tmem_cp_128x256b(uint32_t taddr, uint64_t desc) {
-    asm volatile("tcgen05.cp.cta_group::1.128x256b [%0], %1;" ::"r"(taddr), "l"(desc) : "memory");
-}
 #define TRACE(slot, gi) do { if (p.trace && blockIdx.x == 0 && (gi) >= 8 && (gi) < 24) p.trace[((gi) - 8) * 16 + (slot)] = clock64(); } while (0)
 // ------------------------------------------------------------------ kernel
 template <int KBN, int MODE>

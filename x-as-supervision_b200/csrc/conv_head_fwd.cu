@@ -39,7 +39,8 @@ constexpr int kCvThreads = (kCvEpiWarps + 2 + kCvFinWarps) * 32;
 constexpr int kCvRows = 128;           // UMMA M: output rows per CTA
 constexpr int kCvPix = 128;            // UMMA N: pixels per tile
 constexpr int kCvStages = 2;
-constexpr int kCvAcc = 4;              // TMEM accumulator buffers (4 x 128 columns = all 512)
+constexpr int kCvAcc = 3;              // TMEM accumulator buffers (columns [128,512)); columns [0,128) hold the weight slab
+constexpr int kCvAccCol = 128;
 constexpr int kCvKBBytes = kCvRows * kCvKB * 2;   // 16 KB: one [128 x 64] bf16 k-block (same for W and X tiles)
 
 struct ConvHeadParams {
@@ -129,6 +130,10 @@ __global__ void __launch_bounds__(kCvThreads, 1) conv_head_fwd_kernel(const __gr
         __syncwarp();
     } else if (warp == kCvEpiWarps + 1) {
         // ------------------------------------------------------------ MMA issuer
+        // The item's weight slab goes from its shared-memory landing buffer into TENSOR memory (tcgen05.cp, 8 columns per 16
+        // channels; in order behind the previous item's MMAs) and the buffer is released at once, so the producer prefetches the
+        // next slab a whole item ahead and the MMAs read A from TMEM: with both operands in shared memory an M = N = 128 MMA
+        // needs 128 B/clk of operand reads, which is all the shared memory delivers.
         uint64_t da[KBN], db0[KBN];                                  // descriptors of the slab and of ring stage 0, per k-block
 #pragma unroll
         for (int kb = 0; kb < KBN; ++kb) {
@@ -136,31 +141,39 @@ __global__ void __launch_bounds__(kCvThreads, 1) conv_head_fwd_kernel(const __gr
             db0[kb] = umma_desc_sw128(smem_u32(sX) + kb * kCvKBBytes);
         }
         constexpr uint64_t kStageStep = (uint64_t)((KBN * kCvKBBytes) >> 4);   // start-address field units
-        int g = 0, n = 0;
+        int s = 0, a = 0, n = 0;
+        uint32_t xph = 0, aeph = 1;
         for (int item = blockIdx.x; item < p.items; item += gridDim.x, ++n) {
             mbar_wait(b_wfull, n & 1);
-            for (int t = 0; t < T; ++t, ++g) {
-                const int s = g % kCvStages, it = g / kCvStages, a = g % kCvAcc, ia = g / kCvAcc;
-                mbar_wait(b_aempty + 8 * a, (ia & 1) ^ 1);           // the epilogue has drained this accumulator
-                mbar_wait(b_xfull + 8 * s, it & 1);                  // the tile has landed
+            tc_fence_after();
+            if (lane == 0) {
+#pragma unroll
+                for (int kb = 0; kb < KBN; ++kb)
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) tmem_cp_128x256b(tmem_base + (uint32_t)((kb * 4 + q) * 8), da[kb] + 2 * q);
+                umma_commit(b_wempty);                               // the landing buffer may take the next slab
+            }
+            __syncwarp();
+            for (int t = 0; t < T; ++t) {
+                mbar_wait(b_aempty + 8 * a, aeph);                   // the epilogue has drained this accumulator
+                mbar_wait(b_xfull + 8 * s, xph);                     // the tile has landed
                 tc_fence_after();
                 if (lane == 0) {
-                    const uint32_t acc = tmem_base + (uint32_t)a * kCvPix;
+                    const uint32_t acc = tmem_base + (uint32_t)(kCvAccCol + a * kCvPix);
                     const uint64_t soff = (uint64_t)s * kStageStep;
 #pragma unroll
                     for (int kb = 0; kb < KBN; ++kb) {
-                        const uint64_t a0 = da[kb], b0 = db0[kb] + soff;
+                        const uint64_t b0 = db0[kb] + soff;
                         // +32 B per K step of 16 bf16 inside the 128-byte swizzle atom: +2 in the start-address field
-                        if (kb == 0) umma_f16<false>(acc, a0, b0, kCvIdesc); else umma_f16<true>(acc, a0, b0, kCvIdesc);
-                        umma_f16<true>(acc, a0 + 2, b0 + 2, kCvIdesc);
-                        umma_f16<true>(acc, a0 + 4, b0 + 4, kCvIdesc);
-                        umma_f16<true>(acc, a0 + 6, b0 + 6, kCvIdesc);
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) umma_f16_ts(acc, tmem_base + (uint32_t)((kb * 4 + q) * 8), b0 + 2 * q, kCvIdesc, (kb | q) ? 1u : 0u);
                     }
                     umma_commit(b_xempty + 8 * s);                   // smem stage reusable once these MMAs have read it
                     umma_commit(b_afull + 8 * a);                    // accumulator complete
-                    if (t == T - 1) umma_commit(b_wempty);           // the slab may be replaced
                 }
                 __syncwarp();
+                if (++s == kCvStages) { s = 0; xph ^= 1; }
+                if (++a == kCvAcc) { a = 0; aeph ^= 1; }
             }
         }
     } else if (warp < kCvEpiWarps) {
@@ -183,11 +196,12 @@ __global__ void __launch_bounds__(kCvThreads, 1) conv_head_fwd_kernel(const __gr
                 }
                 float gsum = 0.f;
                 for (int t = 0; t < T; ++t, ++g) {
-                    const int a = g % kCvAcc, ia = g / kCvAcc;
-                    mbar_wait(b_afull + 8 * a, ia & 1);
+                    const int a = g % kCvAcc;
+                    const uint32_t aph = (uint32_t)(g / kCvAcc) & 1u;
+                    mbar_wait(b_afull + 8 * a, aph);
                     tc_fence_after();
                     uint32_t r[32];
-                    tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(a * kCvPix + c0), r);
+                    tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(kCvAccCol + a * kCvPix + c0), r);
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(b_aempty + 8 * a);
@@ -229,11 +243,12 @@ __global__ void __launch_bounds__(kCvThreads, 1) conv_head_fwd_kernel(const __gr
             float m = kNegHuge, s = 0.f, sx = 0.f, sy = 0.f;
             float* lrow = p.logits_out ? p.logits_out + ((size_t)b * p.rows_total + grow) * p.HW : nullptr;
             for (int t = 0; t < T; ++t, ++g) {
-                const int a = g % kCvAcc, ia = g / kCvAcc;
-                mbar_wait(b_afull + 8 * a, ia & 1);
+                const int a = g % kCvAcc;
+                    const uint32_t aph = (uint32_t)(g / kCvAcc) & 1u;
+                    mbar_wait(b_afull + 8 * a, aph);
                 tc_fence_after();
                 uint32_t r[32];
-                tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(a * kCvPix + c0), r);
+                tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(kCvAccCol + a * kCvPix + c0), r);
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(b_aempty + 8 * a);        // values are in registers: release the accumulator early

@@ -81,6 +81,22 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
         : "memory");
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
+// D[tmem] (+)= A[tmem] * B[smem desc]: the A operand (bf16, K-major, 2 elements per 32-bit column) comes from tensor memory
+__device__ __forceinline__ void umma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, uint32_t acc) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t"
+        "}" ::"r"(tmem_d),
+        "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(acc)
+        : "memory");
+}
+// shared memory -> tensor memory, 128 lanes x 256 bits: one [128 rows x 16 bf16] K-slab of a K-major operand (same descriptor
+// as the MMA would use for it); executes in issue order with the MMAs of the issuing thread
+__device__ __forceinline__ void tmem_cp_128x256b(uint32_t taddr, uint64_t desc) {
+    asm volatile("tcgen05.cp.cta_group::1.128x256b [%0], %1;" ::"r"(taddr), "l"(desc) : "memory");
+}
 // MN-major, SWIZZLE_128B operand (cute's canonical ((8,n),(8,k)):((1,LBO),(8,SBO)) in 16-byte units): rows of 128 bytes
 // hold 64 consecutive M/N elements of one K index; 8 K indices form a 1024-byte atom (SBO = 1024); the next 64 M/N
 // elements start `lbo_bytes` further on (leading byte offset, bits [16,30)).  Stepping K by 16 adds 2048 bytes.
