@@ -12,10 +12,11 @@
 //   warp 16      TMA producer: the item's 128 x C weight slab (bf16, K-major, SWIZZLE_128B) as soon as the previous item's
 //                MMAs have retired, then the sample's activations as 128-pixel tiles (channels-last bf16, K-major)
 //                through a 2-stage ring; barrier phases run on across items
-//   warp 17      MMA issuer: one elected thread, tcgen05.mma.cta_group::1.kind::f16 M=128 N=128 K=16, 16 per tile, with
-//                precomputed shared-memory descriptors (the issue loop is ~5 instructions per MMA); accumulators in
-//                TMEM (4 x 128 columns: the epilogue of tile t overlaps the MMAs of t+1..t+3); tcgen05.commit releases
-//                the smem stage and publishes the accumulator
+//   warp 17      MMA issuer: one elected thread; per item the weight slab goes from its landing buffer into tensor memory
+//                (tcgen05.cp, 128 columns) and the buffer is released for the next slab; per tile 16 tcgen05.mma
+//                cta_group::1.kind::f16 M=128 N=128 K=16 with A from TMEM and precomputed shared-memory descriptors for B
+//                (the issue loop is ~5 instructions per MMA); accumulators in TMEM (3 x 128 columns: the epilogue of tile t
+//                overlaps the MMAs of t+1, t+2); tcgen05.commit releases the smem stage and publishes the accumulator
 //   warps 0..15  epilogue: thread = TMEM lane = output row (joint, d); warps w, w+4, w+8, w+12 share a lane quarter and
 //                take 32 columns each; tcgen05.ld; the softmax statistics of the row (running max, sum e, sum w*e,
 //                sum h*e) stay in FOUR registers per thread - rows are depth bins, so the depth marginal pz[d] is simply
