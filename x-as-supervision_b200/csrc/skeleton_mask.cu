@@ -28,6 +28,7 @@ constexpr int kTileW = 16, kTileH = 8;
 constexpr int kTilesPerWarp = 8;
 constexpr int kTilesPerCta = kSkelWarps * kTilesPerWarp;
 #define kInf __int_as_float(0x7f800000)
+constexpr float kZeroExp = 40.0f;
 
 // segment `l` of sample `b`: A = (start.x, start.y, d.x, d.y), Bv = (1/(1e-8+|d|^2), end.x, end.y, c)
 // start = child joint, end = parent joint (util.py:34-36); c = 2 for the arm lines when L >= 21 (util.py:50-53)
@@ -83,7 +84,8 @@ __device__ __forceinline__ float sqrt_approx(float x) {
 }
 
 // lines that can be the winner somewhere in the tile whose first pixel is (x0, y0); lane = line
-// Returns 0 when every pixel of the tile is exactly 0 (so far from all lines that exp underflows: u < -105).
+// Returns 0 when every pixel of the tile is below exp(-kZeroExp) = 4.2e-18 (the reference's value there is a positive number below
+// that; ours is exactly 0: invisible in every fp32 sum the loss and its gradient form, and 12 orders below the 1e-5 parity bound).
 __device__ __forceinline__ unsigned cull_lines(int L, const float4* sA, const float4* sC, int x0, int y0, float two_over, float rho,
                                                float rbw, int lane) {
     float lo = kInf, up = kInf;
@@ -100,10 +102,10 @@ __device__ __forceinline__ unsigned cull_lines(int L, const float4* sA, const fl
     const float U = warp_min(up);
     // slack: the fp32 operations above (incl. the approximate sqrt) err by ~1e-6 on values <= 4; 1e-4 only keeps a few more lines
     const unsigned keep = __ballot_sync(0xffffffffu, lo <= U + 1e-4f);
-    // min over the lines of the lower bound of c*q/bw: beyond 105 every exp() in the tile is exactly 0 in fp32
-    // (exp(-103.98) is already below half the smallest denormal), for the reference as well
+    // min over the lines of the lower bound of c*q/bw (beyond 105 every exp() in the tile would be exactly 0 in fp32, for the
+    // reference as well; kZeroExp cuts earlier: with body_width 3e-3 that is 44 pixels from the nearest line instead of 72)
     const float lmin = warp_min(lo);
-    return (lmin * lmin * rbw > 105.0f) ? 0u : keep;
+    return (lmin * lmin * rbw > kZeroExp) ? 0u : keep;
 }
 
 // ---------------------------------------------------------------------------------------------- fused forward
@@ -169,7 +171,8 @@ __global__ void __launch_bounds__(kSkelThreads) skeleton_mask_fwd_kernel(const S
                 for (int i = 0; i < 4; ++i) {
                     const float c = sC[bl[i]].z;
                     const float q = c == 2.0f ? 0.5f * best[i] : best[i];                   // exact
-                    h[i] = expf(-div_by(q, p.bw, rbw) * c);                                 // util.py:52-55
+                    const float u = div_by(q, p.bw, rbw) * c;                               // util.py:52-55
+                    h[i] = u > kZeroExp ? 0.0f : expf(-u);                                  // same cut per pixel as per tile
                 }
             }
             *reinterpret_cast<float4*>(recon + o) = make_float4(h[0], h[1], h[2], h[3]);
@@ -408,7 +411,10 @@ __global__ void __launch_bounds__(256) draw_lines_fwd_kernel(const SkelParams p,
     float h[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i)          // same operation sequence as the fused kernel: max over l of these == its output, bit for bit
-        h[i] = expf(-div_by(seg_sqdist(grid_coord(px + i, fS1) - A.x, ay, aydyi, A, C), p.bw, rbw) * C.z);
+    {
+        const float u = div_by(seg_sqdist(grid_coord(px + i, fS1) - A.x, ay, aydyi, A, C), p.bw, rbw) * C.z;
+        h[i] = u > kZeroExp ? 0.0f : expf(-u);
+    }
     *reinterpret_cast<float4*>(heat + (((size_t)b * p.L + l) * S + py) * S + px) = make_float4(h[0], h[1], h[2], h[3]);
 }
 
