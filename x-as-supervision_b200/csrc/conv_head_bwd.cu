@@ -67,6 +67,7 @@ struct ConvBwdParams {
     int C, HW, W, rows_total, rows_pad;
     int per_b;                  // items per sample: row groups (MODE_DW) or 128-pixel tiles (MODE_DX)
     int T;                      // streamed tiles per item
+    int last_rows;              // valid rows of an item's last streamed tile (MODE_DX: K*D need not be a multiple of 128), else 128
     int items;
     long long* trace;           // diagnostics: clock64 timeline of CTA 0, tiles 8..23 (XSUP_CONVBWD_TRACE = device pointer)
 };
@@ -238,9 +239,12 @@ __global__ void __launch_bounds__(kBwThreads, 1) conv_head_bwd_kernel(const __gr
                     tc_fence_after();
                     const uint32_t d2 = tmem_base + (uint32_t)kBwD2Col;
                     const uint64_t db = hiK | (uint64_t)(mn_lo0 + (uint32_t)s * kStageStep);
+                    const int nq = t == T - 1 ? (p.last_rows + 15) >> 4 : 8;       // K steps of 16 streamed rows; padding rows are skipped
 #pragma unroll
                     for (int q = 0; q < 8; ++q)
-                        umma_f16_rt(d2, hiK | (uint64_t)(g_lo + (q >> 2) * (kBwKB >> 4) + 2 * (q & 3)), db + (uint64_t)(128 * q), kIdesc2, (t | q) ? 1u : 0u);
+                        if (q < nq)
+                            umma_f16_rt(d2, hiK | (uint64_t)(g_lo + (q >> 2) * (kBwKB >> 4) + 2 * (q & 3)), db + (uint64_t)(128 * q), kIdesc2,
+                                        (t | q) ? 1u : 0u);
                     umma_commit(b_empty + 8 * s);
                     umma_commit(b_gempty);
                     TRACE(5, h);
@@ -295,6 +299,17 @@ __global__ void __launch_bounds__(kBwThreads, 1) conv_head_bwd_kernel(const __gr
                 aph ^= 1;
                 if (threadIdx.x == 0) TRACE(8, gtile);
                 tc_fence_after();
+                if (MODE == MODE_DX && t == T - 1 && part * 32 >= p.last_rows) {
+                    // this warp's 32 columns of the last weight tile are all padding: the second GEMM does not read them
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(b_aempty);
+                    mbar_wait(b_gempty, geph);
+                    geph ^= 1;
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(b_gfull);
+                    ++gtile;
+                    continue;
+                }
                 uint32_t r[32];
                 tmem_ld32(lane_addr + (uint32_t)(kBwSCol + part * 32), r);
                 tc_fence_before();
@@ -353,57 +368,65 @@ __global__ void __launch_bounds__(kBwThreads, 1) conv_head_bwd_kernel(const __gr
             dph ^= 1;
             if (threadIdx.x == 0) TRACE(14, 8 + n);
             tc_fence_after();
-            // D2 [128 x C] fp32 leaves through the (now idle) G buffer: R rows per pass are laid out as [R x 128-byte] blocks with
+            // D2 [128 x C] fp32 leaves through the (now idle) G buffer: 32 rows at a time are laid out as [32 x 128-byte] blocks with
             // the 128-byte swizzle and handed to the TMA (tensor store for d x, fp32 reduce-add for d W), so that every row is
             // written as whole 128-byte lines.  (Storing straight from the TMEM lanes - one row per thread - cost ~7000 cycles per
             // item: 32 different lines per store instruction.)
             constexpr int CW = C / kBwParts;                           // columns per warp: 16, 32, 48 or 64
+            constexpr int NB = C / 64;                                 // [32 rows x 128 B] blocks per 16 KB chunk
             const bool f32o = MODE == MODE_DW || p.dx_f32;
-            const int passes = f32o ? 4 : 2, R = kBwM / passes;        // 32 KB staging: 32 fp32 rows or 64 bf16 rows of C = 256
-            const int out_row0 = MODE == MODE_DW ? j * kBwM : b * p.HW + j * kBwM;
+            // chunks of <= 16 KB ping-pong between the two halves of the buffer, so a chunk is staged while the TMA still reads
+            // the previous one: bf16 - the 32 rows of one lane quarter, all columns; fp32 - 32 rows x half the columns
+            const int n_chunks = f32o ? 8 : 4;
+            const int out_row0 = (MODE == MODE_DW ? j * kBwM : b * p.HW + j * kBwM) + quarter * 32;
             const uint32_t stg = smem_u32(sG);
-            for (int ps = 0; ps < passes; ++ps) {
-                const bool active = f32o ? (quarter == ps) : ((quarter >> 1) == ps);
+            for (int ch = 0; ch < n_chunks; ++ch) {
+                const uint32_t half = stg + (uint32_t)(ch & 1) * (uint32_t)(kBwGBytes / 2);
+                if (ch >= 2) {
+                    if (threadIdx.x == 0) bulk_wait_read1();             // the chunk that used this half two steps ago has been read
+                    asm volatile("bar.sync 1, %0;" ::"n"(kBwEpiWarps * 32) : "memory");
+                }
+                const bool active = f32o ? (quarter == (ch >> 1) && (part >> 1) == (ch & 1)) : (quarter == ch);
                 if (active) {
-                    const uint32_t rloc = f32o ? (uint32_t)lane : (uint32_t)((quarter & 1) * 32 + lane);
-                    const uint32_t rbase = stg + rloc * 128u, rsw = rloc & 7u;
+                    const uint32_t rbase = half + (uint32_t)lane * 128u, rsw = (uint32_t)lane & 7u;
 #pragma unroll
                     for (int q = 0; q < CW / 16; ++q) {
                         uint32_t r[16];
                         tmem_ld16(lane_addr + (uint32_t)(kBwD2Col + part * CW + q * 16), r);
-                        const uint32_t col = (uint32_t)(part * CW + q * 16);
                         if (f32o) {
-                            const uint32_t off = col * 4u, blk = off >> 7, c0 = (off & 127u) >> 4;
+                            const uint32_t off = (uint32_t)((part & 1) * CW + q * 16) * 4u, blk = off >> 7, c0 = (off & 127u) >> 4;
 #pragma unroll
                             for (int c = 0; c < 4; ++c)
-                                asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(rbase + blk * (uint32_t)(R * 128) + (((c0 + c) ^ rsw) << 4)),
-                                             "r"(r[4 * c]), "r"(r[4 * c + 1]), "r"(r[4 * c + 2]), "r"(r[4 * c + 3]) : "memory");
+                                asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(rbase + blk * 4096u + (((c0 + c) ^ rsw) << 4)), "r"(r[4 * c]),
+                                             "r"(r[4 * c + 1]), "r"(r[4 * c + 2]), "r"(r[4 * c + 3]) : "memory");
                         } else {
                             uint32_t ob[8];
 #pragma unroll
                             for (int i = 0; i < 16; i += 2)
                                 asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(ob[i >> 1]) : "f"(__uint_as_float(r[i + 1])), "f"(__uint_as_float(r[i])));
-                            const uint32_t off = col * 2u, blk = off >> 7, c0 = (off & 127u) >> 4;
+                            const uint32_t off = (uint32_t)(part * CW + q * 16) * 2u, blk = off >> 7, c0 = (off & 127u) >> 4;
 #pragma unroll
                             for (int c = 0; c < 2; ++c)
-                                asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(rbase + blk * (uint32_t)(R * 128) + (((c0 + c) ^ rsw) << 4)),
-                                             "r"(ob[4 * c]), "r"(ob[4 * c + 1]), "r"(ob[4 * c + 2]), "r"(ob[4 * c + 3]) : "memory");
+                                asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(rbase + blk * 4096u + (((c0 + c) ^ rsw) << 4)), "r"(ob[4 * c]),
+                                             "r"(ob[4 * c + 1]), "r"(ob[4 * c + 2]), "r"(ob[4 * c + 3]) : "memory");
                         }
                     }
                     fence_proxy_async_smem();
                 }
                 asm volatile("bar.sync 1, %0;" ::"n"(kBwEpiWarps * 32) : "memory");
                 if (threadIdx.x == 0) {
-                    const int nblk = f32o ? C / 32 : C / 64, bcols = f32o ? 32 : 64;
-                    for (int blk = 0; blk < nblk; ++blk) {
-                        if (MODE == MODE_DW) tma_reduce_add_2d(&map_out, stg + (uint32_t)(blk * R * 128), blk * bcols, out_row0 + ps * R);
-                        else tma_store_2d(&map_out, stg + (uint32_t)(blk * R * 128), blk * bcols, out_row0 + ps * R);
+                    // thread 0 sits in quarter 0: the chunk's rows / columns follow from ch, not from this thread's own quarter
+                    const int crow = out_row0 - quarter * 32 + (f32o ? (ch >> 1) : ch) * 32;
+                    const int ccol0 = f32o ? (ch & 1) * (C / 2) : 0, bcols = f32o ? 32 : 64;
+                    for (int blk = 0; blk < NB; ++blk) {
+                        if (MODE == MODE_DW) tma_reduce_add_2d(&map_out, half + (uint32_t)blk * 4096u, ccol0 + blk * bcols, crow);
+                        else tma_store_2d(&map_out, half + (uint32_t)blk * 4096u, ccol0 + blk * bcols, crow);
                     }
                     bulk_commit();
-                    bulk_wait_read0();                                 // the staging buffer may be overwritten
                 }
-                asm volatile("bar.sync 1, %0;" ::"n"(kBwEpiWarps * 32) : "memory");
             }
+            if (threadIdx.x == 0) bulk_wait_read0();                   // the buffer returns to the G tiles of the next item
+            asm volatile("bar.sync 1, %0;" ::"n"(kBwEpiWarps * 32) : "memory");
             if (MODE == MODE_DW) {
                 const int grow_i = j * kBwM + row;
                 if (p.dbias && grow_i < p.rows_total) {
@@ -480,6 +503,7 @@ cudaError_t launch_conv_head_bwd(const void* x_nhwc, const void* w, const float*
         q.dw = dw; q.dbias = dbias;
         q.per_b = p.rows_pad / kBwM;
         q.T = p.HW / kBwM;
+        q.last_rows = kBwM;
         q.items = B * q.per_b;
         if (!make_map_out(&map_o, dw, p.rows_total, C, true, 32)) return cudaErrorNotSupported;
         e = launch_bwd_mode<MODE_DW>(map_w, map_x, map_o, q, num_sms, st);
@@ -490,8 +514,9 @@ cudaError_t launch_conv_head_bwd(const void* x_nhwc, const void* w, const float*
         q.dx = dx; q.dx_f32 = dx_f32;
         q.per_b = p.HW / kBwM;
         q.T = p.rows_pad / kBwM;
+        q.last_rows = p.rows_total - (q.T - 1) * kBwM;
         q.items = B * q.per_b;
-        if (!make_map_out(&map_o, dx, (long long)B * p.HW, C, dx_f32 != 0, dx_f32 ? 32 : 64)) return cudaErrorNotSupported;
+        if (!make_map_out(&map_o, dx, (long long)B * p.HW, C, dx_f32 != 0, 32)) return cudaErrorNotSupported;
         e = launch_bwd_mode<MODE_DX>(map_x, map_w, map_o, q, num_sms, st);
         if (e != cudaSuccess) return e;
     }
