@@ -49,6 +49,8 @@ static bool make_tiling(const xsup_shape_t& s, Tiling& t) {
     while (per % t.U) t.U >>= 1;
     t.task_bytes = 512 * t.U;
     t.parts = (int)(slice_bytes / t.task_bytes);
+    t.parts_log2 = -1;
+    if (is_pow2(t.parts)) { t.parts_log2 = 0; while ((1 << t.parts_log2) < t.parts) ++t.parts_log2; }
     t.rows_per_task = 32 * t.U / t.lpr;
     const long long tu = (long long)s.D * t.parts;
     if (tu > 4096) return false;

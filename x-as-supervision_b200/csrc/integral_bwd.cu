@@ -108,15 +108,15 @@ __global__ void __launch_bounds__(kBwdThreads, 1) integral_bwd_kernel(const BwdP
             const uint64_t pol = policy_evict_first();
             const int total = p.n_units * SPU;
             const int n_chunks = (total + p.chunk - 1) / p.chunk;
-            int s = 0;
+            int slot = 0;
+            uint32_t eph = 1;                                        // parity to wait for on `empty`: the first pass over the ring does not wait
             int cur = atomicAdd(p.counter, 1);
             while (cur < n_chunks) {
                 const int nxt = atomicAdd(p.counter, 1);            // claim ahead
                 const int gs0 = cur * p.chunk, gs1 = min(gs0 + p.chunk, total);
                 int unit = gs0 / SPU, j = gs0 - unit * SPU;
-                for (int gs = gs0; gs < gs1; ++gs, ++s) {
-                    const int slot = s % nst;
-                    if (s >= nst) mbar_wait(empty0 + 8u * slot, ((s / nst) - 1) & 1);
+                for (int gs = gs0; gs < gs1; ++gs) {
+                    mbar_wait(empty0 + 8u * slot, eph);
                     hdr[slot].x = unit;
                     hdr[slot].y = j;
                     const uint8_t* src = static_cast<const uint8_t*>(p.logits) + (size_t)unit * (size_t)t.unit_bytes;
@@ -127,15 +127,16 @@ __global__ void __launch_bounds__(kBwdThreads, 1) integral_bwd_kernel(const BwdP
                     bulk_g2s_hint(dst, src + off, bytes, full0 + 8u * slot, pol);
                     bulk_g2s(dst + t.stage_bytes, p.coef + (size_t)unit * p.coef_stride, coef_bytes, full0 + 8u * slot);
                     if (++j == SPU) { j = 0; ++unit; }
+                    if (++slot == nst) { slot = 0; eph ^= 1; }
                 }
                 cur = nxt;
             }
-            for (int g = 0; g < kGroups; ++g, ++s) {                // end-of-stream sentinel per consumer group
-                const int slot = s % nst;
-                if (s >= nst) mbar_wait(empty0 + 8u * slot, ((s / nst) - 1) & 1);
+            for (int g = 0; g < kGroups; ++g) {                     // end-of-stream sentinel per consumer group
+                mbar_wait(empty0 + 8u * slot, eph);
                 hdr[slot].x = -1;
                 hdr[slot].y = 0;
                 mbar_arrive(full0 + 8u * slot);
+                if (++slot == nst) { slot = 0; eph ^= 1; }
             }
         }
     } else {
@@ -143,16 +144,22 @@ __global__ void __launch_bounds__(kBwdThreads, 1) integral_bwd_kernel(const BwdP
         const int lr = lane >> t.lpr_log2;
         const int w0 = (lane & (t.lpr - 1)) * VEC;
         const float rpi = (float)(32 >> t.lpr_log2);
-        for (int s = g;; s += kGroups) {
-            const int slot = s % nst;
-            mbar_wait(full0 + 8u * slot, (s / nst) & 1);
-            const int unit = hdr[slot].x, j = hdr[slot].y;
+        const uint32_t hdr0 = smem_u32(const_cast<int2*>(hdr));
+        int slot = g;                                                // this group's slots: g, g + kGroups, ... (nst is a multiple of kGroups)
+        uint32_t fph = 0;
+        for (;; slot += kGroups) {
+            if (slot >= nst) { slot -= nst; fph ^= 1; }
+            mbar_wait(full0 + 8u * slot, fph);
+            const int2 hd = lds_int2(hdr0 + 8u * slot);
+            const int unit = hd.x, j = hd.y;
             if (unit < 0) break;
             const int task = j * kTasksPerStage + q;
             if (task < TU) {
                 const uint32_t sbase = ring0 + (uint32_t)slot * p.slot_bytes;
                 const uint32_t addr = sbase + (uint32_t)q * t.task_bytes + lane * 16u;
-                const int d = task / t.parts, part = task - d * t.parts;
+                int d, part;
+                if (t.parts_log2 >= 0) { d = task >> t.parts_log2; part = task & (t.parts - 1); }
+                else { d = task / t.parts; part = task - d * t.parts; }
                 uint4 raw[U];
 #pragma unroll
                 for (int i = 0; i < U; ++i) raw[i] = lds128(addr + i * 512u);

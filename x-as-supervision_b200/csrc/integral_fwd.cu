@@ -34,9 +34,10 @@ __global__ void __launch_bounds__(kFwdThreads, 1) integral_fwd_kernel(const FwdP
     const int SPUP = (SPU + kGroups - 1) / kGroups * kGroups;
 
     uint8_t* ring = smem;
-    float2* pz_table = reinterpret_cast<float2*>(smem + (size_t)nst * t.stage_bytes);   // [2][TU] (m, sum)
-    float4* unit_part = reinterpret_cast<float4*>(pz_table + 2 * TU);                   // [2][kConsumerWarps][2]
-    float* pz_final = reinterpret_cast<float*>(unit_part + 4 * kConsumerWarps);         // [2][kMaxD]
+    float4* lane_part = reinterpret_cast<float4*>(smem + (size_t)nst * t.stage_bytes);  // [2][kConsumerWarps][32] per-lane (sx, sa, sy, sr)
+    float2* pz_table = reinterpret_cast<float2*>(lane_part + 2 * kConsumerWarps * 32);  // [2][TU] (m, sum)
+    float2* warp_hdr = pz_table + 2 * TU;                                               // [2][kConsumerWarps] (m_ref, unit)
+    float* pz_final = reinterpret_cast<float*>(warp_hdr + 2 * kConsumerWarps);          // [2][kMaxD]
     int* peak_bins = reinterpret_cast<int*>(pz_final + 2 * kMaxD);                      // [2][kMaxD]
     uint64_t* bars = reinterpret_cast<uint64_t*>(peak_bins + 2 * kMaxD);
     volatile int2* hdr = reinterpret_cast<volatile int2*>(bars + 2 * kMaxStages + 4);   // [nst] (unit, stage in unit)
@@ -63,14 +64,14 @@ __global__ void __launch_bounds__(kFwdThreads, 1) integral_fwd_kernel(const FwdP
         if (lane == 0) {
             const uint64_t pol = policy_evict_first();
             const uint32_t ring0 = smem_u32(ring);
-            int s = 0;
+            int slot = 0;
+            uint32_t eph = 1;                                        // parity to wait for on `empty`: the first pass over the ring does not wait
             int cur = atomicAdd(p.counter, 1);
             while (cur < p.n_units) {
                 const int nxt = atomicAdd(p.counter, 1);            // claim ahead: the round trip overlaps this unit's copies
                 const uint8_t* src = static_cast<const uint8_t*>(p.logits) + (size_t)cur * (size_t)t.unit_bytes;
-                for (int j = 0; j < SPUP; ++j, ++s) {
-                    const int slot = s % nst;
-                    if (s >= nst) mbar_wait(empty0 + 8u * slot, ((s / nst) - 1) & 1);
+                for (int j = 0; j < SPUP; ++j) {
+                    mbar_wait(empty0 + 8u * slot, eph);
                     hdr[slot].x = cur;
                     hdr[slot].y = j;
                     if (j < SPU) {
@@ -81,15 +82,16 @@ __global__ void __launch_bounds__(kFwdThreads, 1) integral_fwd_kernel(const FwdP
                     } else {
                         mbar_arrive(full0 + 8u * slot);             // padding stage: header only
                     }
+                    if (++slot == nst) { slot = 0; eph ^= 1; }
                 }
                 cur = nxt;
             }
-            for (int g = 0; g < kGroups; ++g, ++s) {                // one end-of-stream sentinel per consumer group
-                const int slot = s % nst;
-                if (s >= nst) mbar_wait(empty0 + 8u * slot, ((s / nst) - 1) & 1);
+            for (int g = 0; g < kGroups; ++g) {                     // one end-of-stream sentinel per consumer group
+                mbar_wait(empty0 + 8u * slot, eph);
                 hdr[slot].x = -1;
                 hdr[slot].y = 0;
                 mbar_arrive(full0 + 8u * slot);
+                if (++slot == nst) { slot = 0; eph ^= 1; }
             }
         }
     } else if (warp > kConsumerWarps) {
@@ -101,18 +103,35 @@ __global__ void __launch_bounds__(kFwdThreads, 1) integral_fwd_kernel(const FwdP
         int* bins_mine = peak_bins + buf * kMaxD;
         for (int it = buf;; it += 2) {
             mbar_wait(pfull0 + 8u * buf, (it >> 1) & 1);
-            float4 up = make_float4(kNegHuge, 0.f, 0.f, 0.f), uq = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (lane < kConsumerWarps) {
-                up = unit_part[(buf * kConsumerWarps + lane) * 2];
-                uq = unit_part[(buf * kConsumerWarps + lane) * 2 + 1];
-            }
-            const int unit = __shfl_sync(0xffffffffu, __float_as_int(uq.z), 0);
+            // the consumers leave their per-LANE partial sums (no shuffles on their side: they are the issue-bound warps, this
+            // one has two unit-times per unit); merge the 16 warps with their log-sum-exp weights, then one reduction per quantity
+            const float2 hd = lane < kConsumerWarps ? warp_hdr[buf * kConsumerWarps + lane] : make_float2(kNegHuge, 0.f);
+            const int unit = __shfl_sync(0xffffffffu, __float_as_int(hd.y), 0);
             if (unit < 0) break;                                     // consumers reached the sentinel
-            const float M = warp_max(up.x);
-            const float wsc = ex2(up.x - M);
+            const float M = warp_max(hd.x);
+            const float wsc = ex2(hd.x - M);
+            // merged in fp64: 2 048 products per unit on a warp with time to spare, and the expectations keep all the bits the
+            // per-lane fp32 partial sums carry (the gradient of a 128^3 unit is sensitive to the last ones)
+            double ax = 0.0, as = 0.0, ay = 0.0, ar = 0.0;
+#pragma unroll
+            for (int w = 0; w < kConsumerWarps; ++w) {
+                const double sc = (double)__shfl_sync(0xffffffffu, wsc, w);
+                const float4 v = lane_part[(buf * kConsumerWarps + w) * 32 + lane];
+                ax = fma((double)v.x, sc, ax);
+                as = fma((double)v.y, sc, as);
+                ay = fma((double)v.z, sc, ay);
+                ar = fma((double)v.w, sc, ar);
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                ax += __shfl_xor_sync(0xffffffffu, ax, o);
+                as += __shfl_xor_sync(0xffffffffu, as, o);
+                ay += __shfl_xor_sync(0xffffffffu, ay, o);
+                ar += __shfl_xor_sync(0xffffffffu, ar, o);
+            }
             // (w-weighted sum) / (sum through the same column accumulators), likewise for rows
-            const float xbar = warp_sum(up.y * wsc) / warp_sum(up.z * wsc);
-            const float ybar = warp_sum(uq.x * wsc) / warp_sum(uq.y * wsc);
+            const float xbar = (float)(ax / as);
+            const float ybar = (float)(ay / ar);
             const float2* tab = pz_table + buf * TU;
             for (int d = lane; d < t.D; d += 32) {
                 float a = 0.f;
@@ -143,10 +162,14 @@ __global__ void __launch_bounds__(kFwdThreads, 1) integral_fwd_kernel(const FwdP
         for (int v = 0; v < P; ++v) acc[v] = pk2(0.f, 0.f);
         const f32x2 l2e2 = pk2(kLog2e, kLog2e);
 
-        for (int s = g;; s += kGroups) {
-            const int slot = s % nst;
-            mbar_wait(full0 + 8u * slot, (s / nst) & 1);
-            const int unit = hdr[slot].x, j = hdr[slot].y;
+        const uint32_t hdr0 = smem_u32(const_cast<int2*>(hdr));
+        int slot = g;                                                // this group's slots: g, g + kGroups, ... (nst is a multiple of kGroups)
+        uint32_t fph = 0;
+        for (;; slot += kGroups) {
+            if (slot >= nst) { slot -= nst; fph ^= 1; }
+            mbar_wait(full0 + 8u * slot, fph);
+            const int2 hd = lds_int2(hdr0 + 8u * slot);
+            const int unit = hd.x, j = hd.y;
             if (unit < 0) break;
             const int buf = it & 1;
             if (fresh) {
@@ -172,7 +195,9 @@ __global__ void __launch_bounds__(kFwdThreads, 1) integral_fwd_kernel(const FwdP
                     sr *= sc;
                     m_ref = mt;
                 }
-                const int d = task / t.parts, part = task - d * t.parts;
+                int d, part;
+                if (t.parts_log2 >= 0) { d = task >> t.parts_log2; part = task & (t.parts - 1); }
+                else { d = task / t.parts; part = task - d * t.parts; }
                 float hf = (float)(part * t.rows_per_task + lr);
                 float tsum = 0.f;
                 const f32x2 nm2 = pk2(-m_ref, -m_ref);
@@ -214,15 +239,10 @@ __global__ void __launch_bounds__(kFwdThreads, 1) integral_fwd_kernel(const FwdP
                     sa += a0 + a1;
                     acc[v] = pk2(0.f, 0.f);
                 }
-                sx = warp_sum(sx);
-                sa = warp_sum(sa);
-                sy = warp_sum(sy);
-                sr = warp_sum(sr);
-                if (lane == 0) {
-                    unit_part[(buf * kConsumerWarps + warp) * 2] = make_float4(m_ref, sx, sa, 0.f);
-                    unit_part[(buf * kConsumerWarps + warp) * 2 + 1] = make_float4(sy, sr, __int_as_float(unit), 0.f);
-                    mbar_arrive(pfull0 + 8u * buf);
-                }
+                lane_part[(buf * kConsumerWarps + warp) * 32 + lane] = make_float4(sx, sa, sy, sr);
+                if (lane == 0) warp_hdr[buf * kConsumerWarps + warp] = make_float2(m_ref, __int_as_float(unit));
+                __syncwarp();
+                if (lane == 0) mbar_arrive(pfull0 + 8u * buf);
                 m_ref = kNegHuge;
                 sy = 0.f;
                 sr = 0.f;
@@ -235,8 +255,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) integral_fwd_kernel(const FwdP
             const int ie = it + e, buf = ie & 1;
             if (ie >= 2) mbar_wait(pempty0 + 8u * buf, ((ie >> 1) - 1) & 1);
             if (lane == 0) {
-                unit_part[(buf * kConsumerWarps + warp) * 2] = make_float4(kNegHuge, 0.f, 0.f, 0.f);
-                unit_part[(buf * kConsumerWarps + warp) * 2 + 1] = make_float4(0.f, 0.f, __int_as_float(-1), 0.f);
+                warp_hdr[buf * kConsumerWarps + warp] = make_float2(kNegHuge, __int_as_float(-1));
                 mbar_arrive(pfull0 + 8u * buf);
             }
         }
@@ -345,8 +364,9 @@ cudaError_t launch_integral_fwd(FwdParams p, bool fast, int dtype, int num_sms, 
         else integral_fwd_generic_kernel<__nv_bfloat16><<<p.n_units, 256, 0, st>>>(p);
         return cudaGetLastError();
     }
-    const size_t fixed = (size_t)2 * p.t.tasks_per_unit * sizeof(float2) + 4 * kConsumerWarps * sizeof(float4) +
-                         4 * kMaxD * sizeof(float) + (size_t)(2 * kMaxStages + 4) * 8 + (size_t)kMaxStages * sizeof(int2);
+    const size_t fixed = (size_t)2 * kConsumerWarps * 32 * sizeof(float4) + (size_t)2 * p.t.tasks_per_unit * sizeof(float2) +
+                         2 * kConsumerWarps * sizeof(float2) + 4 * kMaxD * sizeof(float) + (size_t)(2 * kMaxStages + 4) * 8 +
+                         (size_t)kMaxStages * sizeof(int2);
     int nst = (int)((kSmemBudget - fixed) / p.t.stage_bytes);
     nst = nst > kMaxStages ? kMaxStages : nst;
     // A slot must always be consumed by the same warp group (slot = s % nst, group = s % kGroups): a waiter

@@ -79,6 +79,11 @@ __device__ __forceinline__ uint64_t policy_evict_first() {
     return p;
 }
 
+__device__ __forceinline__ int2 lds_int2(uint32_t addr) {
+    int2 v;
+    asm volatile("ld.shared.v2.s32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr));
+    return v;
+}
 __device__ __forceinline__ uint4 lds128(uint32_t addr) {
     uint4 v;
     asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
@@ -217,6 +222,7 @@ struct Tiling {
     int U;                // vectors per lane per task
     int task_bytes;       // 512*U
     int parts;            // tasks per depth slice
+    int parts_log2;       // log2(parts) when parts is a power of two, else -1 (task -> (slice, part) by shift instead of division)
     int rows_per_task;    // 32*U/lpr
     int tasks_per_unit;   // D*parts
     int stages_per_unit;  // ceil(tasks_per_unit / kTasksPerStage)
