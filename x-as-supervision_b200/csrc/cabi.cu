@@ -55,8 +55,14 @@ static bool make_tiling(const xsup_shape_t& s, Tiling& t) {
     const long long tu = (long long)s.D * t.parts;
     if (tu > 4096) return false;
     t.tasks_per_unit = (int)tu;
-    t.stages_per_unit = (t.tasks_per_unit + kTasksPerStage - 1) / kTasksPerStage;
-    t.stage_bytes = kTasksPerStage * t.task_bytes;
+    // small tasks (2 KB for 32^3 bf16) are batched per warp so that a ring stage stays ~16 KB - the producer / consumer handshake and
+    // the consumers' per-iteration bookkeeping are per stage -, as long as a unit still spans at least one stage per warp group
+    t.rounds = 1;
+    while (t.rounds < 4 && kTasksPerStage * t.task_bytes * t.rounds * 2 <= 16384 && t.tasks_per_unit >= kTasksPerStage * kGroups * t.rounds * 2)
+        t.rounds *= 2;
+    const int per_stage = kTasksPerStage * t.rounds;
+    t.stages_per_unit = (t.tasks_per_unit + per_stage - 1) / per_stage;
+    t.stage_bytes = per_stage * t.task_bytes;
     return true;
 }
 

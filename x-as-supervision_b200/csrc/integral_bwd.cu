@@ -153,10 +153,12 @@ __global__ void __launch_bounds__(kBwdThreads, 1) integral_bwd_kernel(const BwdP
             const int2 hd = lds_int2(hdr0 + 8u * slot);
             const int unit = hd.x, j = hd.y;
             if (unit < 0) break;
-            const int task = j * kTasksPerStage + q;
+            for (int r = 0; r < t.rounds; ++r) {
+            const int task = (j * t.rounds + r) * kTasksPerStage + q;
+            const bool last_round = r == t.rounds - 1;
             if (task < TU) {
                 const uint32_t sbase = ring0 + (uint32_t)slot * p.slot_bytes;
-                const uint32_t addr = sbase + (uint32_t)q * t.task_bytes + lane * 16u;
+                const uint32_t addr = sbase + (uint32_t)(r * kTasksPerStage + q) * t.task_bytes + lane * 16u;
                 int d, part;
                 if (t.parts_log2 >= 0) { d = task >> t.parts_log2; part = task & (t.parts - 1); }
                 else { d = task / t.parts; part = task - d * t.parts; }
@@ -167,8 +169,10 @@ __global__ void __launch_bounds__(kBwdThreads, 1) integral_bwd_kernel(const BwdP
                 const uint4 c5 = lds128(sbase + t.stage_bytes + 16u);
                 float cd;
                 asm volatile("ld.shared.f32 %0, [%1];" : "=f"(cd) : "r"(sbase + t.stage_bytes + 32u + 4u * d));
-                __syncwarp();
-                if (lane == 0) mbar_arrive(empty0 + 8u * slot);
+                if (last_round) {
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(empty0 + 8u * slot);
+                }
 
                 constexpr int P = Vec<T>::P;
                 const float nlse = -__uint_as_float(c4.x), a = __uint_as_float(c4.y), bb = __uint_as_float(c4.z);
@@ -191,9 +195,10 @@ __global__ void __launch_bounds__(kBwdThreads, 1) integral_bwd_kernel(const BwdP
                     *reinterpret_cast<uint4*>(out + i * 512u) = Vec<T>::pack2(x);
                     hf += rpi;
                 }
-            } else {
+            } else if (last_round) {
                 __syncwarp();
                 if (lane == 0) mbar_arrive(empty0 + 8u * slot);
+            }
             }
         }
     }

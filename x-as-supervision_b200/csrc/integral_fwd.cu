@@ -176,15 +176,18 @@ __global__ void __launch_bounds__(kFwdThreads, 1) integral_fwd_kernel(const FwdP
                 if (it >= 2) mbar_wait(pempty0 + 8u * buf, ((it >> 1) - 1) & 1);
                 fresh = false;
             }
-            const int task = j * kTasksPerStage + q;
+            for (int r = 0; r < t.rounds; ++r) {
+            const int task = (j * t.rounds + r) * kTasksPerStage + q;
+            const bool last_round = r == t.rounds - 1;
             if (task < TU) {
-                const uint32_t addr = ring0 + (uint32_t)slot * t.stage_bytes + (uint32_t)q * t.task_bytes + lane * 16u;
+                const uint32_t addr = ring0 + (uint32_t)slot * t.stage_bytes + (uint32_t)(r * kTasksPerStage + q) * t.task_bytes + lane * 16u;
                 uint4 raw[U];
 #pragma unroll
                 for (int i = 0; i < U; ++i) raw[i] = lds128(addr + i * 512u);
-                __syncwarp();
-                if (lane == 0) mbar_arrive(empty0 + 8u * slot);   // data is in registers: free the slot early
-
+                if (last_round) {
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(empty0 + 8u * slot);   // data is in registers: free the slot early
+                }
                 const float mt = warp_max(Vec<T>::template vmax<U>(raw)) * kLog2e;
                 if (mt > m_ref) {                                 // warp-uniform, rare after the first tasks
                     const float sc = ex2(m_ref - mt);
@@ -223,9 +226,10 @@ __global__ void __launch_bounds__(kFwdThreads, 1) integral_fwd_kernel(const FwdP
                 sr += tsum;
                 tsum = warp_sum(tsum);
                 if (lane == 0) pz_table[buf * TU + task] = make_float2(m_ref, tsum);
-            } else {
+            } else if (last_round) {
                 __syncwarp();
                 if (lane == 0) mbar_arrive(empty0 + 8u * slot);
+            }
             }
             if (j + kGroups >= SPUP) {
                 // this warp's last stage of the unit: hand its partials to the finaliser

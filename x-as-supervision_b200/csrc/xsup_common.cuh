@@ -225,8 +225,9 @@ struct Tiling {
     int parts_log2;       // log2(parts) when parts is a power of two, else -1 (task -> (slice, part) by shift instead of division)
     int rows_per_task;    // 32*U/lpr
     int tasks_per_unit;   // D*parts
-    int stages_per_unit;  // ceil(tasks_per_unit / kTasksPerStage)
-    int stage_bytes;      // kTasksPerStage*task_bytes
+    int rounds;           // tasks per warp and stage: small tasks are batched so that a stage (one bulk copy, one handshake) is ~16 KB
+    int stages_per_unit;  // ceil(tasks_per_unit / (kTasksPerStage*rounds))
+    int stage_bytes;      // kTasksPerStage*rounds*task_bytes
     long long unit_bytes;
 };
 
