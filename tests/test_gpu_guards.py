@@ -122,3 +122,33 @@ def test_conv_fused_kernels_keep_inside_their_buffers(pkg, B, K, D, H, C, dx_f32
     assert not bool((out["dw"].t == pat32).any()) and not bool((out["dbias"].t == pat32).any())
     if dx_f32:
         assert not bool((out["dx"].t == pat32).any())
+
+
+def test_conv_fused_reruns_are_bit_identical_where_the_order_is_fixed(pkg):
+    """Stand-in for racecheck on the tensor-core kernels: a race in the ring / TMEM / staging protocols shows up as run-to-run
+    differences.  kps (K7) and d x (K8: every element is written once, by the TMA, from a TMEM accumulator whose summation order
+    is fixed) must be bit-identical over repeated launches; d W / d bias are accumulated across samples by reduce-add / atomics in
+    scheduling order, so they may differ in the last bits - bounded here at 1e-6 of their maximum."""
+    ops = pkg.ops
+    dev = torch.device("cuda:0")
+    B, K, D, C, NH, NS = 20, 17, 64, 256, 3, 15            # 180 + 640 items: several per CTA, so rings and barriers wrap many times
+    g = torch.Generator(device=dev).manual_seed(5)
+    x = torch.randn(B, C, D, D, device=dev, generator=g).to(dtype=torch.bfloat16, memory_format=torch.channels_last)
+    w = torch.randn(K * D, C, device=dev, generator=g) / C ** 0.5
+    bias = torch.randn(K * D, device=dev, generator=g)
+    gk = torch.randn(B, NH, K, 3, device=dev, generator=g)
+    ref = None
+    for _ in range(6):
+        xd = x.clone().requires_grad_(True)
+        wd = w.clone().requires_grad_(True)
+        bd = bias.clone().requires_grad_(True)
+        kps, _, idx = ops.conv_integral_head_train(xd, wd, bd, K, NH, NS)
+        kps.backward(gk)
+        cur = (kps.detach().clone(), idx.clone(), xd.grad.clone(), wd.grad.clone(), bd.grad.clone())
+        if ref is None:
+            ref = cur
+            continue
+        assert torch.equal(cur[0], ref[0]) and torch.equal(cur[1], ref[1]), "forward differs between launches"
+        assert torch.equal(cur[2], ref[2]), "d x differs between launches"
+        for a, b in ((cur[3], ref[3]), (cur[4], ref[4])):
+            assert float((a - b).abs().max()) <= 1e-6 * float(b.abs().max())
