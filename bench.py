@@ -459,7 +459,31 @@ def run_config(x, args, name, steps):
             gbs = B * bytes_per_sample(c) / (ms * 1e-3) / 1e9
             out["cuda_graph"] = {"value": round(B * x.world / (ms * 1e-3), 1), "unit": UNIT, "ms_per_step": round(ms, 4),
                                  "per_gpu_gbs": round(gbs, 1), "frac_of_8TBs": round(gbs / 8000.0, 4)}
-        del gs, step, logits, target, cams
+        del gs
+        # end to end for this config as well: pinned host logits / target / cameras in, loss / slots / coordinates out
+        h_logits = torch.empty(logits.shape, dtype=logits.dtype, pin_memory=True)
+        h_logits.copy_(logits.detach())
+        h_target = target.cpu().pin_memory()
+        h_cams = {k: v.cpu().pin_memory() for k, v in cams.items()}
+        h_out = {"loss": torch.empty(2, pin_memory=True), "sel": torch.empty(2, dtype=torch.int64, pin_memory=True),
+                 "kps": torch.empty(B, c["NH"], c["K"], 3, pin_memory=True)}
+
+        def e2e_step():
+            with torch.no_grad():
+                logits.copy_(h_logits, non_blocking=True)
+                target.copy_(h_target, non_blocking=True)
+                for k in cams:
+                    cams[k].copy_(h_cams[k], non_blocking=True)
+            lp, ls, sel, kps = step()
+            h_out["loss"].copy_(torch.stack((lp.detach(), ls.detach())), non_blocking=True)
+            h_out["sel"].copy_(sel, non_blocking=True)
+            h_out["kps"].copy_(kps.detach(), non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+        e_ms = time_steps(x, e2e_step, 3, 1)
+        h2d = h_logits.numel() * h_logits.element_size() + h_target.numel() * 4 + sum(v.numel() * 4 for v in h_cams.values())
+        out["e2e"] = {"value": round(B * x.world / (e_ms * 1e-3), 1), "unit": UNIT, "ms_per_step": round(e_ms, 3),
+                      "h2d_bytes_per_step": int(h2d) * x.world, "d2h_bytes_per_step": int(2 * 4 + 2 * 8 + h_out["kps"].numel() * 4) * x.world}
+        del h_logits, h_out, step, logits, target, cams
     except torch.cuda.OutOfMemoryError as e:               # every rank sees the same sizes, so every rank lands here together
         out["error"] = "out of memory: %s" % (str(e)[:120],)
     torch.cuda.empty_cache()
