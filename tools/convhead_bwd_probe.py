@@ -1,6 +1,7 @@
 #!/usr/bin/env python
 """Runs only the tensor-core backward of the conv-fused head (xsup_conv_head_bwd) a few times: the target of ncu captures.
-    python tools/convhead_bwd_probe.py [--batch 64] [--iters 3] [--what both|dx|dw]"""
+    python tools/convhead_bwd_probe.py [--batch 64] [--iters 3] [--what both|dx|dw]
+TRACE=1 additionally prints the clock64 timeline of CTA 0 (library built with XSUP_NVCC_EXTRA="-DXSUP_TRACE", see conv_head_bwd.cu)."""
 import argparse, importlib, os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)

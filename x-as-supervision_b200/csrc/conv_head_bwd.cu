@@ -69,7 +69,7 @@ struct ConvBwdParams {
     int T;                      // streamed tiles per item
     int last_rows;              // valid rows of an item's last streamed tile (MODE_DX: K*D need not be a multiple of 128), else 128
     int items;
-    long long* trace;           // diagnostics: clock64 timeline of CTA 0, tiles 8..23 (XSUP_CONVBWD_TRACE = device pointer)
+    long long* trace;           // diagnostics (-DXSUP_TRACE builds only): clock64 timeline of CTA 0, see TRACE below
 };
 
 // ------------------------------------------------------------------ row coefficients
@@ -101,7 +101,14 @@ __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float 
     asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
 
+// Diagnostics, compiled in only with -DXSUP_TRACE (XSUP_NVCC_EXTRA="-DXSUP_TRACE" python -c "import __graft_entry__ as g; g.build(force=True)"):
+// a clock64 timeline of CTA 0, tiles / items 8..23, written to the device buffer whose address is in XSUP_CONVBWD_TRACE
+// (tools/convhead_bwd_probe.py with TRACE=1 allocates and prints it).  This is what found the stalls listed in DESIGN.md (K8).
+#ifdef XSUP_TRACE
 #define TRACE(slot, gi) do { if (p.trace && blockIdx.x == 0 && (gi) >= 8 && (gi) < 24) p.trace[((gi) - 8) * 16 + (slot)] = clock64(); } while (0)
+#else
+#define TRACE(slot, gi) do { } while (0)
+#endif
 // ------------------------------------------------------------------ kernel
 template <int KBN, int MODE>
 __global__ void __launch_bounds__(kBwThreads, 1) conv_head_bwd_kernel(const __grid_constant__ CUtensorMap map_stat,
@@ -483,7 +490,9 @@ cudaError_t launch_conv_head_bwd(const void* x_nhwc, const void* w, const float*
                                  void* dx, int dx_f32, float* dw, float* dbias, int B, int K, int D, int H, int W, int C, int num_sms,
                                  cudaStream_t st) {
     ConvBwdParams p{};
+#ifdef XSUP_TRACE
     if (const char* d = getenv("XSUP_CONVBWD_TRACE")) p.trace = reinterpret_cast<long long*>(strtoull(d, nullptr, 0));
+#endif
     p.rowcoef = rowcoef_ws;
     p.C = C; p.HW = H * W; p.W = W; p.rows_total = K * D; p.rows_pad = conv_bwd_rows_pad(K, D);
     const long long n = (long long)B * p.rows_pad;
