@@ -401,7 +401,7 @@ class GraphedReprojStep:
     """The fused head + reprojection min-loss forward AND backward captured once into a CUDA graph.
 
     Every C-ABI call is capture-safe (caller's stream, no allocation, no synchronisation), so for fixed shapes the
-    ~10 launches and the Python/autograd bookkeeping of a step collapse into one `cudaGraphLaunch`: this is what
+    4 launches (+ the autograd glue) and the Python/autograd bookkeeping of a step collapse into one `cudaGraphLaunch`: this is what
     removes the host-side floor (~0.3 ms) that small batches / small volumes otherwise sit on.
 
         step = GraphedReprojStep(logits, target, cams, num_kp, num_hypo, neighbor_size, **loss_kwargs)
