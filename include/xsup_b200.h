@@ -351,6 +351,12 @@ int xsup_disc_min_loss_bwd(const float* logits, const int64_t* sel, const float*
 int xsup_pack_nhwc_bf16(const float* x_nchw, void* x_nhwc_bf16, int32_t B, int32_t C, int32_t HW, void* stream);
 int xsup_conv_head_fwd(const void* x_nhwc, const void* weight, const float* bias, float* kps, float* depth_prob_map,
                        int64_t* peak_idx, float* stats, float* logits_out, const xsup_shape_t* s, int32_t C, void* stream);
+/* The same with fp32 operands and tf32 tensor-core arithmetic (`tcgen05.mma.kind::tf32`, fp32 accumulation): the precision of
+ * the reference's own `Conv2d` on this GPU (PyTorch runs cuDNN convolutions in TF32 by default).  x_nhwc_f32 [B, H, W, C] fp32
+ * channels-last, weight_f32 [K*D, C] fp32; everything else as xsup_conv_head_fwd; same shape constraints.  About twice the
+ * tensor-core time of the bf16 call (half-rate MMAs, 64-pixel tiles); forward only - the backward call rounds to bf16. */
+int xsup_conv_head_fwd_tf32(const void* x_nhwc_f32, const void* weight_f32, const float* bias, float* kps, float* depth_prob_map,
+                            int64_t* peak_idx, float* stats, float* logits_out, const xsup_shape_t* s, int32_t C, void* stream);
 
 /* Backward of the conv-fused head, logits-free and on the tensor cores (csrc/conv_head_bwd.cu):
  *   (1) xsup_integral_coef turns g_kps + the saved statistics into the per-unit coefficient blocks (the first half of

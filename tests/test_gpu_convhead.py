@@ -242,3 +242,27 @@ def test_conv_fused_reproj_min_loss(ops, oracle, synth, reduction, sym):
     for name, ours, ref in (("dx", xd.grad, x64.grad), ("dW", wd.grad, w64.grad), ("dbias", bd.grad, b64.grad)):
         err = float((ours.cpu().double() - ref).abs().max()) / float(ref.abs().max())
         assert err < 2.0 ** -8, (name, err)
+
+
+@pytest.mark.parametrize("B,K,D,H,C", [(2, 17, 64, 64, 256), (3, 3, 64, 32, 128), (2, 4, 32, 32, 64), (1, 2, 128, 64, 192)])
+def test_conv_head_tf32_variant(ops, oracle, B, K, D, H, C):
+    """precision='tf32' (fp32 operands, kind::tf32 MMAs): the logits against the exact fp64 conv of the UNROUNDED operands at the tf32
+    bound (inputs keep 10 mantissa bits: relative-to-max error of a C-term dot product well under 2e-3), at least 4x closer than
+    the bf16 path on the same inputs, and the head outputs against the streaming kernel run on those very logits."""
+    dev = torch.device("cuda:0")
+    NH, NS = 3, 5
+    g = torch.Generator().manual_seed(B * 3 + K)
+    x = torch.randn(B, C, H, D, generator=g)
+    w = torch.randn(K * D, C, generator=g) / C ** 0.5
+    w[::5] *= 3.0
+    bias = torch.randn(K * D, generator=g)
+    ref = torch.einsum("oc,bchw->bohw", w.double(), x.double()) + bias.double().view(1, -1, 1, 1)
+    kps, dmap, idx, logits = ops.conv_integral_head(x.to(dev), w.to(dev), bias.to(dev), K, NH, NS, return_logits=True, precision="tf32")
+    _, _, _, logits16 = ops.conv_integral_head(x.to(dev), w.to(dev), bias.to(dev), K, NH, NS, return_logits=True, precision="bf16")
+    scale = float(ref.abs().max())
+    e32 = float((logits.cpu().double() - ref).abs().max()) / scale
+    e16 = float((logits16.cpu().double() - ref).abs().max()) / scale
+    assert e32 < 2e-3 and e32 * 4 < e16, (e32, e16)
+    skps, sdmap, sidx = ops.integral_multi_head(logits, K, NH, NS)
+    assert torch.equal(idx, sidx)
+    assert float((kps - skps).abs().max()) < 1e-5 and float((dmap - sdmap).abs().max()) < 1e-5 * float(sdmap.abs().max())

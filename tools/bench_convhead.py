@@ -149,15 +149,21 @@ def main():
             tf, _, tidx = ops.integral_multi_head(F.conv2d(x[:Bp], ws.view(K * D, C, 1, 1), bias), K, NH, NS)
             torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
             ours, _, oidx = ops.conv_integral_head(x[:Bp], ws, bias, K, NH, NS)
+            ours32, _, o32idx = ops.conv_integral_head(x[:Bp], ws, bias, K, NH, NS, precision="tf32")
             same_t, same_o = (tidx == ridx).all(dim=-1), (oidx == ridx).all(dim=-1)       # [B,K]: all NH peak bins agree
+            same_o32 = (o32idx == ridx).all(dim=-1)
 
             def err(a, mask):
                 d = (a - ref).abs()[..., :2]                                            # x, y: defined whatever the peaks do
                 dz = (a - ref).abs()[..., 2][mask.unsqueeze(1).expand(-1, NH, -1)]        # z where the same peaks were picked
                 return {"xy_max": float(d.max()), "xy_mean": float(d.mean()), "z_max_same_peaks": float(dz.max()) if dz.numel() else None,
                         "units_with_same_peaks": float(mask.float().mean())}
-            prec[name] = {"tf32_conv_vs_fp32": err(tf, same_t), "bf16_fused_vs_fp32": err(ours, same_o)}
+            prec[name] = {"tf32_conv_vs_fp32": err(tf, same_t), "bf16_fused_vs_fp32": err(ours, same_o), "tf32_fused_vs_fp32": err(ours32, same_o32)}
         out["operand_precision"] = prec
+        xcl32 = x.contiguous(memory_format=torch.channels_last)
+        ms_tf32 = timeit(lambda: ops.conv_integral_head(xcl32, w, bias, K, NH, NS, precision="tf32"))
+        out["fused_tf32"] = {"ms": round(ms_tf32, 4), "samples_per_s": round(B / ms_tf32 * 1e3, 1),
+                             "note": "xsup_conv_head_fwd_tf32 from channels-last fp32 activations, including the round-to-nearest-tf32 pass over x and W"}
     print(json.dumps(out), flush=True)
 
 

@@ -39,7 +39,7 @@ SYMBOLS = (
     "xsup_geom_patch_to_world", "xsup_geom_patch_to_world_vjp", "xsup_geom_world_to_patch", "xsup_geom_world_to_patch_vjp",
     "xsup_reproj_fused_fwd", "xsup_reproj_fused_bwd", "xsup_integral_bwd_apply", "xsup_pose_sqerr",
     # ABI v11
-    "xsup_conv_bwd_ws_floats", "xsup_conv_head_bwd",
+    "xsup_conv_bwd_ws_floats", "xsup_conv_head_bwd", "xsup_conv_head_fwd_tf32",
 )
 GEOM_NORM, GEOM_MONO, GEOM_PATCH_STAGE, GEOM_CAMERA_STAGE = 1, 2, 4, 8
 SCHED_WORDS = 16
@@ -142,6 +142,8 @@ def _load():
     lib.xsup_mask_loss_bwd.argtypes = [vp, vp, vp, ml, vp, vp, vp, vp]
     lib.xsup_conv_head_fwd.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, C.POINTER(Shape), i32, vp]
     lib.xsup_conv_head_fwd.restype = C.c_int
+    lib.xsup_conv_head_fwd_tf32.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, C.POINTER(Shape), i32, vp]
+    lib.xsup_conv_head_fwd_tf32.restype = C.c_int
     lib.xsup_pack_nhwc_bf16.argtypes = [vp, vp, i32, i32, i32, vp]
     lib.xsup_pack_nhwc_bf16.restype = C.c_int
     lib.xsup_pose_term_fwd.argtypes = [vp, vp, vp, i32, i32, i32, i32, i32, vp, vp, vp]

@@ -633,6 +633,29 @@ int xsup_conv_head_fwd(const void* x_nhwc, const void* weight, const float* bias
     return XSUP_OK;
 }
 
+int xsup_conv_head_fwd_tf32(const void* x_nhwc_f32, const void* weight_f32, const float* bias, float* kps, float* depth_prob_map,
+                            int64_t* peak_idx, float* stats, float* logits_out, const xsup_shape_t* s, int32_t C, void* stream) {
+    if (int rc = check_conv_shape(s, C, "xsup_conv_head_fwd_tf32")) return rc;
+    if (s->B == 0) return XSUP_OK;
+    if (!x_nhwc_f32 || !weight_f32 || !kps || !depth_prob_map || !stats) return fail(XSUP_E_NULL, "xsup_conv_head_fwd_tf32: NULL pointer");
+    if (!aligned16(x_nhwc_f32) || !aligned16(weight_f32) || !aligned16(logits_out))
+        return fail(XSUP_E_ALIGN, "xsup_conv_head_fwd_tf32: x/weight/logits_out must be 16-byte aligned");
+    int sms = 0;
+    if (int rc = device_info(sms)) return rc;
+    FwdParams f{};
+    f.kps = kps; f.dmap = depth_prob_map; f.peak_idx = peak_idx; f.stats = stats;
+    f.n_units = s->B * s->K; f.K = s->K; f.NH = s->NH; f.NS = s->NS; f.head = s->head;
+    f.stats_stride = (int)stats_stride(*s);
+    f.t.D = s->D; f.t.H = s->H; f.t.W = s->W;
+    cudaError_t e = cudaMemsetAsync(stats + (size_t)s->B * s->K * f.stats_stride, 0, kSchedWords * sizeof(int), (cudaStream_t)stream);
+    if (e != cudaSuccess) return cuda_fail(e, "xsup_conv_head_fwd_tf32 scheduling-word reset");
+    e = launch_conv_head_fwd_tf32(x_nhwc_f32, weight_f32, bias, logits_out, f, s->B, C, sms, (cudaStream_t)stream);
+    if (e == cudaErrorNotSupported) return fail(XSUP_E_DEVICE, "xsup_conv_head_fwd_tf32: cuTensorMapEncodeTiled unavailable or rejected the tensors");
+    if (e != cudaSuccess) return cuda_fail(e, "xsup_conv_head_fwd_tf32 launch");
+    count_launches(1);
+    return XSUP_OK;
+}
+
 static int check_conv_shape(const xsup_shape_t* s, int C, const char* who) {
     if (int rc = check_shape(s)) return rc;
     if (128 % s->D) return fail(XSUP_E_SHAPE, "%s: depth_dim %d must divide 128 (output rows per CTA)", who, s->D);

@@ -63,7 +63,11 @@ struct ConvHeadParams {
 constexpr uint32_t kCvIdesc = umma_idesc_bf16(kCvRows, kCvPix);
 
 // ------------------------------------------------------------------ kernel
-template <int KBN, int MODE>            // MODE 0: forward statistics + finaliser; MODE 1: backward, emits d loss / d logits in bf16
+// TF32 = true (forward only): fp32 operands, `kind::tf32` MMAs - the precision of the reference's own conv on this GPU.  A k-block is
+// then 32 channels (still 128 bytes per row), KBN = C/32; the fp32 weight slab (128 KB at C = 256) passes through the 64 KB landing
+// buffer in two halves into 256 TMEM columns; an activation ring stage holds 64 pixels (64 KB), and two stages fill one 128-column
+// accumulator (two accumulators instead of three), so the epilogue and the finalisers are the very same code.
+template <int KBN, int MODE, bool TF32 = false>   // MODE 0: forward statistics + finaliser; MODE 1: backward, emits d loss / d logits in bf16
 __global__ void __launch_bounds__(kCvThreads, 1) conv_head_fwd_kernel(const __grid_constant__ CUtensorMap map_w,
                                                                       const __grid_constant__ CUtensorMap map_x,
                                                                       const ConvHeadParams p) {
@@ -71,9 +75,14 @@ __global__ void __launch_bounds__(kCvThreads, 1) conv_head_fwd_kernel(const __gr
     // the dynamic shared window is only 16-byte aligned by contract: round up to the 1024 B the swizzle needs
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    uint8_t* sW = smem;                                             // [KBN][128 x 64] bf16
-    uint8_t* sX = sW + (size_t)KBN * kCvKBBytes;                    // [stages][KBN][128 x 64] bf16
-    uint64_t* bars = reinterpret_cast<uint64_t*>(sX + (size_t)kCvStages * KBN * kCvKBBytes);
+    constexpr int kWKB = TF32 ? KBN / 2 : KBN;                       // k-blocks the landing buffer holds (TF32: half the slab)
+    constexpr uint32_t kXKBBytes = TF32 ? kCvKBBytes / 2 : kCvKBBytes;   // one k-block of a ring stage: [64 | 128 pixels x 128 B]
+    constexpr int kAcc = TF32 ? 2 : kCvAcc;                          // accumulators of 128 columns
+    constexpr int kAccCol0 = TF32 ? 256 : kCvAccCol;                 // TMEM columns [0, kAccCol0) hold the weight slab
+    static_assert(!TF32 || (MODE == 0 && KBN % 2 == 0), "the tf32 variant is forward-only and needs C % 64 == 0");
+    uint8_t* sW = smem;                                             // [kWKB][128 x 128 B]
+    uint8_t* sX = sW + (size_t)kWKB * kCvKBBytes;                   // [stages][KBN][128 | 64 pixels x 128 B]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sX + (size_t)kCvStages * KBN * kXKBBytes);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 24);
     // MODE 0: row statistics + finaliser scratch (20 KB); MODE 1: the same region (32 KB) stages the gradient tiles
     float4* row_stat = reinterpret_cast<float4*>(bars + 32);                                   // [2 items][kCvParts][128] (m, s, sx, sy)
@@ -111,20 +120,42 @@ __global__ void __launch_bounds__(kCvThreads, 1) conv_head_fwd_kernel(const __gr
     if (warp == kCvEpiWarps) {
         // ------------------------------------------------------------ TMA producer
         if (lane == 0) {
-            int g = 0, n = 0;                                        // tiles / items this CTA has started
+            int g = 0, n = 0;                                        // ring stages / items this CTA has started
             for (int item = blockIdx.x; item < p.items; item += gridDim.x, ++n) {
                 const int b = item / p.groups, row0 = (item - b * p.groups) * kCvRows;
-                mbar_wait(b_wempty, (n & 1) ^ 1);                    // the previous item's MMAs no longer read the slab
-                mbar_arrive_expect_tx(b_wfull, (uint32_t)KBN * kCvKBBytes);
+                if constexpr (!TF32) {
+                    mbar_wait(b_wempty, (n & 1) ^ 1);                // the previous slab has been copied into tensor memory
+                    mbar_arrive_expect_tx(b_wfull, (uint32_t)KBN * kCvKBBytes);
 #pragma unroll
-                for (int kb = 0; kb < KBN; ++kb) tma_load_2d(smem_u32(sW) + kb * kCvKBBytes, &map_w, kb * kCvKB, row0, b_wfull);
-                for (int t = 0; t < T; ++t, ++g) {
-                    const int s = g % kCvStages, it = g / kCvStages;
-                    mbar_wait(b_xempty + 8 * s, (it & 1) ^ 1);
-                    mbar_arrive_expect_tx(b_xfull + 8 * s, (uint32_t)KBN * kCvKBBytes);
-                    const uint32_t dst = smem_u32(sX) + (uint32_t)s * KBN * kCvKBBytes;
+                    for (int kb = 0; kb < KBN; ++kb) tma_load_2d(smem_u32(sW) + kb * kCvKBBytes, &map_w, kb * kCvKB, row0, b_wfull);
+                    for (int t = 0; t < T; ++t, ++g) {
+                        const int s = g % kCvStages, it = g / kCvStages;
+                        mbar_wait(b_xempty + 8 * s, (it & 1) ^ 1);
+                        mbar_arrive_expect_tx(b_xfull + 8 * s, (uint32_t)KBN * kCvKBBytes);
+                        const uint32_t dst = smem_u32(sX) + (uint32_t)s * KBN * kCvKBBytes;
 #pragma unroll
-                    for (int kb = 0; kb < KBN; ++kb) tma_load_2d(dst + kb * kCvKBBytes, &map_x, kb * kCvKB, b * p.HW + t * kCvPix, b_xfull + 8 * s);
+                        for (int kb = 0; kb < KBN; ++kb) tma_load_2d(dst + kb * kCvKBBytes, &map_x, kb * kCvKB, b * p.HW + t * kCvPix, b_xfull + 8 * s);
+                    }
+                } else {
+                    // slab half 0, the first ring stages, slab half 1 (its buffer is free once half 0 sits in TMEM), the rest
+                    for (int ht = -1; ht < 2 * T; ++ht) {
+                        if (ht == -1 || ht == kCvStages - 1) {
+                            const int half = ht == -1 ? 0 : 1, wn = 2 * n + half;
+                            mbar_wait(b_wempty, (wn & 1) ^ 1);
+                            mbar_arrive_expect_tx(b_wfull, (uint32_t)kWKB * kCvKBBytes);
+#pragma unroll
+                            for (int kb = 0; kb < kWKB; ++kb)
+                                tma_load_2d(smem_u32(sW) + kb * kCvKBBytes, &map_w, (half * kWKB + kb) * 32, row0, b_wfull);
+                        }
+                        if (ht < 0) continue;
+                        const int s = g % kCvStages, it = g / kCvStages;
+                        mbar_wait(b_xempty + 8 * s, (it & 1) ^ 1);
+                        mbar_arrive_expect_tx(b_xfull + 8 * s, (uint32_t)KBN * kXKBBytes);
+                        const uint32_t dst = smem_u32(sX) + (uint32_t)s * KBN * kXKBBytes;
+#pragma unroll
+                        for (int kb = 0; kb < KBN; ++kb) tma_load_2d(dst + kb * kXKBBytes, &map_x, kb * 32, b * p.HW + ht * (kCvPix / 2), b_xfull + 8 * s);
+                        ++g;
+                    }
                 }
             }
         }
@@ -135,46 +166,56 @@ __global__ void __launch_bounds__(kCvThreads, 1) conv_head_fwd_kernel(const __gr
         // channels; in order behind the previous item's MMAs) and the buffer is released at once, so the producer prefetches the
         // next slab a whole item ahead and the MMAs read A from TMEM: with both operands in shared memory an M = N = 128 MMA
         // needs 128 B/clk of operand reads, which is all the shared memory delivers.
-        uint64_t da[KBN], db0[KBN];                                  // descriptors of the slab and of ring stage 0, per k-block
+        uint64_t da[kWKB], db0[KBN];                                 // descriptors of the landing buffer and of ring stage 0, per k-block
 #pragma unroll
-        for (int kb = 0; kb < KBN; ++kb) {
-            da[kb] = umma_desc_sw128(smem_u32(sW) + kb * kCvKBBytes);
-            db0[kb] = umma_desc_sw128(smem_u32(sX) + kb * kCvKBBytes);
-        }
-        constexpr uint64_t kStageStep = (uint64_t)((KBN * kCvKBBytes) >> 4);   // start-address field units
+        for (int kb = 0; kb < kWKB; ++kb) da[kb] = umma_desc_sw128(smem_u32(sW) + kb * kCvKBBytes);
+#pragma unroll
+        for (int kb = 0; kb < KBN; ++kb) db0[kb] = umma_desc_sw128(smem_u32(sX) + kb * kXKBBytes);
+        constexpr uint64_t kStageStep = (uint64_t)((KBN * kXKBBytes) >> 4);    // start-address field units
+        constexpr uint32_t kIdesc = TF32 ? umma_idesc_tf32(kCvRows, kCvPix / 2) : kCvIdesc;
         int s = 0, a = 0, n = 0;
         uint32_t xph = 0, aeph = 1;
         for (int item = blockIdx.x; item < p.items; item += gridDim.x, ++n) {
-            mbar_wait(b_wfull, n & 1);
-            tc_fence_after();
-            if (lane == 0) {
 #pragma unroll
-                for (int kb = 0; kb < KBN; ++kb)
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) tmem_cp_128x256b(tmem_base + (uint32_t)((kb * 4 + q) * 8), da[kb] + 2 * q);
-                umma_commit(b_wempty);                               // the landing buffer may take the next slab
-            }
-            __syncwarp();
-            for (int t = 0; t < T; ++t) {
-                mbar_wait(b_aempty + 8 * a, aeph);                   // the epilogue has drained this accumulator
-                mbar_wait(b_xfull + 8 * s, xph);                     // the tile has landed
+            for (int half = 0; half < (TF32 ? 2 : 1); ++half) {
+                mbar_wait(b_wfull, (TF32 ? 2 * n + half : n) & 1);
                 tc_fence_after();
                 if (lane == 0) {
-                    const uint32_t acc = tmem_base + (uint32_t)(kCvAccCol + a * kCvPix);
-                    const uint64_t soff = (uint64_t)s * kStageStep;
 #pragma unroll
-                    for (int kb = 0; kb < KBN; ++kb) {
-                        const uint64_t b0 = db0[kb] + soff;
-                        // +32 B per K step of 16 bf16 inside the 128-byte swizzle atom: +2 in the start-address field
+                    for (int kb = 0; kb < kWKB; ++kb)
 #pragma unroll
-                        for (int q = 0; q < 4; ++q) umma_f16_ts(acc, tmem_base + (uint32_t)((kb * 4 + q) * 8), b0 + 2 * q, kCvIdesc, (kb | q) ? 1u : 0u);
-                    }
-                    umma_commit(b_xempty + 8 * s);                   // smem stage reusable once these MMAs have read it
-                    umma_commit(b_afull + 8 * a);                    // accumulator complete
+                        for (int q = 0; q < 4; ++q)
+                            tmem_cp_128x256b(tmem_base + (uint32_t)(((half * kWKB + kb) * 4 + q) * 8), da[kb] + 2 * q);
+                    umma_commit(b_wempty);                           // the landing buffer may take the next (half) slab
                 }
                 __syncwarp();
-                if (++s == kCvStages) { s = 0; xph ^= 1; }
-                if (++a == kCvAcc) { a = 0; aeph ^= 1; }
+            }
+            for (int t = 0; t < T; ++t) {
+                mbar_wait(b_aempty + 8 * a, aeph);                   // the epilogue has drained this accumulator
+#pragma unroll
+                for (int hf = 0; hf < (TF32 ? 2 : 1); ++hf) {        // TF32: two 64-pixel stages fill one 128-column accumulator
+                    mbar_wait(b_xfull + 8 * s, xph);                 // the tile has landed
+                    tc_fence_after();
+                    if (lane == 0) {
+                        const uint32_t acc = tmem_base + (uint32_t)(kAccCol0 + a * kCvPix + hf * (kCvPix / 2));
+                        const uint64_t soff = (uint64_t)s * kStageStep;
+#pragma unroll
+                        for (int kb = 0; kb < KBN; ++kb) {
+                            const uint64_t b0 = db0[kb] + soff;
+                            // +32 B per K step (16 bf16 / 8 tf32) inside the 128-byte swizzle atom: +2 in the start-address field
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) {
+                                if constexpr (TF32) umma_tf32_ts(acc, tmem_base + (uint32_t)((kb * 4 + q) * 8), b0 + 2 * q, kIdesc, (kb | q) ? 1u : 0u);
+                                else umma_f16_ts(acc, tmem_base + (uint32_t)((kb * 4 + q) * 8), b0 + 2 * q, kIdesc, (kb | q) ? 1u : 0u);
+                            }
+                        }
+                        umma_commit(b_xempty + 8 * s);               // smem stage reusable once these MMAs have read it
+                        if (hf == (TF32 ? 1 : 0)) umma_commit(b_afull + 8 * a);   // accumulator complete
+                    }
+                    __syncwarp();
+                    if (++s == kCvStages) { s = 0; xph ^= 1; }
+                }
+                if (++a == kAcc) { a = 0; aeph ^= 1; }
             }
         }
     } else if (warp < kCvEpiWarps) {
@@ -197,12 +238,12 @@ __global__ void __launch_bounds__(kCvThreads, 1) conv_head_fwd_kernel(const __gr
                 }
                 float gsum = 0.f;
                 for (int t = 0; t < T; ++t, ++g) {
-                    const int a = g % kCvAcc;
-                    const uint32_t aph = (uint32_t)(g / kCvAcc) & 1u;
+                    const int a = g % kAcc;
+                    const uint32_t aph = (uint32_t)(g / kAcc) & 1u;
                     mbar_wait(b_afull + 8 * a, aph);
                     tc_fence_after();
                     uint32_t r[32];
-                    tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(kCvAccCol + a * kCvPix + c0), r);
+                    tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(kAccCol0 + a * kCvPix + c0), r);
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(b_aempty + 8 * a);
@@ -244,12 +285,12 @@ __global__ void __launch_bounds__(kCvThreads, 1) conv_head_fwd_kernel(const __gr
             float m = kNegHuge, s = 0.f, sx = 0.f, sy = 0.f;
             float* lrow = p.logits_out ? p.logits_out + ((size_t)b * p.rows_total + grow) * p.HW : nullptr;
             for (int t = 0; t < T; ++t, ++g) {
-                const int a = g % kCvAcc;
-                    const uint32_t aph = (uint32_t)(g / kCvAcc) & 1u;
+                const int a = g % kAcc;
+                    const uint32_t aph = (uint32_t)(g / kAcc) & 1u;
                     mbar_wait(b_afull + 8 * a, aph);
                 tc_fence_after();
                 uint32_t r[32];
-                tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(kCvAccCol + a * kCvPix + c0), r);
+                tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(kAccCol0 + a * kCvPix + c0), r);
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(b_aempty + 8 * a);        // values are in registers: release the accumulator early
@@ -408,6 +449,44 @@ static cudaError_t launch_conv_head(const void* x_nhwc, const void* w, ConvHeadP
         case 2: return launch_kbn<2, MODE>(map_w, map_x, p, grid, smem, st);
         case 3: return launch_kbn<3, MODE>(map_w, map_x, p, grid, smem, st);
         default: return launch_kbn<4, MODE>(map_w, map_x, p, grid, smem, st);
+    }
+}
+
+// fp32 operands, tf32 tensor-core arithmetic (forward only): x [B, H*W, C] fp32 channels-last, w [K*D, C] fp32
+template <int KBN>
+static cudaError_t launch_kbn_tf32(const CUtensorMap& map_w, const CUtensorMap& map_x, const ConvHeadParams& p, int grid, size_t smem, cudaStream_t st) {
+    auto kern = conv_head_fwd_kernel<KBN, 0, true>;
+    static unsigned long long attr_done = 0;
+    cudaError_t e = ensure_max_smem(kern, attr_done);
+    if (e != cudaSuccess) return e;
+    kern<<<grid, kCvThreads, smem, st>>>(map_w, map_x, p);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_conv_head_fwd_tf32(const void* x_nhwc_f32, const void* w_f32, const float* bias, float* logits_out, FwdParams f, int B, int C,
+                                      int num_sms, cudaStream_t st) {
+    ConvHeadParams p{};
+    p.f = f;
+    p.bias = bias;
+    p.logits_out = logits_out;
+    p.C = C;
+    p.HW = p.f.t.H * p.f.t.W;
+    p.rows_total = p.f.K * p.f.t.D;
+    p.groups = (p.rows_total + kCvRows - 1) / kCvRows;
+    p.n_tiles = p.HW / kCvPix;
+    p.kblocks = C / 32;
+    p.items = B * p.groups;
+    CUtensorMap map_w, map_x;
+    if (!make_map_f32(&map_w, w_f32, p.rows_total, C, kCvRows) || !make_map_f32(&map_x, x_nhwc_f32, (long long)B * p.HW, C, kCvPix / 2))
+        return cudaErrorNotSupported;
+    const size_t scratch = 2 * kCvParts * kCvRows * sizeof(float4) + 2 * kCvFinWarps * kMaxD * 4;
+    const size_t smem = 1024 + (size_t)(p.kblocks / 2) * kCvKBBytes + (size_t)kCvStages * p.kblocks * (kCvKBBytes / 2) + 32 * 8 + scratch;
+    const int grid = p.items < num_sms ? p.items : num_sms;
+    switch (p.kblocks) {
+        case 2: return launch_kbn_tf32<2>(map_w, map_x, p, grid, smem, st);
+        case 4: return launch_kbn_tf32<4>(map_w, map_x, p, grid, smem, st);
+        case 6: return launch_kbn_tf32<6>(map_w, map_x, p, grid, smem, st);
+        default: return launch_kbn_tf32<8>(map_w, map_x, p, grid, smem, st);
     }
 }
 

@@ -124,6 +124,8 @@ cudaError_t launch_disc_min_loss_bwd(const float* logits, const int64_t* sel, co
 cudaError_t launch_conv_head_fwd(const void* x_nhwc, const void* w, const float* bias, float* logits_out, FwdParams f, int B, int C,
                                  int num_sms, cudaStream_t st);
 
+cudaError_t launch_conv_head_fwd_tf32(const void* x_nhwc_f32, const void* w_f32, const float* bias, float* logits_out, FwdParams f, int B, int C,
+                                      int num_sms, cudaStream_t st);
 cudaError_t launch_conv_head_bwd_g(const void* x_nhwc, const void* w, const float* bias, const float* coef, int coef_stride, void* g_out,
                                    float* gbias_part, FwdParams f, int B, int C, int num_sms, cudaStream_t st);
 cudaError_t launch_pack_nhwc_bf16(const float* x, void* y, int B, int C, int HW, cudaStream_t st);

@@ -110,6 +110,20 @@ __host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N, bool a_mn =
     return (1u << 4) | (1u << 7) | (1u << 10) | ((a_mn ? 1u : 0u) << 15) | ((b_mn ? 1u : 0u) << 16) | ((uint32_t)(N >> 3) << 17) |
            ((uint32_t)(M >> 4) << 24);
 }
+// the same for fp32 operands read as tf32 (kind::tf32: K = 8 per instruction, A / B format 2)
+__host__ __device__ constexpr uint32_t umma_idesc_tf32(int M, int N) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, uint32_t acc) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t"
+        "}" ::"r"(tmem_d),
+        "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(acc)
+        : "memory");
+}
 // generic-proxy writes to shared memory (st.shared) made visible to the async proxy (tcgen05.mma operand reads)
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
@@ -141,6 +155,18 @@ static inline bool make_map(CUtensorMap* map, const void* base, long long rows, 
                CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
+
+// [rows, C] fp32 row-major (C contiguous) -> boxes of [box_rows rows x 32 channels] (128 bytes per row), 128-byte swizzle
+static inline bool make_map_f32(CUtensorMap* map, const void* base, long long rows, int C, int box_rows) {
+    EncodeTiledFn enc = encode_tiled();
+    if (!enc) return false;
+    const cuuint64_t dims[2] = {(cuuint64_t)C, (cuuint64_t)rows};
+    const cuuint64_t strides[1] = {(cuuint64_t)C * 4};
+    const cuuint32_t box[2] = {32u, (cuuint32_t)box_rows};
+    const cuuint32_t estr[2] = {1, 1};
+    return enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+               CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
 
 // [rows, cols] row-major output (bf16 or fp32) written / reduced from shared-memory staging: boxes of [box_rows x 128 bytes], 128-byte swizzle
 static inline bool make_map_out(CUtensorMap* map, void* base, long long rows, int cols, bool f32, int box_rows) {

@@ -68,14 +68,16 @@ class KPDetector3DMulti(nn.Module):
         return kps, depth_prob_map
 
     @torch.no_grad()
-    def forward_fused(self, x):
+    def forward_fused(self, x, precision="bf16"):
         """Inference path (eval.py:120) with the final `Conv2d(C, K*D, 1)` of `self.net.head`
         (deconv_head.py:33-35) fused into the head tail on the tensor cores: the `[B, K*D, H, W]` logits are never
         materialised.  Needs the reference's network layout (`net.backbone`, `net.head.features[-1]` a 1x1 conv with
-        bias); returns the same `(kps, depth_prob_map)` as `forward`, with the conv operands rounded to bf16."""
+        bias); returns the same `(kps, depth_prob_map)` as `forward`, with the conv operands rounded to bf16, or - with
+        `precision="tf32"` - to tf32, which is what the reference's own conv computes on this GPU."""
         feats, last = _split_final_conv(self.net)
         y = feats(x)
-        kps, depth_prob_map, _ = ops.conv_integral_head(y, last.weight, last.bias, self.num_kp, self.num_hypo, self.neighbor_size)
+        kps, depth_prob_map, _ = ops.conv_integral_head(y, last.weight, last.bias, self.num_kp, self.num_hypo, self.neighbor_size,
+                                                        precision=precision)
         return kps, depth_prob_map
 
 

@@ -463,8 +463,14 @@ def _nhwc_bf16(x: torch.Tensor) -> torch.Tensor:
     return xb.to(dtype=torch.bfloat16, memory_format=torch.channels_last)
 
 
+def _round_tf32(t: torch.Tensor) -> torch.Tensor:
+    """fp32 -> nearest tf32 value (10 mantissa bits, ties away from zero like cvt.rna.tf32.f32), still stored as fp32; a new tensor
+    with the same strides.  Bit arithmetic on the sign-magnitude pattern: add half an ulp of the kept mantissa, clear the rest."""
+    return ((t.view(torch.int32) + 0x1000) & -0x2000).view(torch.float32)
+
+
 def conv_integral_head(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor], num_kp: int, num_hypo: int,
-                       neighbor_size: int, return_logits: bool = False):
+                       neighbor_size: int, return_logits: bool = False, precision: str = "bf16"):
     """The head's final `Conv2d(C, K*D, 1)` (deconv_head.py:33-35) fused with the integral multi-hypothesis head
     (…_multi.py:69-88), forward only (the eval path, eval.py:120): tcgen05 tensor-core GEMM with the softmax statistics
     taken from the TMEM accumulators, so the `[B, K*D, H, W]` logits are never written to HBM.
@@ -473,8 +479,12 @@ def conv_integral_head(x: torch.Tensor, weight: torch.Tensor, bias: Optional[tor
     backbones produce); anything else is converted once (one extra pass over the activations).
     weight `[K*D, C]` or `[K*D, C, 1, 1]`, bias `[K*D]` or None.  Operands are rounded to bf16, accumulation and all
     statistics are fp32 - the reference's own conv runs in TF32 on the same hardware.
+    `precision="tf32"`: fp32 operands through `tcgen05.mma.kind::tf32` instead (x is taken as fp32 channels-last, converted once if
+    it is not) - what the reference's cuDNN conv computes on this GPU; about twice the tensor-core time, forward / eval only.
     Returns (kps [B,NH,K,3], depth_prob_map [K,D], peak_idx [B,K,NH]) and, with `return_logits`, the fp32 logits."""
     cabi.require_cuda(x, "x")
+    if precision not in ("bf16", "tf32"):
+        raise ValueError("precision must be 'bf16' or 'tf32', got %r" % (precision,))
     B, C, H, W = x.shape
     w2 = weight.detach().reshape(weight.shape[0], -1)
     if w2.shape[1] != C:
@@ -483,8 +493,15 @@ def conv_integral_head(x: torch.Tensor, weight: torch.Tensor, bias: Optional[tor
     if D * num_kp != w2.shape[0]:
         raise ValueError("weight rows %d are not a multiple of num_kp %d" % (w2.shape[0], num_kp))
     dev = x.device
-    xb = _nhwc_bf16(x)
-    wb = w2.to(device=dev, dtype=torch.bfloat16).contiguous()
+    tf32 = precision == "tf32"
+    if tf32:
+        # the tensor core drops the low 13 mantissa bits of a tf32 operand; round to nearest first (what cvt.rna.tf32.f32 and
+        # the library convolutions do), otherwise the truncation bias costs a bit of accuracy
+        xb = _round_tf32(x.detach().to(dtype=torch.float32).contiguous(memory_format=torch.channels_last))
+        wb = _round_tf32(w2.to(device=dev, dtype=torch.float32).contiguous())
+    else:
+        xb = _nhwc_bf16(x)
+        wb = w2.to(device=dev, dtype=torch.bfloat16).contiguous()
     bf = bias.detach().to(device=dev, dtype=torch.float32).contiguous() if bias is not None else None
     shape = cabi.make_shape(B, num_kp, D, H, W, num_hypo, neighbor_size, torch.bfloat16, cabi.HEAD_MULTI)
     kps = torch.empty(B, num_hypo, num_kp, 3, dtype=torch.float32, device=dev)
@@ -492,11 +509,11 @@ def conv_integral_head(x: torch.Tensor, weight: torch.Tensor, bias: Optional[tor
     idx = torch.empty(B, num_kp, num_hypo, dtype=torch.int64, device=dev)
     stats = torch.empty(cabi.lib.xsup_stats_floats(shape), dtype=torch.float32, device=dev)
     logits = torch.empty(B, num_kp * D, H, W, dtype=torch.float32, device=dev) if return_logits else None
+    fn, who = (cabi.lib.xsup_conv_head_fwd_tf32, "xsup_conv_head_fwd_tf32") if tf32 else (cabi.lib.xsup_conv_head_fwd, "xsup_conv_head_fwd")
     with torch.cuda.device(dev):
-        cabi.check(cabi.lib.xsup_conv_head_fwd(xb.data_ptr(), wb.data_ptr(), bf.data_ptr() if bf is not None else None,
-                                               kps.data_ptr(), dmap.data_ptr(), idx.data_ptr(), stats.data_ptr(),
-                                               logits.data_ptr() if return_logits else None, shape, C, cabi.stream_ptr(dev)),
-                   "xsup_conv_head_fwd")
+        cabi.check(fn(xb.data_ptr(), wb.data_ptr(), bf.data_ptr() if bf is not None else None,
+                      kps.data_ptr(), dmap.data_ptr(), idx.data_ptr(), stats.data_ptr(),
+                      logits.data_ptr() if return_logits else None, shape, C, cabi.stream_ptr(dev)), who)
     return (kps, dmap, idx, logits) if return_logits else (kps, dmap, idx)
 
 
