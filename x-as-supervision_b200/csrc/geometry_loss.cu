@@ -650,7 +650,10 @@ __global__ void __launch_bounds__(128) reproj_loss_bwd_kernel(const float* __res
 // with the upstream gradients on kps / kps_world, kept in shared memory; (2) the coefficient blocks of the sample's K
 // units for the streaming head backward (what integral_coef_kernel derives from grad_kps in global memory).  Replaces
 // loss_bwd + the ATen zeros/stack/add glue + integral_coef: the gradient w.r.t. kps never round-trips HBM.
-__global__ void __launch_bounds__(256) reproj_fused_bwd_kernel(const float* __restrict__ kps, const float* __restrict__ target,
+// kLossBwdWarps warps per sample: the hypotheses' vector-Jacobian products on warps 0..NH-1, then one (b,k) unit per warp - with 18
+// warps the 17-18 joints of the reference's skeletons take one round instead of three (the kernel is a chain of dependent loads).
+constexpr int kLossBwdWarps = 18;
+__global__ void __launch_bounds__(kLossBwdWarps * 32) reproj_fused_bwd_kernel(const float* __restrict__ kps, const float* __restrict__ target,
                                                                const xsup_cam_t cam, const int64_t* __restrict__ sel,
                                                                const float* __restrict__ g_lp, const float* __restrict__ g_ls,
                                                                const float* __restrict__ g_kps_in, const float* __restrict__ g_world,
@@ -658,13 +661,13 @@ __global__ void __launch_bounds__(256) reproj_fused_bwd_kernel(const float* __re
     extern __shared__ float sm[];
     const int NH = c.NH, K = c.K;
     float* gz = sm;                       // [NH][32]
-    float* gxp = sm + (size_t)NH * 32;    // [8][32] per-warp partial sums over this warp's hypotheses
-    float* gyp = gxp + 8 * 32;
+    float* gxp = sm + (size_t)NH * 32;    // [kLossBwdWarps][32] per-warp partial sums over this warp's hypotheses
+    float* gyp = gxp + kLossBwdWarps * 32;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, b = blockIdx.x;
     if (b == 0 && threadIdx.x == 0) *p.counter = 0;                          // work-claim counter of the streaming kernel that follows
     const float gl0 = g_lp ? *g_lp : 0.f, gl1 = g_ls ? *g_ls : 0.f;
     float ax = 0.f, ay = 0.f;
-    for (int h = warp; h < NH; h += 8) {
+    for (int h = warp; h < NH; h += kLossBwdWarps) {
         float g[3];
         loss_bwd_warp(kps, target, cam, sel, gl0, gl1, g_kps_in, g_world, c, b, h, lane, g);
         gz[h * 32 + lane] = g[2];
@@ -681,13 +684,13 @@ __global__ void __launch_bounds__(256) reproj_fused_bwd_kernel(const float* __re
     const int D = p.D;
     const float zs = 2.0f / (float)D;
     const int half = p.NS >> 1;
-    for (int k = warp; k < K; k += 8) {
+    for (int k = warp; k < K; k += kLossBwdWarps) {
         const int unit = b * K + k;
         const float* st = p.stats + (size_t)unit * p.stats_stride;
         float* cf = p.coef + (size_t)unit * p.coef_stride;
         float gx = 0.f, gy = 0.f;
 #pragma unroll
-        for (int w = 0; w < 8; ++w) { gx += gxp[w * 32 + k]; gy += gyp[w * 32 + k]; }
+        for (int w = 0; w < kLossBwdWarps; ++w) { gx += gxp[w * 32 + k]; gy += gyp[w * 32 + k]; }
         const float a = gx * (2.0f / (float)p.H);            // x was normalised by H (…_multi.py:78)
         const float bb = gy * (2.0f / (float)p.W);           // y by W (…:79)
         float dot = 0.f;
@@ -719,8 +722,8 @@ __global__ void __launch_bounds__(256) reproj_fused_bwd_kernel(const float* __re
 cudaError_t launch_reproj_fused_bwd(const float* kps, const float* target, const xsup_cam_t& cam, const int64_t* sel, const float* g_lp,
                                     const float* g_ls, const float* g_kps_in, const float* g_world, float* g_kps_out,
                                     const xsup_loss_cfg_t& c, const CoefParams& p, cudaStream_t st) {
-    const size_t smem = ((size_t)c.NH * 32 + 2 * 8 * 32) * sizeof(float);       // <= 34 KB (NH <= 254)
-    reproj_fused_bwd_kernel<<<c.B, 256, smem, st>>>(kps, target, cam, sel, g_lp, g_ls, g_kps_in, g_world, g_kps_out, c, p);
+    const size_t smem = ((size_t)c.NH * 32 + 2 * kLossBwdWarps * 32) * sizeof(float);       // <= 37 KB (NH <= 254)
+    reproj_fused_bwd_kernel<<<c.B, kLossBwdWarps * 32, smem, st>>>(kps, target, cam, sel, g_lp, g_ls, g_kps_in, g_world, g_kps_out, c, p);
     return cudaGetLastError();
 }
 
