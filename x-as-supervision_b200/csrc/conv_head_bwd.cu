@@ -12,11 +12,11 @@
 //
 //   MODE_DW (W-stationary): item = (sample b, 128 weight rows).  The 128 x C weight slab is the stationary operand, the sample's
 //            activations stream through as 128-pixel tiles:   S[128 rows x 128 pix] = Wt_slab * X_tile^T ;  G = f(S) ;
-//            D2[128 rows x C] += G[128 x 128] * X_tile[128 x C].  D2 is flushed once per item with fp32 RED.ADD into d Wt.
+//            D2[128 rows x C] += G[128 x 128] * X_tile[128 x C].  D2 leaves once per item as a TMA fp32 reduce-add into d Wt.
 //   MODE_DX (X-stationary): item = (sample b, 128 pixels).  The 128 x C activation tile is the stationary operand, the weights
 //            stream through as 128-row tiles:   S[128 pix x 128 rows] = X_tile * Wt_tile^T ;  G^T = f(S) ;
 //            D2[128 pix x C] += G^T[128 x 128] * Wt_tile[128 x C].  D2 is the finished d X tile (all K*D rows were summed in
-//            TMEM) and is written once, bf16 or fp32, channels-last.
+//            TMEM) and is written once by the TMA, bf16 or fp32, channels-last.
 //
 // Both modes are ONE kernel.  Every operand tile is [128 x C] bf16 and travels through ONE 3-stage TMA ring (64 KB per stage
 // at C = 256): per item first the stationary tile, then the streamed ones.
@@ -37,6 +37,7 @@
 //                has published G; its tcgen05.commit releases the ring stage and the G buffer
 //   warps 0..15  epilogue: tcgen05.ld (thread = TMEM lane, 32 columns per warp), G = f(S) with packed fp32x2 arithmetic,
 //                st.shared (XOR-swizzled 16-byte chunks), fence.proxy.async, mbarrier arrive; at the end of an item they drain D2
+//                through the idle G buffer (16 KB chunks, swizzled, ping-pong) to the TMA: tensor store (d x) / reduce-add (d W)
 // TMEM: columns [0,128) = stationary operand, [128,256) = S[128 x 128] fp32, [256, 256+C) = D2.
 // Flops: 2 GEMMs of 2*K*D*C*H*W per sample and launch (1.17 TFLOP per launch at B=256, K=17, D=64, C=256).
 #include <stdlib.h>
@@ -97,9 +98,6 @@ __global__ void __launch_bounds__(256) conv_rowcoef_kernel(const float* __restri
     o[6] = e;
 }
 
-__device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
-    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
-}
 
 // Diagnostics, compiled in only with -DXSUP_TRACE (XSUP_NVCC_EXTRA="-DXSUP_TRACE" python -c "import __graft_entry__ as g; g.build(force=True)"):
 // a clock64 timeline of CTA 0, tiles / items 8..23, written to the device buffer whose address is in XSUP_CONVBWD_TRACE
