@@ -14,10 +14,22 @@
 //                per-task depth-slice sum (pz)
 //   warps 17,18  finalisers (even / odd units): log-sum-exp combine of the per-task/per-warp partials, peaks, top-NH,
 //                window depth, outputs + saved-for-backward stats; overlaps the next unit's stream
+#include <stdlib.h>
+
 #include "xsup_internal.h"
 #include "xsup_finalise.cuh"
 
 namespace xsup {
+
+// Diagnostics, compiled in only with -DXSUP_TRACE: clock64 timeline of CTA 0 (units 4..19 of that CTA) into the device buffer whose
+// address is in XSUP_K1_TRACE; [unit - 4][16] slots: 0 producer claims, 1 first stage issued, 2 last stage issued, 4 consumer warp 0
+// sees the first stage, 5 consumer warp 0 flushes, 8 finaliser starts, 9 partials merged, 10 unit finalised.
+#ifdef XSUP_TRACE
+__device__ long long* g_k1_trace = nullptr;
+#define K1TRACE(slot, ui) do { if (g_k1_trace && blockIdx.x == 0 && (ui) >= 4 && (ui) < 20) g_k1_trace[((ui) - 4) * 16 + (slot)] = clock64(); } while (0)
+#else
+#define K1TRACE(slot, ui) do { } while (0)
+#endif
 
 // ----------------------------------------------------------------------------------------------
 // Fast path: TMA-fed ring, one pass over the volume.
@@ -67,7 +79,9 @@ __global__ void __launch_bounds__(kFwdThreads, 1) integral_fwd_kernel(const FwdP
             int slot = 0;
             uint32_t eph = 1;                                        // parity to wait for on `empty`: the first pass over the ring does not wait
             int cur = atomicAdd(p.counter, 1);
+            int lu = 0;                                              // units this CTA has started (trace only)
             while (cur < p.n_units) {
+                K1TRACE(0, lu);
                 const int nxt = atomicAdd(p.counter, 1);            // claim ahead: the round trip overlaps this unit's copies
                 const uint8_t* src = static_cast<const uint8_t*>(p.logits) + (size_t)cur * (size_t)t.unit_bytes;
                 for (int j = 0; j < SPUP; ++j) {
@@ -82,9 +96,12 @@ __global__ void __launch_bounds__(kFwdThreads, 1) integral_fwd_kernel(const FwdP
                     } else {
                         mbar_arrive(full0 + 8u * slot);             // padding stage: header only
                     }
+                    if (j == 0) K1TRACE(1, lu);
+                    if (j == SPUP - 1) K1TRACE(2, lu);
                     if (++slot == nst) { slot = 0; eph ^= 1; }
                 }
                 cur = nxt;
+                ++lu;
             }
             for (int g = 0; g < kGroups; ++g) {                     // one end-of-stream sentinel per consumer group
                 mbar_wait(empty0 + 8u * slot, eph);
@@ -103,6 +120,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) integral_fwd_kernel(const FwdP
         int* bins_mine = peak_bins + buf * kMaxD;
         for (int it = buf;; it += 2) {
             mbar_wait(pfull0 + 8u * buf, (it >> 1) & 1);
+            if (lane == 0) K1TRACE(8, it);
             // the consumers leave their per-LANE partial sums (no shuffles on their side: they are the issue-bound warps, this
             // one has two unit-times per unit); merge the 16 warps with their log-sum-exp weights, then one reduction per quantity
             const float2 hd = lane < kConsumerWarps ? warp_hdr[buf * kConsumerWarps + lane] : make_float2(kNegHuge, 0.f);
@@ -143,8 +161,10 @@ __global__ void __launch_bounds__(kFwdThreads, 1) integral_fwd_kernel(const FwdP
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(pempty0 + 8u * buf);      // partial buffers may be refilled
+            if (lane == 0) K1TRACE(9, it);
             finalise_unit(p, unit, pz_mine, bins_mine, M, xbar, ybar, lane);
             __syncwarp();
+            if (lane == 0) K1TRACE(10, it);
         }
     } else {
         // ------------------------------------------------------------------ consumers
@@ -172,6 +192,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) integral_fwd_kernel(const FwdP
             const int unit = hd.x, j = hd.y;
             if (unit < 0) break;
             const int buf = it & 1;
+            if (fresh && warp == 0 && lane == 0) K1TRACE(4, it);
             if (fresh) {
                 if (it >= 2) mbar_wait(pempty0 + 8u * buf, ((it >> 1) - 1) & 1);
                 fresh = false;
@@ -243,6 +264,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) integral_fwd_kernel(const FwdP
                     sa += a0 + a1;
                     acc[v] = pk2(0.f, 0.f);
                 }
+                if (warp == 0 && lane == 0) K1TRACE(5, it);
                 lane_part[(buf * kConsumerWarps + warp) * 32 + lane] = make_float4(sx, sa, sy, sr);
                 if (lane == 0) warp_hdr[buf * kConsumerWarps + warp] = make_float2(m_ref, __int_as_float(unit));
                 __syncwarp();
@@ -344,6 +366,12 @@ cudaError_t launch_find_peak(const float* pz, int64_t* idx, int rows, int D, int
 // ----------------------------------------------------------------------------------------------
 template <typename T, int U>
 static cudaError_t launch_fast(const FwdParams& p, int grid, size_t smem, cudaStream_t st) {
+#ifdef XSUP_TRACE
+    if (const char* d = getenv("XSUP_K1_TRACE")) {
+        long long* ptr = reinterpret_cast<long long*>(strtoull(d, nullptr, 0));
+        cudaMemcpyToSymbolAsync(g_k1_trace, &ptr, sizeof(ptr), 0, cudaMemcpyHostToDevice, st);
+    }
+#endif
     auto kern = integral_fwd_kernel<T, U>;
     static unsigned long long attr_done = 0;             // per instantiation; one bit per device
     cudaError_t e = ensure_max_smem(kern, attr_done);
