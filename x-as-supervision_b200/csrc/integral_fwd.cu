@@ -12,8 +12,9 @@
 //                registers, early release of the slot, warp-uniform running max (CREDUX.MAX.F32),
 //                one MUFU.EX2 per element, per-lane column accumulators (x), row-weighted sum (y),
 //                per-task depth-slice sum (pz)
-//   warps 17,18  finalisers (even / odd units): log-sum-exp combine of the per-task/per-warp partials, peaks, top-NH,
-//                window depth, outputs + saved-for-backward stats; overlaps the next unit's stream
+//   warps 17..   finalisers (2, or 3 for units of at most 256 KB; unit i of the CTA goes to finaliser i mod n): log-sum-exp
+//                combine of the per-task/per-warp partials, peaks, top-NH, window depth, outputs + saved-for-backward
+//                stats; overlaps the stream of the next n-1 units
 #include <stdlib.h>
 
 #include "xsup_internal.h"
@@ -46,22 +47,24 @@ __global__ void __launch_bounds__(kFwdThreads, 1) integral_fwd_kernel(const FwdP
     const int SPUP = (SPU + kGroups - 1) / kGroups * kGroups;
 
     uint8_t* ring = smem;
-    float4* lane_part = reinterpret_cast<float4*>(smem + (size_t)nst * t.stage_bytes);  // [2][kConsumerWarps][32] per-lane (sx, sa, sy, sr)
-    float2* pz_table = reinterpret_cast<float2*>(lane_part + 2 * kConsumerWarps * 32);  // [2][TU] (m, sum)
-    float2* warp_hdr = pz_table + 2 * TU;                                               // [2][kConsumerWarps] (m_ref, unit)
-    float* pz_final = reinterpret_cast<float*>(warp_hdr + 2 * kConsumerWarps);          // [2][kMaxD]
-    int* peak_bins = reinterpret_cast<int*>(pz_final + 2 * kMaxD);                      // [2][kMaxD]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(peak_bins + 2 * kMaxD);
-    volatile int2* hdr = reinterpret_cast<volatile int2*>(bars + 2 * kMaxStages + 4);   // [nst] (unit, stage in unit)
+    const int NF = p.nfin;                                                              // finaliser warps = partial buffers
+    const int DP = (t.D + 1) & ~1;                                                      // keeps the tables 8-byte aligned
+    float4* lane_part = reinterpret_cast<float4*>(smem + (size_t)nst * t.stage_bytes);  // [NF][kConsumerWarps][32] per-lane (sx, sa, sy, sr)
+    float2* pz_table = reinterpret_cast<float2*>(lane_part + NF * kConsumerWarps * 32); // [NF][TU] (m, sum)
+    float2* warp_hdr = pz_table + NF * TU;                                              // [NF][kConsumerWarps] (m_ref, unit)
+    float* pz_final = reinterpret_cast<float*>(warp_hdr + NF * kConsumerWarps);         // [NF][DP]
+    int* peak_bins = reinterpret_cast<int*>(pz_final + NF * DP);                        // [NF][DP]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(peak_bins + NF * DP);
+    volatile int2* hdr = reinterpret_cast<volatile int2*>(bars + 2 * kMaxStages + 2 * kMaxFinalisers);   // [nst] (unit, stage in unit)
     const uint32_t full0 = smem_u32(bars), empty0 = full0 + 8u * nst;
-    const uint32_t pfull0 = empty0 + 8u * nst, pempty0 = pfull0 + 16u;
+    const uint32_t pfull0 = empty0 + 8u * nst, pempty0 = pfull0 + 8u * kMaxFinalisers;
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < nst; ++i) {
             mbar_init(full0 + 8u * i, 1);
             mbar_init(empty0 + 8u * i, kTasksPerStage);
         }
-        for (int i = 0; i < 2; ++i) {
+        for (int i = 0; i < NF; ++i) {
             mbar_init(pfull0 + 8u * i, kConsumerWarps);
             mbar_init(pempty0 + 8u * i, 1);
         }
@@ -113,13 +116,16 @@ __global__ void __launch_bounds__(kFwdThreads, 1) integral_fwd_kernel(const FwdP
         }
     } else if (warp > kConsumerWarps) {
         // ------------------------------------------------------------------ finalisers
-        // two warps, one per partial buffer: the first takes this CTA's even units, the second the odd ones, so a
-        // unit's epilogue may last two unit-streaming times before it stalls the ring (64 KB bf16 units stream in 1.4 us)
+        // NF warps, one per partial buffer: warp f takes this CTA's units f, f + NF, ..., so a unit's epilogue may last NF
+        // unit-streaming times before it stalls the ring (64 KB bf16 units stream in 1.5 us, their epilogue takes 4 us on a
+        // warp that shares its scheduler with four issue-bound consumers: with two buffers the consumers waited for `pempty`)
         const int buf = warp - kConsumerWarps - 1;
-        float* pz_mine = pz_final + buf * kMaxD;
-        int* bins_mine = peak_bins + buf * kMaxD;
-        for (int it = buf;; it += 2) {
-            mbar_wait(pfull0 + 8u * buf, (it >> 1) & 1);
+        if (buf >= NF) return;
+        float* pz_mine = pz_final + buf * DP;
+        int* bins_mine = peak_bins + buf * DP;
+        uint32_t fpar = 0;                                           // this buffer's use number, mod 2
+        for (int it = buf;; it += NF, fpar ^= 1) {
+            mbar_wait(pfull0 + 8u * buf, fpar);
             if (lane == 0) K1TRACE(8, it);
             // the consumers leave their per-LANE partial sums (no shuffles on their side: they are the issue-bound warps, this
             // one has two unit-times per unit); merge the 16 warps with their log-sum-exp weights, then one reduction per quantity
@@ -174,6 +180,8 @@ __global__ void __launch_bounds__(kFwdThreads, 1) integral_fwd_kernel(const FwdP
         const float rpi = (float)(32 >> t.lpr_log2);
         const uint32_t ring0 = smem_u32(ring);
         int it = 0;                                                  // units this warp has flushed
+        int buf = 0;                                                 // it mod NF
+        uint32_t bpar = 1;                                           // parity of the previous use of partial buffer `buf` (no wait in the first round)
         bool fresh = true;                                           // first stage of a unit: claim the partial buffer
         constexpr int P = Vec<T>::P;
         float m_ref = kNegHuge, sy = 0.f, sr = 0.f;
@@ -191,10 +199,9 @@ __global__ void __launch_bounds__(kFwdThreads, 1) integral_fwd_kernel(const FwdP
             const int2 hd = lds_int2(hdr0 + 8u * slot);
             const int unit = hd.x, j = hd.y;
             if (unit < 0) break;
-            const int buf = it & 1;
             if (fresh && warp == 0 && lane == 0) K1TRACE(4, it);
             if (fresh) {
-                if (it >= 2) mbar_wait(pempty0 + 8u * buf, ((it >> 1) - 1) & 1);
+                if (it >= NF) mbar_wait(pempty0 + 8u * buf, bpar);
                 fresh = false;
             }
             for (int r = 0; r < t.rounds; ++r) {
@@ -273,17 +280,18 @@ __global__ void __launch_bounds__(kFwdThreads, 1) integral_fwd_kernel(const FwdP
                 sy = 0.f;
                 sr = 0.f;
                 ++it;
+                if (++buf == NF) { buf = 0; bpar ^= 1; }
                 fresh = true;
             }
         }
-        // end of stream: pass the sentinel on to both finalisers (the next use of either buffer)
-        for (int e = 0; e < 2; ++e) {
-            const int ie = it + e, buf = ie & 1;
-            if (ie >= 2) mbar_wait(pempty0 + 8u * buf, ((ie >> 1) - 1) & 1);
+        // end of stream: pass the sentinel on to every finaliser (the next use of each buffer)
+        for (int e = 0; e < NF; ++e) {
+            if (it + e >= NF) mbar_wait(pempty0 + 8u * buf, bpar);
             if (lane == 0) {
                 warp_hdr[buf * kConsumerWarps + warp] = make_float2(kNegHuge, __int_as_float(-1));
                 mbar_arrive(pfull0 + 8u * buf);
             }
+            if (++buf == NF) { buf = 0; bpar ^= 1; }
         }
     }
 }
@@ -396,9 +404,24 @@ cudaError_t launch_integral_fwd(FwdParams p, bool fast, int dtype, int num_sms, 
         else integral_fwd_generic_kernel<__nv_bfloat16><<<p.n_units, 256, 0, st>>>(p);
         return cudaGetLastError();
     }
-    const size_t fixed = (size_t)2 * kConsumerWarps * 32 * sizeof(float4) + (size_t)2 * p.t.tasks_per_unit * sizeof(float2) +
-                         2 * kConsumerWarps * sizeof(float2) + 4 * kMaxD * sizeof(float) + (size_t)(2 * kMaxStages + 4) * 8 +
-                         (size_t)kMaxStages * sizeof(int2);
+    // Finaliser warps (= partial buffers): two; for short units (<= 256 KB, whose epilogue outlasts two unit-streaming times) as many
+    // as kMaxFinalisers, as long as their tables do not cost a ring stage.
+    const int dp = (p.t.D + 1) & ~1;
+    auto fixed_for = [&](int nf) {
+        return (size_t)nf * (kConsumerWarps * 32 * sizeof(float4) + p.t.tasks_per_unit * sizeof(float2) + kConsumerWarps * sizeof(float2) +
+                             2 * dp * sizeof(float)) +
+               (size_t)(2 * kMaxStages + 2 * kMaxFinalisers) * 8 + (size_t)kMaxStages * sizeof(int2);
+    };
+    auto stages_for = [&](int nf) {
+        int n = (int)((kSmemBudget - fixed_for(nf)) / p.t.stage_bytes);
+        n = n > kMaxStages ? kMaxStages : n;
+        return n / kGroups * kGroups;
+    };
+    p.nfin = 2;
+    if (p.t.unit_bytes <= 256 * 1024)
+        for (int nf = kMaxFinalisers; nf > 2; --nf)
+            if (stages_for(nf) == stages_for(2)) { p.nfin = nf; break; }
+    const size_t fixed = fixed_for(p.nfin);
     int nst = (int)((kSmemBudget - fixed) / p.t.stage_bytes);
     nst = nst > kMaxStages ? kMaxStages : nst;
     // A slot must always be consumed by the same warp group (slot = s % nst, group = s % kGroups): a waiter

@@ -4,7 +4,8 @@
 
 namespace xsup {
 
-constexpr int kFwdThreads = (kConsumerWarps + 3) * 32;   // 16 consumers + producer + 2 finalisers (even / odd units)
+constexpr int kMaxFinalisers = 3;    // 20 warps = 5 per scheduler partition: the register cap stays at 96 per thread
+constexpr int kFwdThreads = (kConsumerWarps + 1 + kMaxFinalisers) * 32;   // 16 consumers + producer + up to 3 finalisers (FwdParams::nfin)
 constexpr int kBwdThreads = (kConsumerWarps + 1) * 32;   // 16 consumers + producer
 constexpr size_t kSmemBudget = 227 * 1024;               // per-CTA opt-in maximum on sm_100
 constexpr int kMaxStages = 16;
@@ -18,6 +19,7 @@ struct FwdParams {
     float* stats;
     int n_units, K, NH, NS, head, stats_stride;
     int nst;
+    int nfin;          // finaliser warps = partial buffers (2..kMaxFinalisers), set by launch_integral_fwd
     int* counter;      // work-claim counter (zeroed by the launcher), in the caller's stats buffer
     Tiling t;
 };
