@@ -154,7 +154,7 @@ int xsup_geom_world_to_patch_vjp(const float* in, const float* g_out, float* g_i
  * primitives modules/base_losses/loss_func.py:18-52 for one camera.
  *   kps      [B,NH,K,3]  from xsup_integral_fwd        target [B,K,3] pseudo joints
  *   world    [B,NH,K,3]  out: world mm
- *   sample_terms [B,XSUP_LOSS_TERMS,NH] out: per-sample un-normalised sums
+ *   sample_terms [B,XSUP_LOSS_TERMS,NH] out: per-sample un-normalised sums (16-byte aligned: rows are summed as float4s)
  *   partial  [XSUP_LOSS_TERMS,NH] out: their fixed-order sum over this rank's batch
  *            (the only thing that crosses ranks: one all-reduce(SUM) in global scope)          */
 int xsup_reproj_loss_fwd(const float* kps, const float* target, const xsup_cam_t* cam, float* world,

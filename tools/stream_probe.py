@@ -1,7 +1,7 @@
 #!/usr/bin/env python
-"""Runs the streaming forward (xsup_integral_fwd) a few times at one shape; with TRACE=1 and a library built with
-XSUP_NVCC_EXTRA="-DXSUP_TRACE" prints the clock64 timeline of CTA 0 (see integral_fwd.cu K1TRACE).
-    python tools/k1_probe.py [--res 32] [--batch 4096] [--dtype bf16] [--iters 5]"""
+"""Times the streaming forward (xsup_integral_fwd) and backward (xsup_integral_bwd) alone at one shape; with TRACE=1 and a
+library built with XSUP_NVCC_EXTRA="-DXSUP_TRACE" prints the clock64 timeline of CTA 0 of the forward (integral_fwd.cu K1TRACE).
+    python tools/stream_probe.py [--res 32] [--batch 4096] [--dtype bf16] [--iters 5]"""
 import argparse, importlib, os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
@@ -35,7 +35,20 @@ for _ in range(a.iters):
 t1.record()
 torch.cuda.synchronize()
 ms = t0.elapsed_time(t1) / a.iters
-print("res %d B=%d %s: %.4f ms per call, %.1f GB/s" % (R, a.batch, a.dtype, ms, logits.numel() * logits.element_size() / ms / 1e6))
+print("fwd res %d B=%d %s: %.4f ms per call, %.1f GB/s" % (R, a.batch, a.dtype, ms, logits.numel() * logits.element_size() / ms / 1e6))
+_, shape, kps, _, _, stats = ops._head_forward(logits, K, NH, NS, ops.cabi.HEAD_MULTI)
+g_kps = torch.randn(kps.shape, device=dev, generator=g)
+g_logits = torch.empty_like(logits)
+for _ in range(2):
+    ops._head_backward(logits, stats, shape, g_kps, inplace=False)
+torch.cuda.synchronize()
+t0.record()
+for _ in range(a.iters):
+    ops._head_backward(logits, stats, shape, g_kps, inplace=False)
+t1.record()
+torch.cuda.synchronize()
+ms = t0.elapsed_time(t1) / a.iters
+print("bwd res %d B=%d %s: %.4f ms per call (coef + stream), %.1f GB/s" % (R, a.batch, a.dtype, ms, 2 * logits.numel() * logits.element_size() / ms / 1e6))
 if os.environ.get("TRACE"):
     tr = trace.cpu().view(16, 16)
     base = int(tr[0, 0])

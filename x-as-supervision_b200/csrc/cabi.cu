@@ -297,6 +297,7 @@ int xsup_reproj_loss_fwd(const float* kps, const float* target, const xsup_cam_t
     if (int rc = check_cam(cam, "xsup_reproj_loss_fwd")) return rc;
     if (!kps || !target || !world || !sample_terms || !partial) return fail(XSUP_E_NULL, "xsup_reproj_loss_fwd: NULL pointer");
     if (cfg->B == 0) return fail(XSUP_E_SHAPE, "xsup_reproj_loss_fwd: empty batch");
+    if (!aligned16(sample_terms)) return fail(XSUP_E_ALIGN, "xsup_reproj_loss_fwd: sample_terms must be 16-byte aligned");
     cudaError_t e = launch_reproj_loss_fwd(kps, target, *cam, world, sample_terms, partial, *cfg, (cudaStream_t)stream);
     if (e != cudaSuccess) return cuda_fail(e, "xsup_reproj_loss_fwd launch");
     count_launches(2);
@@ -350,6 +351,7 @@ int xsup_reproj_fused_fwd(const float* kps, const float* target, const xsup_cam_
     if (int rc = check_cfg(cfg, "xsup_reproj_fused_fwd")) return rc;
     if (int rc = check_cam(cam, "xsup_reproj_fused_fwd")) return rc;
     if (!kps || !target || !world || !sample_terms || !partial || !loss || !sel || !ticket) return fail(XSUP_E_NULL, "xsup_reproj_fused_fwd: NULL pointer");
+    if (!aligned16(sample_terms)) return fail(XSUP_E_ALIGN, "xsup_reproj_fused_fwd: sample_terms must be 16-byte aligned");
     if (cfg->B == 0) return fail(XSUP_E_SHAPE, "xsup_reproj_fused_fwd: empty batch");
     xsup_xchg_t x{};
     if (xchg) {

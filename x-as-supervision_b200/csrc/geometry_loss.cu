@@ -313,18 +313,47 @@ __global__ void __launch_bounds__(128) reproj_loss_fwd_kernel(const float* __res
     loss_fwd_warp(kps, target, cam, world, sample_terms, c, wid, lane);
 }
 
-// partial[col] = sum_b sample_terms[b,col], col = (term,h); one warp per column, fixed order (lane-strided, then the
-// xor tree), so the sums - and with them the selected slot - are bit-reproducible.  L2 loads: in the fused kernel the
-// terms were written by other CTAs of the same grid.
-__device__ __forceinline__ float partial_col(const float* sample_terms, int B, int stride, int col, int lane) {
-    float a = 0.f;
-    for (int b = lane; b < B; b += 32) a += __ldcg(sample_terms + (size_t)b * stride + col);
-    return warp_sum(a);
+// partial[col] = sum_b sample_terms[b,col], col = (term,h), by one block of 256 threads, in a fixed order, so the sums - and with
+// them the selected slot - are bit-reproducible.  A row is 4*NH floats = NH float4s: thread t owns float4-column t % NHP (NHP = NH
+// rounded up to a power of two) of the rows t / NHP, t / NHP + 256 / NHP, ...: neighbouring threads read neighbouring 16 bytes and
+// every load is independent of the others (B = 4 096, NH = 3: 64 LDG.128 per thread, where one warp per column took 2 x 128 dependent
+// round trips).  Then the xor tree over the lanes that share a column, the 8 warps (or the 256 / NHP row groups) in order.
+// L2 loads: in the fused kernel the terms were written by other CTAs of the same grid.  `sh`: 256 float4.
+static_assert(XSUP_LOSS_TERMS == 4, "a row of sample_terms is read as NH float4s");
+__device__ void partial_block(const float* sample_terms, float* partial, int B, int NH, float4* sh) {
+    const int t = threadIdx.x;
+    int nhp_log2 = 0;
+    while ((1 << nhp_log2) < NH) ++nhp_log2;
+    const int nhp = 1 << nhp_log2, c4 = t & (nhp - 1), rg = t >> nhp_log2, nrg = 256 >> nhp_log2;
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (c4 < NH) {
+        const float4* src = reinterpret_cast<const float4*>(sample_terms) + c4;
+#pragma unroll 8
+        for (int b = rg; b < B; b += nrg) {
+            const float4 v = __ldcg(src + (size_t)b * NH);
+            a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+        }
+    }
+    for (int o = 16; o >= nhp; o >>= 1) {                                     // lanes of a warp that share a column (NHP < 32)
+        a.x += __shfl_xor_sync(0xffffffffu, a.x, o);
+        a.y += __shfl_xor_sync(0xffffffffu, a.y, o);
+        a.z += __shfl_xor_sync(0xffffffffu, a.z, o);
+        a.w += __shfl_xor_sync(0xffffffffu, a.w, o);
+    }
+    sh[t] = a;
+    __syncthreads();
+    const float* shf = reinterpret_cast<const float*>(sh);
+    const int step = nhp < 32 ? 32 : nhp, n = 256 / step;                     // contributors of a column: threads c4, c4 + step, ...
+    for (int col = t; col < XSUP_LOSS_TERMS * NH; col += 256) {
+        float r = 0.f;
+        for (int i = 0; i < n; ++i) r += shf[(i * step + (col >> 2)) * 4 + (col & 3)];
+        partial[col] = r;
+    }
+    __syncthreads();
 }
-__global__ void __launch_bounds__(32) reproj_partial_kernel(const float* __restrict__ sample_terms, float* __restrict__ partial,
-                                                            int B, int NH) {
-    const float a = partial_col(sample_terms, B, XSUP_LOSS_TERMS * NH, blockIdx.x, threadIdx.x);
-    if (threadIdx.x == 0) partial[blockIdx.x] = a;
+__global__ void __launch_bounds__(256) reproj_partial_kernel(const float* sample_terms, float* __restrict__ partial, int B, int NH) {
+    __shared__ float4 sh[256];
+    partial_block(sample_terms, partial, B, NH, sh);
 }
 
 cudaError_t launch_reproj_loss_fwd(const float* kps, const float* target, const xsup_cam_t& cam, float* world,
@@ -333,7 +362,7 @@ cudaError_t launch_reproj_loss_fwd(const float* kps, const float* target, const 
     reproj_loss_fwd_kernel<<<(warps + 3) / 4, 128, 0, st>>>(kps, target, cam, world, sample_terms, c);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
-    reproj_partial_kernel<<<XSUP_LOSS_TERMS * c.NH, 32, 0, st>>>(sample_terms, partial, c.B, c.NH);
+    reproj_partial_kernel<<<1, 256, 0, st>>>(sample_terms, partial, c.B, c.NH);
     return cudaGetLastError();
 }
 
@@ -503,6 +532,7 @@ __global__ void __launch_bounds__(256) reproj_fused_fwd_kernel(const float* __re
                                                                float* partial, float* loss, int64_t* __restrict__ sel,
                                                                const xsup_loss_cfg_t c, const xsup_xchg_t x, unsigned int* ticket) {
     __shared__ int s_last;
+    __shared__ float4 sh_part[256];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int wid = blockIdx.x * 8 + warp;
     if (wid < c.B * c.NH) loss_fwd_warp(kps, target, cam, world, sample_terms, c, wid, lane);
@@ -513,11 +543,7 @@ __global__ void __launch_bounds__(256) reproj_fused_fwd_kernel(const float* __re
     if (!s_last) return;
     __threadfence();
     const int cols = XSUP_LOSS_TERMS * c.NH;
-    for (int col = warp; col < cols; col += 8) {
-        const float a = partial_col(sample_terms, c.B, cols, col, lane);
-        if (lane == 0) partial[col] = a;
-    }
-    __syncthreads();
+    partial_block(sample_terms, partial, c.B, c.NH, sh_part);
     const bool xch = x.peer_bufs != nullptr && x.world > 1;
     if (xch && c.reduction == XSUP_REDUCE_BATCH) xchg_allreduce_block(partial, cols, x.peer_bufs, x.rank, x.world, x.step, x.seq, x.err);
     select_block(kps, target, sample_terms, partial, loss, sel, c);
@@ -650,10 +676,10 @@ __global__ void __launch_bounds__(128) reproj_loss_bwd_kernel(const float* __res
 // with the upstream gradients on kps / kps_world, kept in shared memory; (2) the coefficient blocks of the sample's K
 // units for the streaming head backward (what integral_coef_kernel derives from grad_kps in global memory).  Replaces
 // loss_bwd + the ATen zeros/stack/add glue + integral_coef: the gradient w.r.t. kps never round-trips HBM.
-// kLossBwdWarps warps per sample: the hypotheses' vector-Jacobian products on warps 0..NH-1, then one (b,k) unit per warp - with 18
-// warps the 17-18 joints of the reference's skeletons take one round instead of three (the kernel is a chain of dependent loads).
-constexpr int kLossBwdWarps = 18;
-__global__ void __launch_bounds__(kLossBwdWarps * 32) reproj_fused_bwd_kernel(const float* __restrict__ kps, const float* __restrict__ target,
+// kLossBwdWarps warps per sample: the hypotheses' vector-Jacobian products on warps 0..NH-1, then one (b,k) unit per warp and round
+// (see launch_reproj_fused_bwd for the two configurations).
+template <int kLossBwdWarps, int MINB>
+__global__ void __launch_bounds__(kLossBwdWarps * 32, MINB) reproj_fused_bwd_kernel(const float* __restrict__ kps, const float* __restrict__ target,
                                                                const xsup_cam_t cam, const int64_t* __restrict__ sel,
                                                                const float* __restrict__ g_lp, const float* __restrict__ g_ls,
                                                                const float* __restrict__ g_kps_in, const float* __restrict__ g_world,
@@ -665,6 +691,20 @@ __global__ void __launch_bounds__(kLossBwdWarps * 32) reproj_fused_bwd_kernel(co
     float* gyp = gxp + kLossBwdWarps * 32;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, b = blockIdx.x;
     if (b == 0 && threadIdx.x == 0) *p.counter = 0;                          // work-claim counter of the streaming kernel that follows
+    const int D = p.D;
+    // Second-phase inputs that do not depend on the first phase, fetched before it so that the two round trips to L2 overlap:
+    // lane h holds (peak bin, window sum, window mean) of hypothesis h of this warp's first unit.  (Read inside the window test
+    // of the loop over d they were 2 * NH dependent round trips per unit: the whole kernel is latency.)
+    float t_idx = 0.f, t_sw = 1.f, t_zb = 0.f, pz0 = 0.f, pz1 = 0.f;
+    if (warp < K) {
+        const float* __restrict__ st0 = p.stats + (size_t)(b * K + warp) * p.stats_stride;
+        if (lane < NH) {
+            const float* sh = st0 + 4 + D + 3 * lane;
+            t_idx = sh[0]; t_sw = sh[1]; t_zb = sh[2];
+        }
+        if (lane < D) pz0 = st0[4 + lane];                   // the depth marginal of the first two 32-bin chunks (all of it at D <= 64)
+        if (32 + lane < D) pz1 = st0[4 + 32 + lane];
+    }
     const float gl0 = g_lp ? *g_lp : 0.f, gl1 = g_ls ? *g_ls : 0.f;
     float ax = 0.f, ay = 0.f;
     for (int h = warp; h < NH; h += kLossBwdWarps) {
@@ -681,28 +721,45 @@ __global__ void __launch_bounds__(kLossBwdWarps * 32) reproj_fused_bwd_kernel(co
     gxp[warp * 32 + lane] = ax;
     gyp[warp * 32 + lane] = ay;
     __syncthreads();
-    const int D = p.D;
     const float zs = 2.0f / (float)D;
     const int half = p.NS >> 1;
+    const int nh_reg = NH < 32 ? NH : 32;
     for (int k = warp; k < K; k += kLossBwdWarps) {
         const int unit = b * K + k;
-        const float* st = p.stats + (size_t)unit * p.stats_stride;
-        float* cf = p.coef + (size_t)unit * p.coef_stride;
+        const float* __restrict__ st = p.stats + (size_t)unit * p.stats_stride;
+        float* __restrict__ cf = p.coef + (size_t)unit * p.coef_stride;
+        if (k != warp) {                                     // more joints than warps: this round's inputs
+            if (lane < NH) {
+                const float* sh = st + 4 + D + 3 * lane;
+                t_idx = sh[0]; t_sw = sh[1]; t_zb = sh[2];
+            }
+            pz0 = lane < D ? st[4 + lane] : 0.f;
+            pz1 = 32 + lane < D ? st[4 + 32 + lane] : 0.f;
+        }
         float gx = 0.f, gy = 0.f;
 #pragma unroll
         for (int w = 0; w < kLossBwdWarps; ++w) { gx += gxp[w * 32 + k]; gy += gyp[w * 32 + k]; }
         const float a = gx * (2.0f / (float)p.H);            // x was normalised by H (…_multi.py:78)
         const float bb = gy * (2.0f / (float)p.W);           // y by W (…:79)
         float dot = 0.f;
-        for (int d = lane; d < D; d += 32) {
+        for (int d0 = 0; d0 < D; d0 += 32) {
+            const int d = d0 + lane;
+            const float pzd = d0 == 0 ? pz0 : d0 == 32 ? pz1 : d < D ? st[4 + d] : 0.f;
             float cd = 0.f;
-            for (int h = 0; h < NH; ++h) {
+            for (int h = 0; h < nh_reg; ++h) {               // same terms, same order as integral_coef_kernel
+                const int idx = (int)__shfl_sync(0xffffffffu, t_idx, h);
+                const float sw = __shfl_sync(0xffffffffu, t_sw, h), zb = __shfl_sync(0xffffffffu, t_zb, h);
+                if (d >= idx - half && d <= idx + half) cd += gz[h * 32 + k] * zs * ((float)d - zb) / sw;
+            }
+            for (int h = 32; h < NH; ++h) {
                 const float* sh = st + 4 + D + 3 * h;
                 const int idx = (int)sh[0];
                 if (d >= idx - half && d <= idx + half) cd += gz[h * 32 + k] * zs * ((float)d - sh[2]) / sh[1];
             }
-            cf[8 + d] = cd;
-            dot = fmaf(cd, st[4 + d], dot);
+            if (d < D) {
+                cf[8 + d] = cd;
+                dot = fmaf(cd, pzd, dot);
+            }
         }
         dot = warp_sum(dot);
         if (lane == 0) {
@@ -722,8 +779,16 @@ __global__ void __launch_bounds__(kLossBwdWarps * 32) reproj_fused_bwd_kernel(co
 cudaError_t launch_reproj_fused_bwd(const float* kps, const float* target, const xsup_cam_t& cam, const int64_t* sel, const float* g_lp,
                                     const float* g_ls, const float* g_kps_in, const float* g_world, float* g_kps_out,
                                     const xsup_loss_cfg_t& c, const CoefParams& p, cudaStream_t st) {
-    const size_t smem = ((size_t)c.NH * 32 + 2 * kLossBwdWarps * 32) * sizeof(float);       // <= 37 KB (NH <= 254)
-    reproj_fused_bwd_kernel<<<c.B, kLossBwdWarps * 32, smem, st>>>(kps, target, cam, sel, g_lp, g_ls, g_kps_in, g_world, g_kps_out, c, p);
+    auto smem_for = [&](int warps) { return ((size_t)c.NH * 32 + 2 * warps * 32) * sizeof(float); };    // <= 37 KB (NH <= 254)
+    // The kernel is a chain of two round trips to L2 per CTA, so its duration is CTAs / (CTAs in flight) x that latency.  Up to two
+    // samples per SM: 18 warps (every joint of the reference's skeletons in one round), 56 registers so that two CTAs fit on an SM
+    // (with 87 it was one: B = 256 took two waves).  Beyond that: 9 warps, four CTAs per SM, the joints in two rounds.
+    // Measured, 32^3 NH = 3, us at B = 64 / 256 / 1 024 / 4 096: 18 warps x 1 per SM 10.7 / 14.4 / 30.9 / 100; 18 x 2: 10.6 / 11.8 / 22.6 /
+    // 65.6; 9 x 4: 12.3 / 12.4 / 18.3 / 45.0; 6 x 6: 13.4 / 14.2 / 18.7 / 41.3.
+    if (c.B <= 2 * 148)
+        reproj_fused_bwd_kernel<18, 2><<<c.B, 18 * 32, smem_for(18), st>>>(kps, target, cam, sel, g_lp, g_ls, g_kps_in, g_world, g_kps_out, c, p);
+    else
+        reproj_fused_bwd_kernel<9, 4><<<c.B, 9 * 32, smem_for(9), st>>>(kps, target, cam, sel, g_lp, g_ls, g_kps_in, g_world, g_kps_out, c, p);
     return cudaGetLastError();
 }
 

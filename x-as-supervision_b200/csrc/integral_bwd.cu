@@ -13,6 +13,8 @@
 // Streaming kernel structure: persistent CTA per SM; warp 16 = TMA producer (bulk copy of the
 // stage and of its unit's coefficient block into the same ring slot), warps 0..15 = stateless
 // consumers (LDS.128 -> registers -> one MUFU.EX2 + 3 FP ops per element -> coalesced STG.128).
+#include <stdlib.h>
+
 #include "xsup_internal.h"
 
 namespace xsup {
@@ -38,13 +40,29 @@ __global__ void __launch_bounds__(128) integral_coef_kernel(const CoefParams p) 
     const float zs = 2.0f / (float)D;
     const int half = p.NS >> 1;
     const float zc = p.head == XSUP_HEAD_SINGLE ? rintf(st[4 + D]) : 0.f;   // single head: centre d as well
+    // lane h: (peak bin, window sum, window mean, upstream z gradient) of hypothesis h, one round trip instead of a dependent one per
+    // hypothesis inside the window test below
+    float t_idx = 0.f, t_sw = 1.f, t_zb = 0.f, t_gz = 0.f;
+    if (p.head != XSUP_HEAD_SINGLE && lane < NH) {
+        const float* sh = st + 4 + D + 3 * lane;
+        t_idx = sh[0]; t_sw = sh[1]; t_zb = sh[2];
+        t_gz = p.g_kps[(((size_t)b * NH + lane) * p.K + k) * 3 + 2];
+    }
+    const int nh_reg = NH < 32 ? NH : 32;
     float dot = 0.f;
-    for (int d = lane; d < D; d += 32) {
+    for (int d0 = 0; d0 < D; d0 += 32) {
+        const int d = d0 + lane;
         float c = 0.f;
         if (p.head == XSUP_HEAD_SINGLE) {
             c = p.g_kps[((size_t)b * p.K + k) * 3 + 2] * zs * ((float)d - zc);
         } else {
-            for (int h = 0; h < NH; ++h) {
+            for (int h = 0; h < nh_reg; ++h) {
+                const int idx = (int)__shfl_sync(0xffffffffu, t_idx, h);
+                const float sw = __shfl_sync(0xffffffffu, t_sw, h), zb = __shfl_sync(0xffffffffu, t_zb, h);
+                const float gz = __shfl_sync(0xffffffffu, t_gz, h);
+                if (d >= idx - half && d <= idx + half) c += gz * zs * ((float)d - zb) / sw;
+            }
+            for (int h = 32; h < NH; ++h) {
                 const float* sh = st + 4 + D + 3 * h;
                 const int idx = (int)sh[0];
                 if (d >= idx - half && d <= idx + half) {
@@ -53,8 +71,10 @@ __global__ void __launch_bounds__(128) integral_coef_kernel(const CoefParams p) 
                 }
             }
         }
-        cf[8 + d] = c;
-        dot = fmaf(c, st[4 + d], dot);
+        if (d < D) {
+            cf[8 + d] = c;
+            dot = fmaf(c, st[4 + d], dot);
+        }
     }
     dot = warp_sum(dot);
     if (lane == 0) {
