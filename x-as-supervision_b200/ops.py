@@ -349,18 +349,17 @@ class IntegralReprojMinLoss(torch.autograd.Function):
                 if reduction != "batch":
                     xdist.reduce_partials(loss, group)           # reporting only: the gradient needs just n_total
         ctx.save_for_backward(logits, stats, kps, target, sel, *keep)
-        ctx.shape, ctx.cfg = shape, cfg
+        ctx.shape, ctx.cfg, ctx.cam = shape, cfg, cam          # `cam` holds raw pointers into `keep`, which the line above keeps alive
         ctx.mark_non_differentiable(sel, dmap, idx)
         return loss[0], loss[1], sel, kps, world, dmap, idx
 
     @staticmethod
     def backward(ctx, g_lp, g_ls, _g_sel, g_kps_out, g_world, _g_dmap, _g_idx):
         logits, stats, kps, target, sel, *keep = ctx.saved_tensors
-        shape, cfg = ctx.shape, ctx.cfg
+        shape, cfg, cam = ctx.shape, ctx.cfg, ctx.cam
         dev = logits.device
         if g_lp is None and g_ls is None and g_kps_out is None and g_world is None:
             return (None,) * 18
-        cam = cabi.make_cam(*keep, shape.B)
 
         def ptr(t):                                   # fp32 contiguous device tensor or NULL; no kernels for fp32 inputs
             if t is None:
