@@ -370,7 +370,7 @@ def gate_vs_cpu_port(x, c):
     (lp + ls).backward()
     torch.cuda.synchronize()
     e = {"slots_equal": sel.tolist() == ref["sel"],
-         "loss_rel": abs(float(lp + ls) - (ref["lp"] + ref["ls"])) / max(abs(ref["lp"] + ref["ls"]), 1e-30),
+         "loss_rel": abs(float((lp + ls).detach()) - (ref["lp"] + ref["ls"])) / max(abs(ref["lp"] + ref["ls"]), 1e-30),
          "kps_rel": rel_inf(kps.detach().cpu(), ref["kps"]),
          "grad_rel_inf": rel_inf(xl.grad.float().cpu(), ref["grad"])}
     # the comparator is the reference's own fp32 CPU arithmetic (softmax accurate to ~1e-5 per element)
@@ -424,7 +424,7 @@ def gate_multi_gpu(x, c):
     (rlp + rls).backward()
     shard = all_logits.grad[x.rank * Bs:(x.rank + 1) * Bs]
     tol = 1e-6 if c["dtype"] == "f32" else 2.0 ** -8
-    e_loss = abs(float(lp + ls) - float(rlp + rls)) / max(abs(float(rlp + rls)), 1e-30)
+    e_loss = abs(float((lp + ls).detach()) - float((rlp + rls).detach())) / max(abs(float((rlp + rls).detach())), 1e-30)
     e_grad = rel_inf(logits.grad.float(), shard.float()) if float(shard.float().abs().max()) > 0 else float(logits.grad.float().abs().max())
     ok = sel.tolist() == rsel.tolist() and e_loss < 1e-6 and e_grad < tol and torch.equal(kps.detach(), rkps.detach()[x.rank * Bs:(x.rank + 1) * Bs])
     if isinstance(x.group, x.pkg.dist.PeerExchange):
