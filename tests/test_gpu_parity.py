@@ -235,6 +235,29 @@ def test_fused_loss_against_oracle(ops, oracle, synth, dev, reduction, sym):
     assert rel_l2(x.grad.cpu().numpy(), x64.grad.numpy()) < TOL
 
 
+@pytest.mark.parametrize("reduction", ["batch", "sample"])
+def test_fused_loss_against_oracle_many_samples(ops, oracle, synth, dev, reduction):
+    """More than two samples per SM: the batch sums of the last CTA walk several rows per thread and the loss backward runs
+    with 9 warps per sample (two rounds over the 17 joints)."""
+    B, K, R, NH, NS = 333, 17, 16, 3, 5
+    logits = synth.iid_logits(B, K, R, R, R, seed=51)
+    target = synth.pseudo_joints(B, K, seed=52)
+    cams = synth.cameras(B, seed=53)
+    w = dict(w_mse=1.5, w_bone=0.1, w_kp=0.2, w_kp2d=0.3)
+    x64 = logits.double().requires_grad_(True)
+    olp, ols, osel, okps, oworld, _, _ = oracle.fused_forward(x64, K, NH, NS, target.double(),
+                                                               {k: v.double() for k, v in cams.items()}, reduction=reduction, **w)
+    (olp + 0.7 * ols).backward()
+    x = logits.to(dev).requires_grad_(True)
+    lp, ls, sel, kps, world, _, _ = ops.integral_reproj_min_loss(x, target.to(dev), {k: v.to(dev) for k, v in cams.items()},
+                                                                 K, NH, NS, reduction=reduction, **w)
+    (lp + 0.7 * ls).backward()
+    assert torch.equal(sel.cpu(), osel)
+    np.testing.assert_allclose([lp.item(), ls.item()], [olp.item(), ols.item()], rtol=TOL, atol=1e-9)
+    assert rel_inf(x.grad.cpu().numpy(), x64.grad.numpy()) < TOL
+    assert rel_l2(x.grad.cpu().numpy(), x64.grad.numpy()) < TOL
+
+
 def test_downstream_gradients_through_kps_and_world(ops, oracle, synth, dev):
     """The fused op's kps / kps_world outputs stay differentiable (draw_lines and the generator loss
     consume them in the reference, model.py:91,128-138)."""
@@ -521,7 +544,7 @@ def test_largest_sweep_batch_in_place(ops, synth, dev):
     assert s < 1e-6 * grad.abs().max().item() * R ** 3
 
 
-@pytest.mark.parametrize("R,NH,NS", [(16, 14, 1), (16, 14, 31), (32, 30, 3), (16, 1, 33)])
+@pytest.mark.parametrize("R,NH,NS", [(16, 14, 1), (16, 14, 31), (32, 30, 3), (16, 1, 33), (64, 40, 5)])
 def test_extreme_hypothesis_counts_and_windows(ops, oracle, synth, dev, R, NH, NS):
     """The limits the ABI accepts: NH = D-2 (every interior bin becomes a hypothesis, mostly filler slots), a window of
     one bin, and a window wider than the whole depth axis (the average pools then cover the zero padding only)."""
@@ -572,13 +595,17 @@ def test_geometry_with_general_matrices(ops, oracle, synth, dev):
 # ------------------------------------------------------------------------------------------ fused K2 launches vs the separate calls
 @pytest.mark.parametrize("reduction", ["batch", "sample", "joint"])
 @pytest.mark.parametrize("sym", [False, True])
-def test_fused_loss_launches_equal_the_separate_calls(ops, synth, dev, reduction, sym):
+@pytest.mark.parametrize("dims", [(37, 18, 16, 5, 5),      # 37*5 warps: a ragged last CTA; backward with 18 warps per sample
+                                  (333, 18, 16, 5, 5),     # more than two samples per SM: backward with 9 warps, joints in two rounds
+                                  (5, 17, 64, 40, 5)],     # more hypotheses than lanes: the tail of the window-triple loop
+                         ids=["b37", "b333", "nh40"])
+def test_fused_loss_launches_equal_the_separate_calls(ops, synth, dev, reduction, sym, dims):
     """xsup_reproj_fused_fwd == loss_fwd -> select, and xsup_reproj_fused_bwd == loss_bwd (+ upstream gradients) ->
     integral_coef, through the C ABI: the same device code in one launch each, so the results are bit-identical."""
     if reduction == "joint" and sym:
         pytest.skip("symmetry terms are undefined per joint")
     cabi = importlib.import_module("x-as-supervision_b200._cabi")
-    B, K, R, NH, NS = 37, 18, 16, 5, 5                                   # 37*5 warps: a ragged last CTA
+    B, K, R, NH, NS = dims
     logits = synth.iid_logits(B, K, R, R, R, seed=101).to(dev)
     target = synth.pseudo_joints(B, K, seed=102).to(dev)
     cams = {k: v.to(dev) for k, v in synth.cameras(B, seed=103).items()}
