@@ -236,26 +236,40 @@ def test_fused_loss_against_oracle(ops, oracle, synth, dev, reduction, sym):
 
 
 @pytest.mark.parametrize("reduction", ["batch", "sample"])
-def test_fused_loss_against_oracle_many_samples(ops, oracle, synth, dev, reduction):
+@pytest.mark.parametrize("sym", [False, True])
+def test_fused_loss_against_oracle_many_samples(ops, oracle, synth, dev, reduction, sym):
     """More than two samples per SM: the batch sums of the last CTA walk several rows per thread and the loss backward runs
-    with 9 warps per sample (two rounds over the 17 joints)."""
-    B, K, R, NH, NS = 333, 17, 16, 3, 5
+    with 9 warps per sample (two rounds over the 17 joints).  Among 333 random skeletons some have a bone of ~1 mm (sample 109:
+    joints 4-5, 1.15 mm at world coordinates of a few metres), whose direction no fp32 evaluation resolves: there the element-wise
+    bound is twice the error of the reference's OWN arithmetic run in fp32 (measured: 4.4e-5 .. 7.1e-5 of the largest gradient,
+    2.1e-5 .. 2.4e-5 norm-wise; ours 4.5e-5 .. 5.9e-5 and 7.5e-6 .. 8.9e-6); norm-wise, and element-wise without the symmetry terms,
+    the 1e-5 bound holds as everywhere else."""
+    B, K, R, NH, NS = 333, 17, 32, 3, 5
     logits = synth.iid_logits(B, K, R, R, R, seed=51)
     target = synth.pseudo_joints(B, K, seed=52)
     cams = synth.cameras(B, seed=53)
-    w = dict(w_mse=1.5, w_bone=0.1, w_kp=0.2, w_kp2d=0.3)
-    x64 = logits.double().requires_grad_(True)
-    olp, ols, osel, okps, oworld, _, _ = oracle.fused_forward(x64, K, NH, NS, target.double(),
-                                                               {k: v.double() for k, v in cams.items()}, reduction=reduction, **w)
-    (olp + 0.7 * ols).backward()
+    w = dict(w_mse=1.5, w_bone=0.1 if sym else None, w_kp=0.2 if sym else None, w_kp2d=0.3 if sym else None)
+    ref = {}
+    for dt in (torch.float64, torch.float32):
+        xo = logits.clone().to(dt).requires_grad_(True)
+        olp, ols, osel, _, _, _, _ = oracle.fused_forward(xo, K, NH, NS, target.to(dt), {k: v.to(dt) for k, v in cams.items()},
+                                                          reduction=reduction, **w)
+        (olp + 0.7 * ols).backward()
+        ref[dt] = (olp.item(), ols.item(), osel, xo.grad.double().numpy())
+    olp, ols, osel, g64 = ref[torch.float64]
     x = logits.to(dev).requires_grad_(True)
     lp, ls, sel, kps, world, _, _ = ops.integral_reproj_min_loss(x, target.to(dev), {k: v.to(dev) for k, v in cams.items()},
                                                                  K, NH, NS, reduction=reduction, **w)
     (lp + 0.7 * ls).backward()
     assert torch.equal(sel.cpu(), osel)
-    np.testing.assert_allclose([lp.item(), ls.item()], [olp.item(), ols.item()], rtol=TOL, atol=1e-9)
-    assert rel_inf(x.grad.cpu().numpy(), x64.grad.numpy()) < TOL
-    assert rel_l2(x.grad.cpu().numpy(), x64.grad.numpy()) < TOL
+    np.testing.assert_allclose([lp.item(), ls.item()], [olp, ols], rtol=TOL, atol=1e-9)
+    got = x.grad.cpu().numpy()
+    e_inf, e_l2 = rel_inf(got, g64), rel_l2(got, g64)
+    r_inf, r_l2 = rel_inf(ref[torch.float32][3], g64), rel_l2(ref[torch.float32][3], g64)
+    print("many samples (%s, sym=%s): gradient rel_inf %.2e rel_l2 %.2e; the reference's arithmetic in fp32: %.2e / %.2e"
+          % (reduction, sym, e_inf, e_l2, r_inf, r_l2))
+    assert e_l2 < TOL
+    assert e_inf < (max(TOL, 2.0 * r_inf) if sym else TOL)          # the same order as the reference's own fp32 noise (4.4e-5 .. 7.1e-5)
 
 
 def test_downstream_gradients_through_kps_and_world(ops, oracle, synth, dev):
