@@ -13,8 +13,6 @@
 // Streaming kernel structure: persistent CTA per SM; warp 16 = TMA producer (bulk copy of the
 // stage and of its unit's coefficient block into the same ring slot), warps 0..15 = stateless
 // consumers (LDS.128 -> registers -> one MUFU.EX2 + 3 FP ops per element -> coalesced STG.128).
-#include <stdlib.h>
-
 #include "xsup_internal.h"
 
 namespace xsup {

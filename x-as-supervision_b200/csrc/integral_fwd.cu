@@ -15,7 +15,9 @@
 //   warps 17..   finalisers (2, or 3 for units of at most 256 KB; unit i of the CTA goes to finaliser i mod n): log-sum-exp
 //                combine of the per-task/per-warp partials, peaks, top-NH, window depth, outputs + saved-for-backward
 //                stats; overlaps the stream of the next n-1 units
+#ifdef XSUP_TRACE
 #include <stdlib.h>
+#endif
 
 #include "xsup_internal.h"
 #include "xsup_finalise.cuh"
